@@ -1,0 +1,800 @@
+/*
+ * oracle.c — CPU restatement of the reference Endpoint-Picker hot path (see oracle.h).
+ * TEST INFRASTRUCTURE ONLY — never linked into or called from the product library.
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off -fPIC -shared -pthread (oracle/Makefile).
+ * -ffp-contract=off matters: the shipped reference is GOARCH=amd64/GOAMD64=v1 (Dockerfile:9-10),
+ * for which Go never fuses x += a*b, so the weighted sum is mul-then-add in float64.
+ */
+#define _GNU_SOURCE
+#include "oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* =====================================================================================
+ * XXH64 — public specification (Yann Collet), as implemented by cespare/xxhash/v2 v2.3.0.
+ * Call sites restated: approximateprefix/hashing.go:70-94 (New/Write/Reset/Sum64, seed 0).
+ * ===================================================================================== */
+#define P1 0x9E3779B185EBCA87ULL
+#define P2 0xC2B2AE3D27D4EB4FULL
+#define P3 0x165667B19E3779F9ULL
+#define P4 0x85EBCA77C2B2AE63ULL
+#define P5 0x27D4EB2F165667C5ULL
+
+static inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+static inline uint64_t rd64(const uint8_t *p) {
+  uint64_t v;
+  memcpy(&v, p, 8); /* little-endian host (x86-64) */
+  return v;
+}
+static inline uint32_t rd32(const uint8_t *p) {
+  uint32_t v;
+  memcpy(&v, p, 4);
+  return v;
+}
+static inline uint64_t xxh_round(uint64_t acc, uint64_t in) {
+  acc += in * P2;
+  acc = rotl64(acc, 31);
+  return acc * P1;
+}
+static inline uint64_t xxh_merge(uint64_t h, uint64_t v) {
+  v = xxh_round(0, v);
+  h ^= v;
+  return h * P1 + P4;
+}
+
+uint64_t orc_xxh64(const void *data, size_t len, uint64_t seed) {
+  const uint8_t *p = (const uint8_t *)data;
+  const uint8_t *end = p + len;
+  uint64_t h;
+  if (len >= 32) {
+    uint64_t v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+    const uint8_t *limit = end - 32;
+    do {
+      v1 = xxh_round(v1, rd64(p));
+      v2 = xxh_round(v2, rd64(p + 8));
+      v3 = xxh_round(v3, rd64(p + 16));
+      v4 = xxh_round(v4, rd64(p + 24));
+      p += 32;
+    } while (p <= limit);
+    h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+    h = xxh_merge(h, v1);
+    h = xxh_merge(h, v2);
+    h = xxh_merge(h, v3);
+    h = xxh_merge(h, v4);
+  } else {
+    h = seed + P5;
+  }
+  h += (uint64_t)len;
+  while (p + 8 <= end) {
+    h ^= xxh_round(0, rd64(p));
+    h = rotl64(h, 27) * P1 + P4;
+    p += 8;
+  }
+  if (p + 4 <= end) {
+    h ^= (uint64_t)rd32(p) * P1;
+    h = rotl64(h, 23) * P2 + P3;
+    p += 4;
+  }
+  while (p < end) {
+    h ^= (uint64_t)(*p) * P5;
+    h = rotl64(h, 11) * P1;
+    p++;
+  }
+  h ^= h >> 33;
+  h *= P2;
+  h ^= h >> 29;
+  h *= P3;
+  h ^= h >> 32;
+  return h;
+}
+
+/* hashing.go:70-77: h := xxhash.New(); h.Write(model); if salt != "" { h.Write(salt) }; h.Sum64().
+ * Streaming writes == one-shot over the concatenation. */
+uint64_t orc_model_seed(const void *model, size_t model_len, const void *salt, size_t salt_len) {
+  size_t n = model_len + salt_len;
+  uint8_t stack[256] = {0};
+  uint8_t *buf = n <= sizeof(stack) ? stack : (uint8_t *)malloc(n);
+  if (model_len) memcpy(buf, model, model_len);
+  if (salt_len) memcpy(buf + model_len, salt, salt_len);
+  uint64_t h = orc_xxh64(buf, n, 0);
+  if (buf != stack) free(buf);
+  return h;
+}
+
+/* One chained link: XXH64(block || LE64(prev))  (hashing.go:79-85, toBytes :100-104). */
+static uint64_t hash_link(const uint8_t *block, size_t blen, uint64_t prev) {
+  uint8_t stack[512];
+  size_t n = blen + 8;
+  uint8_t *buf = n <= sizeof(stack) ? stack : (uint8_t *)malloc(n);
+  memcpy(buf, block, blen);
+  memcpy(buf + blen, &prev, 8); /* binary.LittleEndian.PutUint64 */
+  uint64_t h = orc_xxh64(buf, n, 0);
+  if (buf != stack) free(buf);
+  return h;
+}
+
+/* hashPrompt, hashing.go:34-98 (userInput already flattened by the host, getUserInputBytes :106). */
+int32_t orc_hash_prompt(const uint8_t *input, int64_t len, uint64_t model_seed, int32_t block_chars,
+                        int32_t max_blocks, uint64_t *out, int32_t out_cap) {
+  if (block_chars <= 0) return 0;                 /* :51-56 */
+  if (len < (int64_t)block_chars) return 0;       /* :57-60 */
+  int64_t cap = (int64_t)block_chars * (int64_t)max_blocks;
+  if (len > cap) len = cap;                       /* :62-65 (maxBlocks<=0 ⇒ nothing left) */
+  if (len < 0) len = 0;
+  uint64_t prev = model_seed;                     /* :78 */
+  int32_t n = 0;
+  int64_t i = 0;
+  for (; i + block_chars <= len; i += block_chars) { /* :80-87 */
+    if (n >= out_cap) return -1;
+    prev = hash_link(input + i, (size_t)block_chars, prev);
+    out[n++] = prev;
+  }
+  if (i < len) {                                  /* :89-95 trailing partial block */
+    if (n >= out_cap) return -1;
+    out[n++] = hash_link(input + i, (size_t)(len - i), prev);
+  }
+  return n;
+}
+
+/* =====================================================================================
+ * u64 -> u32 open-addressing map with backward-shift deletion (helper; stands in for Go maps).
+ * ===================================================================================== */
+typedef struct {
+  uint64_t *key;
+  uint32_t *val; /* 0 = empty slot, else value+1 */
+  uint64_t cap;  /* power of two */
+  uint64_t n;
+} u64map;
+
+static inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+static void u64map_init(u64map *m, uint64_t cap) {
+  uint64_t c = 16;
+  while (c < cap) c <<= 1;
+  m->cap = c;
+  m->n = 0;
+  m->key = (uint64_t *)calloc(c, sizeof(uint64_t));
+  m->val = (uint32_t *)calloc(c, sizeof(uint32_t));
+}
+static void u64map_free(u64map *m) {
+  free(m->key);
+  free(m->val);
+  m->key = NULL;
+  m->val = NULL;
+}
+static int64_t u64map_find(const u64map *m, uint64_t k) {
+  uint64_t mask = m->cap - 1, i = mix64(k) & mask;
+  while (m->val[i]) {
+    if (m->key[i] == k) return (int64_t)i;
+    i = (i + 1) & mask;
+  }
+  return -1;
+}
+static void u64map_put_nogrow(u64map *m, uint64_t k, uint32_t v) {
+  uint64_t mask = m->cap - 1, i = mix64(k) & mask;
+  while (m->val[i]) {
+    if (m->key[i] == k) {
+      m->val[i] = v + 1;
+      return;
+    }
+    i = (i + 1) & mask;
+  }
+  m->key[i] = k;
+  m->val[i] = v + 1;
+  m->n++;
+}
+static void u64map_put(u64map *m, uint64_t k, uint32_t v) {
+  if ((m->n + 1) * 2 > m->cap) {
+    u64map old = *m;
+    u64map_init(m, old.cap * 2);
+    for (uint64_t i = 0; i < old.cap; i++)
+      if (old.val[i]) u64map_put_nogrow(m, old.key[i], old.val[i] - 1);
+    u64map_free(&old);
+  }
+  u64map_put_nogrow(m, k, v);
+}
+static int u64map_get(const u64map *m, uint64_t k, uint32_t *v) {
+  int64_t i = u64map_find(m, k);
+  if (i < 0) return 0;
+  *v = m->val[i] - 1;
+  return 1;
+}
+static void u64map_del(u64map *m, uint64_t k) {
+  int64_t f = u64map_find(m, k);
+  if (f < 0) return;
+  uint64_t mask = m->cap - 1, i = (uint64_t)f, j = i;
+  m->val[i] = 0;
+  m->n--;
+  for (;;) {
+    j = (j + 1) & mask;
+    if (!m->val[j]) break;
+    uint64_t home = mix64(m->key[j]) & mask;
+    /* move j into the hole i unless home lies cyclically in (i, j] */
+    int between = (i <= j) ? (home > i && home <= j) : (home > i || home <= j);
+    if (!between) {
+      m->key[i] = m->key[j];
+      m->val[i] = m->val[j];
+      m->val[j] = 0;
+      i = j;
+    }
+  }
+}
+
+/* =====================================================================================
+ * LRU with the semantics indexer.go relies on from hashicorp/golang-lru/v2 v2.0.7
+ * (go.mod:13; call sites indexer.go:64,71,139-140,177-178): Add of an existing key refreshes
+ * recency without eviction; a new key is pushed to the front, and if Len() > size the OLDEST
+ * is removed and the eviction callback fires; Remove fires the callback; Keys() oldest→newest.
+ * ===================================================================================== */
+typedef struct {
+  int32_t size; /* capacity */
+  int32_t len;
+  uint64_t *key;
+  int32_t *prev, *next; /* node indices; -1 = none */
+  int32_t head, tail;   /* head = newest, tail = oldest */
+  int32_t free_head;
+  int32_t nodes_cap;
+  u64map items;
+} lru_t;
+
+static lru_t *lru_new(int32_t size) {
+  lru_t *l = (lru_t *)calloc(1, sizeof(lru_t));
+  l->size = size;
+  l->head = l->tail = -1;
+  l->free_head = -1;
+  l->nodes_cap = 0;
+  u64map_init(&l->items, 64);
+  return l;
+}
+static void lru_free(lru_t *l) {
+  if (!l) return;
+  free(l->key);
+  free(l->prev);
+  free(l->next);
+  u64map_free(&l->items);
+  free(l);
+}
+static int32_t lru_alloc_node(lru_t *l) {
+  if (l->free_head >= 0) {
+    int32_t n = l->free_head;
+    l->free_head = l->next[n];
+    return n;
+  }
+  if (l->len >= l->nodes_cap) {
+    int32_t nc = l->nodes_cap ? l->nodes_cap * 2 : 64;
+    l->key = (uint64_t *)realloc(l->key, sizeof(uint64_t) * (size_t)nc);
+    l->prev = (int32_t *)realloc(l->prev, sizeof(int32_t) * (size_t)nc);
+    l->next = (int32_t *)realloc(l->next, sizeof(int32_t) * (size_t)nc);
+    /* nodes [nodes_cap, nc) are fresh: thread all but the first onto the free list */
+    for (int32_t i = nc - 1; i > l->nodes_cap; i--) {
+      l->next[i] = l->free_head;
+      l->free_head = i;
+    }
+    int32_t n = l->nodes_cap;
+    l->nodes_cap = nc;
+    return n;
+  }
+  return -1; /* unreachable */
+}
+static void lru_unlink(lru_t *l, int32_t n) {
+  int32_t p = l->prev[n], q = l->next[n];
+  if (p >= 0) l->next[p] = q; else l->head = q;
+  if (q >= 0) l->prev[q] = p; else l->tail = p;
+}
+static void lru_push_front(lru_t *l, int32_t n) {
+  l->prev[n] = -1;
+  l->next[n] = l->head;
+  if (l->head >= 0) l->prev[l->head] = n;
+  l->head = n;
+  if (l->tail < 0) l->tail = n;
+}
+/* returns 1 and sets *evicted when an eviction happened */
+static int lru_add(lru_t *l, uint64_t k, uint64_t *evicted) {
+  uint32_t n;
+  if (u64map_get(&l->items, k, &n)) {
+    lru_unlink(l, (int32_t)n);
+    lru_push_front(l, (int32_t)n);
+    return 0;
+  }
+  int32_t node = lru_alloc_node(l);
+  l->key[node] = k;
+  lru_push_front(l, node);
+  u64map_put(&l->items, k, (uint32_t)node);
+  l->len++;
+  if (l->len > l->size) {
+    int32_t t = l->tail;
+    *evicted = l->key[t];
+    lru_unlink(l, t);
+    u64map_del(&l->items, l->key[t]);
+    l->next[t] = l->free_head;
+    l->free_head = t;
+    l->len--;
+    return 1;
+  }
+  return 0;
+}
+
+/* =====================================================================================
+ * indexer — approximateprefix/indexer.go:32-195
+ * ===================================================================================== */
+typedef struct {
+  int32_t *ids;
+  int32_t n, cap;
+} podset;
+
+struct orc_index {
+  u64map hash_to_set;   /* hashToPods: blockHash -> index into sets[] */
+  podset *sets;
+  int32_t sets_len, sets_cap;
+  int32_t *free_sets;
+  int32_t free_len, free_cap;
+  lru_t **pod_lru;      /* podToLRU, indexed by server id */
+  int32_t pods_cap;
+  int32_t default_lru;
+};
+
+orc_index *orc_index_new(int32_t default_lru_size) {
+  orc_index *ix = (orc_index *)calloc(1, sizeof(orc_index));
+  u64map_init(&ix->hash_to_set, 1024);
+  ix->default_lru = default_lru_size;
+  return ix;
+}
+void orc_index_free(orc_index *ix) {
+  if (!ix) return;
+  for (int32_t i = 0; i < ix->sets_len; i++) free(ix->sets[i].ids);
+  free(ix->sets);
+  free(ix->free_sets);
+  for (int32_t i = 0; i < ix->pods_cap; i++) lru_free(ix->pod_lru[i]);
+  free(ix->pod_lru);
+  u64map_free(&ix->hash_to_set);
+  free(ix);
+}
+
+/* makeEvictionFn, indexer.go:105-115: delete(podSet, pod); if len(podSet)==0 delete(hashToPods, hash) */
+static void index_evict(orc_index *ix, uint64_t hash, int32_t server) {
+  uint32_t si;
+  if (!u64map_get(&ix->hash_to_set, hash, &si)) return;
+  podset *s = &ix->sets[si];
+  for (int32_t i = 0; i < s->n; i++)
+    if (s->ids[i] == server) {
+      s->ids[i] = s->ids[s->n - 1];
+      s->n--;
+      break;
+    }
+  if (s->n == 0) {
+    u64map_del(&ix->hash_to_set, hash);
+    if (ix->free_len == ix->free_cap) {
+      ix->free_cap = ix->free_cap ? ix->free_cap * 2 : 64;
+      ix->free_sets = (int32_t *)realloc(ix->free_sets, sizeof(int32_t) * (size_t)ix->free_cap);
+    }
+    ix->free_sets[ix->free_len++] = (int32_t)si;
+  }
+}
+
+static void index_set_add(orc_index *ix, uint64_t hash, int32_t server) {
+  uint32_t si;
+  if (!u64map_get(&ix->hash_to_set, hash, &si)) {
+    if (ix->free_len) {
+      si = (uint32_t)ix->free_sets[--ix->free_len];
+    } else {
+      if (ix->sets_len == ix->sets_cap) {
+        ix->sets_cap = ix->sets_cap ? ix->sets_cap * 2 : 1024;
+        ix->sets = (podset *)realloc(ix->sets, sizeof(podset) * (size_t)ix->sets_cap);
+      }
+      si = (uint32_t)ix->sets_len++;
+      ix->sets[si].ids = NULL;
+      ix->sets[si].cap = 0;
+    }
+    ix->sets[si].n = 0;
+    u64map_put(&ix->hash_to_set, hash, si);
+  }
+  podset *s = &ix->sets[si];
+  for (int32_t i = 0; i < s->n; i++)
+    if (s->ids[i] == server) return;
+  if (s->n == s->cap) {
+    s->cap = s->cap ? s->cap * 2 : 4;
+    s->ids = (int32_t *)realloc(s->ids, sizeof(int32_t) * (size_t)s->cap);
+  }
+  s->ids[s->n++] = server;
+}
+
+/* Add, indexer.go:52-83. NOTE the reference order: ALL LRU adds first (evictions fire inside
+ * this loop), THEN the hashToPods update for ALL hashes — so a batch longer than the LRU
+ * capacity leaves hashToPods entries that are no longer in the LRU (restated faithfully). */
+void orc_index_add(orc_index *ix, const uint64_t *hashes, int32_t n, int32_t server,
+                   int32_t num_gpu_blocks) {
+  if (server < 0) return;
+  if (server >= ix->pods_cap) {
+    int32_t nc = ix->pods_cap ? ix->pods_cap : 16;
+    while (nc <= server) nc *= 2;
+    ix->pod_lru = (lru_t **)realloc(ix->pod_lru, sizeof(lru_t *) * (size_t)nc);
+    for (int32_t i = ix->pods_cap; i < nc; i++) ix->pod_lru[i] = NULL;
+    ix->pods_cap = nc;
+  }
+  lru_t *l = ix->pod_lru[server];
+  if (!l) {                                   /* :57-68 */
+    int32_t size = num_gpu_blocks;
+    if (size <= 0) size = ix->default_lru;
+    if (size <= 0) size = 1; /* lru.NewWithEvict errors on size<=0; reference ignores the error (nil LRU would panic) */
+    l = lru_new(size);
+    ix->pod_lru[server] = l;
+  }
+  for (int32_t i = 0; i < n; i++) {           /* :70-72 */
+    uint64_t ev;
+    if (lru_add(l, hashes[i], &ev)) index_evict(ix, ev, server);
+  }
+  for (int32_t i = 0; i < n; i++) index_set_add(ix, hashes[i], server); /* :75-82 */
+}
+
+int32_t orc_index_get(const orc_index *ix, uint64_t hash, int32_t *servers_out, int32_t cap) {
+  uint32_t si;
+  if (!u64map_get(&ix->hash_to_set, hash, &si)) return 0;
+  const podset *s = &ix->sets[si];
+  for (int32_t i = 0; i < s->n && i < cap; i++) servers_out[i] = s->ids[i];
+  return s->n;
+}
+
+/* RemovePod, indexer.go:167-182: for hash in lru.Keys(): lru.Remove(hash) (fires eviction cb); delete(podToLRU, pod) */
+void orc_index_remove_pod(orc_index *ix, int32_t server) {
+  if (server < 0 || server >= ix->pods_cap || !ix->pod_lru[server]) return;
+  lru_t *l = ix->pod_lru[server];
+  for (int32_t n = l->tail; n >= 0; n = l->prev[n]) index_evict(ix, l->key[n], server);
+  lru_free(l);
+  ix->pod_lru[server] = NULL;
+}
+
+int32_t orc_index_lru_len(const orc_index *ix, int32_t server) {
+  if (server < 0 || server >= ix->pods_cap || !ix->pod_lru[server]) return -1;
+  return ix->pod_lru[server]->len;
+}
+int32_t orc_index_lru_keys(const orc_index *ix, int32_t server, uint64_t *out, int32_t cap) {
+  if (server < 0 || server >= ix->pods_cap || !ix->pod_lru[server]) return -1;
+  const lru_t *l = ix->pod_lru[server];
+  int32_t k = 0;
+  for (int32_t n = l->tail; n >= 0 && k < cap; n = l->prev[n]) out[k++] = l->key[n];
+  return l->len;
+}
+int64_t orc_index_num_hashes(const orc_index *ix) { return (int64_t)ix->hash_to_set.n; }
+int32_t orc_index_pods(const orc_index *ix, int32_t *out, int32_t cap) {
+  int32_t k = 0;
+  for (int32_t i = 0; i < ix->pods_cap; i++)
+    if (ix->pod_lru[i]) {
+      if (k < cap) out[k] = i;
+      k++;
+    }
+  return k;
+}
+int64_t orc_index_dump(const orc_index *ix, uint64_t *hash_out, int32_t *server_out, int64_t cap) {
+  int64_t k = 0;
+  for (uint64_t i = 0; i < ix->hash_to_set.cap; i++) {
+    if (!ix->hash_to_set.val[i]) continue;
+    const podset *s = &ix->sets[ix->hash_to_set.val[i] - 1];
+    for (int32_t j = 0; j < s->n; j++) {
+      if (k < cap) {
+        hash_out[k] = ix->hash_to_set.key[i];
+        server_out[k] = s->ids[j];
+      }
+      k++;
+    }
+  }
+  return k;
+}
+
+/* matchLongestPrefix, plugin.go:219-235: greedy walk; STOP at the first hash with an empty pod set;
+ * every pod in a non-empty set gets +1 (count of matching blocks before the first GLOBAL miss). */
+void orc_match_longest_prefix(const orc_index *ix, const uint64_t *hashes, int32_t n, int32_t M,
+                              uint16_t *match_out) {
+  memset(match_out, 0, sizeof(uint16_t) * (size_t)M);
+  if (!ix) return;
+  for (int32_t i = 0; i < n; i++) {
+    uint32_t si;
+    if (!u64map_get(&ix->hash_to_set, hashes[i], &si)) break;
+    const podset *s = &ix->sets[si];
+    if (s->n == 0) break;
+    for (int32_t j = 0; j < s->n; j++)
+      if (s->ids[j] >= 0 && s->ids[j] < M) match_out[s->ids[j]]++;
+  }
+}
+
+/* =====================================================================================
+ * Scorers
+ * ===================================================================================== */
+static inline int is_cand(const uint32_t *mask, int32_t m) {
+  return !mask || ((mask[m >> 5] >> (m & 31)) & 1u);
+}
+
+double orc_enforce_score_range(double s) { /* scheduler_profile.go:194-202 */
+  if (s < 0) return 0;
+  if (s > 1) return 1;
+  return s;
+}
+
+/* kvcache_utilization.go:76-82 */
+void orc_score_kv(const orc_snapshot *s, const uint32_t *mask, double *out) {
+  for (int32_t m = 0; m < s->M; m++)
+    if (is_cand(mask, m)) out[m] = 1 - s->kv_usage[m];
+}
+
+/* queue.go:78-108 (and runningrequest.go:78-108, identical form on RunningRequestsSize) */
+static void score_minmax(int32_t M, const int64_t *q, const uint32_t *mask, double *out) {
+  int64_t mn = INT64_MAX, mx = INT64_MIN; /* math.MaxInt / math.MinInt */
+  for (int32_t m = 0; m < M; m++) {
+    if (!is_cand(mask, m)) continue;
+    if (q[m] < mn) mn = q[m];
+    if (q[m] > mx) mx = q[m];
+  }
+  for (int32_t m = 0; m < M; m++) {
+    if (!is_cand(mask, m)) continue;
+    if (mx == mn)
+      out[m] = 1.0;
+    else
+      out[m] = (double)(mx - q[m]) / (double)(mx - mn);
+  }
+}
+void orc_score_queue(const orc_snapshot *s, const uint32_t *mask, double *out) {
+  score_minmax(s->M, s->queue, mask, out);
+}
+void orc_score_running(const orc_snapshot *s, const uint32_t *mask, double *out) {
+  score_minmax(s->M, s->running, mask, out);
+}
+
+/* lora_affinity.go:76-102; adapter_id < 0 or out of the dictionary ⇒ neither active nor waiting */
+void orc_score_lora(const orc_snapshot *s, const uint32_t *mask, int32_t adapter_id, double *out) {
+  for (int32_t m = 0; m < s->M; m++) {
+    if (!is_cand(mask, m)) continue;
+    int active = 0, waiting = 0;
+    if (adapter_id >= 0 && adapter_id < s->lora_words * 64 && s->lora_active && s->lora_waiting) {
+      int w = adapter_id >> 6, b = adapter_id & 63;
+      active = (int)((s->lora_active[(size_t)m * s->lora_words + w] >> b) & 1);
+      waiting = (int)((s->lora_waiting[(size_t)m * s->lora_words + w] >> b) & 1);
+    }
+    int32_t nmodels = s->lora_nmodels ? s->lora_nmodels[m] : 0;
+    int32_t maxm = s->lora_max ? s->lora_max[m] : 0;
+    if (active)
+      out[m] = 1.0;
+    else if (nmodels < maxm)
+      out[m] = 0.8;
+    else if (waiting)
+      out[m] = 0.6;
+    else
+      out[m] = 0.0;
+  }
+}
+
+/* prefix/plugin.go:95-117: 0 when the attribute is absent or total==0, else match/total */
+void orc_score_prefix(int32_t M, const uint32_t *mask, const uint16_t *match, int32_t total,
+                      int32_t have_info, double *out) {
+  for (int32_t m = 0; m < M; m++) {
+    if (!is_cand(mask, m)) continue;
+    out[m] = 0.0;
+    if (have_info && match && total != 0) out[m] = (double)match[m] / (double)total;
+  }
+}
+
+static inline uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+/* Tie priority (NOT from the reference — the reference is a time-seeded shuffle,
+ * picker/common.go:49-55; this is the engine's documented deterministic stand-in). */
+uint32_t orc_tie_priority(uint64_t seed, int64_t request_index, int32_t endpoint) {
+  uint32_t a = lowbias32((uint32_t)(uint64_t)request_index ^ (uint32_t)seed);
+  return lowbias32(a + (uint32_t)endpoint * 0x9E3779B1U + (uint32_t)(seed >> 32));
+}
+
+static const double LORA_CLASS_SCORE[4] = {0.0, 0.6, 0.8, 1.0};
+
+int32_t orc_schedule_one(const orc_snapshot *s, const orc_profile *p, int64_t request_index,
+                         int32_t adapter_id, const uint32_t *mask, const uint16_t *match,
+                         int32_t total, const float *pair_col, int32_t *pick_out, double *score_out,
+                         int32_t *tie_count_out, uint32_t *tie_set_out, double *weighted_out) {
+  const int32_t M = s->M;
+  /* runFilterPlugins (scheduler_profile.go:130-149) is modelled as the candidate mask */
+  int32_t ncand = 0;
+  for (int32_t m = 0; m < M; m++) ncand += is_cand(mask, m);
+  if (tie_set_out) memset(tie_set_out, 0, sizeof(uint32_t) * (size_t)((M + 31) / 32));
+  if (ncand == 0) { /* scheduler_profile.go:119-121 */
+    *pick_out = -1;
+    *score_out = 0.0;
+    *tie_count_out = 0;
+    if (weighted_out)
+      for (int32_t m = 0; m < M; m++) weighted_out[m] = NAN;
+    return -1;
+  }
+  double *w = (double *)malloc(sizeof(double) * (size_t)M * 2);
+  double *sc = w + M;
+  for (int32_t m = 0; m < M; m++) w[m] = 0.0; /* :155-158 */
+  for (int32_t k = 0; k < p->n_scorers; k++) { /* :160-171 */
+    int kind = p->scorer_kind[k];
+    double weight = p->scorer_weight[k];
+    switch (kind) {
+      case ORC_SCORER_QUEUE: orc_score_queue(s, mask, sc); break;
+      case ORC_SCORER_KV_CACHE: orc_score_kv(s, mask, sc); break;
+      case ORC_SCORER_RUNNING: orc_score_running(s, mask, sc); break;
+      case ORC_SCORER_PREFIX:
+        if (pair_col && match == NULL) { /* dense rows carry match in column x */
+          for (int32_t m = 0; m < M; m++) {
+            sc[m] = 0.0;
+            if (total != 0) sc[m] = (double)(uint16_t)pair_col[(size_t)m * 4 + 0] / (double)total;
+          }
+        } else {
+          orc_score_prefix(M, mask, match, total, match != NULL, sc);
+        }
+        break;
+      case ORC_SCORER_LORA:
+        if (pair_col) { /* dense rows carry the lora class in column y */
+          for (int32_t m = 0; m < M; m++) {
+            int c = (int)pair_col[(size_t)m * 4 + 1];
+            sc[m] = LORA_CLASS_SCORE[c & 3];
+          }
+        } else {
+          orc_score_lora(s, mask, adapter_id, sc);
+        }
+        break;
+      default:
+        if (kind >= ORC_SCORER_ENDPOINT_COL0 && kind < ORC_SCORER_ENDPOINT_COL0 + 4) {
+          const double *col = s->endpoint_col[kind - ORC_SCORER_ENDPOINT_COL0];
+          for (int32_t m = 0; m < M; m++) sc[m] = col ? col[m] : 0.0;
+        } else if (kind >= ORC_SCORER_PAIR_COL0 && kind < ORC_SCORER_PAIR_COL0 + 2) {
+          int c = kind - ORC_SCORER_PAIR_COL0;
+          for (int32_t m = 0; m < M; m++) sc[m] = pair_col ? (double)pair_col[(size_t)m * 4 + 2 + c] : 0.0;
+        } else {
+          for (int32_t m = 0; m < M; m++) sc[m] = 0.0;
+        }
+    }
+    for (int32_t m = 0; m < M; m++) {
+      if (!is_cand(mask, m)) continue;
+      double t = orc_enforce_score_range(sc[m]) * weight; /* rounded product ... */
+      w[m] = w[m] + t;                                    /* ... then rounded add (:168) */
+    }
+  }
+  /* MaxScorePicker (maxscore/picker.go:87-115) as arg-max set */
+  double best = 0;
+  int have = 0;
+  for (int32_t m = 0; m < M; m++) {
+    if (!is_cand(mask, m)) continue;
+    if (!have || w[m] > best) {
+      best = w[m];
+      have = 1;
+    }
+  }
+  int32_t ties = 0, pick = -1;
+  uint32_t best_prio = 0;
+  for (int32_t m = 0; m < M; m++) {
+    if (!is_cand(mask, m) || !(w[m] == best)) continue;
+    ties++;
+    if (tie_set_out) tie_set_out[m >> 5] |= 1u << (m & 31);
+    if (p->tie_mode == ORC_TIE_SEEDED_RANDOM) {
+      uint32_t pr = orc_tie_priority(p->tie_seed, request_index, m);
+      if (pick < 0 || pr > best_prio) {
+        pick = m;
+        best_prio = pr;
+      }
+    } else if (pick < 0) {
+      pick = m;
+    }
+  }
+  *pick_out = pick;
+  *score_out = best;
+  *tie_count_out = ties;
+  if (weighted_out)
+    for (int32_t m = 0; m < M; m++) weighted_out[m] = is_cand(mask, m) ? w[m] : NAN;
+  free(w);
+  return 0;
+}
+
+/* =====================================================================================
+ * Batch driver: one "goroutine" per request, partitioned over pthreads.
+ * ===================================================================================== */
+typedef struct {
+  const orc_snapshot *s;
+  const orc_profile *p;
+  const orc_index *idx;
+  const orc_batch *b;
+  int32_t r0, r1;
+} job_t;
+
+static int profile_has(const orc_profile *p, int kind) {
+  for (int i = 0; i < p->n_scorers; i++)
+    if (p->scorer_kind[i] == kind) return 1;
+  return 0;
+}
+
+static void *batch_worker(void *arg) {
+  job_t *j = (job_t *)arg;
+  const orc_batch *b = j->b;
+  const int32_t M = j->s->M;
+  const int32_t mw = (M + 31) / 32;
+  const int need_prefix = profile_has(j->p, ORC_SCORER_PREFIX) || b->match_blocks || b->total_blocks || b->hashes_out;
+  int32_t hcap = b->max_blocks > 0 ? b->max_blocks : 1;
+  if (b->hashes_in && b->hash_stride > hcap) hcap = b->hash_stride;
+  uint64_t *hashes = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)hcap);
+  uint16_t *match = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)M);
+  for (int32_t r = j->r0; r < j->r1; r++) {
+    int32_t nh = 0;
+    const uint16_t *match_p = NULL;
+    int32_t total = 0;
+    const float *pair = b->dense_feat ? b->dense_feat + (size_t)r * M * 4 : NULL;
+    if (b->dense_feat) {
+      total = b->dense_total ? b->dense_total[r] : 0;
+    } else if (need_prefix && (b->prompt_bytes || b->hashes_in)) {
+      if (b->hashes_in) {
+        nh = b->n_hashes_in[r];
+        memcpy(hashes, b->hashes_in + (size_t)r * b->hash_stride, sizeof(uint64_t) * (size_t)nh);
+      } else {
+        nh = orc_hash_prompt(b->prompt_bytes + b->prompt_off[r], b->prompt_off[r + 1] - b->prompt_off[r],
+                             b->model_seed ? b->model_seed[r] : 0, b->block_chars, b->max_blocks, hashes, hcap);
+        if (nh < 0) nh = 0;
+      }
+      orc_match_longest_prefix(j->idx, hashes, nh, M, match);
+      match_p = match;
+      total = nh;
+    }
+    if (b->hashes_out && !b->dense_feat) {
+      int32_t stride = b->max_blocks;
+      for (int32_t i = 0; i < stride; i++) b->hashes_out[(size_t)r * stride + i] = i < nh ? hashes[i] : 0;
+    }
+    if (b->total_blocks) b->total_blocks[r] = (uint16_t)total;
+    if (b->match_blocks) {
+      for (int32_t m = 0; m < M; m++)
+        b->match_blocks[(size_t)r * M + m] =
+            pair ? (uint16_t)pair[(size_t)m * 4] : (match_p ? match_p[m] : 0);
+    }
+    const uint32_t *mask = b->cand_mask ? b->cand_mask + (size_t)r * mw : NULL;
+    orc_schedule_one(j->s, j->p, b->request_base + r, b->adapter_id ? b->adapter_id[r] : -1, mask, match_p, total,
+                     pair, &b->pick[r], &b->pick_score[r], &b->tie_count[r],
+                     b->tie_set ? b->tie_set + (size_t)r * mw : NULL, NULL);
+  }
+  free(hashes);
+  free(match);
+  return NULL;
+}
+
+int32_t orc_schedule_batch(const orc_snapshot *s, const orc_profile *p, const orc_index *idx,
+                           const orc_batch *b, int32_t n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > b->R) n_threads = b->R > 0 ? b->R : 1;
+  job_t *jobs = (job_t *)calloc((size_t)n_threads, sizeof(job_t));
+  pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+  for (int32_t t = 0; t < n_threads; t++) {
+    jobs[t].s = s;
+    jobs[t].p = p;
+    jobs[t].idx = idx;
+    jobs[t].b = b;
+    jobs[t].r0 = (int32_t)((int64_t)b->R * t / n_threads);
+    jobs[t].r1 = (int32_t)((int64_t)b->R * (t + 1) / n_threads);
+  }
+  if (n_threads == 1) {
+    batch_worker(&jobs[0]);
+  } else {
+    for (int32_t t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
+    for (int32_t t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  }
+  free(jobs);
+  free(th);
+  return 0;
+}
+
+/* PreRequest (plugin.go:169-197) for each request of a batch, in request order. */
+void orc_commit_picks(orc_index *ix, int32_t R, const int32_t *pick, const uint64_t *hashes,
+                      const uint16_t *n_hashes, int32_t hash_stride, const int32_t *gpu_blocks) {
+  for (int32_t r = 0; r < R; r++) {
+    if (pick[r] < 0) continue; /* len(TargetEndpoints)==0 ⇒ return (:173-175) */
+    int32_t cap = gpu_blocks ? gpu_blocks[pick[r]] : 0; /* makeserver :207-216 (0 ⇒ default) */
+    orc_index_add(ix, hashes + (size_t)r * hash_stride, n_hashes[r], pick[r], cap);
+  }
+}

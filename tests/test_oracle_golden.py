@@ -1,0 +1,298 @@
+"""Pins the CPU oracle (oracle/oracle.c) against every golden vector the reference's own tests hold for
+the hot path (tests/golden/reference_vectors.json, transcribed with file:line citations) and against
+two independent XXH64 implementations (tests/golden/xxh64_kat.json).  CPU-only.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as o
+from tests.helpers import kinds, mask_from_list, pack_lora
+
+
+# ---------------------------------------------------------------- XXH64 / hashPrompt
+def test_xxh64_spec_and_raw_vectors(xxh_kat):
+    for v in xxh_kat["spec_vectors"]:
+        assert f"{o.xxh64(v['ascii'].encode()):016x}" == v["xxh64"]
+    for v in xxh_kat["raw"]:
+        assert f"{o.xxh64(bytes.fromhex(v['hex'])):016x}" == v["xxh64"]
+
+
+def test_hash_chain_vectors(xxh_kat):
+    for c in xxh_kat["chains"]:
+        seed = o.model_seed(c["model"], c["salt"])
+        assert f"{seed:016x}" == c["seed"]
+        got = o.hash_prompt(bytes.fromhex(c["prompt_hex"]), seed, c["block_chars"], c["max_blocks"])
+        assert [f"{int(x):016x}" for x in got] == c["hashes"], c
+
+
+def test_hash_counts_reference(golden):
+    for c in golden["hash_counts"]["cases"]:
+        prompt = c["prompt"] if "prompt" in c else c["prompt_repeat"][0] * c["prompt_repeat"][1]
+        got = o.hash_prompt(prompt.encode(), o.model_seed(c["model"]), c["block_chars"], c["max_blocks"])
+        assert len(got) == c["want_n"], c["source"]
+
+
+def test_hash_prompt_edge_cases():
+    seed = o.model_seed("m")
+    assert len(o.hash_prompt(b"", seed, 64, 256)) == 0
+    assert len(o.hash_prompt(b"x" * 63, seed, 64, 256)) == 0          # hashing.go:57-60
+    assert len(o.hash_prompt(b"x" * 64, seed, 64, 256)) == 1
+    assert len(o.hash_prompt(b"x" * 65, seed, 64, 256)) == 2          # trailing partial block (:89-95)
+    assert len(o.hash_prompt(b"x" * 6400, seed, 64, 16)) == 16        # truncation (:62-65)
+    assert len(o.hash_prompt(b"x" * 64, seed, 0, 256)) == 0           # block size must be positive (:51-56)
+    assert len(o.hash_prompt(b"x" * 64, seed, 64, 0)) == 0            # maxBlocks 0 truncates to nothing
+    # different model ⇒ different chain for the same body (:69-71)
+    a = o.hash_prompt(b"x" * 128, o.model_seed("m1"), 64, 256)
+    b = o.hash_prompt(b"x" * 128, o.model_seed("m2"), 64, 256)
+    assert a[0] != b[0] and a[1] != b[1]
+    # cache salt participates in the seed (:72-75)
+    assert o.model_seed("m1", "s") != o.model_seed("m1") and o.model_seed("m1", "s") == o.xxh64(b"m1s")
+
+
+# ---------------------------------------------------------------- scorers
+def _snap_from_endpoints(eps, target_models=()):
+    ids, act, wai, nm, mx = pack_lora(eps, target_models)
+    snap = o.SnapshotData(kv_usage=[e.get("kv", 0.0) for e in eps], queue=[e.get("queue", 0) for e in eps],
+                          lora_active=act, lora_waiting=wai, lora_nmodels=nm, lora_max=mx)
+    return snap, ids
+
+
+def test_kv_scorer(golden):
+    g = golden["kv_scorer"]
+    for c in g["cases"]:
+        snap = o.SnapshotData(kv_usage=c["kv"], queue=np.zeros(len(c["kv"])))
+        got = o.score_single("kv", snap)
+        assert np.allclose(got, c["want"], atol=g["tolerance"], rtol=0)
+
+
+def test_queue_scorer(golden):
+    g = golden["queue_scorer"]
+    for c in g["cases"]:
+        snap = o.SnapshotData(kv_usage=np.zeros(len(c["queue"])), queue=c["queue"])
+        got = o.score_single("queue", snap)
+        assert np.allclose(got, c["want"], atol=g["tolerance"], rtol=0)
+    # the min/max are over the GIVEN endpoints (queue.go:79-91): a mask changes the normalisation
+    snap = o.SnapshotData(kv_usage=np.zeros(3), queue=[10, 5, 0])
+    got = o.score_single("queue", snap, mask=mask_from_list(3, [0, 1]))
+    assert got[0] == 0.0 and got[1] == 1.0 and np.isnan(got[2])
+
+
+def test_lora_scorer(golden):
+    g = golden["lora_scorer"]
+    for c in g["cases"]:
+        if not c["endpoints"]:
+            continue
+        snap, ids = _snap_from_endpoints(c["endpoints"], [c["target"]])
+        got = o.score_single("lora", snap, adapter_id=ids[c["target"]])
+        assert np.allclose(got, c["want"], atol=g["tolerance"], rtol=0), c["name"]
+    # an adapter outside the dictionary is never active/waiting; the capacity rule still applies
+    snap, _ = _snap_from_endpoints([{"active": ["a"], "waiting": [], "max_active": 2},
+                                    {"active": ["a", "b"], "waiting": [], "max_active": 2}])
+    assert list(o.score_single("lora", snap, adapter_id=-1)) == [0.8, 0.0]
+
+
+def test_prefix_scorer(golden):
+    for c in golden["prefix_scorer"]["cases"]:
+        got = o.score_prefix(c["match"], c["total"], len(c["match"]))
+        assert list(got) == c["want_exact"]                       # assert.Equal in the reference: exact
+    assert list(o.score_prefix([3, 1], 0, 2)) == [0.0, 0.0]       # total==0 ⇒ 0 (plugin.go:108)
+    assert list(o.score_prefix([3, 1], 4, 2, have_info=False)) == [0.0, 0.0]  # attribute absent ⇒ 0 (:100-106)
+
+
+def test_enforce_score_range(golden):
+    for x, want in golden["enforce_score_range"]["cases"]:
+        assert o.lib().orc_enforce_score_range(x) == want
+    r = golden["enforce_score_range"]["run_out_of_range"]
+    snap = o.SnapshotData(kv_usage=[0.0], queue=[0], endpoint_cols=[[r["scores"][0]], [r["scores"][1]]])
+    prof = o.make_profile([(8, r["weights"][0]), (9, r["weights"][1])])
+    assert o.schedule_one(snap, prof)["score"] == r["want_score_exact"]
+
+
+# ---------------------------------------------------------------- SchedulerProfile.Run / Scheduler.Schedule
+def test_schedule_finds_optimal_endpoint(golden):
+    for c in golden["schedule"]:
+        eps = c["endpoints"]
+        if c.get("want_error"):
+            snap = o.SnapshotData(kv_usage=np.zeros(0), queue=np.zeros(0))
+            res = o.schedule_one(snap, o.make_profile(kinds(c["scorers"])))
+            assert res["rc"] == -1 and res["pick"] == -1
+            continue
+        snap, ids = _snap_from_endpoints(eps, [c["target_model"]])
+        res = o.schedule_one(snap, o.make_profile(kinds(c["scorers"])), adapter_id=ids[c["target_model"]])
+        assert eps[res["pick"]]["name"] == c["want_pick"]
+        assert res["score"] == c["want_score_exact"]              # `==` on float64 in the reference (types.go:148-150)
+        assert res["tie_count"] == 1
+
+
+def test_weighted_constant_scorers(golden):
+    for c in golden["weighted_constant_scorers"]:
+        n = c["n_endpoints"]
+        cols = [[s] * n for s in c["scores"]]
+        snap = o.SnapshotData(kv_usage=np.zeros(n), queue=np.zeros(n), endpoint_cols=cols)
+        prof = o.make_profile([(8 + i, w) for i, w in enumerate(c["weights"])])
+        res = o.schedule_one(snap, prof, mask=mask_from_list(n, c["filter_keep"]))
+        if c.get("want_error"):
+            assert res["rc"] == -1 and res["pick"] == -1 and res["tie_count"] == 0
+        else:
+            assert res["score"] == c["want_score_exact"]
+            assert res["tie_count"] == c["want_tie_count"] and res["pick"] in c["filter_keep"]
+            assert res["tie_set"] == c["filter_keep"]
+
+
+def test_integration_routing(golden):
+    g = golden["integration_routing"]
+    for c in g["cases"]:
+        scorers = c.get("scorers", g["scorers"])
+        eps = [{"queue": q, "kv": kv, "active": models, "waiting": [], "max_active": 0} for _, q, kv, models in c["pods"]]
+        snap, ids = _snap_from_endpoints(eps, [c["target_model"]])
+        idx = o.Index()
+        hashes = o.hash_prompt(c["prompt"].encode(), o.model_seed(c["target_model"]), 64, 256)
+        match = idx.match(hashes, len(eps))
+        mask = mask_from_list(len(eps), c["subset"]) if "subset" in c else None
+        res = o.schedule_one(snap, o.make_profile(kinds(scorers)), adapter_id=ids[c["target_model"]], mask=mask,
+                             match=match, total=len(hashes))
+        if c.get("want_error"):
+            assert res["rc"] == -1, c["name"]
+        else:
+            assert res["pick"] == c["want_pick"], c["name"]
+            assert res["tie_count"] == 1, c["name"]
+
+
+def test_picker_vectors(golden):
+    # maxscore/picker_test.go: order by score desc; ties compared as SETS (tieBreakCandidates)
+    for c in golden["picker"]["cases"]:
+        n = len(c["scores"])
+        snap = o.SnapshotData(kv_usage=np.zeros(n), queue=np.zeros(n), endpoint_cols=[[s / 100.0 for s in c["scores"]]])
+        res = o.schedule_one(snap, o.make_profile([(8, 100.0)]))
+        order = sorted(range(n), key=lambda m: -res["weighted"][m])[: c["max_num"]]
+        k = c["tie_break_candidates"]
+        assert sorted(order[:k]) == sorted(c["want_order"][:k]) and order[k:] == c["want_order"][k:], c["name"]
+        top = max(c["scores"])
+        assert res["tie_set"] == [m for m in range(n) if c["scores"][m] == top]
+        assert res["pick"] == res["tie_set"][0]
+        # seeded-random tie mode: the pick stays inside the reference's tie set and is reproducible
+        picks = set()
+        for r in range(64):
+            pr = o.make_profile([(8, 100.0)], tie_mode=o.TIE_SEEDED_RANDOM, tie_seed=7)
+            rr = o.schedule_one(snap, pr, request_index=r)
+            assert rr["pick"] in res["tie_set"]
+            picks.add(rr["pick"])
+        assert picks == set(res["tie_set"])  # every tie member is reachable
+
+
+# ---------------------------------------------------------------- prefix producer + indexer
+def test_prepare_empty_index(golden):
+    c = golden["prepare_empty_index"]
+    idx = o.Index()
+    h = o.hash_prompt(c["prompt"].encode(), o.model_seed(c["model"]), c["block_chars"], c["max_blocks"])
+    assert len(h) == c["want_total"]
+    assert list(idx.match(h, c["n_endpoints"])) == c["want_match"]
+
+
+def test_pre_request(golden):
+    c = golden["pre_request"]
+    idx = o.Index()
+    h = o.hash_prompt(c["prompt"].encode(), o.model_seed(c["model"]), c["block_chars"], c["max_blocks"])
+    idx.add(h, c["pick"])
+    for x in h:
+        assert c["pick"] in idx.get(x)
+
+
+def test_prefix_completion(golden):
+    c = golden["prefix_completion"]
+    idx = o.Index()
+    seed = o.model_seed(c["model"])
+    h1 = o.hash_prompt(c["first_prompt"].encode(), seed, c["block_chars"], c["max_blocks"])
+    assert len(h1) == c["first_total"]
+    for s in c["commit_to"]:                                      # primary pick + "prefill" profile pick (plugin.go:177-184)
+        idx.add(h1, s)
+    h2 = o.hash_prompt(c["second_prompt"].encode(), seed, c["block_chars"], c["max_blocks"])
+    assert len(h2) == c["want_total"]
+    assert list(idx.match(h2, c["n_endpoints"])) == c["want_match"]
+
+
+def test_indexer_add_and_get(golden):
+    c = golden["indexer"]["add_and_get"]
+    idx = o.Index(c["default_lru"])
+    for st in c["steps"]:
+        idx.add(st["add"], 0, c["gpu_blocks"])
+        assert idx.lru_len(0) == st["want_len"]
+        for h, want in st.get("want_get", {}).items():
+            assert sorted(idx.get(int(h))) == want
+
+
+def test_indexer_remove_pod_and_eviction(golden):
+    n = golden["indexer"]["remove_pod_and_eviction"]["indexer_size"]
+    idx = o.Index(n)
+    for j in range(n):
+        idx.add([j], 1)
+        idx.add([j], 2)
+    assert idx.lru_len(1) == n and idx.lru_len(2) == n
+    for j in range(n):
+        assert idx.get(j) == {1, 2}
+    idx.add([n], 1)                                               # evicts hash 0 from server1
+    assert idx.lru_len(1) == n
+    assert idx.get(0) == {2}
+    idx.remove_pod(2)
+    assert idx.get(0) == set()
+    assert idx.lru_len(2) == -1 and idx.pods() == [1]
+    assert idx.num_hashes() == n                                  # hashes 1..n, all only on server1
+    for j in range(1, n + 1):
+        assert idx.get(j) == {1}
+    assert idx.lru_keys(1) == list(range(1, n + 1))               # Keys(): oldest → newest
+
+
+def test_indexer_lru_semantics():
+    idx = o.Index(3)
+    idx.add([1, 2, 3], 0)
+    idx.add([1], 0)                                               # refresh recency, no eviction
+    assert idx.lru_keys(0) == [2, 3, 1]
+    idx.add([4], 0)                                               # evicts 2 (oldest)
+    assert idx.lru_keys(0) == [3, 1, 4] and idx.get(2) == set()
+    # one Add longer than the capacity: LRU adds (with evictions) happen BEFORE the hashToPods
+    # update (indexer.go:70-82) ⇒ evicted-in-this-call hashes are re-inserted into hashToPods (stale)
+    idx2 = o.Index(2)
+    idx2.add([10, 11, 12], 0)
+    assert idx2.lru_keys(0) == [11, 12]
+    assert idx2.get(10) == {0} and idx2.get(11) == {0} and idx2.get(12) == {0}
+    # matchLongestPrefix stops at the first globally-unknown hash, not per pod (plugin.go:224-233)
+    idx3 = o.Index(100)
+    idx3.add([1, 2, 3], 0)
+    idx3.add([1, 3], 1)
+    assert list(idx3.match([1, 2, 3, 4, 5], 3)) == [3, 2, 0]     # pod1 counts hash 3 although it lacks hash 2
+    assert list(idx3.match([9, 1, 2], 3)) == [0, 0, 0]
+    # Get does not touch recency (indexer.go:86-102)
+    idx4 = o.Index(2)
+    idx4.add([1, 2], 0)
+    idx4.get(1)
+    idx4.add([3], 0)
+    assert idx4.lru_keys(0) == [2, 3]
+
+
+def test_batch_matches_single_and_threads_agree():
+    from tests.helpers import synth_prompts, synth_snapshot, zipf_adapters
+    M, R = 96, 300
+    sd = synth_snapshot(M, seed=3, tie_heavy=True)
+    snap = o.SnapshotData(**sd)
+    prof = o.make_profile(kinds([("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)]))
+    prompts, off, _ = synth_prompts(R, prompt_len=512, groups=7, shared=256, seed=3)
+    seeds = np.full(R, o.model_seed("m"), dtype=np.uint64)
+    idx = o.Index(1000)
+    warm = o.schedule_batch(snap, prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds,
+                            adapter_id=zipf_adapters(R, seed=3), want_hashes=True, max_blocks=16)
+    idx.commit(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    a = o.schedule_batch(snap, prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds,
+                         adapter_id=zipf_adapters(R, seed=3), want_match=True, want_hashes=True, max_blocks=16,
+                         n_threads=1)
+    b = o.schedule_batch(snap, prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds,
+                         adapter_id=zipf_adapters(R, seed=3), want_match=True, want_hashes=True, max_blocks=16,
+                         n_threads=4)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert a["match_blocks"].max() > 0 and (a["total_blocks"] == 8).all()
+    ad = zipf_adapters(R, seed=3)
+    for r in (0, 1, 17, R - 1):
+        one = o.schedule_one(snap, prof, request_index=r, adapter_id=int(ad[r]), match=a["match_blocks"][r],
+                             total=int(a["total_blocks"][r]))
+        assert one["pick"] == a["pick"][r] and one["score"] == a["pick_score"][r]
+        assert one["tie_count"] == a["tie_count"][r]
