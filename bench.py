@@ -1,0 +1,490 @@
+#!/usr/bin/env python
+"""bench.py — endpoint picks/sec at 64K requests x 1024 endpoints (BASELINE.json headline), all four
+scorers (queue 2, kv 2, prefix 3, lora 1), 2 KB shared-prefix prompts, on N B200s of one node.
+
+A "step" = one pass of the hot path over one batch of R requests per GPU:
+    hash_prompts_kernel (chained XXH64 of every prompt)  →  score_pick_fused_kernel (table probe,
+    4 scorers, weighted float64 sum, arg-max pick)        — 2 kernel launches, nothing else.
+`value`  : whole-job picks/s with the inputs already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same metric through the C ABI with HOST (pinned) buffers: H2D of prompts/seeds/adapters
+           and D2H of picks/scores/tie counts inside the timed region.
+`roofline`: algorithmic bytes of the dominant kernel / its CUDA-event duration, vs MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle port (oracle/oracle.c; the Go reference cannot be built here) on the
+           box's host cores, same workload.
+`--impl reference` times that CPU port alone (all host threads) with the same JSON contract.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests.helpers import synth_prompts, synth_snapshot, zipf_adapters  # noqa: E402  (seeded workload generators)
+
+R_PER_GPU = 65536
+M = 1024
+A = 64
+PROMPT_LEN = 2048
+BLOCK_CHARS = 64
+MAX_BLOCKS = 256
+SCORERS = [("queue", 2.0), ("kv", 2.0), ("prefix", 3.0), ("lora", 1.0)]
+NSETS = 4  # rotating input sets: 4 x 128 MiB of prompts > 126 MB L2, so no step re-reads L2-resident inputs
+METRIC = "endpoint picks/sec at 64K reqs x 1024 endpoints"
+WORKLOAD = "headline: 64K requests/GPU x 1024 endpoints, queue+kv+prefix+lora, 2KB prompts (150 shared-prefix groups), B=32 blocks"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def config_dict(n_gpus):
+    return {"workload": WORKLOAD, "requests_per_gpu": R_PER_GPU, "endpoints": M, "adapters": A,
+            "prompt_bytes": PROMPT_LEN, "block_chars": BLOCK_CHARS, "scorers": "queue:2,kv:2,prefix:3,lora:1",
+            "picker": "max-score (lowest-index tie-break)", "parallelism": f"request-sharded x{n_gpus}",
+            "l2": f"inputs rotate over {NSETS} x 128MiB prompt sets (> L2); prefix table + snapshot steady-state resident"}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload (identical on the GPU arm and the CPU arm)
+# ------------------------------------------------------------------------------------------------
+def build_workload(rank: int, nsets: int, R: int):
+    snap = synth_snapshot(M, A=A, seed=0)
+    sets = []
+    for s in range(nsets):
+        prompts, off, _ = synth_prompts(R, prompt_len=PROMPT_LEN, groups=150, shared=1024, seed=100 * rank + s, prefix_seed=7)
+        sets.append(dict(prompts=prompts, off=off, adapters=zipf_adapters(R, A=A, seed=100 * rank + s)))
+    return snap, sets
+
+
+def oracle_setup(snap):
+    """CPU oracle objects + the warm prefix index (4*M earlier requests routed and committed)."""
+    from oracle import oracle_py as o
+    osnap = o.SnapshotData(**snap)
+    prof = o.make_profile([({"queue": 0, "kv": 1, "prefix": 2, "lora": 3}[k], w) for k, w in SCORERS])
+    idx = o.Index()
+    seed = o.model_seed("bench-model")
+    wp, woff, _ = synth_prompts(4 * M, prompt_len=PROMPT_LEN, groups=150, shared=1024, seed=4242, prefix_seed=7)
+    nthreads = os.cpu_count() or 1
+    warm = o.schedule_batch(osnap, prof, idx, 4 * M, prompt_bytes=wp, prompt_off=woff,
+                            model_seed=np.full(4 * M, seed, np.uint64), adapter_id=zipf_adapters(4 * M, A=A, seed=4242),
+                            block_chars=BLOCK_CHARS, max_blocks=MAX_BLOCKS, want_hashes=True, n_threads=nthreads)
+    idx.commit(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    return o, osnap, prof, idx, seed, warm
+
+
+def time_oracle(o, osnap, prof, idx, seed, wset, R, n_threads, min_seconds=2.0, max_iters=20):
+    seeds = np.full(R, seed, np.uint64)
+    times = []
+    t_all = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        o.schedule_batch(osnap, prof, idx, R, prompt_bytes=wset["prompts"][: wset["off"][R]], prompt_off=wset["off"][: R + 1],
+                         model_seed=seeds, adapter_id=wset["adapters"][:R], block_chars=BLOCK_CHARS, max_blocks=MAX_BLOCKS,
+                         n_threads=n_threads)
+        times.append(time.perf_counter() - t0)
+        if len(times) >= max_iters or (time.perf_counter() - t_all) > min_seconds and len(times) >= 3:
+            break
+    return float(np.median(times)), len(times)
+
+
+# ------------------------------------------------------------------------------------------------
+# --impl reference : the CPU port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    R = 16384  # bounded sample of the workload per step (the CPU arm processes the same kind of requests)
+    snap, sets = build_workload(0, 1, R)
+    o, osnap, prof, idx, seed, _ = oracle_setup(snap)
+    cores = os.cpu_count() or 1
+    seeds = np.full(R, seed, np.uint64)
+
+    def step():
+        o.schedule_batch(osnap, prof, idx, R, prompt_bytes=sets[0]["prompts"], prompt_off=sets[0]["off"], model_seed=seeds,
+                         adapter_id=sets[0]["adapters"], block_chars=BLOCK_CHARS, max_blocks=MAX_BLOCKS, n_threads=cores)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = R * args.steps / dt
+    sample = f"{R} requests x {M} endpoints per step (same generator as the GPU arm), all {cores} host threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "picks/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "picks/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "picks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU port (oracle/oracle.c) of the Go reference path; no Go toolchain in this image, so oracle/_ref does not exist"}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (NVML)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import _pkg
+    _pkg.load_build().build()
+    pkg = _pkg.load()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    R = R_PER_GPU
+    snap, sets = build_workload(rank, NSETS, R)
+
+    eng = pkg.Engine(pkg.default_config(SCORERS, max_endpoints=M, max_adapters=A, block_chars=BLOCK_CHARS,
+                                        max_blocks=MAX_BLOCKS, prefix_capacity=1 << 19), device=local)
+    stream = torch.cuda.Stream(device=dev)  # an explicit stream: events and every launch below share it
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+
+    # ---- endpoint snapshot: built on rank 0, ONE NCCL broadcast of the packed tile over NVLink ----
+    order = ["kv_usage", "queue", "running", "lora_active", "lora_waiting", "lora_nmodels", "lora_max"]
+    packed = np.concatenate([np.ascontiguousarray(snap[k]).view(np.uint8).reshape(-1) for k in order])
+    tpack = torch.from_numpy(packed).to(dev) if rank == 0 else torch.empty(len(packed), dtype=torch.uint8, device=dev)
+    if world > 1:
+        dist.broadcast(tpack, src=0)
+    views, o_ = {}, 0
+    for k in order:
+        nb = np.ascontiguousarray(snap[k]).nbytes
+        views[k] = tpack.data_ptr() + o_
+        o_ += nb
+    torch.cuda.synchronize()
+    eng.set_snapshot(views["kv_usage"], views["queue"], views["running"], views["lora_active"], views["lora_waiting"],
+                     views["lora_nmodels"], views["lora_max"], device=True, stream=sptr, M=M, lora_words=1)
+
+    # ---- prefix table: rank 0 replays 4*M earlier requests (oracle-routed) through commit_picks, then the device
+    #      image (key slots + bitset rows) is replicated with NCCL broadcasts ----
+    o = osnap = prof = idx = seed = None
+    if rank == 0:
+        o, osnap, prof, idx, seed, warm = oracle_setup(snap)
+        eng.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    info = eng.prefix_image_info()
+    meta = torch.tensor(info["meta"], dtype=torch.int64, device=dev)
+    seed_t = torch.from_numpy(np.array([seed if rank == 0 else 0], np.uint64).view(np.int64)).to(dev)
+    if world > 1:
+        dist.broadcast(meta, src=0)
+        dist.broadcast(seed_t, src=0)
+        m = [int(x) for x in meta.cpu()]
+
+        def as_tensor(ptr, nbytes):
+            class _W:  # expose a raw device pointer to torch via the CUDA array interface
+                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+            return torch.as_tensor(_W(), device=dev)
+
+        ts = as_tensor(info["slots_ptr"], m[0] * 16)
+        dist.broadcast(ts, src=0)
+        if m[2] > 0:
+            tr = as_tensor(info["rows_ptr"], m[2] * m[1] * 4)
+            dist.broadcast(tr, src=0)
+        torch.cuda.synchronize()
+        if rank != 0:
+            eng.prefix_image_adopt(m)
+    seed = int(seed_t.cpu().numpy().view(np.uint64)[0])
+
+    # ---- device-resident inputs ----
+    dsets = []
+    for s in sets:
+        dsets.append(dict(prompts=torch.from_numpy(s["prompts"]).to(dev), off=torch.from_numpy(s["off"]).to(dev),
+                          seeds=torch.from_numpy(np.full(R, seed, np.uint64).view(np.int64)).to(dev),
+                          adapters=torch.from_numpy(s["adapters"]).to(dev)))
+    out = dict(pick=torch.empty(R, dtype=torch.int32, device=dev), pick_score=torch.empty(R, dtype=torch.float64, device=dev),
+               tie_count=torch.empty(R, dtype=torch.int32, device=dev))
+
+    def step(i):
+        d = dsets[i % NSETS]
+        eng.schedule(R, prompt_bytes=d["prompts"], prompt_off=d["off"], model_seed=d["seeds"], adapter_id=d["adapters"],
+                     request_base=rank * R, device=True, stream=sptr, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- parity spot check against the oracle (rank 0) before any timing ----
+    parity = None
+    if rank == 0:
+        n = 4096
+        step(0)
+        torch.cuda.synchronize()
+        want = o.schedule_batch(osnap, prof, idx, n, prompt_bytes=sets[0]["prompts"][: sets[0]["off"][n]],
+                                prompt_off=sets[0]["off"][: n + 1], model_seed=np.full(n, seed, np.uint64),
+                                adapter_id=sets[0]["adapters"][:n], block_chars=BLOCK_CHARS, max_blocks=MAX_BLOCKS,
+                                n_threads=os.cpu_count() or 1)
+        parity = bool(np.array_equal(out["pick"][:n].cpu().numpy(), want["pick"]) and
+                      np.array_equal(out["pick_score"][:n].cpu().numpy(), want["pick_score"]) and
+                      np.array_equal(out["tie_count"][:n].cpu().numpy(), want["tie_count"]))
+        if not parity:
+            raise SystemExit("bench: GPU picks differ from the oracle — refusing to report a number")
+
+    # ---- value: K steps, device-resident, CUDA events on the launch stream, max over ranks ----
+    for i in range(args.warmup):
+        step(i)
+    clocks = ClockSampler(local)
+    launches0 = eng.stats().kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks.stop()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.stats().kernel_launches - launches0
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = world * R * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: the same steps through the host-buffer C-ABI call (pinned host memory) ----
+    hsets = []
+    for s in sets:
+        hp = torch.from_numpy(s["prompts"]).pin_memory()
+        hs = torch.from_numpy(np.full(R, seed, np.uint64).view(np.int64)).pin_memory()
+        ha = torch.from_numpy(s["adapters"]).pin_memory()
+        ho = torch.from_numpy(s["off"]).pin_memory()
+        hsets.append(dict(prompts=hp.numpy(), off=ho.numpy(), seeds=hs.numpy().view(np.uint64), adapters=ha.numpy(),
+                          keep=(hp, hs, ha, ho)))
+    h2d = int(hsets[0]["prompts"].nbytes + hsets[0]["off"].nbytes + hsets[0]["seeds"].nbytes + hsets[0]["adapters"].nbytes)
+    d2h = R * (4 + 8 + 4)
+
+    def e2e_step(i):
+        h = hsets[i % NSETS]
+        return eng.schedule(R, prompt_bytes=h["prompts"], prompt_off=h["off"], model_seed=h["seeds"], adapter_id=h["adapters"],
+                            request_base=rank * R, want_total=False)
+
+    e2e_steps = max(5, min(args.steps, 50))
+    for i in range(3):
+        e2e_step(i)
+    lat = []
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        t1 = time.perf_counter()
+        res = e2e_step(3 + i)
+        lat.append(time.perf_counter() - t1)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    barrier()
+    tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+    e2e_value = world * R * e2e_steps / float(tdt.item())
+
+    extra = {}
+    if rank == 0:
+        # ---- per-kernel timing for the roofline (each kernel alone, rotating inputs) ----
+        hashes = torch.empty((R, MAX_BLOCKS), dtype=torch.uint64, device=dev)
+        nh = torch.empty(R, dtype=torch.uint16, device=dev)
+        L = pkg.lib()
+
+        def hash_only(i):
+            d = dsets[i % NSETS]
+            rc = L.eppscore_hash_prompts(eng._h, R, 1, d["prompts"].data_ptr(), d["off"].data_ptr(), None, d["seeds"].data_ptr(),
+                                         BLOCK_CHARS, MAX_BLOCKS, hashes.data_ptr(), nh.data_ptr(), sptr)
+            assert rc == 0
+
+        hsets_dev = []
+        for i in range(NSETS):
+            hash_only(i)
+            hsets_dev.append((hashes.clone(), nh.clone()))
+        torch.cuda.synchronize()
+
+        def score_only(i):
+            hh, nn = hsets_dev[i % NSETS]
+            eng.schedule(R, hashes_in=hh, n_hashes_in=nn, hash_stride=MAX_BLOCKS, adapter_id=dsets[i % NSETS]["adapters"],
+                         request_base=rank * R, device=True, stream=sptr, out=out)
+
+        def time_kernel(fn, iters=40):
+            for i in range(5):
+                fn(i)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(stream)
+            for i in range(iters):
+                fn(5 + i)
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters * 1e-3
+
+        t_hash = time_kernel(hash_only)
+        t_score = time_kernel(score_only)
+        nhv = hsets_dev[0][1].cpu().numpy().astype(np.int64)
+        B = float(nhv.mean())
+        # matched blocks per request = blocks probed before the first global miss (row reads)
+        res_m = eng.schedule(4096, prompt_bytes=sets[0]["prompts"][: sets[0]["off"][4096]], prompt_off=sets[0]["off"][:4097],
+                             model_seed=np.full(4096, seed, np.uint64), want_match=True)
+        hits = float(res_m["match_blocks"].max(axis=1).mean())
+        row_bytes = eng.cfg.max_endpoints // 8  # one bitset row (M bits)
+        bytes_score = R * (B * 8 + min(B, hits + 1) * 16 + hits * row_bytes + 2 + 4 + 2 * row_bytes + 16) + M * 8
+        bytes_hash = float(sets[0]["off"][R]) + R * (8 + 8 + B * 8 + 2)
+        peak, peak_src = peaks()
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f)
+        dom, t_dom, b_dom = ("score_pick_fused_kernel", t_score, bytes_score) if t_score >= t_hash else ("hash_prompts_kernel", t_hash, bytes_hash)
+        extra["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": b_dom / t_dom / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": b_dom / t_dom / 1e9 / peak, "traffic": (traffic or {}).get(dom), "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": b_dom, "us_per_launch": t_dom * 1e6,
+                             "note": "fused path never materialises the R x M score matrix; its algorithmic bytes are hashes + table probes + outputs, mostly L2 hits — the kernel is issue-bound, see DESIGN.md §6"}
+        extra["kernels"] = {"hash_prompts_kernel": {"us": t_hash * 1e6, "algorithmic_bytes": bytes_hash, "gbs": bytes_hash / t_hash / 1e9,
+                                                   "frac_of_peak": bytes_hash / t_hash / 1e9 / peak},
+                            "score_pick_fused_kernel": {"us": t_score * 1e6, "algorithmic_bytes": bytes_score,
+                                                        "gbs": bytes_score / t_score / 1e9, "frac_of_peak": bytes_score / t_score / 1e9 / peak},
+                            "avg_blocks_per_request": B, "avg_matched_blocks": hits}
+        # ---- dense-row mode (the R x M float4 feature rows streamed from HBM): reported beside the headline ----
+        try:
+            Rd = 32768
+            feat = torch.zeros((Rd, M, 4), dtype=torch.float32, device=dev)
+            feat[:, :, 0] = (torch.rand((Rd, M), device=dev) < 0.02).float() * 16
+            feat[:, :, 1] = torch.randint(0, 4, (Rd, M), device=dev).float()
+            feats = [feat, feat.clone()]
+            dtot = torch.full((Rd,), 32, dtype=torch.uint16, device=dev)
+            outd = dict(pick=out["pick"][:Rd], pick_score=out["pick_score"][:Rd], tie_count=out["tie_count"][:Rd])
+
+            def dense_only(i):
+                eng.schedule(Rd, dense_feat=feats[i % 2], dense_total=dtot, device=True, stream=sptr, out=outd)
+
+            t_dense = time_kernel(dense_only, iters=20)
+            bytes_dense = 16.0 * Rd * M + 48.0 * M + 16.0 * Rd
+            extra["dense_mode"] = {"requests": Rd, "us": t_dense * 1e6, "picks_per_s": Rd / t_dense, "algorithmic_bytes": bytes_dense,
+                                   "gbs": bytes_dense / t_dense / 1e9, "frac_of_peak": bytes_dense / t_dense / 1e9 / peak,
+                                   "note": "2 x 512 MiB feature sets alternate (> L2)"}
+            del feat, feats
+        except Exception as ex:  # noqa: BLE001
+            extra["dense_mode"] = {"error": str(ex)}
+        # ---- R = 1 latency through the host API ----
+        one = []
+        for i in range(200):
+            t1 = time.perf_counter()
+            eng.schedule(1, prompt_bytes=hsets[0]["prompts"][:PROMPT_LEN], prompt_off=np.array([0, PROMPT_LEN], np.int64),
+                         model_seed=hsets[0]["seeds"][:1], adapter_id=hsets[0]["adapters"][:1], want_total=False)
+            one.append(time.perf_counter() - t1)
+        extra["latency_ms"] = {"p50_batch_e2e": 1e3 * float(np.median(lat)), "p50_single_request_e2e": 1e3 * float(np.median(one[20:])),
+                               "p50_batch_device": ms_max / args.steps}
+        # ---- CPU baseline: the oracle port on this box's cores, same workload ----
+        if world == 1:
+            cores = os.cpu_count() or 1
+            Rc = 32768
+            t_mt, n_mt = time_oracle(o, osnap, prof, idx, seed, sets[0], Rc, cores)
+            t_1, n_1 = time_oracle(o, osnap, prof, idx, seed, sets[0], 4096, 1, min_seconds=1.0, max_iters=5)
+            extra["cpu_baseline"] = {"value": Rc / t_mt, "unit": "picks/s", "cores": cores, "kind": "port",
+                                     "sample": f"{Rc} requests of the same workload x {n_mt} runs (median), {cores} threads; "
+                                               f"single-thread: {4096 / t_1:.0f} picks/s",
+                                     "single_thread_value": 4096 / t_1}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "picks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config_dict(world),
+                "e2e": {"value": e2e_value, "unit": "picks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "ms_per_step": 1e3 * float(tdt.item()) / e2e_steps, "host_memory": "pinned"},
+                "gpu_launches": int(launches), "clocks": clocks.summary(), "parity_checked": parity,
+                "target": {"picks_per_s": 1e8, "met": bool(value >= 1e8)}}
+        line.update(extra)
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

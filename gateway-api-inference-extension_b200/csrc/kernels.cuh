@@ -1,0 +1,162 @@
+// kernels.cuh — device-side data layout and launchers of the Endpoint-Picker kernel family.
+//
+// Data layout in HBM:
+//   * endpoint tile: per-endpoint float64 "term" arrays (clamp(score)*weight, already rounded exactly
+//     as scheduler_profile.go:168 would) in natural endpoint order, staged into shared memory once
+//     per CTA;
+//   * every per-endpoint BIT structure (prefix-table rows, LoRA class planes) uses one lane-major
+//     permutation so that a lane owns the same endpoints in all of them:
+//         endpoint m = (j*EPL + k)*32 + lane   <->   bit k of 32-bit word (j*32 + lane)
+//     (EPL = endpoints per lane per pass = 8/16/32 chosen from M, j = pass).  Natural-order arrays
+//     (terms, candidate masks, dense rows, match output) are then read/written with consecutive
+//     lanes touching consecutive endpoints — coalesced and bank-conflict free;
+//   * prefix table: open-addressing key slots {hash, row, count} + bitset rows of J*32 words.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace eppscore {
+
+constexpr int kMaxSteps = 8;
+constexpr int kLutMax = 256;         // per-warp prefix LUT covers total <= 256 (defaultMaxPrefixBlocks)
+constexpr uint32_t kEmptyRow = 0xFFFFFFFFu;
+
+struct __align__(16) Slot {
+  uint64_t key;
+  uint32_t row;  // kEmptyRow = never used
+  uint32_t cnt;  // |endpoint set|; 0 = emptied (a miss, like a deleted hashToPods key)
+};
+
+enum StepKind : int32_t {
+  STEP_EP_TERM = 0,  // + term[arg][m]                  (request-independent scorer, precomputed)
+  STEP_PREFIX = 1,   // + clamp(match/total)*w          (scorer/prefix/plugin.go:95-117)
+  STEP_LORA = 2,     // + clamp(class score)*w          (scorer/loraaffinity/lora_affinity.go:76-102)
+  STEP_PAIR = 3,     // + clamp(double(feat[arg]))*w    (dense per-pair column)
+  STEP_MINMAX = 4    // + clamp((max-q)/(max-min))*w over the candidate set (queue.go:78-108), arg: 0 queue 1 running
+};
+
+struct Plan {
+  int32_t n_steps;
+  int32_t kind[kMaxSteps];
+  int32_t arg[kMaxSteps];
+  double weight[kMaxSteps];
+  double lora_term[kMaxSteps][4];  // per LoRA step: clamp({0,0.6,0.8,1.0})*w, rounded on the host (one IEEE multiply)
+  int32_t tie_mode;
+  uint32_t seed_lo, seed_hi;
+  int32_t n_terms;      // number of term arrays the steps reference (staged to shared memory)
+};
+
+// Geometry derived from M.
+struct Geo {
+  int32_t M;
+  int32_t log_epl;  // 3,4,5
+  int32_t J;        // passes; Mpad = J*32*EPL
+  int32_t Mpad;
+  int32_t row_words;  // J*32
+};
+
+inline Geo make_geo(int32_t M) {
+  Geo g;
+  g.M = M;
+  g.log_epl = M <= 256 ? 3 : (M <= 512 ? 4 : 5);
+  const int per_pass = 32 << g.log_epl;
+  g.J = (M + per_pass - 1) / per_pass;
+  if (g.J < 1) g.J = 1;
+  // J is a template parameter; round up to the instantiated set {1,2,4,8}
+  int J = 1;
+  while (J < g.J) J <<= 1;
+  g.J = J;
+  g.Mpad = g.J * per_pass;
+  g.row_words = g.J * 32;
+  return g;
+}
+
+// bit position of endpoint m inside a permuted bitset row (word = pos>>5, bit = pos&31)
+__host__ __device__ inline uint32_t perm_bitpos(uint32_t m, int log_epl) {
+  const uint32_t lane = m & 31u, t = m >> 5;  // t = j*EPL + k
+  const uint32_t k = t & ((1u << log_epl) - 1u), j = t >> log_epl;
+  return ((j * 32u + lane) << 5) + k;
+}
+
+struct ScoreArgs {
+  Geo geo;
+  Plan plan;
+  int32_t R;
+  int64_t request_base;
+  // endpoint tile (natural order, Mpad entries each; padding scores are never candidates)
+  const double* term[kMaxSteps];
+  const int64_t* minmax_q[2];   // queue / running raw values for STEP_MINMAX (masked mode)
+  // LoRA class planes, permuted layout: [A+1][row_words] each; row A = "adapter not in dictionary"
+  const uint32_t* cls_lo;
+  const uint32_t* cls_hi;
+  int32_t A;
+  const int32_t* adapter_id;    // [R] or null
+  const uint32_t* cand_mask;    // [R][mask_words] natural order or null
+  int32_t mask_words;
+  // prefix
+  const uint64_t* hashes;       // [R][hash_stride] or null
+  const uint16_t* n_hashes;     // [R]
+  int32_t hash_stride;
+  const Slot* slots;
+  uint64_t slot_mask;           // capacity-1 (0 = no table)
+  const uint32_t* rows;
+  // dense rows
+  const float4* dense;          // [R][M]
+  const uint16_t* dense_total;  // [R]
+  // outputs
+  int32_t* pick;
+  double* pick_score;
+  int32_t* tie_count;
+  uint16_t* match_out;          // [R][M] or null
+  uint16_t* total_out;          // [R] or null
+  double* scores_out;           // [R][M] or null (diagnostics)
+};
+
+struct HashArgs {
+  int32_t R;
+  const uint8_t* bytes;
+  const int64_t* off;       // [R+1]
+  const int32_t* len;       // [R] or null
+  const uint64_t* seed;     // [R] or null (=> 0)
+  int32_t block_chars;
+  int32_t max_blocks;
+  uint64_t* hashes;         // [R][stride]
+  int32_t stride;
+  uint16_t* n_hashes;       // [R]
+};
+
+struct PrepareArgs {
+  Geo geo;
+  int32_t n_scorers;
+  int32_t kind[kMaxSteps];
+  double weight[kMaxSteps];
+  // raw snapshot (device)
+  const double* kv;
+  const int64_t* queue;
+  const int64_t* running;
+  const uint64_t* act;
+  const uint64_t* wait;
+  const int32_t* nmodels;
+  const int32_t* maxm;
+  const double* col[4];
+  int32_t lora_words;
+  int32_t A;
+  // outputs
+  double* term[kMaxSteps];      // per scorer (null where not an endpoint term)
+  double* fold_unmasked;        // leading run folded (or null)
+  int32_t fold_unmasked_n;
+  double* fold_masked;
+  int32_t fold_masked_n;
+  uint32_t* cls_lo;
+  uint32_t* cls_hi;
+};
+
+// launchers (kernels.cu). Each returns the number of kernels it launched (for gpu_launches).
+int launch_hash_prompts(const HashArgs& a, cudaStream_t s);
+int launch_prepare_snapshot(const PrepareArgs& a, cudaStream_t s);
+int launch_score_pick(const ScoreArgs& a, bool dense, cudaStream_t s, int sm_count);
+int launch_scatter_u32(uint32_t* dst, const uint32_t* idx, const uint32_t* val, int64_t n, cudaStream_t s);
+int launch_scatter_slots(Slot* dst, const uint32_t* idx, const Slot* val, int64_t n, cudaStream_t s);
+
+}  // namespace eppscore

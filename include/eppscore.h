@@ -1,0 +1,219 @@
+/*
+ * eppscore.h — C ABI of the B200-native batched Endpoint-Picker scoring engine (libeppscore.so).
+ *
+ * This is the drop-in boundary for ONE hot path of kubernetes-sigs/gateway-api-inference-extension
+ * (reference @ c4c8fef; paths below are relative to it): the per-request Filter → Score → Pick
+ * loop behind Scheduler.Schedule() plus the approximate-prefix producer that feeds it, executed
+ * for a BATCH of R requests against M endpoints by hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI today (pure Go, CGO_ENABLED=0, Dockerfile:8); these entry points are
+ * exactly what a cgo shim behind requestcontrol.Scheduler (pkg/epp/requestcontrol/director.go:68-70)
+ * would bind.  INTEGRATION.md shows that shim.  Conventions:
+ *   - plain C types, caller-owned contiguous little-endian arrays, no callbacks, no torch types;
+ *   - every function returns int32 status (EPPSCORE_OK == 0, negative = error) and
+ *     eppscore_last_error() gives the message; handles are opaque;
+ *   - one engine per CUDA device; calls on one engine are serialised by the caller
+ *     (the Go shim holds a mutex), different engines are independent;
+ *   - there is NO CPU fallback: eppscore_create fails (EPPSCORE_ERR_NO_DEVICE) without a GPU.
+ *
+ * Numerics contract: all scheduler arithmetic is IEEE float64, multiply then add
+ * without FMA contraction, accumulated in scorer order from 0.0 — bit-identical to
+ * pkg/epp/scheduling/scheduler_profile.go:155-168 on GOARCH=amd64.  Block hashes are XXH64
+ * (seed 0) chained as approximateprefix/hashing.go:70-94.  Picks are the arg-max; ties are
+ * reported (tie_count) and broken deterministically (see eppscore_tie_mode) where the reference
+ * breaks them with a time-seeded shuffle (picker/common.go:49-55, maxscore/picker.go:91-102).
+ */
+#ifndef EPPSCORE_H
+#define EPPSCORE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPPSCORE_ABI_VERSION 1
+#define EPPSCORE_MAX_SCORERS 8
+#define EPPSCORE_MAX_ENDPOINT_COLS 4
+#define EPPSCORE_MAX_BLOCKS 65535 /* match/total are uint16 (attribute/prefix/data_types.go:27-34 are Go ints) */
+
+typedef struct eppscore_engine eppscore_engine; /* opaque */
+
+typedef enum eppscore_status {
+  EPPSCORE_OK = 0,
+  EPPSCORE_ERR_INVALID = -1,     /* bad argument / config */
+  EPPSCORE_ERR_CUDA = -2,        /* CUDA runtime error (message in last_error) */
+  EPPSCORE_ERR_CAPACITY = -3,    /* M / A / table capacity exceeded */
+  EPPSCORE_ERR_NO_SNAPSHOT = -4, /* schedule called before set_snapshot */
+  EPPSCORE_ERR_NO_DEVICE = -5    /* no CUDA device: the engine has no CPU path */
+} eppscore_status;
+
+/* Scorer kinds, in the sense of framework.Scorer (interface/scheduling/plugins.go:68-72). */
+typedef enum eppscore_scorer_kind {
+  EPPSCORE_SCORER_QUEUE = 0,    /* queue-scorer: scorer/queuedepth/queue.go:78-108 */
+  EPPSCORE_SCORER_KV_CACHE = 1, /* kv-cache-utilization-scorer: scorer/kvcacheutilization/kvcache_utilization.go:76-82 */
+  EPPSCORE_SCORER_PREFIX = 2,   /* prefix-cache-scorer: scorer/prefix/plugin.go:95-117 (+ producer approximateprefix/) */
+  EPPSCORE_SCORER_LORA = 3,     /* lora-affinity-scorer: scorer/loraaffinity/lora_affinity.go:76-102 */
+  EPPSCORE_SCORER_RUNNING = 4,  /* running-requests-size-scorer: scorer/runningrequests/runningrequest.go:78-108 */
+  /* 8+k: a host-computed, request-independent scorer supplied as float64 column k of the snapshot
+   * (any custom framework.Scorer whose output does not depend on the request); clamped+weighted in-kernel. */
+  EPPSCORE_SCORER_ENDPOINT_COL0 = 8,
+  /* 16+k: a per-(request,endpoint) float32 column k∈{0,1} of the dense feature rows (e.g. the
+   * latency-scorer output folded into the score matrix, scorer/latency/plugin.go:144). */
+  EPPSCORE_SCORER_PAIR_COL0 = 16
+} eppscore_scorer_kind;
+
+typedef enum eppscore_tie_mode {
+  EPPSCORE_TIE_LOWEST_INDEX = 0, /* deterministic: lowest endpoint index in the arg-max set */
+  /* counter-based stand-in for the reference's shuffle: the arg-max member with the largest
+   * lowbias32-mixed priority of (tie_seed, request_base + r, endpoint) wins — uniform over the
+   * tie set, reproducible, order-independent (so every GPU shard agrees). */
+  EPPSCORE_TIE_SEEDED_RANDOM = 1
+} eppscore_tie_mode;
+
+/* Scheduler profile + engine sizing.  Replaces SchedulerProfile{scorers, picker}
+ * (pkg/epp/scheduling/scheduler_profile.go:41-98) and the approximateprefix config
+ * (approximateprefix/types.go:77-141). Zero-initialise, set struct_size = sizeof, fill. */
+typedef struct eppscore_config {
+  uint32_t struct_size;
+  int32_t n_scorers;                              /* profile order matters: float64 adds are not associative */
+  int32_t scorer_kind[EPPSCORE_MAX_SCORERS];
+  double scorer_weight[EPPSCORE_MAX_SCORERS];     /* WeightedScorer.Weight(), weighted_scorer.go:32 */
+  int32_t block_chars;     /* blockSizeTokens*averageCharactersPerToken; default 16*4 (types.go:91,112) */
+  int32_t max_blocks;      /* defaultMaxPrefixBlocks = 256 (types.go:98) */
+  int32_t tie_mode;        /* eppscore_tie_mode */
+  uint64_t tie_seed;
+  int32_t max_endpoints;   /* capacity for M (rounded up internally); default 1024 */
+  int32_t max_adapters;    /* capacity for the LoRA adapter dictionary A; default 64 */
+  int64_t prefix_capacity; /* max distinct block hashes resident in the device table; default 1<<20 */
+  int32_t lru_capacity_default; /* defaultLRUCapacityPerServer = 31250 (types.go:109) */
+} eppscore_config;
+
+/* Immutable metrics snapshot: the fields of fwkdl.Metrics the path reads
+ * (interface/datalayer/metrics.go:26-42), packed SoA.  LoRA maps become dictionary bitmasks:
+ * bit a of lora_active[m*lora_words + a/64] ⇔ adapter a ∈ ActiveModels of endpoint m. */
+typedef struct eppscore_snapshot {
+  uint32_t struct_size;
+  int32_t M;
+  int32_t lora_words;            /* ceil(A/64) */
+  int32_t location;              /* 0 = host pointers, 1 = device pointers (e.g. an NCCL-broadcast buffer) */
+  const double *kv_usage;        /* KVCacheUsagePercent            [M] */
+  const int64_t *queue;          /* WaitingQueueSize               [M] */
+  const int64_t *running;        /* RunningRequestsSize            [M] (may be NULL) */
+  const uint64_t *lora_active;   /* [M*lora_words] (may be NULL ⇒ empty) */
+  const uint64_t *lora_waiting;  /* [M*lora_words] */
+  const int32_t *lora_nmodels;   /* len(ActiveModels)+len(WaitingModels) as MAP sizes (lora_affinity.go:90) [M] */
+  const int32_t *lora_max;       /* MaxActiveModels                [M] */
+  const double *endpoint_col[EPPSCORE_MAX_ENDPOINT_COLS]; /* optional generic score columns [M] */
+  uint64_t epoch;                /* caller's snapshot generation, echoed by eppscore_stats */
+  void *stream;                  /* cudaStream_t for location==1 (NULL = engine stream) */
+} eppscore_snapshot;
+
+/* One batch = R concurrent Scheduler.Schedule() calls (pkg/epp/scheduling/scheduler.go:54). */
+typedef struct eppscore_batch {
+  uint32_t struct_size;
+  int32_t R;
+  int32_t location;            /* 0 = host pointers (copies happen inside the call), 1 = device pointers */
+  int32_t reserved0;
+  int64_t request_base;        /* global index of request 0 (multi-GPU shards; feeds the tie priority) */
+  /* --- prefix producer inputs: EITHER prompts (hashed on the GPU) OR precomputed hashes --- */
+  const uint8_t *prompt_bytes; /* flattened getUserInputBytes() output (hashing.go:106-135), concatenated */
+  const int64_t *prompt_off;   /* [R+1] byte offsets into prompt_bytes */
+  const int32_t *prompt_len;   /* optional [R]: explicit lengths, so a host may pad every prompt START to 16 bytes
+                                  (fast aligned hash path); NULL ⇒ len[r] = prompt_off[r+1]-prompt_off[r] */
+  const uint64_t *model_seed;  /* [R] XXH64(TargetModel || cacheSalt) (hashing.go:70-77); see eppscore_model_seed */
+  const uint64_t *hashes_in;   /* [R*hash_stride] optional: block hashes computed elsewhere */
+  const uint16_t *n_hashes_in; /* [R] */
+  int32_t hash_stride;
+  int32_t block_chars;         /* 0 ⇒ config default; per call because autotune reads endpoints[0] (plugin.go:238-250) */
+  int32_t max_blocks;          /* 0 ⇒ config default */
+  int32_t reserved1;
+  /* --- per-request scorer inputs --- */
+  const int32_t *adapter_id;   /* [R] dictionary id of TargetModel, -1 = not a known adapter; NULL ⇒ all -1 */
+  const uint32_t *cand_mask;   /* [R*ceil(M/32)] filter-chain result (scheduler_profile.go:130-149); NULL ⇒ all M */
+  /* --- dense feature rows (optional; replaces the in-kernel prefix match and LoRA lookup) ---
+   * float4 per (r,m): {x = matchBlocks (integer valued), y = lora class 0..3 ↦ {0,0.6,0.8,1.0},
+   *                    z = pair column 0, w = pair column 1}                                        */
+  const float *dense_feat;     /* [R*M*4] */
+  const uint16_t *dense_total; /* [R] totalBlocks for the dense rows */
+  /* --- outputs --- */
+  int32_t *pick;               /* [R] chosen endpoint, -1 = "no endpoints available" (scheduler_profile.go:119-121) */
+  double *pick_score;          /* [R] weighted score of the pick (ScoredEndpoint.Score, types.go:152-155) */
+  int32_t *tie_count;          /* [R] size of the arg-max set */
+  uint16_t *match_blocks;      /* optional [R*M]: PrefixCacheMatchInfo.matchBlocks per endpoint */
+  uint16_t *total_blocks;      /* optional [R]:   PrefixCacheMatchInfo.totalBlocks */
+  uint64_t *hashes_out;        /* optional [R*max_blocks]: block hashes (state for eppscore_commit_picks / PreRequest) */
+  double *scores_out;          /* optional [R*M]: the whole weightedScorePerEndpoint map (scheduler_profile.go:155-174),
+                                  NaN for non-candidates — diagnostics / parity tests; 8*R*M bytes of HBM writes */
+  void *stream;                /* cudaStream_t for location==1 (NULL = engine stream); the call is async on it */
+} eppscore_batch;
+
+typedef struct eppscore_stats {
+  uint32_t struct_size;
+  int32_t M;
+  uint64_t epoch;
+  uint64_t kernel_launches;     /* CUDA kernels launched by this engine since creation */
+  int64_t prefix_hashes;        /* distinct block hashes resident (len(hashToPods) incl. emptied rows) */
+  int64_t prefix_live_hashes;   /* hashes with a non-empty endpoint set == len(hashToPods) of the reference */
+  int64_t prefix_capacity;
+  int64_t prefix_table_bytes;   /* device bytes: key slots + endpoint bitset rows */
+  int64_t lru_entries;          /* Σ per-endpoint LRU lengths (prefix_indexer_size metric, metrics.go:349) */
+} eppscore_stats;
+
+/* ---- lifecycle ---- */
+int32_t eppscore_abi_version(void);
+void eppscore_config_default(eppscore_config *cfg); /* default-config weights queue 2, kv 2, prefix 3 (loader/defaults.go:46-103) */
+int32_t eppscore_create(int32_t device, const eppscore_config *cfg, struct eppscore_engine **out);
+void eppscore_destroy(struct eppscore_engine *e);
+const char *eppscore_last_error(const struct eppscore_engine *e); /* e may be NULL: last create() error */
+int32_t eppscore_get_stats(const struct eppscore_engine *e, eppscore_stats *out);
+
+/* ---- snapshot (replaces the per-request deep clone, director.go:342-349) ---- */
+int32_t eppscore_set_snapshot(struct eppscore_engine *e, const eppscore_snapshot *s);
+
+/* ---- the hot path: Filter(mask) → Score → Pick for R requests ---- */
+int32_t eppscore_schedule_batch(struct eppscore_engine *e, const eppscore_batch *b);
+
+/* ---- stand-alone stages (same kernels; for parity tests and hosts that only want one stage) ---- */
+/* hashPrompt for R prompts (hashing.go:34-98). hashes_out [R*max_blocks], n_hashes_out [R]. */
+int32_t eppscore_hash_prompts(struct eppscore_engine *e, int32_t R, int32_t location, const uint8_t *prompt_bytes,
+                              const int64_t *prompt_off, const int32_t *prompt_len /*optional*/,
+                              const uint64_t *model_seed, int32_t block_chars, int32_t max_blocks,
+                              uint64_t *hashes_out, uint16_t *n_hashes_out, void *stream);
+/* host helper: XXH64(model || salt), hashing.go:70-77 */
+uint64_t eppscore_model_seed(const void *model, size_t model_len, const void *salt, size_t salt_len);
+uint64_t eppscore_xxh64(const void *data, size_t len, uint64_t seed);
+
+/* ---- prefix index (approximateprefix/indexer.go) ----
+ * The engine keeps the per-endpoint LRUs on the host (exact hashicorp/golang-lru semantics) and the
+ * hash → endpoint-set map on the device as an open-addressing key table + bitset rows. */
+/* PreRequest for the batch (plugin.go:169-197): for r in order: indexer.Add(hashes[r], pick[r]).
+ * lru_capacity: optional [M] CacheNumBlocks per endpoint (autotune, plugin.go:207-216); NULL/<=0 ⇒ default. */
+int32_t eppscore_commit_picks(struct eppscore_engine *e, int32_t R, const int32_t *pick, const uint64_t *hashes,
+                              const uint16_t *n_hashes, int32_t hash_stride, const int32_t *lru_capacity);
+/* indexer.Add for one server (tests, the "prefill" profile's pick plugin.go:180-184). */
+int32_t eppscore_prefix_add(struct eppscore_engine *e, const uint64_t *hashes, int32_t n, int32_t endpoint,
+                            int32_t lru_capacity);
+/* Raw deltas for hosts that keep their own LRU: op 0 = insert (hash,endpoint), 1 = evict. */
+int32_t eppscore_prefix_apply(struct eppscore_engine *e, int64_t n, const uint64_t *hash, const int32_t *endpoint,
+                              const uint8_t *op);
+int32_t eppscore_prefix_remove_endpoint(struct eppscore_engine *e, int32_t endpoint); /* indexer.RemovePod :167-182 */
+/* indexer.Get (reads the DEVICE table): bitset_out[ceil(M/32)] words; returns set size or <0. */
+int32_t eppscore_prefix_get(struct eppscore_engine *e, uint64_t hash, uint32_t *bitset_out, int32_t words);
+int32_t eppscore_prefix_lru_len(const struct eppscore_engine *e, int32_t endpoint); /* -1: endpoint has no LRU */
+int32_t eppscore_prefix_lru_keys(const struct eppscore_engine *e, int32_t endpoint, uint64_t *out, int32_t cap);
+/* Replication across GPUs: export the device table image of one engine / adopt it on another
+ * (the image buffers are what a rank broadcasts with NCCL). */
+int32_t eppscore_prefix_image_info(struct eppscore_engine *e, void **slots_dev, int64_t *slots_bytes, void **rows_dev,
+                                   int64_t *rows_bytes, int64_t *meta /*[4]: cap, row_words, n_rows, n_keys*/);
+int32_t eppscore_prefix_image_adopt(struct eppscore_engine *e, const int64_t *meta);
+
+/* pinned host memory for callers that want the fast copy path (cudaHostAlloc / cudaFreeHost) */
+void *eppscore_host_alloc(size_t bytes);
+void eppscore_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPPSCORE_H */

@@ -757,7 +757,8 @@ static void *batch_worker(void *arg) {
     const uint32_t *mask = b->cand_mask ? b->cand_mask + (size_t)r * mw : NULL;
     orc_schedule_one(j->s, j->p, b->request_base + r, b->adapter_id ? b->adapter_id[r] : -1, mask, match_p, total,
                      pair, &b->pick[r], &b->pick_score[r], &b->tie_count[r],
-                     b->tie_set ? b->tie_set + (size_t)r * mw : NULL, NULL);
+                     b->tie_set ? b->tie_set + (size_t)r * mw : NULL,
+                     b->weighted_out ? b->weighted_out + (size_t)r * M : NULL);
   }
   free(hashes);
   free(match);

@@ -142,6 +142,7 @@ typedef struct orc_batch {
   uint16_t *match_blocks;        /* optional R x M */
   uint16_t *total_blocks;        /* optional R */
   uint64_t *hashes_out;          /* optional R x max_blocks */
+  double *weighted_out;          /* optional R x M: weightedScorePerEndpoint, NaN for non-candidates */
 } orc_batch;
 
 /* Whole hot path for a batch (hash → match → score → pick), requests partitioned over n_threads

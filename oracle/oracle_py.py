@@ -50,7 +50,8 @@ class Batch(C.Structure):
                 ("cand_mask", C.c_void_p), ("dense_feat", C.c_void_p), ("dense_total", C.c_void_p),
                 ("block_chars", C.c_int32), ("max_blocks", C.c_int32), ("pick", C.c_void_p),
                 ("pick_score", C.c_void_p), ("tie_count", C.c_void_p), ("tie_set", C.c_void_p),
-                ("match_blocks", C.c_void_p), ("total_blocks", C.c_void_p), ("hashes_out", C.c_void_p)]
+                ("match_blocks", C.c_void_p), ("total_blocks", C.c_void_p), ("hashes_out", C.c_void_p),
+                ("weighted_out", C.c_void_p)]
 
 
 _lib = None
@@ -284,7 +285,8 @@ def schedule_one(snap: SnapshotData, profile: Profile, request_index=0, adapter_
 def schedule_batch(snap: SnapshotData, profile: Profile, index: Index | None, R: int, *, prompt_bytes=None,
                    prompt_off=None, model_seed=None, hashes_in=None, n_hashes_in=None, adapter_id=None,
                    cand_mask=None, dense_feat=None, dense_total=None, block_chars=64, max_blocks=256,
-                   request_base=0, n_threads=1, want_match=False, want_hashes=False, want_tie_set=False):
+                   request_base=0, n_threads=1, want_match=False, want_hashes=False, want_tie_set=False,
+                   want_scores=False):
     M = snap.M
     mw = (M + 31) // 32
     b = Batch()
@@ -318,6 +320,8 @@ def schedule_batch(snap: SnapshotData, profile: Profile, index: Index | None, R:
         out["hashes_out"] = np.zeros((R, max_blocks), np.uint64)
     if want_tie_set:
         out["tie_set"] = np.zeros((R, mw), np.uint32)
+    if want_scores:
+        out["weighted_out"] = np.zeros((R, M), np.float64)
     for k, v in out.items():
         setattr(b, k, _ptr(v))
     lib().orc_schedule_batch(C.byref(snap.struct), C.byref(profile), index._h if index is not None else None,

@@ -77,11 +77,14 @@ def synth_snapshot(M, A=64, seed=0, tie_heavy=False):
                 lora_max=mx)
 
 
-def synth_prompts(R, prompt_len=2048, groups=150, shared=1024, seed=0):
-    """Shared-prefix prompts: one of `groups` x `shared`-byte prefixes + unique tail, bytes a..z."""
+def synth_prompts(R, prompt_len=2048, groups=150, shared=1024, seed=0, prefix_seed=None):
+    """Shared-prefix prompts: one of `groups` x `shared`-byte prefixes + unique tail, bytes a..z.
+    The prefix pool depends only on prefix_seed (default: seed), so batches with different `seed`
+    but the same `prefix_seed` share their system prompts — what makes the prefix index hit."""
     rng = np.random.Generator(np.random.PCG64(seed + 1000))
     shared = min(shared, prompt_len)
-    prefixes = rng.integers(97, 123, size=(groups, shared), dtype=np.uint8)
+    prng = np.random.Generator(np.random.PCG64((seed if prefix_seed is None else prefix_seed) + 5000))
+    prefixes = prng.integers(97, 123, size=(groups, shared), dtype=np.uint8)
     g = rng.integers(0, groups, size=R)
     out = np.empty((R, prompt_len), dtype=np.uint8)
     out[:, :shared] = prefixes[g]

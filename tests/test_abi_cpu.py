@@ -1,0 +1,75 @@
+"""CPU-side checks of the drop-in boundary: the library builds, loads, and exports exactly the
+symbols include/eppscore.h declares; without a GPU it refuses to create an engine (no CPU path)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import _pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    _pkg.load_build().build()
+    return _pkg.load()
+
+
+def test_header_symbols_all_exported(pkg):
+    header = open(os.path.join(ROOT, "include", "eppscore.h")).read()
+    declared = set(re.findall(r"\b(eppscore_[a-z0-9_]+)\s*\(", header))
+    bound = {name for name, _, _ in pkg.ABI_SYMBOLS}
+    assert declared == bound, (declared ^ bound)
+    L = pkg.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.eppscore_abi_version() == 1
+
+
+def test_struct_sizes_match_header_layout(pkg):
+    # natural C layout on x86-64 (computed by hand from include/eppscore.h)
+    assert C.sizeof(pkg.Config) == 4 + 4 + 32 + 64 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4
+    assert C.sizeof(pkg.Snapshot) == 16 + 7 * 8 + 4 * 8 + 8 + 8
+    assert C.sizeof(pkg.Batch) == 16 + 8 + 6 * 8 + 16 + 4 * 8 + 7 * 8 + 8
+    assert C.sizeof(pkg.Stats) == 8 + 8 + 8 + 5 * 8
+
+
+def test_default_config_is_reference_default(pkg):
+    cfg = pkg.default_config()
+    # pkg/epp/config/loader/defaults.go:46-103: queue 2, kv 2, prefix 3
+    assert cfg.n_scorers == 3
+    assert [cfg.scorer_kind[i] for i in range(3)] == [pkg.SCORER["queue"], pkg.SCORER["kv"], pkg.SCORER["prefix"]]
+    assert [cfg.scorer_weight[i] for i in range(3)] == [2.0, 2.0, 3.0]
+    assert cfg.block_chars == 64 and cfg.max_blocks == 256 and cfg.lru_capacity_default == 31250
+
+
+def test_host_helpers_match_oracle(pkg, xxh_kat):
+    from oracle import oracle_py as o
+    L = pkg.lib()
+    for v in xxh_kat["raw"][:40]:
+        b = bytes.fromhex(v["hex"])
+        assert f"{L.eppscore_xxh64(b, len(b), 0):016x}" == v["xxh64"]
+    assert pkg.Engine.model_seed("test-model1") == 0x55B9CE9184DD8509 == o.model_seed("test-model1")
+    assert pkg.Engine.model_seed("m", "salt") == o.model_seed("m", "salt")
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    with pytest.raises(pkg.EppscoreError) as ei:
+        pkg.Engine()
+    assert ei.value.code == -5  # EPPSCORE_ERR_NO_DEVICE
+
+
+def test_invalid_config_rejected(pkg):
+    cfg = pkg.default_config()
+    cfg.struct_size = 3
+    h = C.c_void_p()
+    assert pkg.lib().eppscore_create(0, C.byref(cfg), C.byref(h)) == -1
+    cfg = pkg.default_config([("queue", 1.0)])
+    cfg.scorer_kind[0] = 99
+    assert pkg.lib().eppscore_create(0, C.byref(cfg), C.byref(h)) == -1
+    assert b"scorer" in pkg.lib().eppscore_last_error(None)

@@ -1,0 +1,519 @@
+"""GPU parity tests: every result of the CUDA engine, obtained THROUGH THE C ABI (libeppscore.so via
+ctypes), is compared with the CPU oracle on the same seeded inputs — bit-exact for hashes, match
+counts, picks, tie counts and float64 scores — and with the reference's own golden vectors."""
+import numpy as np
+import pytest
+
+import _pkg
+from oracle import oracle_py as o
+from tests.helpers import (kinds, mask_from_list, pack_lora, synth_prompts, synth_ragged_prompts, synth_snapshot,
+                           zipf_adapters)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    _pkg.load_build().build()
+    return _pkg.load()
+
+
+def make_engine(pkg, scorers, M, **kw):
+    kw.setdefault("prefix_capacity", 1 << 14)
+    return pkg.Engine(pkg.default_config(scorers, max_endpoints=max(M, 1), **kw))
+
+
+def profile_of(pkg, scorers, tie_mode=0, tie_seed=0):
+    return o.make_profile([(pkg.SCORER[k], w) for k, w in scorers], tie_mode=tie_mode, tie_seed=tie_seed)
+
+
+def assert_same(got, want, keys=("pick", "pick_score", "tie_count")):
+    for k in keys:
+        g, w = got[k], want["weighted_out" if k == "scores_out" else k]
+        if g.dtype.kind == "f":
+            # bit-exact except that NaN payloads (non-candidates) may differ
+            both = ~(np.isnan(g) | np.isnan(w))
+            assert np.array_equal(np.isnan(g), np.isnan(w)), k
+            assert np.array_equal(g[both].view(np.uint64), w[both].view(np.uint64)), k
+        else:
+            assert np.array_equal(g, w), k
+
+
+# ------------------------------------------------------------------------------------------ hashing
+def test_hash_chain_golden_vectors(pkg, xxh_kat):
+    """hashPrompt on the GPU against the XXH64 known-answer chains (block sizes 4..256, partial blocks,
+    truncation), both with unaligned back-to-back prompts and with 16-byte aligned starts."""
+    eng = make_engine(pkg, [("prefix", 1.0)], 8)
+    by_cfg = {}
+    for c in xxh_kat["chains"]:
+        by_cfg.setdefault((c["block_chars"], c["max_blocks"]), []).append(c)
+    for (bc, mb), cases in by_cfg.items():
+        prompts = [bytes.fromhex(c["prompt_hex"]) for c in cases]
+        seeds = np.array([int(c["seed"], 16) for c in cases], np.uint64)
+        for aligned in (False, True):
+            off = np.zeros(len(prompts) + 1, np.int64)
+            lens = np.array([len(p) for p in prompts], np.int32)
+            buf = bytearray()
+            for i, p in enumerate(prompts):
+                if aligned:
+                    buf.extend(b"\0" * ((-len(buf)) % 16))
+                off[i] = len(buf)
+                buf.extend(p)
+            off[-1] = len(buf)
+            data = np.frombuffer(bytes(buf) + b"\0", np.uint8)
+            hashes, n = eng.hash_prompts(data, off, seeds, prompt_len=lens, block_chars=bc, max_blocks=mb)
+            for i, c in enumerate(cases):
+                assert [f"{int(x):016x}" for x in hashes[i, : n[i]]] == c["hashes"], (bc, mb, aligned, i)
+    eng.close()
+
+
+def test_hash_matches_oracle_ragged(pkg):
+    eng = make_engine(pkg, [("prefix", 1.0)], 8)
+    for bc, mb, seed in ((64, 256, 1), (64, 4, 2), (32, 256, 3), (4, 256, 4), (100, 7, 5), (128, 2, 6)):
+        R = 257
+        data, off = synth_ragged_prompts(R, max_len=900, seed=seed)
+        seeds = np.arange(R, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)
+        hashes, n = eng.hash_prompts(data, off, seeds, block_chars=bc, max_blocks=mb)
+        for r in range(R):
+            want = o.hash_prompt(bytes(data[off[r]:off[r + 1]]), int(seeds[r]), bc, mb)
+            assert n[r] == len(want), (bc, mb, r)
+            assert np.array_equal(hashes[r, : n[r]], want), (bc, mb, r)
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------ golden vectors
+def _snapshot_from_endpoints(eps, target_models=()):
+    ids, act, wai, nm, mx = pack_lora(eps, target_models)
+    sd = dict(kv_usage=np.array([e.get("kv", 0.0) for e in eps], np.float64),
+              queue=np.array([e.get("queue", 0) for e in eps], np.int64),
+              lora_active=act, lora_waiting=wai, lora_nmodels=nm, lora_max=mx)
+    return sd, ids
+
+
+def test_schedule_finds_optimal_endpoint(pkg, golden):
+    """pkg/epp/scheduling/scheduler_test.go:86-143 — pod2 with Score == 2.8 exactly."""
+    c = golden["schedule"][0]
+    sd, ids = _snapshot_from_endpoints(c["endpoints"], [c["target_model"]])
+    eng = make_engine(pkg, c["scorers"], len(c["endpoints"]))
+    eng.set_snapshot(**sd)
+    res = eng.schedule(1, adapter_id=np.array([ids[c["target_model"]]], np.int32), want_scores=True)
+    assert c["endpoints"][res["pick"][0]]["name"] == c["want_pick"]
+    assert res["pick_score"][0] == c["want_score_exact"]
+    assert res["tie_count"][0] == 1
+    # the whole weighted map, as the Go test would see it in DEBUG logs: 0.8+1+0+0 , 0.8+1+0+1, 0.2+0+0+0.8
+    assert list(res["scores_out"][0]) == [1.8, 2.8, 1.0]
+    eng.close()
+
+
+def test_no_candidates_is_an_error_pick(pkg, golden):
+    """scheduler_test.go:69-78 / scheduler_profile.go:119-121: empty candidate set ⇒ no pick."""
+    eng = make_engine(pkg, [("kv", 1), ("queue", 1)], 4)
+    eng.set_snapshot(np.array([0.1, 0.2, 0.3, 0.4]), np.array([1, 2, 3, 4]))
+    res = eng.schedule(2, cand_mask=np.array([[0], [0b0100]], np.uint32))
+    assert res["pick"][0] == -1 and res["tie_count"][0] == 0
+    assert res["pick"][1] == 2 and res["tie_count"][1] == 1
+    eng.close()
+
+
+def test_weighted_constant_scorers_and_clamp(pkg, golden):
+    """scheduler_profile_test.go:63-108,350-413 — weight math exact (1.1, 50), clamp of out-of-range scores."""
+    for c in golden["weighted_constant_scorers"]:
+        n = c["n_endpoints"]
+        eng = make_engine(pkg, [("col0", c["weights"][0]), ("col1", c["weights"][1])], n)
+        eng.set_snapshot(np.zeros(n), np.zeros(n, np.int64), endpoint_cols=[np.full(n, c["scores"][0]), np.full(n, c["scores"][1])])
+        res = eng.schedule(1, cand_mask=mask_from_list(n, c["filter_keep"]).reshape(1, -1))
+        if c.get("want_error"):
+            assert res["pick"][0] == -1 and res["tie_count"][0] == 0
+        else:
+            assert res["pick_score"][0] == c["want_score_exact"]
+            assert res["tie_count"][0] == c["want_tie_count"] and res["pick"][0] in c["filter_keep"]
+        eng.close()
+    r = golden["enforce_score_range"]["run_out_of_range"]
+    eng = make_engine(pkg, [("col0", r["weights"][0]), ("col1", r["weights"][1])], 1)
+    eng.set_snapshot(np.zeros(1), np.zeros(1, np.int64), endpoint_cols=[np.array([r["scores"][0]]), np.array([r["scores"][1]])])
+    assert eng.schedule(1)["pick_score"][0] == r["want_score_exact"]
+    eng.close()
+    for x, want in golden["enforce_score_range"]["cases"]:
+        eng = make_engine(pkg, [("col0", 1.0)], 1)
+        eng.set_snapshot(np.zeros(1), np.zeros(1, np.int64), endpoint_cols=[np.array([x])])
+        assert eng.schedule(1)["pick_score"][0] == want
+        eng.close()
+
+
+def test_single_scorer_tables(pkg, golden):
+    """The per-scorer table tests of the reference, read back through scores_out (weight 1)."""
+    for c in golden["kv_scorer"]["cases"]:
+        eng = make_engine(pkg, [("kv", 1.0)], len(c["kv"]))
+        eng.set_snapshot(np.array(c["kv"]), np.zeros(len(c["kv"]), np.int64))
+        got = eng.schedule(1, want_scores=True)["scores_out"][0]
+        assert np.allclose(got, c["want"], atol=golden["kv_scorer"]["tolerance"], rtol=0)
+        eng.close()
+    for c in golden["queue_scorer"]["cases"]:
+        eng = make_engine(pkg, [("queue", 1.0)], len(c["queue"]))
+        eng.set_snapshot(np.zeros(len(c["queue"])), np.array(c["queue"], np.int64))
+        got = eng.schedule(1, want_scores=True)["scores_out"][0]
+        assert np.allclose(got, c["want"], atol=golden["queue_scorer"]["tolerance"], rtol=0)
+        eng.close()
+    for c in golden["lora_scorer"]["cases"]:
+        if not c["endpoints"]:
+            continue
+        sd, ids = _snapshot_from_endpoints(c["endpoints"], [c["target"]])
+        eng = make_engine(pkg, [("lora", 1.0)], len(c["endpoints"]))
+        eng.set_snapshot(**sd)
+        got = eng.schedule(1, adapter_id=np.array([ids[c["target"]]], np.int32), want_scores=True)["scores_out"][0]
+        assert np.allclose(got, c["want"], atol=golden["lora_scorer"]["tolerance"], rtol=0), c["name"]
+        eng.close()
+    for c in golden["prefix_scorer"]["cases"]:
+        n = len(c["match"])
+        eng = make_engine(pkg, [("prefix", 1.0)], n)
+        eng.set_snapshot(np.zeros(n), np.zeros(n, np.int64))
+        feat = np.zeros((1, n, 4), np.float32)
+        feat[0, :, 0] = c["match"]
+        got = eng.schedule(1, dense_feat=feat, dense_total=np.array([c["total"]], np.uint16), want_scores=True)
+        assert list(got["scores_out"][0]) == c["want_exact"]  # assert.Equal in the reference
+        eng.close()
+
+
+def test_integration_routing(pkg, golden):
+    """test/integration/epp routing scenarios (queue+kv+prefix+lora, weight 1, incl. subset masks)."""
+    g = golden["integration_routing"]
+    for c in g["cases"]:
+        scorers = c.get("scorers", g["scorers"])
+        eps = [{"queue": q, "kv": kv, "active": models, "waiting": [], "max_active": 0} for _, q, kv, models in c["pods"]]
+        sd, ids = _snapshot_from_endpoints(eps, [c["target_model"]])
+        eng = make_engine(pkg, scorers, len(eps))
+        eng.set_snapshot(**sd)
+        prompt = np.frombuffer(c["prompt"].encode(), np.uint8)
+        kw = dict(prompt_bytes=prompt, prompt_off=np.array([0, len(prompt)], np.int64),
+                  model_seed=np.array([eng.model_seed(c["target_model"])], np.uint64),
+                  adapter_id=np.array([ids[c["target_model"]]], np.int32))
+        if "subset" in c:
+            kw["cand_mask"] = mask_from_list(len(eps), c["subset"]).reshape(1, -1)
+        res = eng.schedule(1, **kw)
+        if c.get("want_error"):
+            assert res["pick"][0] == -1, c["name"]
+        else:
+            assert res["pick"][0] == c["want_pick"], c["name"]
+            assert res["tie_count"][0] == 1, c["name"]
+            assert res["total_blocks"][0] == 0  # prompts shorter than one block (hashing.go:57-60)
+        eng.close()
+
+
+def test_picker_vectors(pkg, golden):
+    """maxscore/picker_test.go:43-110: arg-max, ties as sets; seeded-random mode stays inside the tie set."""
+    for c in golden["picker"]["cases"]:
+        n = len(c["scores"])
+        col = np.array([s / 100.0 for s in c["scores"]])
+        top = max(c["scores"])
+        tie_set = [m for m in range(n) if c["scores"][m] == top]
+        eng = make_engine(pkg, [("col0", 100.0)], n)
+        eng.set_snapshot(np.zeros(n), np.zeros(n, np.int64), endpoint_cols=[col])
+        res = eng.schedule(1)
+        assert res["pick"][0] == tie_set[0] and res["tie_count"][0] == len(tie_set)
+        eng.close()
+        eng = make_engine(pkg, [("col0", 100.0)], n, tie_mode=pkg.TIE_SEEDED_RANDOM, tie_seed=7)
+        eng.set_snapshot(np.zeros(n), np.zeros(n, np.int64), endpoint_cols=[col])
+        res = eng.schedule(64)
+        snap = o.SnapshotData(kv_usage=np.zeros(n), queue=np.zeros(n), endpoint_cols=[col])
+        want = o.schedule_batch(snap, o.make_profile([(8, 100.0)], tie_mode=1, tie_seed=7), None, 64)
+        assert np.array_equal(res["pick"], want["pick"])
+        assert set(res["pick"]) == set(tie_set)
+        eng.close()
+
+
+# ------------------------------------------------------------------------------------------ prefix index
+def test_prefix_completion_and_prerequest(pkg, golden):
+    """approximateprefix/plugin_test.go:37-227: empty index ⇒ 0 of 2; after pick(pod1)+prefill(pod3) of
+    "aaaaaa", "aaaabbbb" matches pod1=1, pod3=1, pod2=0 of 2; PreRequest maps every hash to the pick."""
+    c = golden["prefix_completion"]
+    M = c["n_endpoints"]
+    eng = make_engine(pkg, [("prefix", 1.0)], M, block_chars=c["block_chars"], max_blocks=c["max_blocks"])
+    eng.set_snapshot(np.zeros(M), np.zeros(M, np.int64))
+    seed = np.array([eng.model_seed(c["model"])], np.uint64)
+
+    def run(prompt):
+        p = np.frombuffer(prompt.encode(), np.uint8)
+        return eng.schedule(1, prompt_bytes=p, prompt_off=np.array([0, len(p)], np.int64), model_seed=seed,
+                            want_match=True, want_hashes=True)
+
+    r1 = run(c["first_prompt"])
+    assert r1["total_blocks"][0] == c["first_total"] and not r1["match_blocks"].any()
+    h1 = r1["hashes_out"][0, : r1["total_blocks"][0]]
+    for s in c["commit_to"]:
+        eng.prefix_add(h1, s)
+    r2 = run(c["second_prompt"])
+    assert list(r2["match_blocks"][0]) == c["want_match"] and r2["total_blocks"][0] == c["want_total"]
+    for h in h1:
+        assert eng.prefix_get(int(h)) == set(c["commit_to"])
+    # PreRequest via commit_picks
+    eng2 = make_engine(pkg, [("prefix", 1.0)], M, block_chars=4)
+    eng2.set_snapshot(np.zeros(M), np.zeros(M, np.int64))
+    p = np.frombuffer(golden["pre_request"]["prompt"].encode(), np.uint8)
+    r = eng2.schedule(1, prompt_bytes=p, prompt_off=np.array([0, len(p)], np.int64), model_seed=seed, want_hashes=True)
+    eng2.commit_picks(np.array([golden["pre_request"]["pick"]], np.int32), r["hashes_out"], r["total_blocks"])
+    for h in r["hashes_out"][0, : r["total_blocks"][0]]:
+        assert golden["pre_request"]["pick"] in eng2.prefix_get(int(h))
+    eng.close()
+    eng2.close()
+
+
+def test_indexer_vectors_on_device(pkg, golden):
+    """approximateprefix/indexer_test.go:27-113 with Get() answered by the DEVICE table."""
+    c = golden["indexer"]["add_and_get"]
+    eng = make_engine(pkg, [("prefix", 1.0)], 4, lru_capacity_default=c["default_lru"])
+    for st in c["steps"]:
+        eng.prefix_add(st["add"], 0, c["gpu_blocks"])
+        assert eng.prefix_lru_len(0) == st["want_len"]
+        for h, want in st.get("want_get", {}).items():
+            assert sorted(eng.prefix_get(int(h))) == want
+    eng.close()
+    n = golden["indexer"]["remove_pod_and_eviction"]["indexer_size"]
+    eng = make_engine(pkg, [("prefix", 1.0)], 4, lru_capacity_default=n)
+    for j in range(n):
+        eng.prefix_add([j], 1)
+        eng.prefix_add([j], 2)
+    for j in range(n):
+        assert eng.prefix_get(j) == {1, 2}
+    eng.prefix_add([n], 1)
+    assert eng.prefix_lru_len(1) == n and eng.prefix_get(0) == {2}
+    eng.prefix_remove_endpoint(2)
+    assert eng.prefix_get(0) == set() and eng.prefix_lru_len(2) == -1
+    for j in range(1, n + 1):
+        assert eng.prefix_get(j) == {1}
+    assert eng.stats().prefix_live_hashes == n
+    assert eng.prefix_lru_keys(1) == list(range(1, n + 1))
+    # over-long Add leaves stale hashToPods entries (indexer.go:70-82), like the oracle
+    eng2 = make_engine(pkg, [("prefix", 1.0)], 4, lru_capacity_default=2)
+    eng2.prefix_add([10, 11, 12], 0)
+    assert eng2.prefix_lru_keys(0) == [11, 12] and eng2.prefix_get(10) == {0}
+    # raw deltas
+    eng2.prefix_apply(np.array([77, 77, 78], np.uint64), np.array([1, 3, 1], np.int32), np.array([0, 0, 0], np.uint8))
+    assert eng2.prefix_get(77) == {1, 3}
+    eng2.prefix_apply(np.array([77], np.uint64), np.array([1], np.int32), np.array([1], np.uint8))
+    assert eng2.prefix_get(77) == {3} and eng2.prefix_get(78) == {1}
+    eng.close()
+    eng2.close()
+
+
+def test_commit_replay_matches_oracle_index(pkg):
+    """A few rounds of schedule → commit on both sides: LRU state, evictions and match counts stay identical
+    (small LRU capacity so evictions, including start-of-chain gaps, really happen)."""
+    M, R = 48, 400
+    scorers = [("queue", 2), ("kv", 2), ("prefix", 3)]
+    eng = make_engine(pkg, scorers, M, lru_capacity_default=150, max_blocks=16, tie_mode=1, tie_seed=3)
+    sd = synth_snapshot(M, seed=5, tie_heavy=True)
+    eng.set_snapshot(**sd)
+    snap = o.SnapshotData(**sd)
+    prof = profile_of(pkg, scorers, tie_mode=1, tie_seed=3)
+    idx = o.Index(150)
+    caps = np.where(np.arange(M) % 3 == 0, 30, 0).astype(np.int32)  # autotune: some endpoints report CacheNumBlocks
+    for rnd in range(4):
+        prompts, off, _ = synth_prompts(R, prompt_len=640, groups=9, shared=384, seed=20 + rnd % 2, prefix_seed=77)
+        seeds = np.full(R, eng.model_seed("m"), np.uint64)
+        got = eng.schedule(R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds, want_match=True, want_hashes=True,
+                           request_base=rnd * R)
+        want = o.schedule_batch(snap, prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds, max_blocks=16,
+                                want_match=True, want_hashes=True, request_base=rnd * R)
+        assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks", "match_blocks"))
+        nh = want["total_blocks"]
+        for r in range(R):
+            assert np.array_equal(got["hashes_out"][r, : nh[r]], want["hashes_out"][r, : nh[r]])
+        eng.commit_picks(got["pick"], got["hashes_out"], got["total_blocks"], lru_capacity=caps)
+        idx.commit(want["pick"], want["hashes_out"], want["total_blocks"], gpu_blocks=caps)
+        for m in range(M):
+            assert eng.prefix_lru_keys(m) == idx.lru_keys(m), (rnd, m)
+        assert eng.stats().prefix_live_hashes == idx.num_hashes()
+        if rnd > 0:
+            assert got["match_blocks"].max() > 0
+    assert max(eng.prefix_lru_len(m) for m in range(M)) == 150 and eng.prefix_lru_len(0) == 30  # evictions happened
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------ synthetic parity
+CASES = [
+    # name, M, R, scorers, kwargs
+    ("config_A_cpu_case", 4, 1, [("queue", 1)], {}),
+    ("config_B_kv_queue", 256, 4096, [("kv", 1), ("queue", 1)], {}),
+    ("config_B_tie_heavy_random", 256, 4096, [("kv", 1), ("queue", 1)], dict(tie_heavy=True, tie_mode=1)),
+    ("config_C_prefix", 512, 2048, [("queue", 2), ("kv", 2), ("prefix", 3)], dict(prefix=True)),
+    ("config_D_lora_kv", 1024, 4096, [("lora", 1), ("kv", 1)], dict(lora=True)),
+    ("headline_all_four", 1024, 4096, [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)], dict(prefix=True, lora=True)),
+    ("reference_test_order", 1024, 1024, [("kv", 1), ("queue", 1), ("prefix", 1), ("lora", 1)], dict(prefix=True, lora=True, tie_heavy=True)),
+    ("prefix_first_order", 300, 1024, [("prefix", 3), ("queue", 2), ("lora", 1), ("kv", 2)], dict(prefix=True, lora=True)),
+    ("odd_M_1000", 1000, 1024, [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)], dict(prefix=True, lora=True)),
+    ("M_4096", 4096, 512, [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)], dict(prefix=True, lora=True)),
+    ("M_2048_running", 2048, 512, [("running", 1), ("kv", 2), ("prefix", 3)], dict(prefix=True)),
+    ("negative_weight", 64, 512, [("queue", -1.5), ("kv", 2), ("lora", 0.25)], dict(lora=True)),
+    ("masked_all_four", 1024, 2048, [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)], dict(prefix=True, lora=True, mask=0.5)),
+    ("masked_sparse_small", 96, 1024, [("kv", 1), ("queue", 1), ("running", 1)], dict(mask=0.1, tie_heavy=True)),
+    ("masked_queue_first_M4096", 4096, 256, [("queue", 1), ("prefix", 1), ("kv", 1)], dict(prefix=True, mask=0.7)),
+]
+
+
+@pytest.mark.parametrize("name,M,R,scorers,opt", CASES, ids=[c[0] for c in CASES])
+def test_synthetic_parity(pkg, name, M, R, scorers, opt):
+    import zlib
+    seed = zlib.crc32(name.encode()) % 1000
+    tie_mode = opt.get("tie_mode", 0)
+    eng = make_engine(pkg, scorers, M, tie_mode=tie_mode, tie_seed=99, prefix_capacity=1 << 18)
+    sd = synth_snapshot(M, seed=seed, tie_heavy=opt.get("tie_heavy", False))
+    eng.set_snapshot(**sd)
+    snap = o.SnapshotData(**sd)
+    prof = profile_of(pkg, scorers, tie_mode=tie_mode, tie_seed=99)
+    kw = {}
+    idx = None
+    if opt.get("prefix"):
+        prompts, off, _ = synth_prompts(R, prompt_len=2048, groups=24, shared=1024, seed=seed)
+        kw.update(prompt_bytes=prompts, prompt_off=off, model_seed=np.full(R, eng.model_seed("model-x"), np.uint64))
+        # warm the index on both sides with an earlier batch routed by the oracle
+        idx = o.Index()
+        wp, woff, _ = synth_prompts(min(R, 4 * M), prompt_len=2048, groups=24, shared=1024, seed=seed)
+        nw = len(woff) - 1
+        warm = o.schedule_batch(snap, prof, idx, nw, prompt_bytes=wp, prompt_off=woff,
+                                model_seed=np.full(nw, eng.model_seed("model-x"), np.uint64), want_hashes=True, n_threads=8)
+        idx.commit(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+        eng.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    if opt.get("lora"):
+        kw["adapter_id"] = zipf_adapters(R, seed=seed)
+    if "mask" in opt:
+        rng = np.random.Generator(np.random.PCG64(seed + 7))
+        bits = rng.random((R, M)) < opt["mask"]
+        bits[0, :] = False  # one request with an empty candidate set
+        mask = np.zeros((R, (M + 31) // 32), np.uint32)
+        for w in range(mask.shape[1]):
+            chunk = bits[:, w * 32:(w + 1) * 32]
+            mask[:, w] = (chunk * (1 << np.arange(chunk.shape[1], dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+        kw["cand_mask"] = mask
+    got = eng.schedule(R, want_match=True, want_scores=True, **kw)
+    want = o.schedule_batch(snap, prof, idx, R, want_match=True, want_scores=True, want_tie_set=True, n_threads=8, **kw)
+    assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks", "match_blocks", "scores_out"))
+    # reference semantics: the pick is a member of the arg-max set the reference would shuffle over
+    ts = want["tie_set"]
+    ok = got["pick"] >= 0
+    r = np.nonzero(ok)[0]
+    assert ((ts[r, got["pick"][r] >> 5] >> (got["pick"][r] & 31).astype(np.uint32)) & 1).all()
+    if opt.get("prefix"):
+        assert got["match_blocks"].max() > 0
+    if "mask" in opt:
+        assert got["pick"][0] == -1
+    eng.close()
+
+
+def test_dense_rows_parity(pkg):
+    """Dense float4 feature rows {match, lora class, pair0, pair1} streamed from HBM, incl. pair columns."""
+    for M, R, masked in ((1024, 2048, False), (333, 1024, True), (4096, 300, False)):
+        scorers = [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1), ("pair0", 1.5), ("pair1", 0.5)]
+        eng = make_engine(pkg, scorers, M, tie_mode=1, tie_seed=5)
+        sd = synth_snapshot(M, seed=M)
+        eng.set_snapshot(**sd)
+        rng = np.random.Generator(np.random.PCG64(M))
+        feat = np.zeros((R, M, 4), np.float32)
+        total = rng.integers(0, 40, R).astype(np.uint16)
+        feat[:, :, 0] = np.minimum(rng.integers(0, 48, (R, M)) * (rng.random((R, M)) < 0.05), total[:, None] + 2)
+        feat[:, :, 1] = rng.integers(0, 4, (R, M))
+        feat[:, :, 2] = rng.random((R, M)).astype(np.float32) * 1.4 - 0.2  # exercises the clamp
+        feat[:, :, 3] = np.round(rng.random((R, M)), 1)
+        kw = dict(dense_feat=feat, dense_total=total)
+        if masked:
+            mask = rng.integers(0, 2 ** 32, (R, (M + 31) // 32), dtype=np.uint64).astype(np.uint32)
+            kw["cand_mask"] = mask
+        got = eng.schedule(R, want_match=True, want_scores=True, **kw)
+        want = o.schedule_batch(o.SnapshotData(**sd), profile_of(pkg, scorers, 1, 5), None, R, want_match=True,
+                                want_scores=True, n_threads=8, **kw)
+        assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks", "match_blocks", "scores_out"))
+        eng.close()
+
+
+def test_hashes_in_path_and_small_blocks(pkg):
+    """Pre-hashed input (a host that hashes itself) and the generic (block_chars=4, unaligned) hash path."""
+    M, R = 128, 600
+    scorers = [("prefix", 3), ("kv", 1)]
+    eng = make_engine(pkg, scorers, M, block_chars=4, max_blocks=300, prefix_capacity=1 << 17)
+    sd = synth_snapshot(M, seed=8)
+    eng.set_snapshot(**sd)
+    data, off = synth_ragged_prompts(R, max_len=500, seed=8, groups=5, shared=120)
+    seeds = np.full(R, eng.model_seed("tiny"), np.uint64)
+    snap, prof, idx = o.SnapshotData(**sd), profile_of(pkg, scorers), o.Index()
+    w = o.schedule_batch(snap, prof, idx, R, prompt_bytes=data, prompt_off=off, model_seed=seeds, block_chars=4,
+                         max_blocks=300, want_hashes=True)
+    idx.commit(w["pick"], w["hashes_out"], w["total_blocks"])
+    eng.commit_picks(w["pick"], w["hashes_out"], w["total_blocks"])
+    want = o.schedule_batch(snap, prof, idx, R, prompt_bytes=data, prompt_off=off, model_seed=seeds, block_chars=4,
+                            max_blocks=300, want_match=True)
+    got = eng.schedule(R, prompt_bytes=data, prompt_off=off, model_seed=seeds, want_match=True)
+    assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks", "match_blocks"))
+    assert got["match_blocks"].max() >= 30  # 120-byte shared prefixes / 4-byte blocks
+    got2 = eng.schedule(R, hashes_in=w["hashes_out"], n_hashes_in=w["total_blocks"], want_match=True)
+    assert_same(got2, want, ("pick", "pick_score", "tie_count", "total_blocks", "match_blocks"))
+    eng.close()
+
+
+def test_device_resident_api_with_torch(pkg):
+    """location=1: CUDA tensors in, CUDA tensors out, asynchronous on the caller's stream."""
+    import torch
+    M, R = 1024, 8192
+    scorers = [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)]
+    eng = make_engine(pkg, scorers, M, prefix_capacity=1 << 19)
+    sd = synth_snapshot(M, seed=2)
+    dev = torch.device("cuda:0")
+    t = {k: torch.from_numpy(v).to(dev) for k, v in sd.items()}
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        eng.set_snapshot(t["kv_usage"], t["queue"], t["running"], t["lora_active"], t["lora_waiting"], t["lora_nmodels"],
+                         t["lora_max"], device=True, stream=stream.cuda_stream, M=M, lora_words=1)
+    prompts, off, _ = synth_prompts(R, seed=2)
+    seeds = np.full(R, eng.model_seed("dev"), np.uint64)
+    ad = zipf_adapters(R, seed=2)
+    snap, prof, idx = o.SnapshotData(**sd), profile_of(pkg, scorers), o.Index()
+    w = o.schedule_batch(snap, prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds, adapter_id=ad,
+                         want_hashes=True, n_threads=8)
+    idx.commit(w["pick"], w["hashes_out"], w["total_blocks"])
+    eng.commit_picks(w["pick"], w["hashes_out"], w["total_blocks"])
+    want = o.schedule_batch(snap, prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds, adapter_id=ad,
+                            n_threads=8)
+    out = dict(pick=torch.empty(R, dtype=torch.int32, device=dev), pick_score=torch.empty(R, dtype=torch.float64, device=dev),
+               tie_count=torch.empty(R, dtype=torch.int32, device=dev), total_blocks=torch.empty(R, dtype=torch.uint16, device=dev))
+    with torch.cuda.stream(stream):
+        eng.schedule(R, prompt_bytes=torch.from_numpy(prompts).to(dev), prompt_off=torch.from_numpy(off).to(dev),
+                     model_seed=torch.from_numpy(seeds).to(dev), adapter_id=torch.from_numpy(ad).to(dev), device=True,
+                     stream=stream.cuda_stream, out=out)
+    stream.synchronize()
+    assert np.array_equal(out["pick"].cpu().numpy(), want["pick"])
+    assert np.array_equal(out["pick_score"].cpu().numpy(), want["pick_score"])
+    assert np.array_equal(out["tie_count"].cpu().numpy(), want["tie_count"])
+    assert eng.stats().kernel_launches >= 3
+    eng.close()
+
+
+def test_full_size_headline_parity(pkg):
+    """BASELINE.json headline shape: 64K requests x 1024 endpoints, all four scorers, 2 KB prompts."""
+    M, R = 1024, 65536
+    scorers = [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)]
+    eng = make_engine(pkg, scorers, M, prefix_capacity=1 << 18)
+    sd = synth_snapshot(M, seed=0)
+    eng.set_snapshot(**sd)
+    snap, prof, idx = o.SnapshotData(**sd), profile_of(pkg, scorers), o.Index()
+    seed = eng.model_seed("headline")
+    wp, woff, _ = synth_prompts(4 * M, seed=0)
+    ws = np.full(4 * M, seed, np.uint64)
+    warm = o.schedule_batch(snap, prof, idx, 4 * M, prompt_bytes=wp, prompt_off=woff, model_seed=ws, want_hashes=True,
+                            n_threads=8)
+    idx.commit(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    eng.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    prompts, off, _ = synth_prompts(R, seed=0)
+    seeds = np.full(R, seed, np.uint64)
+    ad = zipf_adapters(R, seed=0)
+    got = eng.schedule(R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds, adapter_id=ad, want_match=True)
+    want = o.schedule_batch(snap, prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds, adapter_id=ad,
+                            want_match=True, n_threads=16)
+    assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks", "match_blocks"))
+    assert (got["total_blocks"] == 32).all() and got["match_blocks"].max() == 16
+    # size-independent properties: determinism, and shard-invariance (two half batches == one batch)
+    again = eng.schedule(R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds, adapter_id=ad)
+    assert np.array_equal(again["pick"], got["pick"])
+    h = R // 2
+    lo = eng.schedule(h, prompt_bytes=prompts[: off[h]], prompt_off=off[: h + 1], model_seed=seeds[:h], adapter_id=ad[:h])
+    hi = eng.schedule(R - h, prompt_bytes=prompts[off[h]:], prompt_off=off[h:] - off[h], model_seed=seeds[h:],
+                      adapter_id=ad[h:], request_base=h)
+    assert np.array_equal(np.concatenate([lo["pick"], hi["pick"]]), got["pick"])
+    eng.close()
