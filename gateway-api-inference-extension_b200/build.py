@@ -1,16 +1,21 @@
 """Builds libeppscore.so (sm_100a only) in-tree with nvcc.  No JIT, no torch extension machinery:
-the C-ABI library has no torch types in it, so it is a plain `nvcc -shared`."""
+the C-ABI library has no torch types in it, so it is plain `nvcc -c` per source (in parallel) and one
+`nvcc -shared` link."""
 from __future__ import annotations
 
+import concurrent.futures
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeppscore.so")
-SOURCES = ["capi.cu", "kernels.cu"]
-HEADERS = ["kernels.cuh", "xxh64.cuh", "prefix_index.hpp", os.path.join("..", "..", "include", "eppscore.h")]
+SOURCES = ["capi.cu", "hash_kernel.cu", "prepare_kernel.cu", "score_generic.cu", "score_dense.cu", "pick_sparse.cu",
+           "table_kernels.cu"]
+HEADERS = ["kernels.cuh", "device_common.cuh", "xxh64.cuh", "prefix_index.hpp",
+           os.path.join("..", "..", "include", "eppscore.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -18,36 +23,53 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-fmad=false",            # never contract a*b+c: float64 parity with the reference (GOAMD64=v1 never fuses)
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
-    "-shared",
-    "-cudart", "static",
 ]
 
 
 def nvcc() -> str:
-    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
-        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
             return c
     return "nvcc"
 
 
-def is_stale() -> bool:
-    if not os.path.exists(LIB):
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libeppscore.so")
-    if verbose:
-        sys.stderr.write(r.stdout + r.stderr)
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        if force or _stale(obj, [os.path.join(CSRC, src)] + hdrs):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, r
+
+    if jobs:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for src, r in ex.map(compile_one, jobs):
+                if r.returncode != 0:
+                    sys.stderr.write(r.stdout + r.stderr)
+                    raise RuntimeError(f"nvcc failed on {src}")
+                if verbose:
+                    sys.stderr.write(r.stdout + r.stderr)
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        cmd = [nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc link failed")
     return LIB
 
 

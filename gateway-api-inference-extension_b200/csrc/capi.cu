@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -60,6 +61,7 @@ struct eppscore_engine {
   cudaEvent_t ev_snapshot = nullptr, ev_table = nullptr;
   std::string err;
   uint64_t launches = 0;
+  bool force_generic = false;  // EPPSCORE_FORCE_GENERIC=1: skip the specialised kernels (A/B tests, profiling)
 
   // snapshot
   bool have_snapshot = false;
@@ -68,7 +70,9 @@ struct eppscore_engine {
   DevBuf raw_kv, raw_queue, raw_running, raw_act, raw_wait, raw_nmodels, raw_max, raw_col[4];
   bool have_col[4] = {false, false, false, false};
   bool have_running = false;
-  DevBuf term[kMaxSteps], fold_unmasked, fold_masked, cls_lo, cls_hi;
+  const int64_t* cur_queue = nullptr;    // raw WaitingQueueSize / RunningRequestsSize of the current snapshot
+  const int64_t* cur_running = nullptr;  // (engine copy for host snapshots, the caller's buffer for device ones)
+  DevBuf term[kMaxSteps], fold_unmasked, fold_masked, cls_lo, cls_hi, summ, tiemask;
   PlanSet plan_unmasked{}, plan_masked{};
 
   // prefix table
@@ -157,6 +161,23 @@ void build_plan(eppscore_engine* e, bool masked, PlanSet* ps) {
   p.tie_mode = c.tie_mode;
   p.seed_lo = (uint32_t)c.tie_seed;
   p.seed_hi = (uint32_t)(c.tie_seed >> 32);
+  // packed kind sequence: selects the template-specialised streaming kernels (score_dense.cu)
+  p.seq = 0;
+  if (ns <= 7)
+    for (int i = 0; i < ns; i++) p.seq |= (uint32_t)(p.kind[i] + 1) << (4 * i);
+  // sparse fast path (pick_sparse.cu): unmasked, only E/P/L steps, at most one prefix step and its
+  // weight >= 0 (monotonicity: a positive match can only raise an endpoint's score)
+  int n_prefix = 0;
+  bool ok = !masked;
+  for (int i = 0; i < ns; i++) {
+    if (p.kind[i] == STEP_PREFIX) {
+      n_prefix++;
+      if (!(p.weight[i] >= 0.0)) ok = false;
+    } else if (p.kind[i] != STEP_EP_TERM && p.kind[i] != STEP_LORA) {
+      ok = false;
+    }
+  }
+  p.sparse_ok = (ok && n_prefix <= 1) ? 1 : 0;
 }
 
 int32_t flush_table(eppscore_engine* e) {
@@ -236,8 +257,12 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
   const PlanSet& ps = masked ? e->plan_masked : e->plan_unmasked;
 
   if (s != e->stream) {
-    CK(e, cudaStreamWaitEvent(s, e->ev_snapshot, 0));
-    CK(e, cudaStreamWaitEvent(s, e->ev_table, 0));
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {  // see eppscore_set_snapshot: no outside dependencies under capture
+      CK(e, cudaStreamWaitEvent(s, e->ev_snapshot, 0));
+      CK(e, cudaStreamWaitEvent(s, e->ev_table, 0));
+    }
   }
 
   ScoreArgs a{};
@@ -247,10 +272,12 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
   a.R = b.R;
   a.request_base = b.request_base;
   for (int t = 0; t < ps.plan.n_terms; t++) a.term[t] = ps.term_ptr[t];
-  a.minmax_q[0] = e->raw_queue.as<int64_t>();
-  a.minmax_q[1] = e->have_running ? e->raw_running.as<int64_t>() : nullptr;
+  a.minmax_q[0] = e->cur_queue;
+  a.minmax_q[1] = e->cur_running;
   a.cls_lo = e->cls_lo.as<uint32_t>();
   a.cls_hi = e->cls_hi.as<uint32_t>();
+  a.summ = ps.plan.sparse_ok ? e->summ.as<AdapterSummary>() : nullptr;
+  a.tiemask = ps.plan.sparse_ok ? e->tiemask.as<uint32_t>() : nullptr;
   a.A = e->A;
   a.adapter_id = b.adapter_id;
   a.cand_mask = b.cand_mask;
@@ -294,7 +321,7 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
         h.hashes = hashes;
         h.stride = mb;
         h.n_hashes = e->s_nh.as<uint16_t>();
-        e->launches += launch_hash_prompts(h, s);
+        e->launches += launch_hash_prompts(h, s, e->sm_count);
         a.hashes = hashes;
         a.n_hashes = h.n_hashes;
         a.hash_stride = mb;
@@ -306,7 +333,11 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
       }
     }
   }
-  e->launches += launch_score_pick(a, dense, s, e->sm_count);
+  // dispatch: specialised fast paths first, the fully general kernels otherwise
+  int launched = 0;
+  if (!e->force_generic) launched = dense ? launch_score_dense_fast(a, s, e->sm_count) : launch_pick_sparse(a, s, e->sm_count);
+  if (launched == 0) launched = launch_score_pick(a, dense, s, e->sm_count);
+  e->launches += launched;
   CK(e, cudaGetLastError());
   return EPPSCORE_OK;
 }
@@ -390,6 +421,10 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   if (prop.major < 10)
     return fail(nullptr, EPPSCORE_ERR_NO_DEVICE, "device is not sm_100-class (this library ships sm_100a code only)");
   ep->sm_count = prop.multiProcessorCount;
+  {
+    const char* fg = getenv("EPPSCORE_FORCE_GENERIC");
+    ep->force_generic = fg && fg[0] == '1';
+  }
   CK(nullptr, cudaStreamCreateWithFlags(&ep->stream, cudaStreamNonBlocking));
   CK(nullptr, cudaEventCreateWithFlags(&ep->ev_snapshot, cudaEventDisableTiming));
   CK(nullptr, cudaEventCreateWithFlags(&ep->ev_table, cudaEventDisableTiming));
@@ -408,6 +443,10 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   CK(nullptr, ep->fold_masked.reserve(mp * 8));
   CK(nullptr, ep->cls_lo.reserve((size_t)(ep->A_cap + 1) * ep->geo.row_words * 4));
   CK(nullptr, ep->cls_hi.reserve((size_t)(ep->A_cap + 1) * ep->geo.row_words * 4));
+  CK(nullptr, ep->summ.reserve((size_t)(ep->A_cap + 1) * sizeof(AdapterSummary)));
+  CK(nullptr, ep->tiemask.reserve((size_t)(ep->A_cap + 1) * ep->geo.row_words * 4));
+  build_plan(ep, false, &ep->plan_unmasked);
+  build_plan(ep, true, &ep->plan_masked);
   // prefix table
   ep->index = std::make_unique<PrefixIndex>(ep->geo, ep->cfg.prefix_capacity, ep->cfg.lru_capacity_default);
   const size_t nslots = ep->index->slots().size();
@@ -429,7 +468,7 @@ void eppscore_destroy(eppscore_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   DevBuf* bufs[] = {&e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
-                    &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->st_idx, &e->st_val, &e->st_slot,
+                    &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->st_idx, &e->st_val, &e->st_slot,
                     &e->probe_out, &e->s_prompts, &e->s_off, &e->s_len, &e->s_seed, &e->s_hashes, &e->s_nh, &e->s_adapter,
                     &e->s_mask, &e->s_dense, &e->s_dtotal, &e->s_pick, &e->s_score, &e->s_tie, &e->s_match, &e->s_total, &e->s_scores};
   for (DevBuf* b : bufs) b->release();
@@ -468,28 +507,30 @@ int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
   if (s->lora_words < 0 || s->lora_words * 64 > e->A_cap) return fail(e, EPPSCORE_ERR_CAPACITY, "lora_words*64 exceeds config.max_adapters");
   if (s->M > 0 && (!s->kv_usage || !s->queue)) return fail(e, EPPSCORE_ERR_INVALID, "kv_usage and queue are required");
   CK(e, cudaSetDevice(e->device));
-  cudaStream_t st = (s->location == 1 && s->stream) ? (cudaStream_t)s->stream : e->stream;
-  const cudaMemcpyKind kind = s->location == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const bool on_device = s->location == 1;
+  cudaStream_t st = (on_device && s->stream) ? (cudaStream_t)s->stream : e->stream;
   const size_t M = (size_t)s->M;
-  auto cp = [&](DevBuf& dst, const void* src, size_t bytes) -> cudaError_t {
-    if (!src || bytes == 0) return cudaSuccess;
-    return cudaMemcpyAsync(dst.p, src, bytes, kind, st);
-  };
-  CK(e, cp(e->raw_kv, s->kv_usage, M * 8));
-  CK(e, cp(e->raw_queue, s->queue, M * 8));
-  CK(e, cp(e->raw_running, s->running, M * 8));
-  e->have_running = s->running != nullptr;
   const bool have_lora = s->lora_active && s->lora_waiting && s->lora_words > 0;
-  if (have_lora) {
-    CK(e, cp(e->raw_act, s->lora_active, M * s->lora_words * 8));
-    CK(e, cp(e->raw_wait, s->lora_waiting, M * s->lora_words * 8));
+  // Host snapshots are copied into the engine's tile buffers; device snapshots (e.g. the buffer an NCCL
+  // broadcast just filled) are used IN PLACE — they must stay valid until the next set_snapshot.
+  if (!on_device) {
+    auto cp = [&](DevBuf& dst, const void* src, size_t bytes) -> cudaError_t {
+      if (!src || bytes == 0) return cudaSuccess;
+      return cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    CK(e, cp(e->raw_kv, s->kv_usage, M * 8));
+    CK(e, cp(e->raw_queue, s->queue, M * 8));
+    CK(e, cp(e->raw_running, s->running, M * 8));
+    if (have_lora) {
+      CK(e, cp(e->raw_act, s->lora_active, M * s->lora_words * 8));
+      CK(e, cp(e->raw_wait, s->lora_waiting, M * s->lora_words * 8));
+    }
+    CK(e, cp(e->raw_nmodels, s->lora_nmodels, M * 4));
+    CK(e, cp(e->raw_max, s->lora_max, M * 4));
+    for (int i = 0; i < 4; i++) CK(e, cp(e->raw_col[i], s->endpoint_col[i], M * 8));
   }
-  CK(e, cp(e->raw_nmodels, s->lora_nmodels, M * 4));
-  CK(e, cp(e->raw_max, s->lora_max, M * 4));
-  for (int i = 0; i < 4; i++) {
-    e->have_col[i] = s->endpoint_col[i] != nullptr;
-    CK(e, cp(e->raw_col[i], s->endpoint_col[i], M * 8));
-  }
+  e->cur_queue = on_device ? s->queue : e->raw_queue.as<int64_t>();
+  e->cur_running = s->running ? (on_device ? s->running : e->raw_running.as<int64_t>()) : nullptr;
   e->M = s->M;
   e->lora_words = have_lora ? s->lora_words : 0;
   e->A = e->lora_words * 64;
@@ -504,14 +545,15 @@ int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
     pa.weight[i] = e->cfg.scorer_weight[i];
     pa.term[i] = is_endpoint_term_kind(pa.kind[i], false) ? e->term[i].as<double>() : nullptr;
   }
-  pa.kv = e->raw_kv.as<double>();
-  pa.queue = e->raw_queue.as<int64_t>();
-  pa.running = e->have_running ? e->raw_running.as<int64_t>() : nullptr;
-  pa.act = have_lora ? e->raw_act.as<uint64_t>() : nullptr;
-  pa.wait = have_lora ? e->raw_wait.as<uint64_t>() : nullptr;
-  pa.nmodels = s->lora_nmodels ? e->raw_nmodels.as<int32_t>() : nullptr;
-  pa.maxm = s->lora_max ? e->raw_max.as<int32_t>() : nullptr;
-  for (int i = 0; i < 4; i++) pa.col[i] = e->have_col[i] ? e->raw_col[i].as<double>() : nullptr;
+  pa.kv = on_device ? s->kv_usage : e->raw_kv.as<double>();
+  pa.queue = e->cur_queue;
+  pa.running = e->cur_running;
+  pa.act = have_lora ? (on_device ? s->lora_active : e->raw_act.as<uint64_t>()) : nullptr;
+  pa.wait = have_lora ? (on_device ? s->lora_waiting : e->raw_wait.as<uint64_t>()) : nullptr;
+  pa.nmodels = s->lora_nmodels ? (on_device ? s->lora_nmodels : e->raw_nmodels.as<int32_t>()) : nullptr;
+  pa.maxm = s->lora_max ? (on_device ? s->lora_max : e->raw_max.as<int32_t>()) : nullptr;
+  for (int i = 0; i < 4; i++)
+    pa.col[i] = s->endpoint_col[i] ? (on_device ? s->endpoint_col[i] : e->raw_col[i].as<double>()) : nullptr;
   pa.lora_words = e->lora_words;
   pa.A = e->A;
   int lead_u = 0, lead_m = 0;
@@ -523,13 +565,21 @@ int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
   pa.fold_masked_n = lead_m;
   pa.cls_lo = e->cls_lo.as<uint32_t>();
   pa.cls_hi = e->cls_hi.as<uint32_t>();
+  pa.plan_u = e->plan_unmasked.plan;
+  for (int t = 0; t < kMaxSteps; t++) pa.plan_term[t] = e->plan_unmasked.term_ptr[t];
+  pa.summ = e->plan_unmasked.plan.sparse_ok ? e->summ.as<AdapterSummary>() : nullptr;
+  pa.tiemask = e->tiemask.as<uint32_t>();
   e->launches += launch_prepare_snapshot(pa, st);
   CK(e, cudaGetLastError());
-  CK(e, cudaEventRecord(e->ev_snapshot, st));
-  if (st != e->stream) CK(e, cudaStreamWaitEvent(e->stream, e->ev_snapshot, 0));
-  if (s->location != 1) CK(e, cudaStreamSynchronize(st));  // host arrays may be reused by the caller
-  build_plan(e, false, &e->plan_unmasked);
-  build_plan(e, true, &e->plan_masked);
+  // Cross-stream ordering through an event — skipped while the caller's stream is being captured into a
+  // CUDA graph (a captured stream may not take dependencies from outside its capture; in-stream order suffices).
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st != e->stream) cudaStreamIsCapturing(st, &cap);
+  if (cap == cudaStreamCaptureStatusNone) {
+    CK(e, cudaEventRecord(e->ev_snapshot, st));
+    if (st != e->stream) CK(e, cudaStreamWaitEvent(e->stream, e->ev_snapshot, 0));
+    if (!on_device) CK(e, cudaStreamSynchronize(st));  // host arrays may be reused by the caller
+  }
   e->have_snapshot = true;
   return EPPSCORE_OK;
 }
@@ -660,7 +710,7 @@ int32_t eppscore_hash_prompts(eppscore_engine* e, int32_t R, int32_t location, c
     h.seed = model_seed;
     h.hashes = hashes_out;
     h.n_hashes = n_hashes_out;
-    e->launches += launch_hash_prompts(h, stream ? (cudaStream_t)stream : e->stream);
+    e->launches += launch_hash_prompts(h, stream ? (cudaStream_t)stream : e->stream, e->sm_count);
     CK(e, cudaGetLastError());
     return EPPSCORE_OK;
   }
@@ -681,7 +731,7 @@ int32_t eppscore_hash_prompts(eppscore_engine* e, int32_t R, int32_t location, c
   CK(e, cudaMemsetAsync(e->s_hashes.p, 0, (size_t)R * mb * 8, e->stream));
   h.hashes = e->s_hashes.as<uint64_t>();
   h.n_hashes = e->s_nh.as<uint16_t>();
-  e->launches += launch_hash_prompts(h, e->stream);
+  e->launches += launch_hash_prompts(h, e->stream, e->sm_count);
   CK(e, cudaGetLastError());
   CK(e, cudaMemcpyAsync(hashes_out, h.hashes, (size_t)R * mb * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaMemcpyAsync(n_hashes_out, h.n_hashes, (size_t)R * 2, cudaMemcpyDeviceToHost, e->stream));

@@ -1,0 +1,129 @@
+// device_common.cuh — small device helpers shared by the scoring kernels.
+// All float64 arithmetic goes through the _rn intrinsics: never contracted into FMA, so every
+// product and sum rounds exactly like the reference's Go code on GOARCH=amd64 (SURVEY.md "Key facts").
+#pragma once
+#include "kernels.cuh"
+
+namespace eppscore {
+
+__device__ __forceinline__ double clamp01(double s) {  // enforceScoreRange, scheduler_profile.go:194-202
+  if (s < 0.0) return 0.0;
+  if (s > 1.0) return 1.0;
+  return s;
+}
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int o) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, o);
+  hi = __shfl_xor_sync(0xffffffffu, hi, o);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ long long shfl_xor_i64(long long v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ double nan64() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// clamp(match/total)*w, prefix/plugin.go:108-110 + scheduler_profile.go:168 (the slow, LUT-less form)
+static __device__ __noinline__ double prefix_term_direct(int c, int total, double w) {
+  double sc = 0.0;
+  if (total != 0) sc = __ddiv_rn((double)c, (double)total);
+  return __dmul_rn(clamp01(sc), w);
+}
+
+// Arg-max state: MaxScorePicker (maxscore/picker.go:87-115) as "max, size of the arg-max set, chosen member".
+struct Best {
+  double score;
+  int32_t m;  // -1 = none yet
+  int32_t cnt;
+  uint32_t prio;
+};
+__device__ __forceinline__ Best best_none() {
+  Best b;
+  b.score = 0.0;
+  b.m = -1;
+  b.cnt = 0;
+  b.prio = 0;
+  return b;
+}
+__device__ __forceinline__ uint32_t tie_prio(uint32_t areq, int m, uint32_t seed_hi) {
+  return lowbias32(areq + (uint32_t)m * 0x9E3779B1U + seed_hi);
+}
+__device__ __forceinline__ uint32_t tie_areq(int64_t request_index, uint32_t seed_lo) {
+  return lowbias32((uint32_t)(uint64_t)request_index ^ seed_lo);
+}
+// candidates must arrive in ascending m per thread (ties then keep the lowest index in tie_mode 0)
+__device__ __forceinline__ void best_update(Best& b, double s, int m, int tie_mode, uint32_t areq, uint32_t seed_hi) {
+  if (b.m < 0 || s > b.score) {
+    b.score = s;
+    b.m = m;
+    b.cnt = 1;
+    if (tie_mode) b.prio = tie_prio(areq, m, seed_hi);
+  } else if (s == b.score) {
+    b.cnt++;
+    if (tie_mode) {
+      const uint32_t pr = tie_prio(areq, m, seed_hi);
+      if (pr > b.prio) {
+        b.prio = pr;
+        b.m = m;
+      }
+    }
+  }
+}
+// commutative + associative merge of two partial results
+__device__ __forceinline__ void best_merge(Best& b, double os, int om, int oc, uint32_t op, int tie_mode) {
+  if (om < 0) return;
+  if (b.m < 0 || os > b.score) {
+    b.score = os;
+    b.m = om;
+    b.cnt = oc;
+    b.prio = op;
+  } else if (os == b.score) {
+    b.cnt += oc;
+    const bool take = tie_mode ? (op > b.prio || (op == b.prio && om < b.m)) : (om < b.m);
+    if (take) {
+      b.m = om;
+      b.prio = op;
+    }
+  }
+}
+template <int WIDTH = 32>
+__device__ __forceinline__ void best_group_reduce(Best& b, int tie_mode) {
+#pragma unroll
+  for (int o = WIDTH / 2; o; o >>= 1) {
+    const double os = shfl_xor_f64(b.score, o);
+    const int om = __shfl_xor_sync(0xffffffffu, b.m, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, b.cnt, o);
+    const uint32_t op = __shfl_xor_sync(0xffffffffu, b.prio, o);
+    best_merge(b, os, om, oc, op, tie_mode);
+  }
+}
+
+// Weighted score of one (request, endpoint) pair, steps in profile order from 0.0
+// (scheduler_profile.go:155-168). Runtime-generic: used on rare paths (exceptions, summaries).
+__device__ __forceinline__ double eval_steps(const Plan& plan, const double* const* term, int m, int c, int total, int cls) {
+  double acc = 0.0;
+  for (int s = 0; s < plan.n_steps; s++) {
+    const int kind = plan.kind[s];
+    double t;
+    if (kind == STEP_EP_TERM) {
+      t = __ldg(term[plan.arg[s]] + m);
+    } else if (kind == STEP_PREFIX) {
+      t = (c == 0) ? __dmul_rn(0.0, plan.weight[s]) : prefix_term_direct(c, total, plan.weight[s]);
+    } else if (kind == STEP_LORA) {
+      const double* lt = plan.lora_term[s];
+      t = cls == 3 ? lt[3] : (cls == 2 ? lt[2] : (cls == 1 ? lt[1] : lt[0]));
+    } else {
+      t = __dmul_rn(0.0, plan.weight[s]);
+    }
+    acc = __dadd_rn(acc, t);
+  }
+  return acc;
+}
+
+}  // namespace eppscore

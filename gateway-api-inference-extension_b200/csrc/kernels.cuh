@@ -2,13 +2,13 @@
 //
 // Data layout in HBM:
 //   * endpoint tile: per-endpoint float64 "term" arrays (clamp(score)*weight, already rounded exactly
-//     as scheduler_profile.go:168 would) in natural endpoint order, staged into shared memory once
-//     per CTA;
-//   * every per-endpoint BIT structure (prefix-table rows, LoRA class planes) uses one lane-major
-//     permutation so that a lane owns the same endpoints in all of them:
+//     as scheduler_profile.go:168 would) in natural endpoint order; the streaming kernels stage them
+//     into shared memory once per CTA;
+//   * every per-endpoint BIT structure (prefix-table rows, LoRA class planes, tie masks) uses one
+//     lane-major permutation so that a lane owns the same endpoints in all of them:
 //         endpoint m = (j*EPL + k)*32 + lane   <->   bit k of 32-bit word (j*32 + lane)
-//     (EPL = endpoints per lane per pass = 8/16/32 chosen from M, j = pass).  Natural-order arrays
-//     (terms, candidate masks, dense rows, match output) are then read/written with consecutive
+//     (EPL = endpoints per lane per pass = 8/16/32 chosen from max_endpoints, j = pass).  Natural-order
+//     arrays (terms, candidate masks, dense rows, match output) are then read/written with consecutive
 //     lanes touching consecutive endpoints — coalesced and bank-conflict free;
 //   * prefix table: open-addressing key slots {hash, row, count} + bitset rows of J*32 words.
 #pragma once
@@ -19,7 +19,7 @@
 namespace eppscore {
 
 constexpr int kMaxSteps = 8;
-constexpr int kLutMax = 256;         // per-warp prefix LUT covers total <= 256 (defaultMaxPrefixBlocks)
+constexpr int kLutMax = 256;  // per-warp prefix LUT covers total <= 256 (defaultMaxPrefixBlocks)
 constexpr uint32_t kEmptyRow = 0xFFFFFFFFu;
 
 struct __align__(16) Slot {
@@ -44,10 +44,12 @@ struct Plan {
   double lora_term[kMaxSteps][4];  // per LoRA step: clamp({0,0.6,0.8,1.0})*w, rounded on the host (one IEEE multiply)
   int32_t tie_mode;
   uint32_t seed_lo, seed_hi;
-  int32_t n_terms;      // number of term arrays the steps reference (staged to shared memory)
+  int32_t n_terms;       // number of term arrays the steps reference
+  uint32_t seq;          // the step kinds packed 4 bits each (kind+1), 0 = end: selects a specialised kernel
+  int32_t sparse_ok;     // unmasked plan only: steps are E/P/L with at most one prefix step of weight >= 0
 };
 
-// Geometry derived from M.
+// Geometry derived from config.max_endpoints (fixed per engine); M varies per snapshot.
 struct Geo {
   int32_t M;
   int32_t log_epl;  // 3,4,5
@@ -61,11 +63,10 @@ inline Geo make_geo(int32_t M) {
   g.M = M;
   g.log_epl = M <= 256 ? 3 : (M <= 512 ? 4 : 5);
   const int per_pass = 32 << g.log_epl;
-  g.J = (M + per_pass - 1) / per_pass;
-  if (g.J < 1) g.J = 1;
-  // J is a template parameter; round up to the instantiated set {1,2,4,8}
-  int J = 1;
-  while (J < g.J) J <<= 1;
+  int need = (M + per_pass - 1) / per_pass;
+  if (need < 1) need = 1;
+  int J = 1;  // J is a template parameter; round up to the instantiated set {1,2,4,8}
+  while (J < need) J <<= 1;
   g.J = J;
   g.Mpad = g.J * per_pass;
   g.row_words = g.J * 32;
@@ -79,6 +80,14 @@ __host__ __device__ inline uint32_t perm_bitpos(uint32_t m, int log_epl) {
   return ((j * 32u + lane) << 5) + k;
 }
 
+// Per-adapter summary of the request-independent part of the score map (sparse fast path):
+// over all endpoints m, G[a][m] = score with zero prefix match for a request whose adapter is a.
+struct __align__(16) AdapterSummary {
+  double gmax;   // max_m G[a][m]
+  int32_t garg;  // lowest m attaining it (-1 when M == 0)
+  int32_t gcnt;  // how many endpoints attain it
+};
+
 struct ScoreArgs {
   Geo geo;
   Plan plan;
@@ -91,6 +100,8 @@ struct ScoreArgs {
   const uint32_t* cls_lo;
   const uint32_t* cls_hi;
   int32_t A;
+  const AdapterSummary* summ;   // [A+1]  (sparse path)
+  const uint32_t* tiemask;      // [A+1][row_words] permuted bits: G[a][m] == gmax  (sparse path)
   const int32_t* adapter_id;    // [R] or null
   const uint32_t* cand_mask;    // [R][mask_words] natural order or null
   int32_t mask_words;
@@ -99,7 +110,7 @@ struct ScoreArgs {
   const uint16_t* n_hashes;     // [R]
   int32_t hash_stride;
   const Slot* slots;
-  uint64_t slot_mask;           // capacity-1 (0 = no table)
+  uint64_t slot_mask;           // capacity-1
   const uint32_t* rows;
   // dense rows
   const float4* dense;          // [R][M]
@@ -142,20 +153,27 @@ struct PrepareArgs {
   const double* col[4];
   int32_t lora_words;
   int32_t A;
-  // outputs
+  // outputs of the endpoint kernel
   double* term[kMaxSteps];      // per scorer (null where not an endpoint term)
   double* fold_unmasked;        // leading run folded (or null)
   int32_t fold_unmasked_n;
   double* fold_masked;
   int32_t fold_masked_n;
+  // outputs of the adapter kernel
   uint32_t* cls_lo;
   uint32_t* cls_hi;
+  Plan plan_u;                  // the unmasked plan (evaluated with zero prefix match for the summaries)
+  const double* plan_term[kMaxSteps];
+  AdapterSummary* summ;         // null unless plan_u.sparse_ok
+  uint32_t* tiemask;
 };
 
-// launchers (kernels.cu). Each returns the number of kernels it launched (for gpu_launches).
-int launch_hash_prompts(const HashArgs& a, cudaStream_t s);
+// launchers. Each returns the number of kernels it launched (for gpu_launches).
+int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count);
 int launch_prepare_snapshot(const PrepareArgs& a, cudaStream_t s);
-int launch_score_pick(const ScoreArgs& a, bool dense, cudaStream_t s, int sm_count);
+int launch_score_pick(const ScoreArgs& a, bool dense, cudaStream_t s, int sm_count);   // generic (any plan, masks, diagnostics)
+int launch_score_dense_fast(const ScoreArgs& a, cudaStream_t s, int sm_count);         // 0 if no specialisation applies
+int launch_pick_sparse(const ScoreArgs& a, cudaStream_t s, int sm_count);              // 0 if not applicable
 int launch_scatter_u32(uint32_t* dst, const uint32_t* idx, const uint32_t* val, int64_t n, cudaStream_t s);
 int launch_scatter_slots(Slot* dst, const uint32_t* idx, const Slot* val, int64_t n, cudaStream_t s);
 

@@ -1,328 +1,19 @@
-// kernels.cu — hand-written sm_100a kernels of the Endpoint-Picker hot path.
-//
-//   hash_prompts_kernel      hashPrompt for a batch            (approximateprefix/hashing.go:34-98)
-//   prepare_snapshot_kernel  request-independent scorer terms   (kvcache_utilization.go:76-82, queue.go:78-108,
-//                            + LoRA class planes                 lora_affinity.go:76-102)
-//   score_pick_fused_kernel  matchLongestPrefix + 4 scorers + weighted sum + arg-max, one warp per request,
-//                            the R x M score matrix never touches HBM
-//                                                               (approximateprefix/plugin.go:219-235,
-//                                                                scheduler_profile.go:151-192, maxscore/picker.go:87-115)
-//   score_pick_dense_kernel  same Score+Pick over caller-supplied float4 feature rows streamed from HBM
-//
-// No tensor cores: there is no dense contraction on this path — it is integer hashing, table probes,
-// float64 adds and row arg-max.  float64 uses explicit _rn intrinsics so no FMA contraction can occur
-// (the reference's GOARCH=amd64 build never fuses, SURVEY.md "Key facts").
-#include "kernels.cuh"
-#include "xxh64.cuh"
+// score_generic.cu — the fully general Score+Pick kernels: any scorer order, candidate masks, pair
+// columns, diagnostics outputs (match_out / scores_out).  One warp per request; every (request,
+// endpoint) pair is evaluated.  The specialised fast paths live in score_dense.cu (streaming float4
+// rows) and pick_sparse.cu (per-adapter summaries + per-request exceptions); this file is their
+// fallback and the reference point the fast paths are tested against.
+//   matchLongestPrefix  approximateprefix/plugin.go:219-235
+//   scorers + sum       scheduler_profile.go:151-174 (+ the four Score bodies)
+//   picker              maxscore/picker.go:87-115
+#include "device_common.cuh"
 
 namespace eppscore {
-
-// ---------------------------------------------------------------------------------------------
-// small device helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double clamp01(double s) {  // enforceScoreRange, scheduler_profile.go:194-202
-  if (s < 0.0) return 0.0;
-  if (s > 1.0) return 1.0;
-  return s;
-}
-__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
-  x ^= x >> 16;
-  x *= 0x7feb352dU;
-  x ^= x >> 15;
-  x *= 0x846ca68bU;
-  x ^= x >> 16;
-  return x;
-}
-__device__ __forceinline__ double shfl_xor_f64(double v, int o) {
-  int lo = __double2loint(v), hi = __double2hiint(v);
-  lo = __shfl_xor_sync(0xffffffffu, lo, o);
-  hi = __shfl_xor_sync(0xffffffffu, hi, o);
-  return __hiloint2double(hi, lo);
-}
-__device__ __forceinline__ long long shfl_xor_i64(long long v, int o) {
-  return __shfl_xor_sync(0xffffffffu, v, o);
-}
-__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-
-// ---------------------------------------------------------------------------------------------
-// hashPrompt for a batch: one warp owns a tile of 32 requests.
-//   phase 1  lanes = blocks: body state of 32 blocks of one request at a time (block bytes only)
-//   phase 2  lanes = requests: the serial chain (one tail round + avalanche per link)
-//   phase 3  lanes = blocks: coalesced store of the 32 hashes of each request
-// Requests whose block size is not a multiple of 32 or whose start is not 16-byte aligned take the
-// generic serial path in phase 2 (every block fully hashed by the request's lane).
-// ---------------------------------------------------------------------------------------------
-constexpr int kHashWarps = 4;
-
-__device__ __forceinline__ uint64_t block_body_state(const uint8_t* p, int bc) {
-  uint64_t v1 = XP1 + XP2, v2 = XP2, v3 = 0, v4 = 0 - XP1;
-  for (int s = 0; s < bc; s += 32) {
-    const uint4 x = ldg16(p + s), y = ldg16(p + s + 16);
-    v1 = xround(v1, ((uint64_t)x.y << 32) | x.x);
-    v2 = xround(v2, ((uint64_t)x.w << 32) | x.z);
-    v3 = xround(v3, ((uint64_t)y.y << 32) | y.x);
-    v4 = xround(v4, ((uint64_t)y.w << 32) | y.z);
-  }
-  return xfinish_lanes(v1, v2, v3, v4) + (uint64_t)(bc + 8);
-}
-
-__global__ void __launch_bounds__(kHashWarps * 32) hash_prompts_kernel(HashArgs a) {
-  __shared__ uint64_t s_body[kHashWarps][32][33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gw = blockIdx.x * kHashWarps + warp, nw = gridDim.x * kHashWarps;
-  const int bc = a.block_chars;
-  const bool bc_fast = bc > 0 && (bc & 31) == 0;
-  const int ntiles = (a.R + 31) >> 5;
-  uint64_t(*body)[33] = s_body[warp];
-
-  for (int tile = gw; tile < ntiles; tile += nw) {
-    const int r = tile * 32 + lane;
-    const uint8_t* p = nullptr;
-    uint64_t prev = 0;
-    int nfull = 0, rem = 0;
-    bool fast = false;
-    if (r < a.R) {
-      const int64_t o = a.off[r];
-      int64_t len = a.len ? (int64_t)a.len[r] : a.off[r + 1] - o;
-      p = a.bytes + o;
-      prev = a.seed ? a.seed[r] : 0ULL;
-      if (bc > 0 && len >= bc) {                         // hashing.go:51-60
-        const int64_t cap = (int64_t)bc * (int64_t)a.max_blocks;
-        if (len > cap) len = cap;                        // :62-65
-        nfull = (int)(len / bc);
-        rem = (int)(len - (int64_t)nfull * bc);
-      }
-      fast = bc_fast && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
-    }
-    int maxfull = nfull;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) maxfull = max(maxfull, __shfl_xor_sync(0xffffffffu, maxfull, o));
-
-    for (int c0 = 0; c0 < maxfull; c0 += 32) {
-      // phase 1
-      for (int q = 0; q < 32; q++) {
-        const int nf_q = __shfl_sync(0xffffffffu, nfull, q);
-        const int fast_q = __shfl_sync(0xffffffffu, (int)fast, q);
-        const unsigned long long p_q = __shfl_sync(0xffffffffu, (unsigned long long)p, q);
-        if (!fast_q) continue;
-        const int b = c0 + lane;
-        if (b < nf_q) body[q][lane] = block_body_state(reinterpret_cast<const uint8_t*>(p_q) + (size_t)b * bc, bc);
-      }
-      __syncwarp();
-      // phase 2
-      const int nb = min(32, nfull - c0);
-      for (int i = 0; i < nb; i++) {
-        if (fast)
-          prev = xchain_aligned(body[lane][i], prev);
-        else
-          prev = xxh64_link<false>(p + (size_t)(c0 + i) * bc, (uint32_t)bc, prev);  // hashing.go:80-87
-        body[lane][i] = prev;
-      }
-      __syncwarp();
-      // phase 3
-      for (int q = 0; q < 32; q++) {
-        const int nf_q = __shfl_sync(0xffffffffu, nfull, q);
-        const int b = c0 + lane;
-        if (b < nf_q) a.hashes[(size_t)(tile * 32 + q) * a.stride + b] = body[q][lane];
-      }
-      __syncwarp();
-    }
-    if (r < a.R) {
-      if (rem > 0) {                                     // trailing partial block, hashing.go:89-95
-        const uint8_t* t = p + (size_t)nfull * bc;
-        const uint64_t h = ((reinterpret_cast<uintptr_t>(t) & 7) == 0) ? xxh64_link<true>(t, (uint32_t)rem, prev)
-                                                                        : xxh64_link<false>(t, (uint32_t)rem, prev);
-        a.hashes[(size_t)r * a.stride + nfull] = h;
-      }
-      a.n_hashes[r] = (uint16_t)(nfull + (rem > 0 ? 1 : 0));
-    }
-  }
-}
-
-int launch_hash_prompts(const HashArgs& a, cudaStream_t s) {
-  if (a.R <= 0) return 0;
-  const int ntiles = (a.R + 31) / 32;
-  const int blocks = (ntiles + kHashWarps - 1) / kHashWarps;
-  hash_prompts_kernel<<<blocks, kHashWarps * 32, 0, s>>>(a);
-  return 1;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Snapshot preparation (once per metrics snapshot, not per request).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) prepare_snapshot_kernel(PrepareArgs a) {
-  __shared__ long long s_red[2][2][32];  // [queue|running][min|max][warp]
-  __shared__ long long s_mm[2][2];
-  const int M = a.geo.M, Mpad = a.geo.Mpad;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // min / max of WaitingQueueSize and RunningRequestsSize over ALL endpoints (queue.go:79-91)
-  for (int which = 0; which < 2; which++) {
-    const int64_t* q = which == 0 ? a.queue : a.running;
-    long long mn = 0x7fffffffffffffffLL, mx = (long long)0x8000000000000000ULL;
-    if (q)
-      for (int m = tid; m < M; m += blockDim.x) {
-        const long long v = q[m];
-        mn = v < mn ? v : mn;
-        mx = v > mx ? v : mx;
-      }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const long long omn = shfl_xor_i64(mn, o), omx = shfl_xor_i64(mx, o);
-      mn = omn < mn ? omn : mn;
-      mx = omx > mx ? omx : mx;
-    }
-    if (lane == 0) {
-      s_red[which][0][warp] = mn;
-      s_red[which][1][warp] = mx;
-    }
-  }
-  __syncthreads();
-  if (tid < 4) {
-    const int which = tid >> 1, isx = tid & 1;
-    long long v = s_red[which][isx][0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
-      const long long o = s_red[which][isx][w];
-      v = isx ? (o > v ? o : v) : (o < v ? o : v);
-    }
-    s_mm[which][isx] = v;
-  }
-  __syncthreads();
-
-  // per-scorer terms: clamp(score) * weight, the rounded product of scheduler_profile.go:168
-  for (int s = 0; s < a.n_scorers; s++) {
-    double* out = a.term[s];
-    if (!out) continue;
-    const int kind = a.kind[s];
-    const double w = a.weight[s];
-    for (int m = tid; m < Mpad; m += blockDim.x) {
-      double sc = 0.0;
-      if (m < M) {
-        if (kind == 1) {
-          sc = __dsub_rn(1.0, a.kv[m]);                                   // kvcache_utilization.go:79
-        } else if (kind == 0 || kind == 4) {
-          const int which = kind == 0 ? 0 : 1;
-          const int64_t* q = which == 0 ? a.queue : a.running;
-          const long long mn = s_mm[which][0], mx = s_mm[which][1];
-          if (!q || mx == mn)
-            sc = 1.0;                                                      // queue.go:95-98
-          else
-            sc = __ddiv_rn(__ll2double_rn(mx - q[m]), __ll2double_rn(mx - mn));  // queue.go:99
-        } else {
-          const double* col = a.col[kind - 8];
-          sc = col ? col[m] : 0.0;
-        }
-      }
-      out[m] = (m < M) ? __dmul_rn(clamp01(sc), w) : 0.0;
-    }
-  }
-  __syncthreads();
-  // folded leading runs: ((0.0 + t0) + t1) + ... in scorer order
-  for (int pass = 0; pass < 2; pass++) {
-    double* out = pass == 0 ? a.fold_unmasked : a.fold_masked;
-    const int n = pass == 0 ? a.fold_unmasked_n : a.fold_masked_n;
-    if (!out) continue;
-    for (int m = tid; m < Mpad; m += blockDim.x) {
-      double acc = 0.0;
-      for (int s = 0; s < n; s++) acc = __dadd_rn(acc, a.term[s][m]);
-      out[m] = acc;
-    }
-  }
-  // LoRA class planes (permuted layout): class 3 active, 2 has capacity, 1 waiting, 0 none — the
-  // precedence of lora_affinity.go:84-99. Row A is the "adapter not in the dictionary" row.
-  if (a.cls_lo) {
-    const int rw = a.geo.row_words, log_epl = a.geo.log_epl, epl = 1 << log_epl;
-    const int total = (a.A + 1) * rw;
-    for (int t = tid; t < total; t += blockDim.x) {
-      const int ai = t / rw, word = t - ai * rw;
-      const int j = word >> 5, ln = word & 31;
-      uint32_t lo = 0, hi = 0;
-      for (int k = 0; k < epl; k++) {
-        const int m = ((j << log_epl) + k) * 32 + ln;
-        if (m >= M) continue;
-        bool active = false, waiting = false;
-        if (ai < a.A && a.act && a.wait) {
-          const uint64_t bit = 1ULL << (ai & 63);
-          active = (a.act[(size_t)m * a.lora_words + (ai >> 6)] & bit) != 0;
-          waiting = (a.wait[(size_t)m * a.lora_words + (ai >> 6)] & bit) != 0;
-        }
-        const int nm = a.nmodels ? a.nmodels[m] : 0, mxm = a.maxm ? a.maxm[m] : 0;
-        const int cls = active ? 3 : (nm < mxm ? 2 : (waiting ? 1 : 0));
-        lo |= (uint32_t)(cls & 1) << k;
-        hi |= (uint32_t)(cls >> 1) << k;
-      }
-      a.cls_lo[t] = lo;
-      a.cls_hi[t] = hi;
-    }
-  }
-}
-
-int launch_prepare_snapshot(const PrepareArgs& a, cudaStream_t s) {
-  prepare_snapshot_kernel<<<1, 1024, 0, s>>>(a);
-  return 1;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Score + Pick
 // ---------------------------------------------------------------------------------------------
 constexpr int kScoreWarps = 8;
-
-struct Best {
-  double score;
-  int32_t m;     // -1 = none yet
-  int32_t cnt;
-  uint32_t prio;
-};
-
-__device__ __forceinline__ void best_update(Best& b, double s, int m, int tie_mode, uint32_t areq, uint32_t seed_hi) {
-  if (b.m < 0 || s > b.score) {
-    b.score = s;
-    b.m = m;
-    b.cnt = 1;
-    if (tie_mode) b.prio = lowbias32(areq + (uint32_t)m * 0x9E3779B1U + seed_hi);
-  } else if (s == b.score) {
-    b.cnt++;
-    if (tie_mode) {
-      const uint32_t pr = lowbias32(areq + (uint32_t)m * 0x9E3779B1U + seed_hi);
-      if (pr > b.prio) {
-        b.prio = pr;
-        b.m = m;
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void best_warp_reduce(Best& b, int tie_mode) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    const double os = shfl_xor_f64(b.score, o);
-    const int om = __shfl_xor_sync(0xffffffffu, b.m, o);
-    const int oc = __shfl_xor_sync(0xffffffffu, b.cnt, o);
-    const uint32_t op = __shfl_xor_sync(0xffffffffu, b.prio, o);
-    if (om >= 0) {
-      if (b.m < 0 || os > b.score) {
-        b.score = os;
-        b.m = om;
-        b.cnt = oc;
-        b.prio = op;
-      } else if (os == b.score) {
-        b.cnt += oc;
-        const bool take = tie_mode ? (op > b.prio || (op == b.prio && om < b.m)) : (om < b.m);
-        if (take) {
-          b.m = om;
-          b.prio = op;
-        }
-      }
-    }
-  }
-}
-
-// Per-request prefix LUT: lut[c] = clamp(c/total)*w for c <= min(total,kLutMax) (prefix/plugin.go:108-110)
-__device__ __forceinline__ double prefix_term_direct(int c, int total, double w) {
-  double sc = 0.0;
-  if (total != 0) sc = __ddiv_rn((double)c, (double)total);
-  return __dmul_rn(clamp01(sc), w);
-}
 
 template <int LOG_EPL, int J, int NP, bool MASKED>
 __global__ void __launch_bounds__(kScoreWarps * 32) score_pick_fused_kernel(const __grid_constant__ ScoreArgs a) {
@@ -457,12 +148,8 @@ __global__ void __launch_bounds__(kScoreWarps * 32) score_pick_fused_kernel(cons
         }
     }
 
-    const uint32_t areq = lowbias32((uint32_t)(uint64_t)(a.request_base + r) ^ plan.seed_lo);
-    Best best;
-    best.score = 0.0;
-    best.m = -1;
-    best.cnt = 0;
-    best.prio = 0;
+    const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
+    Best best = best_none();
 
     // ---------------- Score (scheduler_profile.go:151-174) + Pick (maxscore/picker.go:87-115) ----------------
 #pragma unroll
@@ -498,7 +185,11 @@ __global__ void __launch_bounds__(kScoreWarps * 32) score_pick_fused_kernel(cons
             case STEP_PREFIX:
               term = (s == prefix_step && total <= kLutMax) ? lut[c] : prefix_term_direct(c, total, plan.weight[s]);
               break;
-            case STEP_LORA: term = plan.lora_term[s][cls]; break;
+            case STEP_LORA: {
+              const double* lt = plan.lora_term[s];
+              term = cls == 3 ? lt[3] : (cls == 2 ? lt[2] : (cls == 1 ? lt[1] : lt[0]));
+              break;
+            }
             case STEP_MINMAX: {
               const int which = plan.arg[s];
               double sc = 1.0;                               // queue.go:95-98
@@ -512,11 +203,11 @@ __global__ void __launch_bounds__(kScoreWarps * 32) score_pick_fused_kernel(cons
           }
           acc = __dadd_rn(acc, term);  // += enforceScoreRange(score) * weight, scheduler_profile.go:168
         }
-        if (a.scores_out && m < M) a.scores_out[(size_t)r * M + m] = cand ? acc : __longlong_as_double(0x7ff8000000000000LL);
+        if (a.scores_out && m < M) a.scores_out[(size_t)r * M + m] = cand ? acc : nan64();
         if (cand) best_update(best, acc, m, tie_mode, areq, plan.seed_hi);
       }
     }
-    best_warp_reduce(best, tie_mode);
+    best_group_reduce<32>(best, tie_mode);
     if (lane == 0) {
       a.pick[r] = best.m;
       a.pick_score[r] = best.m >= 0 ? best.score : 0.0;
@@ -592,12 +283,8 @@ __global__ void __launch_bounds__(kScoreWarps * 32) score_pick_dense_kernel(cons
           mx[which] = omx > mx[which] ? omx : mx[which];
         }
     }
-    const uint32_t areq = lowbias32((uint32_t)(uint64_t)(a.request_base + r) ^ plan.seed_lo);
-    Best best;
-    best.score = 0.0;
-    best.m = -1;
-    best.cnt = 0;
-    best.prio = 0;
+    const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
+    Best best = best_none();
     const float4* row = a.dense + (size_t)r * M;
 #pragma unroll 4
     for (int i = 0; i < nchunks; i++) {
@@ -620,7 +307,11 @@ __global__ void __launch_bounds__(kScoreWarps * 32) score_pick_dense_kernel(cons
                                                                           : prefix_term_direct(cc, total, plan.weight[s]);
             break;
           }
-          case STEP_LORA: term = plan.lora_term[s][cls]; break;
+          case STEP_LORA: {
+              const double* lt = plan.lora_term[s];
+              term = cls == 3 ? lt[3] : (cls == 2 ? lt[2] : (cls == 1 ? lt[1] : lt[0]));
+              break;
+            }
           case STEP_PAIR:
             term = __dmul_rn(clamp01((double)(plan.arg[s] == 0 ? f.z : f.w)), plan.weight[s]);
             break;
@@ -636,10 +327,10 @@ __global__ void __launch_bounds__(kScoreWarps * 32) score_pick_dense_kernel(cons
         }
         acc = __dadd_rn(acc, term);
       }
-      if (a.scores_out && m < M) a.scores_out[(size_t)r * M + m] = cand ? acc : __longlong_as_double(0x7ff8000000000000LL);
+      if (a.scores_out && m < M) a.scores_out[(size_t)r * M + m] = cand ? acc : nan64();
       if (cand) best_update(best, acc, m, tie_mode, areq, plan.seed_hi);
     }
-    best_warp_reduce(best, tie_mode);
+    best_group_reduce<32>(best, tie_mode);
     if (lane == 0) {
       a.pick[r] = best.m;
       a.pick_score[r] = best.m >= 0 ? best.score : 0.0;
@@ -702,28 +393,6 @@ int launch_score_pick(const ScoreArgs& a, bool dense, cudaStream_t s, int sm_cou
     case 4: return launch_fused_geo<5, 4>(a, np_class, masked, s, sm_count);
     default: return launch_fused_geo<5, 8>(a, np_class, masked, s, sm_count);
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// prefix-table maintenance: the host mirror is authoritative; these scatter its dirty words/slots.
-// ---------------------------------------------------------------------------------------------
-__global__ void scatter_u32_kernel(uint32_t* dst, const uint32_t* idx, const uint32_t* val, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[idx[i]] = val[i];
-}
-__global__ void scatter_slots_kernel(Slot* dst, const uint32_t* idx, const Slot* val, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[idx[i]] = val[i];
-}
-int launch_scatter_u32(uint32_t* dst, const uint32_t* idx, const uint32_t* val, int64_t n, cudaStream_t s) {
-  if (n <= 0) return 0;
-  scatter_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, idx, val, n);
-  return 1;
-}
-int launch_scatter_slots(Slot* dst, const uint32_t* idx, const Slot* val, int64_t n, cudaStream_t s) {
-  if (n <= 0) return 0;
-  scatter_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, idx, val, n);
-  return 1;
 }
 
 }  // namespace eppscore

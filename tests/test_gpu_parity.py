@@ -325,7 +325,9 @@ def test_commit_replay_matches_oracle_index(pkg):
         assert eng.stats().prefix_live_hashes == idx.num_hashes()
         if rnd > 0:
             assert got["match_blocks"].max() > 0
-    assert max(eng.prefix_lru_len(m) for m in range(M)) == 150 and eng.prefix_lru_len(0) == 30  # evictions happened
+    lens = [eng.prefix_lru_len(m) for m in range(M)]
+    assert max(lens) <= 150 and max(lens[0::3]) <= 30  # per-endpoint capacities (default / CacheNumBlocks) respected
+    assert eng.stats().lru_entries == sum(x for x in lens if x > 0)
     eng.close()
 
 
@@ -387,6 +389,9 @@ def test_synthetic_parity(pkg, name, M, R, scorers, opt):
     got = eng.schedule(R, want_match=True, want_scores=True, **kw)
     want = o.schedule_batch(snap, prof, idx, R, want_match=True, want_scores=True, want_tie_set=True, n_threads=8, **kw)
     assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks", "match_blocks", "scores_out"))
+    # the same call without per-pair diagnostics takes the specialised kernels (pick_sparse / no R x M pass)
+    fast = eng.schedule(R, **kw)
+    assert_same(fast, want, ("pick", "pick_score", "tie_count", "total_blocks"))
     # reference semantics: the pick is a member of the arg-max set the reference would shuffle over
     ts = want["tie_set"]
     ok = got["pick"] >= 0
@@ -421,6 +426,63 @@ def test_dense_rows_parity(pkg):
         want = o.schedule_batch(o.SnapshotData(**sd), profile_of(pkg, scorers, 1, 5), None, R, want_match=True,
                                 want_scores=True, n_threads=8, **kw)
         assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks", "match_blocks", "scores_out"))
+        fast = eng.schedule(R, **kw)  # template-specialised streaming kernel (unmasked) / generic (masked)
+        assert_same(fast, want, ("pick", "pick_score", "tie_count", "total_blocks"))
+        eng.close()
+    # the specialised sequences of score_dense.cu, each against the oracle
+    for scorers in ([("kv", 1)], [("queue", 2), ("kv", 2), ("prefix", 3)], [("kv", 1), ("lora", 1)], [("lora", 1), ("kv", 1)],
+                    [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)], [("kv", 1), ("prefix", 3), ("lora", 1), ("pair0", 2)],
+                    [("prefix", 1)], [("prefix", 2), ("lora", 1)], [("lora", 1), ("prefix", 2), ("kv", 1)]):
+        M, R = 777, 1500
+        eng = make_engine(pkg, scorers, M, tie_mode=0)
+        sd = synth_snapshot(M, seed=len(scorers), tie_heavy=True)
+        eng.set_snapshot(**sd)
+        rng = np.random.Generator(np.random.PCG64(len(scorers) + 40))
+        feat = np.zeros((R, M, 4), np.float32)
+        total = rng.integers(0, 300, R).astype(np.uint16)  # some totals exceed the 256-entry LUT
+        feat[:, :, 0] = rng.integers(0, 320, (R, M)) * (rng.random((R, M)) < 0.1)
+        feat[:, :, 1] = rng.integers(0, 4, (R, M))
+        feat[:, :, 2] = np.round(rng.random((R, M)), 2)
+        kw = dict(dense_feat=feat, dense_total=total)
+        fast = eng.schedule(R, **kw)
+        want = o.schedule_batch(o.SnapshotData(**sd), profile_of(pkg, scorers), None, R, n_threads=8, **kw)
+        assert_same(fast, want, ("pick", "pick_score", "tie_count", "total_blocks"))
+        eng.close()
+
+
+def test_sparse_path_stress(pkg):
+    """pick_sparse.cu against the oracle where its case analysis is exercised hardest: tie-heavy snapshots,
+    hot prefixes cached on MANY endpoints (hundreds of exceptions), both tie modes, several geometries."""
+    for M, R, tie_mode, scorers in ((1024, 3000, 0, [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)]),
+                                    (1024, 3000, 1, [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)]),
+                                    (200, 2000, 1, [("kv", 1), ("prefix", 1)]),
+                                    (500, 2000, 0, [("prefix", 0.0), ("kv", 1), ("lora", 2)]),
+                                    (3000, 700, 1, [("lora", 1), ("prefix", 0.5), ("kv", 1), ("queue", 1)]),
+                                    (6000, 300, 0, [("queue", 2), ("kv", 2), ("prefix", 3)]),
+                                    (64, 2000, 1, [("kv", 1), ("queue", 1)]),
+                                    (1024, 2000, 1, [("lora", 1), ("kv", 1)])):
+        eng = make_engine(pkg, scorers, M, tie_mode=tie_mode, tie_seed=1234, prefix_capacity=1 << 16, max_blocks=64)
+        sd = synth_snapshot(M, seed=M + tie_mode, tie_heavy=True)
+        sd["kv_usage"] = np.round(sd["kv_usage"], 1)  # very tie heavy
+        eng.set_snapshot(**sd)
+        snap, prof, idx = o.SnapshotData(**sd), profile_of(pkg, scorers, tie_mode, 1234), o.Index()
+        rng = np.random.Generator(np.random.PCG64(M))
+        prompts, off, _ = synth_prompts(R, prompt_len=1024, groups=6, shared=512, seed=M, prefix_seed=3)
+        seeds = np.full(R, eng.model_seed("s"), np.uint64)
+        hashes, nh = eng.hash_prompts(prompts, off, seeds, max_blocks=64)
+        # cache group prefixes on many endpoints: group g's first blocks on a random ~30% of the endpoints
+        for r in range(0, 60):
+            eps = np.nonzero(rng.random(M) < 0.3)[0]
+            depth = int(rng.integers(1, 9))
+            for ep in eps[:200]:
+                eng.prefix_add(hashes[r, :depth], int(ep))
+                idx.add(hashes[r, :depth], int(ep))
+        ad = zipf_adapters(R, seed=M)
+        kw = dict(prompt_bytes=prompts, prompt_off=off, model_seed=seeds, adapter_id=ad, request_base=7000)
+        fast = eng.schedule(R, max_blocks=64, **kw)
+        want = o.schedule_batch(snap, prof, idx, R, max_blocks=64, want_match=True, n_threads=8, **kw)
+        assert_same(fast, want, ("pick", "pick_score", "tie_count", "total_blocks"))
+        assert (want["match_blocks"] > 0).sum(axis=1).max() >= min(M, 150) * 0.2  # really many exceptions per request
         eng.close()
 
 
