@@ -75,3 +75,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+
+
+HOST_TEST = os.path.join(HERE, "host", "host_test")
+
+
+def build_host_test(force: bool = False) -> str:
+    """C++ host mirror tests (host/host_test.cpp): plain g++, linked against libeppscore.so."""
+    build()
+    src = os.path.join(HERE, "host", "host_test.cpp")
+    deps = [src, os.path.join(HERE, "host", "epp_scheduler.hpp"), LIB]
+    if force or _stale(HOST_TEST, deps):
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", src, "-o", HOST_TEST, "-L" + HERE, "-leppscore",
+               "-Wl,-rpath,$ORIGIN/.."]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed building host_test")
+    return HOST_TEST

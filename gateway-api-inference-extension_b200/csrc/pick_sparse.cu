@@ -56,66 +56,130 @@ __global__ void __launch_bounds__(kSparseWarps * 32) pick_sparse_kernel(const __
     const int r = rbase + gi;
     const bool valid = r < a.R;
     const int n = (valid && a.hashes) ? (int)a.n_hashes[r] : 0;
+    int ad = (valid && a.adapter_id) ? a.adapter_id[r] : -1;
+    if (ad < 0 || ad >= a.A) ad = a.A;
+    const AdapterSummary sm = a.summ[ad];  // issued early: only consumed after the probe / row phase
     uint32_t any[QW][4];
 #pragma unroll
     for (int q = 0; q < QW; q++) any[q][0] = any[q][1] = any[q][2] = any[q][3] = 0;
 
-    // ---------------- matchLongestPrefix: probe G hashes per round, stop at the first global miss ----------------
+    // ---------------- matchLongestPrefix: probe U*G hashes per round, stop at the first global miss ----------------
+    // Consecutive blocks of a prompt are usually cached on the SAME endpoints, so consecutive rows are usually
+    // identical: rows are run-length merged (one 128-bit compare per row) and the counters are bumped once per run.
+    uint4 prevw[QW];
+    int run[QW];
+#pragma unroll
+    for (int q = 0; q < QW; q++) {
+      prevw[q] = make_uint4(0u, 0u, 0u, 0u);
+      run[q] = 0;
+    }
+    auto flush = [&](int q) {  // res[server] += run for every server in the run's set (plugin.go:229-231)
+      if (run[q] > 0 && (prevw[q].x | prevw[q].y | prevw[q].z | prevw[q].w)) {
+        const uint32_t ww[4] = {prevw[q].x, prevw[q].y, prevw[q].z, prevw[q].w};
+        const int w0 = (q * G + gl) * 4;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          uint32_t x = ww[t];
+          while (x) {
+            const int k = __ffs(x) - 1;
+            x &= x - 1;
+            cnt[(w0 + t) * 32 + k] += (CNT)run[q];
+          }
+        }
+      }
+    };
     if (have_table) {
+      constexpr int U = 4;            // hashes probed per lane per round (independent loads in flight)
+      constexpr int BATCH = (QW == 1) ? 4 : 2;  // row loads in flight per lane
       bool stop = n == 0;
       int c0 = 0;
       while (__any_sync(0xffffffffu, !stop)) {
-        const int i = c0 + gl;
-        uint32_t row = kEmptyRow;
-        if (!stop && i < n) {
-          const uint64_t h = a.hashes[(size_t)r * a.hash_stride + i];
-          uint64_t idx = h & a.slot_mask;
-          for (;;) {                                            // indexer.Get, indexer.go:86-102
-            const uint4 sv = ldg16(&a.slots[idx]);
-            if (sv.z == kEmptyRow) break;
-            if ((((uint64_t)sv.y << 32) | sv.x) == h) {
-              if (sv.w != 0) row = sv.z;                        // emptied set == deleted key
-              break;
+        uint64_t h[U], idx[U];
+        uint4 sv[U];
+        uint32_t row[U];
+        bool act[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int i = c0 + u * G + gl;
+          act[u] = !stop && i < n;
+          h[u] = act[u] ? a.hashes[(size_t)r * a.hash_stride + i] : 0ULL;
+          idx[u] = h[u] & a.slot_mask;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (act[u]) sv[u] = ldg16(&a.slots[idx[u]]);
+#pragma unroll
+        for (int u = 0; u < U; u++) {                           // indexer.Get, indexer.go:86-102
+          row[u] = kEmptyRow;
+          if (act[u]) {
+            for (;;) {
+              if (sv[u].z == kEmptyRow) break;                  // never-used slot: hash unknown
+              if ((((uint64_t)sv[u].y << 32) | sv[u].x) == h[u]) {
+                if (sv[u].w != 0) row[u] = sv[u].z;             // emptied set == deleted key
+                break;
+              }
+              idx[u] = (idx[u] + 1) & a.slot_mask;
+              sv[u] = ldg16(&a.slots[idx[u]]);
             }
-            idx = (idx + 1) & a.slot_mask;
           }
         }
-        const uint32_t miss = __ballot_sync(0xffffffffu, row == kEmptyRow);
-        const uint32_t gmiss = (G == 32) ? miss : ((miss >> (gi * G)) & ((1u << G) - 1u));
-        const int nh = stop ? 0 : (gmiss ? (__ffs(gmiss) - 1) : G);
-        const int maxnh = __reduce_max_sync(0xffffffffu, nh);
-        for (int i2 = 0; i2 < maxnh; i2++) {
-          const uint32_t rr = __shfl_sync(0xffffffffu, row, gi * G + (i2 < G ? i2 : 0));
-          if (i2 < nh) {
+        int nh_total = 0;   // blocks matched in this round before the first global miss
+        bool open = !stop;
 #pragma unroll
-            for (int q = 0; q < QW; q++) {
-              const int w0 = (q * G + gl) * 4;
-              const uint4 w = ldg16(a.rows + (size_t)rr * RW + w0);
-              if (w.x | w.y | w.z | w.w) {                      // res[server]++ for every server in the set
-                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        for (int u = 0; u < U; u++) {
+          const uint32_t miss = __ballot_sync(0xffffffffu, row[u] == kEmptyRow);
+          const uint32_t gmiss = (G == 32) ? miss : ((miss >> (gi * G)) & ((1u << G) - 1u));
+          if (open) {
+            const int nh_u = gmiss ? (__ffs(gmiss) - 1) : G;
+            nh_total += nh_u;
+            if (nh_u < G) open = false;
+          }
+        }
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                  uint32_t x = ww[t];
-                  any[q][t] |= x;
-                  while (x) {
-                    const int k = __ffs(x) - 1;
-                    x &= x - 1;
-                    cnt[(w0 + t) * 32 + k] += 1;
+        for (int u = 0; u < U; u++) {
+          int nh_u = nh_total - u * G;
+          nh_u = nh_u < 0 ? 0 : (nh_u > G ? G : nh_u);
+          const int maxnh = __reduce_max_sync(0xffffffffu, nh_u);
+          for (int i0 = 0; i0 < maxnh; i0 += BATCH) {
+            uint4 wb[BATCH][QW];
+#pragma unroll
+            for (int b = 0; b < BATCH; b++) {
+              const int i2 = i0 + b;
+              const uint32_t rr = __shfl_sync(0xffffffffu, row[u], gi * G + (i2 < G ? i2 : G - 1));
+#pragma unroll
+              for (int q = 0; q < QW; q++)
+                wb[b][q] = (i2 < nh_u) ? ldg16(a.rows + (size_t)rr * RW + (q * G + gl) * 4) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int b = 0; b < BATCH; b++) {
+              if (i0 + b < nh_u) {
+#pragma unroll
+                for (int q = 0; q < QW; q++) {
+                  const uint4 w = wb[b][q];
+                  any[q][0] |= w.x;
+                  any[q][1] |= w.y;
+                  any[q][2] |= w.z;
+                  any[q][3] |= w.w;
+                  if (w.x == prevw[q].x && w.y == prevw[q].y && w.z == prevw[q].z && w.w == prevw[q].w) {
+                    run[q]++;
+                  } else {
+                    flush(q);
+                    prevw[q] = w;
+                    run[q] = 1;
                   }
                 }
               }
             }
           }
         }
-        c0 += G;
-        if (nh < G || c0 >= n) stop = true;
+        c0 += U * G;
+        if (nh_total < U * G || c0 >= n) stop = true;
       }
+#pragma unroll
+      for (int q = 0; q < QW; q++) flush(q);
     }
 
     // ---------------- exceptions: endpoints with a non-zero match count ----------------
-    int ad = (valid && a.adapter_id) ? a.adapter_id[r] : -1;
-    if (ad < 0 || ad >= a.A) ad = a.A;
-    const AdapterSummary sm = a.summ[ad];
     const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
     Best best = best_none();
     int xg = 0;
@@ -127,19 +191,20 @@ __global__ void __launch_bounds__(kSparseWarps * 32) pick_sparse_kernel(const __
         if (x) {
           const int wi = (q * G + gl) * 4 + t;
           const uint32_t clo = __ldg(a.cls_lo + (size_t)ad * RW + wi), chi = __ldg(a.cls_hi + (size_t)ad * RW + wi);
+          const uint32_t tmw = __ldg(a.tiemask + (size_t)ad * RW + wi);  // bit k: G[ad][m] == gmax
           const int j = wi >> 5, ln = wi & 31;
           while (x) {                                             // ascending k == ascending m for this lane
             const int k = __ffs(x) - 1;
             x &= x - 1;
-            const int c = (int)cnt[wi * 32 + k];
+            int c = (int)cnt[wi * 32 + k];   // stored modulo 2^bits(CNT); touched slots hold c >= 1, so 0 means 2^bits
+            if (c == 0) c = 1 << (8 * (int)sizeof(CNT));
             cnt[wi * 32 + k] = 0;
             const int m = (((j << LOG_EPL) + k) << 5) + ln;
             if (m < M) {
               const int cls = (int)((clo >> k) & 1u) | ((int)((chi >> k) & 1u) << 1);
               const double s_true = eval_steps(plan, a.term, m, c, n, cls);
-              const double s_zero = eval_steps(plan, a.term, m, 0, n, cls);
               best_update(best, s_true, m, tie_mode, areq, plan.seed_hi);
-              xg += (s_zero == sm.gmax) ? 1 : 0;
+              xg += (int)((tmw >> k) & 1u);
             }
           }
         }
@@ -227,7 +292,7 @@ static int launch_sparse_inst(const ScoreArgs& a, cudaStream_t s, int sm_count) 
 template <int LOG_EPL, int J>
 static int launch_sparse_geo(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   const int maxn = a.hashes ? a.hash_stride : 0;
-  if (maxn <= 255) return launch_sparse_inst<LOG_EPL, J, uint8_t>(a, s, sm_count);
+  if (maxn <= 256) return launch_sparse_inst<LOG_EPL, J, uint8_t>(a, s, sm_count);  // incl. defaultMaxPrefixBlocks
   return launch_sparse_inst<LOG_EPL, J, uint16_t>(a, s, sm_count);
 }
 

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kAdapterThreads) prepare_adapters_kernel(const
   __shared__ double s_bs[kAdapterThreads / 32];
   __shared__ int s_bm[kAdapterThreads / 32], s_bc[kAdapterThreads / 32];
   __shared__ double s_gmax;
-  const int rw = a.geo.row_words, log_epl = a.geo.log_epl, epl = 1 << log_epl;
+  const int rw = a.geo.row_words, log_epl = a.geo.log_epl;
   const int M = a.geo.M;
   const int ai = blockIdx.x;  // adapter row; row A = "adapter not in the dictionary"
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,29 +99,27 @@ __global__ void __launch_bounds__(kAdapterThreads) prepare_adapters_kernel(const
   uint32_t* s_hi = s_u32 + rw;
   uint32_t* s_tie = s_u32 + 2 * rw;
 
-  // LoRA class planes: class 3 active, 2 has capacity, 1 waiting, 0 none (lora_affinity.go:84-99)
-  for (int word = tid; word < rw; word += blockDim.x) {
-    const int j = word >> 5, ln = word & 31;
-    uint32_t lo = 0, hi = 0;
-    for (int k = 0; k < epl; k++) {
-      const int m = ((j << log_epl) + k) * 32 + ln;
-      if (m >= M) continue;
-      bool active = false, waiting = false;
-      if (ai < a.A && a.act && a.wait) {
-        const uint64_t bit = 1ULL << (ai & 63);
-        active = (a.act[(size_t)m * a.lora_words + (ai >> 6)] & bit) != 0;
-        waiting = (a.wait[(size_t)m * a.lora_words + (ai >> 6)] & bit) != 0;
-      }
-      const int nm = a.nmodels ? a.nmodels[m] : 0, mxm = a.maxm ? a.maxm[m] : 0;
-      const int cls = active ? 3 : (nm < mxm ? 2 : (waiting ? 1 : 0));
-      lo |= (uint32_t)(cls & 1) << k;
-      hi |= (uint32_t)(cls >> 1) << k;
+  // LoRA class planes: class 3 active, 2 has capacity, 1 waiting, 0 none (lora_affinity.go:84-99).
+  // One thread per endpoint (coalesced reads of the snapshot), bits merged into the permuted planes in smem.
+  for (int word = tid; word < 3 * rw; word += blockDim.x) s_u32[word] = 0;
+  __syncthreads();
+  for (int m = tid; m < M; m += blockDim.x) {
+    bool active = false, waiting = false;
+    if (ai < a.A && a.act && a.wait) {
+      const uint64_t bit = 1ULL << (ai & 63);
+      active = (a.act[(size_t)m * a.lora_words + (ai >> 6)] & bit) != 0;
+      waiting = (a.wait[(size_t)m * a.lora_words + (ai >> 6)] & bit) != 0;
     }
-    s_lo[word] = lo;
-    s_hi[word] = hi;
-    s_tie[word] = 0;
-    a.cls_lo[(size_t)ai * rw + word] = lo;
-    a.cls_hi[(size_t)ai * rw + word] = hi;
+    const int nm = a.nmodels ? a.nmodels[m] : 0, mxm = a.maxm ? a.maxm[m] : 0;
+    const int cls = active ? 3 : (nm < mxm ? 2 : (waiting ? 1 : 0));
+    const uint32_t pos = perm_bitpos((uint32_t)m, log_epl);
+    if (cls & 1) atomicOr(&s_lo[pos >> 5], 1u << (pos & 31));
+    if (cls & 2) atomicOr(&s_hi[pos >> 5], 1u << (pos & 31));
+  }
+  __syncthreads();
+  for (int word = tid; word < rw; word += blockDim.x) {
+    a.cls_lo[(size_t)ai * rw + word] = s_lo[word];
+    a.cls_hi[(size_t)ai * rw + word] = s_hi[word];
   }
   if (!a.summ) return;
   __syncthreads();

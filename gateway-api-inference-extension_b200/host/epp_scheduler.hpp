@@ -1,0 +1,356 @@
+// epp_scheduler.hpp — host side of the drop-in: the reference's Scheduler / SchedulerProfile / Filter /
+// Scorer / Picker plugin interface for THIS path, restated in C++ above the C ABI (include/eppscore.h).
+//
+// The reference's toolchain (Go) is not in this image, so the layer a Go maintainer would write with cgo
+//  is written here in C++ with the same names, argument meaning and error behaviour:
+//   Scheduler.Schedule            pkg/epp/scheduling/scheduler.go:54-102
+//   SchedulerProfile              pkg/epp/scheduling/scheduler_profile.go:41-128   (filters → scorers → picker)
+//   WeightedScorer                pkg/epp/scheduling/weighted_scorer.go:32
+//   Filter / Scorer / Picker      pkg/epp/framework/interface/scheduling/plugins.go:43-78
+//   InferenceRequest / Endpoint / ScoredEndpoint / ProfileRunResult / SchedulingResult
+//                                 pkg/epp/framework/interface/scheduling/types.go:44-170
+//   Metrics                       pkg/epp/framework/interface/datalayer/metrics.go:26-42
+//   SingleProfileHandler          pkg/epp/framework/plugins/scheduling/profile/single_profile_handler.go:66-99
+//   PrepareRequestData/PreRequest pkg/epp/framework/plugins/requestcontrol/dataproducer/approximateprefix/plugin.go:140-205
+// Scorers here are DESCRIPTORS: they name which kernel-side scorer runs and with what weight; the arithmetic
+// itself happens in the CUDA kernels.  Filters run on the host exactly like the reference's filter chain and
+// become the per-request candidate mask.  One Scheduler owns one engine (one GPU).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/eppscore.h"
+
+namespace epp {
+
+struct NamespacedName {
+  std::string Namespace, Name;
+  std::string String() const { return Namespace + "/" + Name; }
+  bool operator==(const NamespacedName& o) const { return Namespace == o.Namespace && Name == o.Name; }
+};
+
+// fwkdl.Metrics — the fields this path reads
+struct Metrics {
+  std::map<std::string, int> ActiveModels, WaitingModels;
+  int MaxActiveModels = 0;
+  int RunningRequestsSize = 0;
+  int WaitingQueueSize = 0;
+  double KVCacheUsagePercent = 0.0;
+  int CacheBlockSize = 0;   // tokens; autotune source for the prefix block size (approximateprefix/plugin.go:238-250)
+  int CacheNumBlocks = 0;   // autotune source for the per-endpoint LRU capacity (plugin.go:207-216)
+};
+
+struct EndpointMetadata {
+  NamespacedName NamespacedName_;
+};
+
+struct Endpoint {
+  EndpointMetadata Metadata;
+  Metrics Metrics_;
+  const EndpointMetadata* GetMetadata() const { return &Metadata; }
+  const Metrics* GetMetrics() const { return &Metrics_; }
+};
+inline Endpoint NewEndpoint(const std::string& name, const Metrics& m, const std::string& ns = "") {
+  Endpoint e;
+  e.Metadata.NamespacedName_ = NamespacedName{ns, name};
+  e.Metrics_ = m;
+  return e;
+}
+
+struct InferenceRequest {
+  std::string RequestId;
+  std::string TargetModel;
+  std::string Prompt;     // getUserInputBytes() output (hashing.go:106-135): Completions prompt or marshalled messages
+  std::string CacheSalt;
+};
+
+struct ScoredEndpoint {
+  const Endpoint* Endpoint_ = nullptr;
+  int Index = -1;  // position in the candidate slice given to Schedule
+  double Score = 0.0;
+  int TieCount = 0;  // size of the arg-max set the reference would shuffle over (picker/maxscore/picker.go:91-102)
+};
+struct ProfileRunResult {
+  std::vector<ScoredEndpoint> TargetEndpoints;
+};
+struct SchedulingResult {
+  std::map<std::string, ProfileRunResult> ProfileResults;
+  std::string PrimaryProfileName;
+};
+
+// errcommon.Error{Code: Internal, ...} / fmt.Errorf of the reference, as an exception with the same text
+struct SchedulingError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+// ---- plugins (descriptors) ----
+struct Scorer {
+  std::string Type;
+  int32_t Kind;
+  virtual ~Scorer() = default;
+  Scorer(std::string t, int32_t k) : Type(std::move(t)), Kind(k) {}
+};
+struct KVCacheUtilizationScorer : Scorer { KVCacheUtilizationScorer() : Scorer("kv-cache-utilization-scorer", EPPSCORE_SCORER_KV_CACHE) {} };
+struct QueueScorer : Scorer { QueueScorer() : Scorer("queue-scorer", EPPSCORE_SCORER_QUEUE) {} };
+struct LoraAffinityScorer : Scorer { LoraAffinityScorer() : Scorer("lora-affinity-scorer", EPPSCORE_SCORER_LORA) {} };
+struct PrefixCacheScorer : Scorer { PrefixCacheScorer() : Scorer("prefix-cache-scorer", EPPSCORE_SCORER_PREFIX) {} };
+struct RunningRequestsScorer : Scorer { RunningRequestsScorer() : Scorer("running-requests-size-scorer", EPPSCORE_SCORER_RUNNING) {} };
+
+struct WeightedScorer {
+  std::shared_ptr<Scorer> Scorer_;
+  double Weight_;
+  double Weight() const { return Weight_; }
+};
+inline WeightedScorer NewWeightedScorer(std::shared_ptr<Scorer> s, double w) { return WeightedScorer{std::move(s), w}; }
+
+// framework.Filter: given the request and the current candidates (indices into the slice passed to Schedule),
+// return the ones to keep.  Runs on the host, chained in order, early exit on empty (scheduler_profile.go:130-149).
+struct Filter {
+  virtual ~Filter() = default;
+  virtual std::vector<int> Filter_(const InferenceRequest& req, const std::vector<Endpoint>& endpoints,
+                                   const std::vector<int>& candidates) = 0;
+};
+
+struct MaxScorePicker {
+  int MaxNumOfEndpoints = 1;  // picker.DefaultMaxNumOfEndpoints (picker/common.go:36); only 1 is supported on the GPU path
+};
+
+class SchedulerProfile {
+ public:
+  SchedulerProfile& WithFilters(std::vector<std::shared_ptr<Filter>> f) { filters_ = std::move(f); return *this; }
+  SchedulerProfile& WithScorers(std::vector<WeightedScorer> s) { scorers_ = std::move(s); return *this; }
+  SchedulerProfile& WithPicker(MaxScorePicker p) { picker_ = p; return *this; }
+  const std::vector<std::shared_ptr<Filter>>& filters() const { return filters_; }
+  const std::vector<WeightedScorer>& scorers() const { return scorers_; }
+  const MaxScorePicker& picker() const { return picker_; }
+
+ private:
+  std::vector<std::shared_ptr<Filter>> filters_;
+  std::vector<WeightedScorer> scorers_;
+  MaxScorePicker picker_;
+};
+
+// approximateprefix config (types.go:77-141)
+struct PrefixConfig {
+  bool AutoTune = true;
+  int BlockSizeTokens = 16;
+  int MaxPrefixBlocksToMatch = 256;
+  int MaxPrefixTokensToMatch = 0;
+  int LRUCapacityPerServer = 31250;
+};
+
+struct SchedulerConfig {
+  std::string ProfileName = "default";  // SingleProfileHandler: exactly one profile
+  SchedulerProfile Profile;
+  PrefixConfig Prefix;
+  int Device = 0;
+  int MaxEndpoints = 1024;
+  int MaxAdapters = 64;
+  int64_t PrefixCapacity = 1 << 18;
+  int TieMode = EPPSCORE_TIE_LOWEST_INDEX;
+  uint64_t TieSeed = 0;
+};
+
+class Scheduler {
+ public:
+  explicit Scheduler(const SchedulerConfig& cfg) : cfg_(cfg) {
+    eppscore_config c;
+    eppscore_config_default(&c);
+    const auto& sc = cfg.Profile.scorers();
+    if (sc.size() > EPPSCORE_MAX_SCORERS) throw SchedulingError("too many scorers in profile");
+    if (cfg.Profile.picker().MaxNumOfEndpoints != 1) throw SchedulingError("GPU path supports maxNumOfEndpoints == 1 only");
+    c.n_scorers = (int32_t)sc.size();
+    for (size_t i = 0; i < sc.size(); i++) {
+      c.scorer_kind[i] = sc[i].Scorer_->Kind;
+      c.scorer_weight[i] = sc[i].Weight();
+    }
+    c.block_chars = cfg.Prefix.BlockSizeTokens * 4;  // averageCharactersPerToken (types.go:112)
+    c.max_blocks = cfg.Prefix.MaxPrefixBlocksToMatch;
+    c.lru_capacity_default = cfg.Prefix.LRUCapacityPerServer;
+    c.max_endpoints = cfg.MaxEndpoints;
+    c.max_adapters = cfg.MaxAdapters;
+    c.prefix_capacity = cfg.PrefixCapacity;
+    c.tie_mode = cfg.TieMode;
+    c.tie_seed = cfg.TieSeed;
+    if (eppscore_create(cfg.Device, &c, &eng_) != EPPSCORE_OK) throw SchedulingError(std::string("eppscore_create: ") + eppscore_last_error(nullptr));
+  }
+  ~Scheduler() { eppscore_destroy(eng_); }
+  Scheduler(const Scheduler&) = delete;
+  Scheduler& operator=(const Scheduler&) = delete;
+
+  // Schedule one request (scheduler.go:54): a batch of one.
+  SchedulingResult Schedule(const InferenceRequest& request, const std::vector<Endpoint>& candidateEndpoints) {
+    auto res = ScheduleBatch({request}, candidateEndpoints);
+    if (!res[0].error.empty()) throw SchedulingError(res[0].error);
+    return res[0].result;
+  }
+
+  struct BatchItem {
+    SchedulingResult result;
+    std::string error;  // non-empty ⇒ the reference would have returned this error for that request
+  };
+
+  // R concurrent Schedule() calls against the same candidate slice, as ONE engine batch.
+  std::vector<BatchItem> ScheduleBatch(const std::vector<InferenceRequest>& requests, const std::vector<Endpoint>& endpoints) {
+    const int R = (int)requests.size(), M = (int)endpoints.size();
+    std::vector<BatchItem> out((size_t)R);
+    last_hashes_.clear();
+    last_nh_.clear();
+    if (R == 0) return out;
+    if (M == 0) {  // scheduler_profile.go:119-121 → single_profile_handler.go:89-91
+      for (auto& o : out) o.error = "failed to run scheduler profile '" + cfg_.ProfileName + "'";
+      return out;
+    }
+    PackSnapshot(endpoints);
+    // --- filters → candidate mask ---
+    const int mw = (M + 31) / 32;
+    std::vector<uint32_t> mask;
+    const bool have_filters = !cfg_.Profile.filters().empty();
+    if (have_filters) {
+      mask.assign((size_t)R * mw, 0u);
+      std::vector<int> all((size_t)M);
+      for (int m = 0; m < M; m++) all[m] = m;
+      for (int r = 0; r < R; r++) {
+        std::vector<int> cand = all;
+        for (auto& f : cfg_.Profile.filters()) {
+          cand = f->Filter_(requests[r], endpoints, cand);
+          if (cand.empty()) break;
+        }
+        for (int m : cand) mask[(size_t)r * mw + (m >> 5)] |= 1u << (m & 31);
+      }
+    }
+    // --- PrepareRequestData inputs (approximateprefix/plugin.go:140-165) ---
+    int block_tokens = cfg_.Prefix.BlockSizeTokens;                        // GetBlockSize: endpoints[0] when autotuning
+    if (cfg_.Prefix.AutoTune && endpoints[0].GetMetrics()->CacheBlockSize > 0) block_tokens = endpoints[0].GetMetrics()->CacheBlockSize;
+    int max_blocks = cfg_.Prefix.MaxPrefixBlocksToMatch;
+    if (cfg_.Prefix.MaxPrefixTokensToMatch > 0 && block_tokens > 0) max_blocks = cfg_.Prefix.MaxPrefixTokensToMatch / block_tokens;
+    std::vector<uint8_t> bytes;
+    std::vector<int64_t> off((size_t)R + 1, 0);
+    std::vector<int32_t> len((size_t)R), adapter((size_t)R);
+    std::vector<uint64_t> seed((size_t)R);
+    for (int r = 0; r < R; r++) {
+      while (bytes.size() % 16) bytes.push_back(0);  // 16-byte aligned starts: the fast hash path
+      off[r] = (int64_t)bytes.size();
+      len[r] = (int32_t)requests[r].Prompt.size();
+      bytes.insert(bytes.end(), requests[r].Prompt.begin(), requests[r].Prompt.end());
+      seed[r] = eppscore_model_seed(requests[r].TargetModel.data(), requests[r].TargetModel.size(),
+                                    requests[r].CacheSalt.data(), requests[r].CacheSalt.size());
+      auto it = adapter_ids_.find(requests[r].TargetModel);
+      adapter[r] = it == adapter_ids_.end() ? -1 : it->second;
+    }
+    off[R] = (int64_t)bytes.size();
+    bytes.resize(bytes.size() + 64, 0);
+    const bool want_prefix = max_blocks > 0 && block_tokens > 0;
+    std::vector<int32_t> pick((size_t)R), ties((size_t)R);
+    std::vector<double> score((size_t)R);
+    last_nh_.assign((size_t)R, 0);
+    last_stride_ = want_prefix ? max_blocks : 1;
+    last_hashes_.assign((size_t)R * last_stride_, 0);
+    eppscore_batch b{};
+    b.struct_size = sizeof(b);
+    b.R = R;
+    b.prompt_bytes = want_prefix ? bytes.data() : nullptr;
+    b.prompt_off = off.data();
+    b.prompt_len = len.data();
+    b.model_seed = seed.data();
+    b.block_chars = block_tokens * 4;
+    b.max_blocks = max_blocks;
+    b.adapter_id = adapter.data();
+    b.cand_mask = have_filters ? mask.data() : nullptr;
+    b.pick = pick.data();
+    b.pick_score = score.data();
+    b.tie_count = ties.data();
+    b.total_blocks = last_nh_.data();
+    b.hashes_out = want_prefix ? last_hashes_.data() : nullptr;
+    if (eppscore_schedule_batch(eng_, &b) != EPPSCORE_OK) throw SchedulingError(std::string("eppscore_schedule_batch: ") + eppscore_last_error(eng_));
+    last_endpoints_ = &endpoints;
+    for (int r = 0; r < R; r++) {
+      if (pick[r] < 0) {  // "no endpoints available for the given request" → profile result nil → ProcessResults error
+        out[r].error = "failed to run scheduler profile '" + cfg_.ProfileName + "'";
+        continue;
+      }
+      ScoredEndpoint se;
+      se.Endpoint_ = &endpoints[(size_t)pick[r]];
+      se.Index = pick[r];
+      se.Score = score[r];
+      se.TieCount = ties[r];
+      out[r].result.ProfileResults[cfg_.ProfileName].TargetEndpoints.push_back(se);
+      out[r].result.PrimaryProfileName = cfg_.ProfileName;
+    }
+    return out;
+  }
+
+  // PreRequest for the last ScheduleBatch (approximateprefix/plugin.go:169-197): records the picks in the index.
+  void PreRequest(const std::vector<BatchItem>& results) {
+    if (!last_endpoints_ || last_hashes_.empty()) return;
+    const int R = (int)results.size();
+    std::vector<int32_t> pick((size_t)R, -1);
+    for (int r = 0; r < R; r++)
+      if (results[r].error.empty()) pick[r] = results[r].result.ProfileResults.at(cfg_.ProfileName).TargetEndpoints[0].Index;
+    std::vector<int32_t> cap(last_endpoints_->size(), 0);
+    for (size_t m = 0; m < cap.size(); m++)  // makeserver, plugin.go:207-216
+      cap[m] = (cfg_.Prefix.AutoTune && (*last_endpoints_)[m].GetMetrics()->CacheNumBlocks > 0) ? (*last_endpoints_)[m].GetMetrics()->CacheNumBlocks : 0;
+    if (eppscore_commit_picks(eng_, R, pick.data(), last_hashes_.data(), last_nh_.data(), last_stride_, cap.data()) != EPPSCORE_OK)
+      throw SchedulingError(std::string("eppscore_commit_picks: ") + eppscore_last_error(eng_));
+  }
+
+  const std::vector<uint16_t>& LastTotalBlocks() const { return last_nh_; }
+  eppscore_engine* engine() { return eng_; }
+
+ private:
+  // Metrics maps → the packed SoA snapshot; adapter names get dictionary ids in first-seen order.
+  void PackSnapshot(const std::vector<Endpoint>& eps) {
+    const int M = (int)eps.size();
+    adapter_ids_.clear();
+    for (auto& e : eps) {
+      for (auto& kv : e.GetMetrics()->ActiveModels) adapter_ids_.emplace(kv.first, (int)adapter_ids_.size());
+      for (auto& kv : e.GetMetrics()->WaitingModels) adapter_ids_.emplace(kv.first, (int)adapter_ids_.size());
+    }
+    const int words = (int)((adapter_ids_.size() + 63) / 64) > 0 ? (int)((adapter_ids_.size() + 63) / 64) : 1;
+    std::vector<double> kv((size_t)M);
+    std::vector<int64_t> queue((size_t)M), running((size_t)M);
+    std::vector<uint64_t> act((size_t)M * words, 0), wait((size_t)M * words, 0);
+    std::vector<int32_t> nm((size_t)M), mx((size_t)M);
+    for (int m = 0; m < M; m++) {
+      const Metrics* x = eps[(size_t)m].GetMetrics();
+      kv[m] = x->KVCacheUsagePercent;
+      queue[m] = x->WaitingQueueSize;
+      running[m] = x->RunningRequestsSize;
+      for (auto& a : x->ActiveModels) act[(size_t)m * words + (adapter_ids_[a.first] >> 6)] |= 1ULL << (adapter_ids_[a.first] & 63);
+      for (auto& a : x->WaitingModels) wait[(size_t)m * words + (adapter_ids_[a.first] >> 6)] |= 1ULL << (adapter_ids_[a.first] & 63);
+      nm[m] = (int32_t)(x->ActiveModels.size() + x->WaitingModels.size());  // len()+len() as MAP sizes (lora_affinity.go:90)
+      mx[m] = x->MaxActiveModels;
+    }
+    eppscore_snapshot s{};
+    s.struct_size = sizeof(s);
+    s.M = M;
+    s.lora_words = words;
+    s.kv_usage = kv.data();
+    s.queue = queue.data();
+    s.running = running.data();
+    s.lora_active = act.data();
+    s.lora_waiting = wait.data();
+    s.lora_nmodels = nm.data();
+    s.lora_max = mx.data();
+    s.epoch = ++epoch_;
+    if (eppscore_set_snapshot(eng_, &s) != EPPSCORE_OK) throw SchedulingError(std::string("eppscore_set_snapshot: ") + eppscore_last_error(eng_));
+  }
+
+  SchedulerConfig cfg_;
+  eppscore_engine* eng_ = nullptr;
+  std::unordered_map<std::string, int> adapter_ids_;
+  uint64_t epoch_ = 0;
+  std::vector<uint64_t> last_hashes_;
+  std::vector<uint16_t> last_nh_;
+  int32_t last_stride_ = 1;
+  const std::vector<Endpoint>* last_endpoints_ = nullptr;
+};
+
+inline Scheduler* NewSchedulerWithConfig(const SchedulerConfig& c) { return new Scheduler(c); }
+
+}  // namespace epp

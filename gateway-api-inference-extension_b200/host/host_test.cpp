@@ -1,0 +1,195 @@
+// host_test.cpp — the reference's own scheduler tests, restated against the C++ host mirror
+// (epp_scheduler.hpp) so they run on the GPU engine through the C ABI.  Needs a B200; built by
+// __graft_entry__.build() and executed by tests/test_host_cpp.py (-m gpu).
+//   TestSchedule                      pkg/epp/scheduling/scheduler_test.go:42-159
+//   TestSchedulePlugins (filters)     pkg/epp/scheduling/scheduler_profile_test.go:33-183
+//   integration routing scenarios     test/integration/epp/common_tests.go:283-312, hermetic_test.go:120-272
+//   TestPrefixPluginCompletion        .../approximateprefix/plugin_test.go:161-227 (via PreRequest)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "epp_scheduler.hpp"
+
+using namespace epp;
+
+static int g_fail = 0;
+#define CHECK(cond)                                                        \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond);          \
+      g_fail++;                                                            \
+    }                                                                      \
+  } while (0)
+
+static Metrics M_(int queue, double kv, int maxActive, std::vector<std::string> active, std::vector<std::string> waiting = {}) {
+  Metrics m;
+  m.WaitingQueueSize = queue;
+  m.KVCacheUsagePercent = kv;
+  m.MaxActiveModels = maxActive;
+  for (auto& a : active) m.ActiveModels[a] = 1;
+  for (auto& w : waiting) m.WaitingModels[w] = 1;
+  return m;
+}
+
+static SchedulerConfig DefaultFourScorerConfig() {
+  // scheduler_test.go:49-57: kv, queue, prefix, lora — all weight 1, max-score picker
+  SchedulerConfig c;
+  c.Profile.WithScorers({NewWeightedScorer(std::make_shared<KVCacheUtilizationScorer>(), 1),
+                         NewWeightedScorer(std::make_shared<QueueScorer>(), 1),
+                         NewWeightedScorer(std::make_shared<PrefixCacheScorer>(), 1),
+                         NewWeightedScorer(std::make_shared<LoraAffinityScorer>(), 1)})
+      .WithPicker(MaxScorePicker{});
+  c.MaxEndpoints = 64;
+  c.PrefixCapacity = 1 << 12;
+  return c;
+}
+
+static void TestSchedule() {
+  Scheduler scheduler(DefaultFourScorerConfig());
+  {  // "no candidate endpoints" → error
+    bool threw = false;
+    try {
+      scheduler.Schedule(InferenceRequest{"id0", "any-model", "", ""}, {});
+    } catch (const SchedulingError& e) {
+      threw = std::strstr(e.what(), "failed to run scheduler profile 'default'") != nullptr;
+    }
+    CHECK(threw);
+  }
+  {  // "finds optimal endpoint": pod2, Score == 2.8 (compared with == in the reference)
+    std::vector<Endpoint> input = {NewEndpoint("pod1", M_(0, 0.2, 2, {"foo", "bar"})),
+                                   NewEndpoint("pod2", M_(0, 0.2, 2, {"foo", "critical"})),
+                                   NewEndpoint("pod3", M_(10, 0.8, 2, {"foo"}))};
+    auto got = scheduler.Schedule(InferenceRequest{"id1", "critical", "", ""}, input);
+    CHECK(got.PrimaryProfileName == "default");
+    const auto& te = got.ProfileResults.at("default").TargetEndpoints;
+    CHECK(te.size() == 1);
+    CHECK(te[0].Endpoint_->GetMetadata()->NamespacedName_.Name == "pod2");
+    CHECK(te[0].Score == 2.8);
+    CHECK(te[0].TieCount == 1);
+  }
+}
+
+// scheduler_profile_test.go's testPlugin as a Filter: keeps the endpoints whose names are listed
+struct NameFilter : Filter {
+  std::vector<std::string> keep;
+  int calls = 0, seen = 0;
+  explicit NameFilter(std::vector<std::string> k) : keep(std::move(k)) {}
+  std::vector<int> Filter_(const InferenceRequest&, const std::vector<Endpoint>& eps, const std::vector<int>& cand) override {
+    calls++;
+    seen = (int)cand.size();
+    std::vector<int> out;
+    for (int m : cand)
+      for (auto& k : keep)
+        if (eps[(size_t)m].GetMetadata()->NamespacedName_.Name == k) out.push_back(m);
+    return out;
+  }
+};
+
+static void TestFilterChain() {
+  std::vector<Endpoint> input = {NewEndpoint("pod1", M_(5, 0.5, 0, {})), NewEndpoint("pod2", M_(0, 0.1, 0, {})),
+                                 NewEndpoint("pod3", M_(0, 0.0, 0, {}))};
+  {  // filters narrow 3 → 3 → 2 (tp1 then tp2); pod3 would win unfiltered, pod2 wins among {pod1, pod2}
+    auto f1 = std::make_shared<NameFilter>(std::vector<std::string>{"pod1", "pod2", "pod3"});
+    auto f2 = std::make_shared<NameFilter>(std::vector<std::string>{"pod1", "pod2"});
+    SchedulerConfig c;
+    c.Profile.WithFilters({f1, f2})
+        .WithScorers({NewWeightedScorer(std::make_shared<QueueScorer>(), 1), NewWeightedScorer(std::make_shared<KVCacheUtilizationScorer>(), 1)})
+        .WithPicker(MaxScorePicker{});
+    c.MaxEndpoints = 8;
+    c.PrefixCapacity = 64;
+    Scheduler s(c);
+    auto got = s.Schedule(InferenceRequest{"id", "test-model", "", ""}, input);
+    CHECK(got.ProfileResults.at("default").TargetEndpoints[0].Endpoint_->GetMetadata()->NamespacedName_.Name == "pod2");
+    CHECK(f1->calls == 1 && f2->calls == 1);   // each filter called once
+    CHECK(f1->seen == 3 && f2->seen == 3);     // chained: f2 received f1's output
+    // the queue scorer normalises over the FILTERED set {5, 0}: pod2 = 1.0 + 0.9
+    CHECK(got.ProfileResults.at("default").TargetEndpoints[0].Score == 1.0 + (1 - 0.1));
+  }
+  {  // "filter all" ⇒ error (no available endpoints after the filters)
+    auto f1 = std::make_shared<NameFilter>(std::vector<std::string>{"pod1", "pod2", "pod3"});
+    auto fall = std::make_shared<NameFilter>(std::vector<std::string>{});
+    auto never = std::make_shared<NameFilter>(std::vector<std::string>{"pod1"});
+    SchedulerConfig c;
+    c.Profile.WithFilters({f1, fall, never}).WithScorers({NewWeightedScorer(std::make_shared<QueueScorer>(), 1)}).WithPicker(MaxScorePicker{});
+    c.MaxEndpoints = 8;
+    c.PrefixCapacity = 64;
+    Scheduler s(c);
+    bool threw = false;
+    try {
+      s.Schedule(InferenceRequest{"id", "test-model", "", ""}, input);
+    } catch (const SchedulingError&) {
+      threw = true;
+    }
+    CHECK(threw);
+    CHECK(never->calls == 0);  // early break once the candidate list is empty (scheduler_profile.go:141-144)
+  }
+}
+
+static std::vector<Endpoint> Pods(std::vector<std::tuple<int, int, double, std::vector<std::string>>> ps) {
+  std::vector<Endpoint> out;
+  for (auto& p : ps)  // P(idx, queue, kv, models...): models ACTIVE, MaxActiveModels = 0 (harness.go:386-391)
+    out.push_back(NewEndpoint("pod" + std::to_string(std::get<0>(p)), M_(std::get<1>(p), std::get<2>(p), 0, std::get<3>(p))));
+  return out;
+}
+
+static void TestIntegrationRouting() {
+  // testdata/default-config.yaml: queue, kv, prefix, lora (weight 1)
+  SchedulerConfig c;
+  c.Profile.WithScorers({NewWeightedScorer(std::make_shared<QueueScorer>(), 1), NewWeightedScorer(std::make_shared<KVCacheUtilizationScorer>(), 1),
+                         NewWeightedScorer(std::make_shared<PrefixCacheScorer>(), 1), NewWeightedScorer(std::make_shared<LoraAffinityScorer>(), 1)})
+      .WithPicker(MaxScorePicker{});
+  c.MaxEndpoints = 8;
+  c.PrefixCapacity = 256;
+  Scheduler s(c);
+  auto pick = [&](const std::string& model, const std::string& prompt, std::vector<Endpoint> pods) {
+    return s.Schedule(InferenceRequest{"r", model, prompt, ""}, pods).ProfileResults.at("default").TargetEndpoints[0].Index;
+  };
+  CHECK(pick("my-model-12345", "test1", Pods({{0, 3, 0.2, {}}, {1, 0, 0.1, {}}, {2, 10, 0.2, {}}})) == 1);
+  CHECK(pick("sql-lora-1fdg2", "test2", Pods({{0, 0, 0.2, {"foo", "bar"}}, {1, 0, 0.1, {"foo", "sql-lora-1fdg2"}}, {2, 10, 0.2, {"foo", "bar"}}})) == 1);
+  CHECK(pick("sql-lora-1fdg2", "test3", Pods({{0, 10, 0.2, {"foo", "bar"}}, {1, 10, 0.4, {"foo", "sql-lora-1fdg2"}}, {2, 10, 0.3, {"foo"}}})) == 1);
+  CHECK(pick("sql-lora-1fdg2", "test4", Pods({{0, 6, 0.2, {"foo", "bar", "sql-lora-1fdg2"}}, {1, 0, 0.85, {"foo"}}, {2, 10, 0.9, {"foo"}}})) == 0);
+}
+
+static void TestPrefixCompletionViaPreRequest() {
+  // BlockSizeTokens 1 (4 chars), no autotune: "aaaaaa" → 2 hashes; after PreRequest(pick) "aaaabbbb" matches 1 of 2 there
+  SchedulerConfig c;
+  c.Profile.WithScorers({NewWeightedScorer(std::make_shared<PrefixCacheScorer>(), 1)}).WithPicker(MaxScorePicker{});
+  c.Prefix.AutoTune = false;
+  c.Prefix.BlockSizeTokens = 1;
+  c.MaxEndpoints = 8;
+  c.PrefixCapacity = 256;
+  Scheduler s(c);
+  std::vector<Endpoint> eps = {NewEndpoint("pod1", Metrics{}), NewEndpoint("pod2", Metrics{}), NewEndpoint("pod3", Metrics{})};
+  auto r1 = s.ScheduleBatch({InferenceRequest{"a", "test-model1", "aaaaaa", ""}}, eps);
+  CHECK(s.LastTotalBlocks()[0] == 2);
+  CHECK(r1[0].error.empty() && r1[0].result.ProfileResults.at("default").TargetEndpoints[0].TieCount == 3);  // empty index: all tie at 0
+  const int first = r1[0].result.ProfileResults.at("default").TargetEndpoints[0].Index;
+  s.PreRequest(r1);
+  auto r2 = s.ScheduleBatch({InferenceRequest{"b", "test-model1", "aaaabbbb", ""}}, eps);
+  const auto& te = r2[0].result.ProfileResults.at("default").TargetEndpoints[0];
+  CHECK(te.Index == first);       // the endpoint that cached "aaaa" now wins
+  CHECK(te.Score == 0.5);         // 1 matching block of 2 (prefix/plugin.go:108-110)
+  CHECK(te.TieCount == 1);
+  // a different model name changes the chain seed (hashing.go:69-71): no match any more
+  auto r3 = s.ScheduleBatch({InferenceRequest{"c", "other-model", "aaaabbbb", ""}}, eps);
+  CHECK(r3[0].result.ProfileResults.at("default").TargetEndpoints[0].Score == 0.0);
+}
+
+int main() {
+  try {
+    TestSchedule();
+    TestFilterChain();
+    TestIntegrationRouting();
+    TestPrefixCompletionViaPreRequest();
+  } catch (const std::exception& e) {
+    std::printf("FAIL exception: %s\n", e.what());
+    return 2;
+  }
+  if (g_fail) {
+    std::printf("%d check(s) failed\n", g_fail);
+    return 1;
+  }
+  std::printf("host_test: all checks passed\n");
+  return 0;
+}

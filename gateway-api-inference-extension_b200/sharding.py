@@ -1,0 +1,43 @@
+"""Host-side helpers for the multi-GPU layout: the request batch shards by request with no
+data-path collective; the endpoint snapshot is packed into ONE contiguous tile so that a single broadcast
+(NCCL over NVLink on GPUs, gloo in the CPU tests) replicates it, and each rank's engine then ingests it in
+place (eppscore_set_snapshot, location=1)."""
+from __future__ import annotations
+
+import numpy as np
+
+# field order and dtypes of the packed tile (== eppscore_snapshot's arrays)
+SNAPSHOT_FIELDS = (("kv_usage", np.float64), ("queue", np.int64), ("running", np.int64), ("lora_active", np.uint64),
+                   ("lora_waiting", np.uint64), ("lora_nmodels", np.int32), ("lora_max", np.int32))
+
+
+def snapshot_layout(M: int, lora_words: int):
+    """[(name, byte offset, nbytes, dtype, shape)] — every field starts 16-byte aligned."""
+    out, off = [], 0
+    for name, dt in SNAPSHOT_FIELDS:
+        shape = (M, lora_words) if name in ("lora_active", "lora_waiting") else (M,)
+        nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
+        out.append((name, off, nbytes, np.dtype(dt), shape))
+        off += (nbytes + 15) // 16 * 16
+    return out, off
+
+
+def pack_snapshot(snap: dict):
+    M = len(snap["kv_usage"])
+    lw = int(np.asarray(snap["lora_active"]).size // M) if M else 1
+    layout, total = snapshot_layout(M, lw)
+    buf = np.zeros(total, np.uint8)
+    for name, off, nbytes, dt, shape in layout:
+        buf[off:off + nbytes] = np.ascontiguousarray(snap[name], dtype=dt).reshape(-1).view(np.uint8)
+    return buf, layout
+
+
+def unpack_snapshot(buf: np.ndarray, layout):
+    return {name: buf[off:off + nbytes].view(dt).reshape(shape) for name, off, nbytes, dt, shape in layout}
+
+
+def shard_range(R_total: int, rank: int, world: int):
+    """Contiguous request shard of a global batch; request_base = start keeps tie priorities shard-invariant."""
+    start = R_total * rank // world
+    stop = R_total * (rank + 1) // world
+    return start, stop

@@ -486,6 +486,32 @@ def test_sparse_path_stress(pkg):
         eng.close()
 
 
+def test_sparse_path_full_256_block_match(pkg):
+    """defaultMaxPrefixBlocks = 256 matched blocks on an endpoint: the sparse kernel's 8-bit match counters
+    wrap to 0 at 256 and must still decode to 256 (score 1.0 * weight)."""
+    M, R = 96, 40
+    scorers = [("kv", 1), ("prefix", 3)]
+    eng = make_engine(pkg, scorers, M, prefix_capacity=1 << 12)
+    sd = synth_snapshot(M, seed=12)
+    eng.set_snapshot(**sd)
+    snap, prof, idx = o.SnapshotData(**sd), profile_of(pkg, scorers), o.Index()
+    prompts, off, _ = synth_prompts(R, prompt_len=256 * 64, groups=3, shared=250 * 64, seed=12)
+    seeds = np.full(R, eng.model_seed("long"), np.uint64)
+    hashes, nh = eng.hash_prompts(prompts, off, seeds)
+    assert (nh == 256).all()
+    for r, ep in ((0, 5), (1, 70), (2, 5), (3, 33)):   # request r's whole 256-block chain cached on endpoint ep
+        eng.prefix_add(hashes[r], ep)
+        idx.add(hashes[r], ep)
+    kw = dict(prompt_bytes=prompts, prompt_off=off, model_seed=seeds)
+    fast = eng.schedule(R, **kw)
+    want = o.schedule_batch(snap, prof, idx, R, want_match=True, n_threads=4, **kw)
+    assert_same(fast, want, ("pick", "pick_score", "tie_count", "total_blocks"))
+    assert want["match_blocks"].max() == 256 and set(fast["pick"][:4]) <= {5, 70, 33}
+    full = eng.schedule(R, want_match=True, **kw)
+    assert_same(full, want, ("pick", "pick_score", "tie_count", "match_blocks"))
+    eng.close()
+
+
 def test_hashes_in_path_and_small_blocks(pkg):
     """Pre-hashed input (a host that hashes itself) and the generic (block_chars=4, unaligned) hash path."""
     M, R = 128, 600
