@@ -72,7 +72,8 @@ struct eppscore_engine {
   bool have_running = false;
   const int64_t* cur_queue = nullptr;    // raw WaitingQueueSize / RunningRequestsSize of the current snapshot
   const int64_t* cur_running = nullptr;  // (engine copy for host snapshots, the caller's buffer for device ones)
-  DevBuf term[kMaxSteps], fold_unmasked, fold_masked, cls_lo, cls_hi, summ, tiemask;
+  DevBuf term[kMaxSteps], fold_unmasked, fold_masked, cls_lo, cls_hi, summ, tiemask, prefix_lut2d;
+  bool have_lut2d = false;
   PlanSet plan_unmasked{}, plan_masked{};
 
   // prefix table
@@ -278,6 +279,7 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
   a.cls_hi = e->cls_hi.as<uint32_t>();
   a.summ = ps.plan.sparse_ok ? e->summ.as<AdapterSummary>() : nullptr;
   a.tiemask = ps.plan.sparse_ok ? e->tiemask.as<uint32_t>() : nullptr;
+  a.prefix_lut2d = e->have_lut2d ? e->prefix_lut2d.as<double>() : nullptr;
   a.A = e->A;
   a.adapter_id = b.adapter_id;
   a.cand_mask = b.cand_mask;
@@ -447,6 +449,25 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   CK(nullptr, ep->tiemask.reserve((size_t)(ep->A_cap + 1) * ep->geo.row_words * 4));
   build_plan(ep, false, &ep->plan_unmasked);
   build_plan(ep, true, &ep->plan_masked);
+  // engine-wide prefix term table for the sparse path: lut2d[total][c] = clamp(c/total) * w  (prefix/plugin.go:108-110,
+  // scheduler_profile.go:168) — one IEEE divide and one multiply per entry, computed here on the host (no contraction:
+  // this file is compiled with -ffp-contract=off)
+  for (int sidx = 0; sidx < ep->plan_unmasked.plan.n_steps; sidx++) {
+    if (ep->plan_unmasked.plan.kind[sidx] != STEP_PREFIX) continue;
+    const double w = ep->plan_unmasked.plan.weight[sidx];
+    std::vector<double> lut((size_t)(kLutMax + 1) * (kLutMax + 1), 0.0);
+    for (int total = 0; total <= kLutMax; total++)
+      for (int c = 0; c <= kLutMax; c++) {
+        volatile double sc = 0.0;
+        if (total != 0) sc = (double)c / (double)total;
+        volatile double cl = clamp01_host(sc);
+        lut[(size_t)total * (kLutMax + 1) + c] = cl * w;
+      }
+    CK(nullptr, ep->prefix_lut2d.reserve(lut.size() * 8));
+    CK(nullptr, cudaMemcpy(ep->prefix_lut2d.p, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice));
+    ep->have_lut2d = true;
+    break;
+  }
   // prefix table
   ep->index = std::make_unique<PrefixIndex>(ep->geo, ep->cfg.prefix_capacity, ep->cfg.lru_capacity_default);
   const size_t nslots = ep->index->slots().size();
@@ -468,7 +489,7 @@ void eppscore_destroy(eppscore_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   DevBuf* bufs[] = {&e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
-                    &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->st_idx, &e->st_val, &e->st_slot,
+                    &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->prefix_lut2d, &e->st_idx, &e->st_val, &e->st_slot,
                     &e->probe_out, &e->s_prompts, &e->s_off, &e->s_len, &e->s_seed, &e->s_hashes, &e->s_nh, &e->s_adapter,
                     &e->s_mask, &e->s_dense, &e->s_dtotal, &e->s_pick, &e->s_score, &e->s_tie, &e->s_match, &e->s_total, &e->s_scores};
   for (DevBuf* b : bufs) b->release();

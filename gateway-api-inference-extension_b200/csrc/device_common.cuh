@@ -59,21 +59,23 @@ __device__ __forceinline__ uint32_t tie_areq(int64_t request_index, uint32_t see
 }
 // candidates must arrive in ascending m per thread (ties then keep the lowest index in tie_mode 0)
 __device__ __forceinline__ void best_update(Best& b, double s, int m, int tie_mode, uint32_t areq, uint32_t seed_hi) {
-  if (b.m < 0 || s > b.score) {
-    b.score = s;
-    b.m = m;
-    b.cnt = 1;
-    if (tie_mode) b.prio = tie_prio(areq, m, seed_hi);
-  } else if (s == b.score) {
-    b.cnt++;
-    if (tie_mode) {
+  // branch-free in the common (lowest-index) mode: two compares and a handful of selects
+  const bool first = b.m < 0;
+  const bool gt = first || s > b.score;
+  const bool eq = !first && s == b.score;
+  if (tie_mode) {  // warp-uniform
+    if (gt || eq) {
       const uint32_t pr = tie_prio(areq, m, seed_hi);
-      if (pr > b.prio) {
+      if (gt || pr > b.prio) {
         b.prio = pr;
         b.m = m;
       }
     }
+  } else {
+    b.m = gt ? m : b.m;
   }
+  b.score = gt ? s : b.score;
+  b.cnt = gt ? 1 : b.cnt + (eq ? 1 : 0);
 }
 // commutative + associative merge of two partial results
 __device__ __forceinline__ void best_merge(Best& b, double os, int om, int oc, uint32_t op, int tie_mode) {

@@ -102,6 +102,7 @@ struct ScoreArgs {
   int32_t A;
   const AdapterSummary* summ;   // [A+1]  (sparse path)
   const uint32_t* tiemask;      // [A+1][row_words] permuted bits: G[a][m] == gmax  (sparse path)
+  const double* prefix_lut2d;   // [(kLutMax+1)^2]: lut2d[total*(kLutMax+1)+c] = clamp(c/total)*w_prefix, or null
   const int32_t* adapter_id;    // [R] or null
   const uint32_t* cand_mask;    // [R][mask_words] natural order or null
   int32_t mask_words;

@@ -23,8 +23,35 @@ namespace eppscore {
 
 constexpr int kSparseWarps = 8;
 
-template <int LOG_EPL, int J, typename CNT>
+// Score of an exception endpoint with the scorer sequence known at compile time (SEQ packs kind+1 per step,
+// 4 bits each; SEQ == 0 selects the runtime-generic eval_steps).  The prefix term comes from the engine-wide
+// table lut2d[total][c] = clamp(c/total)*w (built once on the host: one IEEE divide, one multiply per entry).
+template <uint32_t SEQ>
+__device__ __forceinline__ double eval_exception(const ScoreArgs& a, int m, int c, int total, int cls) {
+  if (SEQ == 0) return eval_steps(a.plan, a.term, m, c, total, cls);
+  double acc = 0.0;
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const int kind = (int)((SEQ >> (4 * s)) & 15u) - 1;
+    if (kind < 0) break;
+    double t;
+    if (kind == STEP_EP_TERM) {
+      t = __ldg(a.term[a.plan.arg[s]] + m);
+    } else if (kind == STEP_PREFIX) {
+      t = (a.prefix_lut2d && total <= kLutMax) ? __ldg(a.prefix_lut2d + total * (kLutMax + 1) + c)
+                                               : prefix_term_direct(c, total, a.plan.weight[s]);
+    } else {  // STEP_LORA
+      const double* lt = a.plan.lora_term[s];
+      t = cls == 3 ? lt[3] : (cls == 2 ? lt[2] : (cls == 1 ? lt[1] : lt[0]));
+    }
+    acc = __dadd_rn(acc, t);
+  }
+  return acc;
+}
+
+template <int J, typename CNT, uint32_t SEQ>
 __global__ void __launch_bounds__(kSparseWarps * 32) pick_sparse_kernel(const __grid_constant__ ScoreArgs a) {
+  const int LOG_EPL = a.geo.log_epl;
   constexpr int RW = J * 32;                       // words per bitset row
   constexpr int G = (RW / 4 < 32) ? RW / 4 : 32;   // lanes per request
   constexpr int QW = RW / (4 * G);                 // 16-byte quads per lane per row
@@ -202,7 +229,7 @@ __global__ void __launch_bounds__(kSparseWarps * 32) pick_sparse_kernel(const __
             const int m = (((j << LOG_EPL) + k) << 5) + ln;
             if (m < M) {
               const int cls = (int)((clo >> k) & 1u) | ((int)((chi >> k) & 1u) << 1);
-              const double s_true = eval_steps(plan, a.term, m, c, n, cls);
+              const double s_true = eval_exception<SEQ>(a, m, c, n, cls);
               best_update(best, s_true, m, tie_mode, areq, plan.seed_hi);
               xg += (int)((tmw >> k) & 1u);
             }
@@ -269,12 +296,12 @@ __global__ void __launch_bounds__(kSparseWarps * 32) pick_sparse_kernel(const __
   }
 }
 
-template <int LOG_EPL, int J, typename CNT>
+template <int J, typename CNT, uint32_t SEQ>
 static int launch_sparse_inst(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   constexpr int RW = J * 32;
   constexpr int G = (RW / 4 < 32) ? RW / 4 : 32;
   constexpr int RPW = 32 / G;
-  auto kernel = pick_sparse_kernel<LOG_EPL, J, CNT>;
+  auto kernel = pick_sparse_kernel<J, CNT, SEQ>;
   const size_t smem = (size_t)kSparseWarps * RPW * RW * 32 * sizeof(CNT);
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int occ = 1;
@@ -289,25 +316,37 @@ static int launch_sparse_inst(const ScoreArgs& a, cudaStream_t s, int sm_count) 
   return 1;
 }
 
-template <int LOG_EPL, int J>
+constexpr uint32_t sparse_seq() { return 0; }
+template <typename... Rest>
+constexpr uint32_t sparse_seq(int k, Rest... rest) {
+  return (uint32_t)(k + 1) | (sparse_seq(rest...) << 4);
+}
+
+template <int J, typename CNT>
+static int launch_sparse_seq(const ScoreArgs& a, cudaStream_t s, int sm_count) {
+  constexpr uint32_t EPL_ = sparse_seq(STEP_EP_TERM, STEP_PREFIX, STEP_LORA);  // queue,kv folded | prefix | lora
+  constexpr uint32_t EP_ = sparse_seq(STEP_EP_TERM, STEP_PREFIX);              // the reference's default config
+  if (a.plan.seq == EPL_) return launch_sparse_inst<J, CNT, EPL_>(a, s, sm_count);
+  if (a.plan.seq == EP_) return launch_sparse_inst<J, CNT, EP_>(a, s, sm_count);
+  return launch_sparse_inst<J, CNT, 0>(a, s, sm_count);
+}
+
+template <int J>
 static int launch_sparse_geo(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   const int maxn = a.hashes ? a.hash_stride : 0;
-  if (maxn <= 256) return launch_sparse_inst<LOG_EPL, J, uint8_t>(a, s, sm_count);  // incl. defaultMaxPrefixBlocks
-  return launch_sparse_inst<LOG_EPL, J, uint16_t>(a, s, sm_count);
+  if (maxn <= 256) return launch_sparse_seq<J, uint8_t>(a, s, sm_count);  // incl. defaultMaxPrefixBlocks
+  return launch_sparse_seq<J, uint16_t>(a, s, sm_count);
 }
 
 // Applicable when: unmasked, not dense, no per-pair diagnostics, plan flagged sparse_ok, summaries present.
 int launch_pick_sparse(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
   if (!a.plan.sparse_ok || !a.summ || !a.tiemask || a.cand_mask || a.dense || a.match_out || a.scores_out) return 0;
-  const Geo& g = a.geo;
-  if (g.log_epl == 3) return launch_sparse_geo<3, 1>(a, s, sm_count);
-  if (g.log_epl == 4) return launch_sparse_geo<4, 1>(a, s, sm_count);
-  switch (g.J) {
-    case 1: return launch_sparse_geo<5, 1>(a, s, sm_count);
-    case 2: return launch_sparse_geo<5, 2>(a, s, sm_count);
-    case 4: return launch_sparse_geo<5, 4>(a, s, sm_count);
-    default: return launch_sparse_geo<5, 8>(a, s, sm_count);
+  switch (a.geo.J) {
+    case 1: return launch_sparse_geo<1>(a, s, sm_count);
+    case 2: return launch_sparse_geo<2>(a, s, sm_count);
+    case 4: return launch_sparse_geo<4>(a, s, sm_count);
+    default: return launch_sparse_geo<8>(a, s, sm_count);
   }
 }
 

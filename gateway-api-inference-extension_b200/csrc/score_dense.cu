@@ -2,11 +2,12 @@
 //
 // Input: float4 per (request, endpoint) = {matchBlocks, lora class, pair col 0, pair col 1}, R x M rows in
 // HBM (16*R*M bytes — the kernel is a pure stream over them: DESIGN.md §6 "dense-row accounting").
-// One warp per request row; lane l reads endpoint i*32+l with a 128-bit coalesced load; the endpoint tile
-// (folded request-independent terms), the per-step LoRA terms and a per-warp prefix LUT live in shared
-// memory; float64 accumulate in profile order (scheduler_profile.go:155-168); warp-shuffle arg-max
-// (maxscore/picker.go:87-115).  The scorer sequence is a template parameter pack so the inner loop has no
-// dispatch at all; sequences without a specialisation fall back to score_generic.cu.
+// One warp per request row; lane l reads endpoint i*32+l with a 128-bit coalesced load, four loads in
+// flight per lane; the endpoint tile (folded request-independent terms), the per-step LoRA terms and a
+// per-warp prefix LUT live in shared memory; float64 accumulate in profile order
+// (scheduler_profile.go:155-168); warp-shuffle arg-max (maxscore/picker.go:87-115).  The scorer sequence
+// is a template parameter pack, so the inner loop has no dispatch; sequences without a specialisation
+// fall back to score_generic.cu.
 #include "device_common.cuh"
 
 namespace eppscore {
@@ -14,31 +15,51 @@ namespace eppscore {
 constexpr int kDenseWarps = 8;
 
 struct DenseCtx {
-  const double* s_term;   // [n_terms][MP]
-  const double* s_lora;   // [kMaxSteps][4]
-  const double* lut;      // per warp [kLutMax+1]
+  const double* s_term;  // [n_terms][MP]
+  const double* s_lora;  // [kMaxSteps][4]
+  const double* lut;     // per warp [kLutMax+1]
   int MP;
   int total;
   const Plan* plan;
 };
 
-template <int KIND>
-__device__ __forceinline__ double dense_term(const DenseCtx& cx, int s, int m, const float4& f, int c, int cls);
-template <>
-__device__ __forceinline__ double dense_term<STEP_EP_TERM>(const DenseCtx& cx, int s, int m, const float4&, int, int) {
-  return cx.s_term[cx.plan->arg[s] * cx.MP + m];
-}
-template <>
-__device__ __forceinline__ double dense_term<STEP_PREFIX>(const DenseCtx& cx, int, int, const float4&, int c, int) {
-  return cx.lut[c];  // c already clamped to <= total <= kLutMax
-}
-template <>
-__device__ __forceinline__ double dense_term<STEP_LORA>(const DenseCtx& cx, int s, int, const float4&, int, int cls) {
-  return cx.s_lora[s * 4 + cls];
-}
-template <>
-__device__ __forceinline__ double dense_term<STEP_PAIR>(const DenseCtx& cx, int s, int, const float4& f, int, int) {
+template <int KIND, bool LUT_OK>
+__device__ __forceinline__ double dense_term(const DenseCtx& cx, int s, int m, const float4& f, int c, int cls) {
+  if (KIND == STEP_EP_TERM) return cx.s_term[cx.plan->arg[s] * cx.MP + m];
+  if (KIND == STEP_PREFIX) return LUT_OK ? cx.lut[c] : prefix_term_direct(c, cx.total, cx.plan->weight[s]);
+  if (KIND == STEP_LORA) return cx.s_lora[s * 4 + cls];
+  // STEP_PAIR: float32 feature widened exactly, clamped, weighted
   return __dmul_rn(clamp01((double)(cx.plan->arg[s] == 0 ? f.z : f.w)), cx.plan->weight[s]);
+}
+
+template <bool LUT_OK, int... KINDS>
+__device__ __forceinline__ void dense_pair(const DenseCtx& cx, const float4& f, int m, Best& best, int tie_mode,
+                                           uint32_t areq, uint32_t seed_hi) {
+  int c = (int)(__float2uint_rz(f.x) & 0xFFFFu);
+  if (LUT_OK) c = c < cx.total ? c : cx.total;  // match > total clamps to score 1 == lut[total]
+  const int cls = __float2int_rz(f.y) & 3;
+  double acc = 0.0;  // weightedScorePerEndpoint[endpoint] = float64(0)
+  int s = 0;
+  ((acc = __dadd_rn(acc, dense_term<KINDS, LUT_OK>(cx, s, m, f, c, cls)), s++), ...);
+  best_update(best, acc, m, tie_mode, areq, seed_hi);
+}
+
+// one request row: full 32-endpoint chunks with four 128-bit loads in flight, then the ragged tail
+template <bool LUT_OK, int... KINDS>
+__device__ __forceinline__ void dense_row(const DenseCtx& cx, const float4* __restrict__ row, int M, int lane, Best& best,
+                                          int tie_mode, uint32_t areq, uint32_t seed_hi) {
+  const int nfull = M >> 5;
+  int i = 0;
+  for (; i + 4 <= nfull; i += 4) {
+    float4 f[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) f[u] = __ldg(row + (i + u) * 32 + lane);
+#pragma unroll
+    for (int u = 0; u < 4; u++) dense_pair<LUT_OK, KINDS...>(cx, f[u], (i + u) * 32 + lane, best, tie_mode, areq, seed_hi);
+  }
+  for (; i < nfull; i++) dense_pair<LUT_OK, KINDS...>(cx, __ldg(row + i * 32 + lane), i * 32 + lane, best, tie_mode, areq, seed_hi);
+  const int m = nfull * 32 + lane;
+  if (m < M) dense_pair<LUT_OK, KINDS...>(cx, __ldg(row + m), m, best, tie_mode, areq, seed_hi);
 }
 
 template <int... KINDS>
@@ -51,6 +72,7 @@ __global__ void __launch_bounds__(kDenseWarps * 32) score_dense_fast_kernel(cons
   double* s_lora = s_term + (size_t)plan.n_terms * MP;
   double* s_lut = s_lora + kMaxSteps * 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // stage the endpoint tile once per CTA
   for (int t = 0; t < plan.n_terms; t++)
     for (int m = threadIdx.x; m < MP; m += blockDim.x) s_term[(size_t)t * MP + m] = m < M ? a.term[t][m] : 0.0;
   if (threadIdx.x < kMaxSteps * 4) s_lora[threadIdx.x] = plan.lora_term[threadIdx.x >> 2][threadIdx.x & 3];
@@ -64,7 +86,6 @@ __global__ void __launch_bounds__(kDenseWarps * 32) score_dense_fast_kernel(cons
   }
   int lut_total = -1;
   const int tie_mode = plan.tie_mode;
-  const int nchunks = MP >> 5;
   DenseCtx cx;
   cx.s_term = s_term;
   cx.s_lora = s_lora;
@@ -74,17 +95,12 @@ __global__ void __launch_bounds__(kDenseWarps * 32) score_dense_fast_kernel(cons
 
   const int gw = blockIdx.x * kDenseWarps + warp, nw = gridDim.x * kDenseWarps;
   for (int r = gw; r < a.R; r += nw) {
-    int total = a.dense_total ? a.dense_total[r] : 0;
-    // totals beyond the LUT are handled by clamping the index: c/total for c<=kLutMax is still exact in the LUT
-    // only when total <= kLutMax; larger totals take the generic kernel (launcher guarantees dense_total<=kLutMax
-    // cannot be known for device batches, so the LUT is built for min(total,kLutMax) and larger c use it only if
-    // total<=kLutMax; otherwise the row is recomputed by the slow per-pair division below).
-    const bool lut_ok = total <= kLutMax;
-    if (prefix_step >= 0 && total != lut_total) {
+    const int total = a.dense_total ? a.dense_total[r] : 0;
+    const bool lut_ok = prefix_step < 0 || total <= kLutMax;  // larger totals divide per pair (rare: > 256 blocks)
+    if (prefix_step >= 0 && lut_ok && total != lut_total) {
       const double w = plan.weight[prefix_step];
-      const int top = total < kLutMax ? total : kLutMax;
       __syncwarp();
-      for (int c = lane; c <= top; c += 32) lut[c] = prefix_term_direct(c, total, w);
+      for (int c = lane; c <= total; c += 32) lut[c] = prefix_term_direct(c, total, w);
       lut_total = total;
       __syncwarp();
     }
@@ -92,28 +108,10 @@ __global__ void __launch_bounds__(kDenseWarps * 32) score_dense_fast_kernel(cons
     const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
     Best best = best_none();
     const float4* row = a.dense + (size_t)r * M;
-#pragma unroll 4
-    for (int i = 0; i < nchunks; i++) {
-      const int m = i * 32 + lane;
-      const bool cand = m < M;
-      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (cand) f = __ldg(row + m);
-      int c = (int)(__float2uint_rz(f.x) & 0xFFFFu);
-      const int cls = __float2int_rz(f.y) & 3;
-      double acc = 0.0;
-      if (lut_ok) {
-        c = c < total ? c : total;  // match > total clamps to score 1 == lut[total]
-        int s = 0;
-        ((acc = __dadd_rn(acc, dense_term<KINDS>(cx, s, m, f, c, cls)), s++), ...);
-      } else {
-        int s = 0;
-        ((acc = __dadd_rn(acc, KINDS == STEP_PREFIX ? prefix_term_direct(c, total, plan.weight[s])
-                                                     : dense_term<KINDS>(cx, s, m, f, 0, cls)),
-          s++),
-         ...);
-      }
-      if (cand) best_update(best, acc, m, tie_mode, areq, plan.seed_hi);
-    }
+    if (lut_ok)
+      dense_row<true, KINDS...>(cx, row, M, lane, best, tie_mode, areq, plan.seed_hi);
+    else
+      dense_row<false, KINDS...>(cx, row, M, lane, best, tie_mode, areq, plan.seed_hi);
     best_group_reduce<32>(best, tie_mode);
     if (lane == 0) {
       a.pick[r] = best.m;
