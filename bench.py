@@ -231,10 +231,12 @@ def run_gpu(args):
         o_ += np.ascontiguousarray(snap[k]).nbytes
     torch.cuda.synchronize()
 
-    def apply_snapshot(e):
+    side = torch.cuda.Stream(device=dev)  # snapshot preparation runs here, concurrently with the prompt hashing
+
+    def apply_snapshot(e, on=None):
         # device-resident snapshot, used in place: 2 kernels (prepare_endpoints, prepare_adapters)
         e.set_snapshot(views["kv_usage"], views["queue"], views["running"], views["lora_active"], views["lora_waiting"],
-                       views["lora_nmodels"], views["lora_max"], device=True, stream=sptr, M=M, lora_words=1)
+                       views["lora_nmodels"], views["lora_max"], device=True, stream=(on or sptr), M=M, lora_words=1)
 
     apply_snapshot(eng)
 
@@ -280,7 +282,8 @@ def run_gpu(args):
         """One full pass of the hot path from raw inputs: snapshot preparation + prompt hashing + score/pick."""
         e = e or eng
         d = dsets[i % NSETS]
-        apply_snapshot(e)
+        side.wait_stream(stream)                    # fork: the snapshot does not depend on the prompts ...
+        apply_snapshot(e, side.cuda_stream)         # ... so it is prepared on a second stream while the batch is hashed;
         e.schedule(R, prompt_bytes=d["prompts"], prompt_off=d["off"], model_seed=d["seeds"], adapter_id=d["adapters"],
                    request_base=rank * R, device=True, stream=sptr, out=out)
 
@@ -536,7 +539,7 @@ def run_gpu(args):
 
     if rank == 0:
         cfg = config_dict(world)
-        cfg["step"] = "prepare_endpoints + prepare_adapters + hash_prompts + pick_sparse (snapshot re-prepared every step)"
+        cfg["step"] = "prepare_endpoints + prepare_adapters (side stream) || hash_bodies + hash_chain, then pick_sparse; snapshot re-prepared every step"
         cfg["cuda_graph"] = use_graph
         line = {"metric": METRIC, "value": value, "unit": "picks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -59,6 +59,8 @@ struct eppscore_engine {
   int32_t A_cap = 64;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_snapshot = nullptr, ev_table = nullptr;
+  cudaStream_t snapshot_stream = nullptr;        // stream the last snapshot preparation ran on
+  unsigned long long snapshot_capture_id = 0;    // != 0: ev_snapshot was recorded inside that CUDA-graph capture
   std::string err;
   uint64_t launches = 0;
   bool force_generic = false;  // EPPSCORE_FORCE_GENERIC=1: skip the specialised kernels (A/B tests, profiling)
@@ -257,14 +259,17 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
   const bool masked = b.cand_mask != nullptr;
   const PlanSet& ps = masked ? e->plan_masked : e->plan_unmasked;
 
-  if (s != e->stream) {
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(s, &cap);
-    if (cap == cudaStreamCaptureStatusNone) {  // see eppscore_set_snapshot: no outside dependencies under capture
-      CK(e, cudaStreamWaitEvent(s, e->ev_snapshot, 0));
-      CK(e, cudaStreamWaitEvent(s, e->ev_table, 0));
-    }
-  }
+  // Ordering against the snapshot preparation and the table flush, which may have run on other streams.
+  // The hash kernels depend on neither, so the snapshot wait is issued only before the pick kernel: a caller
+  // may prepare the snapshot on a second stream concurrently with the hashing of the batch.
+  // Under CUDA-graph capture a stream may only wait on events recorded inside the SAME capture.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  unsigned long long cap_id = 0;
+  cudaStreamGetCaptureInfo(s, &cap, &cap_id);
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
+  if (!capturing && s != e->stream) CK(e, cudaStreamWaitEvent(s, e->ev_table, 0));
+  const bool wait_snapshot = capturing ? (e->snapshot_capture_id != 0 && e->snapshot_capture_id == cap_id)
+                                       : (e->snapshot_capture_id == 0 && s != e->snapshot_stream);
 
   ScoreArgs a{};
   a.geo = e->geo;
@@ -335,6 +340,7 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
       }
     }
   }
+  if (wait_snapshot) CK(e, cudaStreamWaitEvent(s, e->ev_snapshot, 0));
   // dispatch: specialised fast paths first, the fully general kernels otherwise
   int launched = 0;
   if (!e->force_generic) launched = dense ? launch_score_dense_fast(a, s, e->sm_count) : launch_pick_sparse(a, s, e->sm_count);
@@ -595,11 +601,16 @@ int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
   // Cross-stream ordering through an event — skipped while the caller's stream is being captured into a
   // CUDA graph (a captured stream may not take dependencies from outside its capture; in-stream order suffices).
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (st != e->stream) cudaStreamIsCapturing(st, &cap);
+  unsigned long long cap_id = 0;
+  cudaStreamGetCaptureInfo(st, &cap, &cap_id);
+  CK(e, cudaEventRecord(e->ev_snapshot, st));  // inside a capture this becomes a graph edge other captured streams can join on
+  e->snapshot_stream = st;
   if (cap == cudaStreamCaptureStatusNone) {
-    CK(e, cudaEventRecord(e->ev_snapshot, st));
+    e->snapshot_capture_id = 0;
     if (st != e->stream) CK(e, cudaStreamWaitEvent(e->stream, e->ev_snapshot, 0));
     if (!on_device) CK(e, cudaStreamSynchronize(st));  // host arrays may be reused by the caller
+  } else {
+    e->snapshot_capture_id = cap_id;
   }
   e->have_snapshot = true;
   return EPPSCORE_OK;

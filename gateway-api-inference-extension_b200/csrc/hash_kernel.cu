@@ -5,15 +5,19 @@
 namespace eppscore {
 
 // ---------------------------------------------------------------------------------------------
-// hashPrompt for a batch: a CTA of 4 warps owns a tile of 32 requests.
-//   phase 1  all warps, lanes = blocks: the stripe state ("body") of the 32 blocks of one request at a
-//            time — depends on the block's own bytes only, so all of it is parallel;
-//   phase 2  warp 0, lanes = requests: the serial chain (one 8-byte tail round + avalanche per link);
-//   phase 3  all warps, lanes = blocks: coalesced store of each request's 32 hashes.
-// Splitting a tile over 4 warps (instead of one warp per tile) quadruples the warps in flight: at 64K
-// requests a one-warp-per-tile layout leaves only ~14 warps per SM and the kernel was latency bound
-// (profiles/r1_v0_ncu_hash_prompts.txt).  Requests whose block size is not a multiple of 32 or whose
-// start is not 16-byte aligned take the generic serial path in phase 2.
+// hashPrompt for a batch, as two kernels:
+//   hash_bodies_kernel  one lane per (request, block): the stripe state ("body") of a block depends on the
+//                       block's own bytes only (the chain value is just the LAST 8 bytes of each link), so
+//                       this is an embarrassingly parallel stream over the prompts — no barriers, high
+//                       occupancy; it writes the 8-byte body states into the hashes buffer;
+//   hash_chain_kernel   one warp per 32 requests: loads their body states (coalesced) into shared memory,
+//                       runs the serial chain (one 8-byte tail round + avalanche per link, lane = request),
+//                       and stores the hashes back in place (coalesced); also the trailing partial block
+//                       (hashing.go:89-95), the generic path and n_hashes.
+// A single fused kernel (r1_v2) stalled 3 of 4 warps at the barrier around the serial chain
+// (profiles/r1_v4_ncu_hash_pick_prepare.txt: barrier + long-scoreboard stalls, IPC 1.9).
+// Requests whose block size is not a multiple of 32 or whose start is not 16-byte aligned are hashed
+// entirely by the chain kernel's generic serial path.
 // ---------------------------------------------------------------------------------------------
 constexpr int kHashWarps = 4;
 
@@ -44,98 +48,130 @@ __device__ __forceinline__ uint64_t block_body_state(const uint8_t* p, int bc) {
   return xfinish_lanes(v1, v2, v3, v4) + (uint64_t)(bc + 8);
 }
 
+
+struct ReqDesc {
+  const uint8_t* p;
+  uint64_t seed;
+  int nfull, rem;
+  bool fast;
+};
+__device__ __forceinline__ ReqDesc load_desc(const HashArgs& a, int r, int bc) {
+  ReqDesc d;
+  const int64_t o = a.off[r];
+  int64_t len = a.len ? (int64_t)a.len[r] : a.off[r + 1] - o;
+  d.p = a.bytes + o;
+  d.seed = a.seed ? a.seed[r] : 0ULL;
+  d.nfull = 0;
+  d.rem = 0;
+  if (bc > 0 && len >= bc) {                             // hashing.go:51-60
+    const int64_t cap = (int64_t)bc * (int64_t)a.max_blocks;
+    if (len > cap) len = cap;                            // :62-65
+    d.nfull = (int)(len / bc);
+    d.rem = (int)(len - (int64_t)d.nfull * bc);
+  }
+  d.fast = bc > 0 && (bc & 31) == 0 && ((reinterpret_cast<uintptr_t>(d.p) & 15) == 0);
+  return d;
+}
+
+constexpr int kBodyWarps = 8;
+
 template <int BC>
-__global__ void __launch_bounds__(kHashWarps * 32, 8) hash_prompts_kernel(HashArgs a) {
-  __shared__ uint64_t body[32][33];
-  __shared__ unsigned long long s_p[32];
-  __shared__ int s_nfull[32], s_fast[32], s_maxfull;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(kBodyWarps * 32) hash_bodies_kernel(HashArgs a) {
+  const int lane = threadIdx.x & 31;
   const int bc = BC ? BC : a.block_chars;
-  const bool bc_fast = bc > 0 && (bc & 31) == 0;
+  const int gw = blockIdx.x * kBodyWarps + (threadIdx.x >> 5), nw = gridDim.x * kBodyWarps;
+  for (int r = gw; r < a.R; r += nw) {                   // one warp per request, 32 blocks per pass
+    const ReqDesc d = load_desc(a, r, bc);               // same address in every lane: one broadcast load each
+    if (!d.fast) continue;
+    for (int b = lane; b < d.nfull; b += 32)
+      a.hashes[(size_t)r * a.stride + b] = block_body_state<BC>(d.p + (size_t)b * bc, bc);
+  }
+}
+
+__global__ void __launch_bounds__(kHashWarps * 32) hash_chain_kernel(HashArgs a) {
+  __shared__ uint64_t s_body[kHashWarps][32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bc = a.block_chars;
   const int ntiles = (a.R + 31) >> 5;
-
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    // request descriptors (warp 0: lane = request); prev / rem stay in warp 0's registers
+  uint64_t(*body)[33] = s_body[warp];
+  for (int tile = blockIdx.x * kHashWarps + warp; tile < ntiles; tile += gridDim.x * kHashWarps) {
     const int r = tile * 32 + lane;
-    const uint8_t* p = nullptr;
-    uint64_t prev = 0;
-    int nfull = 0, rem = 0;
-    bool fast = false;
-    if (warp == 0) {
-      if (r < a.R) {
-        const int64_t o = a.off[r];
-        int64_t len = a.len ? (int64_t)a.len[r] : a.off[r + 1] - o;
-        p = a.bytes + o;
-        prev = a.seed ? a.seed[r] : 0ULL;
-        if (bc > 0 && len >= bc) {                         // hashing.go:51-60
-          const int64_t cap = (int64_t)bc * (int64_t)a.max_blocks;
-          if (len > cap) len = cap;                        // :62-65
-          nfull = (int)(len / bc);
-          rem = (int)(len - (int64_t)nfull * bc);
-        }
-        fast = bc_fast && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
-      }
-      int maxfull = nfull;
+    ReqDesc d;
+    d.p = nullptr;
+    d.seed = 0;
+    d.nfull = 0;
+    d.rem = 0;
+    d.fast = false;
+    if (r < a.R) d = load_desc(a, r, bc);
+    uint64_t prev = d.seed;
+    int maxfull = d.nfull;
 #pragma unroll
-      for (int o = 16; o; o >>= 1) maxfull = max(maxfull, __shfl_xor_sync(0xffffffffu, maxfull, o));
-      s_p[lane] = (unsigned long long)p;
-      s_nfull[lane] = nfull;
-      s_fast[lane] = fast ? 1 : 0;
-      if (lane == 0) s_maxfull = maxfull;
-    }
-    __syncthreads();
-    const int maxfull = s_maxfull;
-
+    for (int o = 16; o; o >>= 1) maxfull = max(maxfull, __shfl_xor_sync(0xffffffffu, maxfull, o));
     for (int c0 = 0; c0 < maxfull; c0 += 32) {
-      // phase 1
-      for (int q = warp; q < 32; q += kHashWarps) {
-        const int b = c0 + lane;
-        if (s_fast[q] && b < s_nfull[q])
-          body[q][lane] = block_body_state<BC>(reinterpret_cast<const uint8_t*>(s_p[q]) + (size_t)b * bc, bc);
-      }
-      __syncthreads();
-      // phase 2
-      if (warp == 0) {
-        const int nb = min(32, nfull - c0);
-        for (int i = 0; i < nb; i++) {
-          if (fast)
-            prev = xchain_aligned(body[lane][i], prev);
-          else
-            prev = xxh64_link<false>(p + (size_t)(c0 + i) * bc, (uint32_t)bc, prev);  // hashing.go:80-87
-          body[lane][i] = prev;
+      // body states in (coalesced: lanes = blocks of one request); 8 independent loads in flight per lane
+      for (int q0 = 0; q0 < 32; q0 += 8) {
+        uint64_t v[8];
+        bool on[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int q = q0 + u;
+          const int nf_q = __shfl_sync(0xffffffffu, d.nfull, q);
+          const int fast_q = __shfl_sync(0xffffffffu, (int)d.fast, q);
+          const int b = c0 + lane;
+          on[u] = fast_q && b < nf_q;
+          v[u] = on[u] ? a.hashes[(size_t)(tile * 32 + q) * a.stride + b] : 0ULL;
         }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (on[u]) body[q0 + u][lane] = v[u];
       }
-      __syncthreads();
-      // phase 3
-      for (int q = warp; q < 32; q += kHashWarps) {
+      __syncwarp();
+      // the chain (lanes = requests)
+      const int nb = min(32, d.nfull - c0);
+      for (int i = 0; i < nb; i++) {
+        if (d.fast)
+          prev = xchain_aligned(body[lane][i], prev);
+        else
+          prev = xxh64_link<false>(d.p + (size_t)(c0 + i) * bc, (uint32_t)bc, prev);  // hashing.go:80-87
+        body[lane][i] = prev;
+      }
+      __syncwarp();
+      // hashes out (coalesced)
+      for (int q = 0; q < 32; q++) {
+        const int nf_q = __shfl_sync(0xffffffffu, d.nfull, q);
         const int b = c0 + lane;
-        if (tile * 32 + q < a.R && b < s_nfull[q]) a.hashes[(size_t)(tile * 32 + q) * a.stride + b] = body[q][lane];
+        if (tile * 32 + q < a.R && b < nf_q) a.hashes[(size_t)(tile * 32 + q) * a.stride + b] = body[q][lane];
       }
-      __syncthreads();
+      __syncwarp();
     }
-    if (warp == 0 && r < a.R) {
-      if (rem > 0) {                                       // trailing partial block, hashing.go:89-95
-        const uint8_t* t = p + (size_t)nfull * bc;
-        const uint64_t h = ((reinterpret_cast<uintptr_t>(t) & 7) == 0) ? xxh64_link<true>(t, (uint32_t)rem, prev)
-                                                                        : xxh64_link<false>(t, (uint32_t)rem, prev);
-        a.hashes[(size_t)r * a.stride + nfull] = h;
+    if (r < a.R) {
+      if (d.rem > 0) {                                   // trailing partial block, hashing.go:89-95
+        const uint8_t* t = d.p + (size_t)d.nfull * bc;
+        const uint64_t h = ((reinterpret_cast<uintptr_t>(t) & 7) == 0) ? xxh64_link<true>(t, (uint32_t)d.rem, prev)
+                                                                        : xxh64_link<false>(t, (uint32_t)d.rem, prev);
+        a.hashes[(size_t)r * a.stride + d.nfull] = h;
       }
-      a.n_hashes[r] = (uint16_t)(nfull + (rem > 0 ? 1 : 0));
+      a.n_hashes[r] = (uint16_t)(d.nfull + (d.rem > 0 ? 1 : 0));
     }
-    __syncthreads();  // descriptors are rewritten by the next tile
   }
 }
 
 int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
+  int launched = 0;
+  if (a.block_chars > 0 && (a.block_chars & 31) == 0) {
+    long long blocks = ((long long)a.R + kBodyWarps - 1) / kBodyWarps;
+    const long long cap = (long long)sm_count * 64;      // grid-stride beyond a few waves
+    if (blocks > cap) blocks = cap;
+    if (a.block_chars == 64)
+      hash_bodies_kernel<64><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
+    else
+      hash_bodies_kernel<0><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
+    launched++;
+  }
   const int ntiles = (a.R + 31) / 32;
-  (void)sm_count;
-  const int blocks = ntiles;  // one tile per CTA: the hardware scheduler balances the ~1.7 waves better than a static stride
-  if (a.block_chars == 64)
-    hash_prompts_kernel<64><<<blocks, kHashWarps * 32, 0, s>>>(a);
-  else
-    hash_prompts_kernel<0><<<blocks, kHashWarps * 32, 0, s>>>(a);
-  return 1;
+  hash_chain_kernel<<<(ntiles + kHashWarps - 1) / kHashWarps, kHashWarps * 32, 0, s>>>(a);
+  return launched + 1;
 }
 
 }  // namespace eppscore

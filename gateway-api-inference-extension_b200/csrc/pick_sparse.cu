@@ -50,7 +50,7 @@ __device__ __forceinline__ double eval_exception(const ScoreArgs& a, int m, int 
 }
 
 template <int J, typename CNT, uint32_t SEQ>
-__global__ void __launch_bounds__(kSparseWarps * 32) pick_sparse_kernel(const __grid_constant__ ScoreArgs a) {
+__global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const __grid_constant__ ScoreArgs a) {
   const int LOG_EPL = a.geo.log_epl;
   constexpr int RW = J * 32;                       // words per bitset row
   constexpr int G = (RW / 4 < 32) ? RW / 4 : 32;   // lanes per request

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const __grid_co
   }
 }
 
-constexpr int kAdapterThreads = 256;
+constexpr int kAdapterThreads = 1024;  // one endpoint per thread at M = 1024: the kernel is latency bound, not work bound
 
 __global__ void __launch_bounds__(kAdapterThreads) prepare_adapters_kernel(const __grid_constant__ PrepareArgs a) {
   extern __shared__ uint32_t s_u32[];  // [3][row_words]: class lo plane, hi plane, tie mask
