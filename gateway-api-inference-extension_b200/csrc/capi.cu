@@ -420,7 +420,7 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   if (e->cfg.lru_capacity_default <= 0) e->cfg.lru_capacity_default = 31250;
   e->geo = make_geo(e->cfg.max_endpoints);
   e->A_cap = (e->cfg.max_adapters + 63) / 64 * 64;
-  if ((uint64_t)e->cfg.prefix_capacity * (uint64_t)e->geo.row_words >= (1ULL << 32))
+  if (((uint64_t)e->cfg.prefix_capacity + 1) * (uint64_t)e->geo.row_words >= (1ULL << 32))
     return fail(nullptr, EPPSCORE_ERR_CAPACITY, "prefix_capacity * row_words must be < 2^32");
   eppscore_engine* ep = e.get();
   CK(nullptr, cudaSetDevice(device));
@@ -478,9 +478,9 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   ep->index = std::make_unique<PrefixIndex>(ep->geo, ep->cfg.prefix_capacity, ep->cfg.lru_capacity_default);
   const size_t nslots = ep->index->slots().size();
   CK(nullptr, cudaMalloc(&ep->d_slots, nslots * sizeof(Slot)));
-  CK(nullptr, cudaMalloc(&ep->d_rows, (size_t)ep->cfg.prefix_capacity * ep->geo.row_words * 4));
+  CK(nullptr, cudaMalloc(&ep->d_rows, ((size_t)ep->cfg.prefix_capacity + 1) * ep->geo.row_words * 4));
   CK(nullptr, cudaMemsetAsync(ep->d_slots, 0xFF, nslots * sizeof(Slot), ep->stream));
-  CK(nullptr, cudaMemsetAsync(ep->d_rows, 0, (size_t)ep->cfg.prefix_capacity * ep->geo.row_words * 4, ep->stream));
+  CK(nullptr, cudaMemsetAsync(ep->d_rows, 0, ((size_t)ep->cfg.prefix_capacity + 1) * ep->geo.row_words * 4, ep->stream));
   CK(nullptr, ep->probe_out.reserve((size_t)(2 + ep->geo.row_words) * 4));
   CK(nullptr, cudaEventRecord(ep->ev_table, ep->stream));
   CK(nullptr, cudaEventRecord(ep->ev_snapshot, ep->stream));
@@ -893,7 +893,7 @@ int32_t eppscore_prefix_image_adopt(eppscore_engine* e, const int64_t* meta) {
   if (!e || !meta) return EPPSCORE_ERR_INVALID;
   if (meta[0] != (int64_t)e->index->slots().size() || meta[1] != e->geo.row_words)
     return fail(e, EPPSCORE_ERR_INVALID, "image geometry differs (engines must share max_endpoints and prefix_capacity)");
-  if (meta[2] > e->index->capacity_rows()) return fail(e, EPPSCORE_ERR_CAPACITY, "image has more rows than prefix_capacity");
+  if (meta[2] > e->index->capacity_rows() + 1) return fail(e, EPPSCORE_ERR_CAPACITY, "image has more rows than prefix_capacity");
   e->index->adopt_counts(meta[2], meta[3]);
   e->index->clear_dirty();
   e->table_adopted = true;

@@ -91,33 +91,11 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
     for (int q = 0; q < QW; q++) any[q][0] = any[q][1] = any[q][2] = any[q][3] = 0;
 
     // ---------------- matchLongestPrefix: probe U*G hashes per round, stop at the first global miss ----------------
-    // Consecutive blocks of a prompt are usually cached on the SAME endpoints, so consecutive rows are usually
-    // identical: rows are run-length merged (one 128-bit compare per row) and the counters are bumped once per run.
-    uint4 prevw[QW];
-    int run[QW];
-#pragma unroll
-    for (int q = 0; q < QW; q++) {
-      prevw[q] = make_uint4(0u, 0u, 0u, 0u);
-      run[q] = 0;
-    }
-    auto flush = [&](int q) {  // res[server] += run for every server in the run's set (plugin.go:229-231)
-      if (run[q] > 0 && (prevw[q].x | prevw[q].y | prevw[q].z | prevw[q].w)) {
-        const uint32_t ww[4] = {prevw[q].x, prevw[q].y, prevw[q].z, prevw[q].w};
-        const int w0 = (q * G + gl) * 4;
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-          uint32_t x = ww[t];
-          while (x) {
-            const int k = __ffs(x) - 1;
-            x &= x - 1;
-            cnt[(w0 + t) * 32 + k] += (CNT)run[q];
-          }
-        }
-      }
-    };
+    // Hashes whose endpoint sets are identical share ONE interned row (prefix_index.hpp), and consecutive blocks
+    // of a prompt are normally cached on the same endpoints: the hits are run-length merged by row id and each
+    // distinct set is read once, its members' counters bumped by the run length.
     if (have_table) {
       constexpr int U = 4;            // hashes probed per lane per round (independent loads in flight)
-      constexpr int BATCH = (QW == 1) ? 4 : 2;  // row loads in flight per lane
       bool stop = n == 0;
       int c0 = 0;
       while (__any_sync(0xffffffffu, !stop)) {
@@ -166,33 +144,34 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
         for (int u = 0; u < U; u++) {
           int nh_u = nh_total - u * G;
           nh_u = nh_u < 0 ? 0 : (nh_u > G ? G : nh_u);
-          const int maxnh = __reduce_max_sync(0xffffffffu, nh_u);
-          for (int i0 = 0; i0 < maxnh; i0 += BATCH) {
-            uint4 wb[BATCH][QW];
-#pragma unroll
-            for (int b = 0; b < BATCH; b++) {
-              const int i2 = i0 + b;
-              const uint32_t rr = __shfl_sync(0xffffffffu, row[u], gi * G + (i2 < G ? i2 : G - 1));
-#pragma unroll
-              for (int q = 0; q < QW; q++)
-                wb[b][q] = (i2 < nh_u) ? ldg16(a.rows + (size_t)rr * RW + (q * G + gl) * 4) : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t prev_rr = __shfl_up_sync(0xffffffffu, row[u], 1, G);
+          const bool boundary = gl < nh_u && (gl == 0 || row[u] != prev_rr);
+          const uint32_t ball = __ballot_sync(0xffffffffu, boundary);
+          uint32_t bm = (G == 32) ? ball : ((ball >> (gi * G)) & ((1u << G) - 1u));
+          while (__any_sync(0xffffffffu, bm != 0)) {
+            int s0 = 0, len = 0;
+            if (bm) {
+              s0 = __ffs(bm) - 1;
+              bm &= bm - 1;
+              len = (bm ? (__ffs(bm) - 1) : nh_u) - s0;
             }
+            const uint32_t rr = __shfl_sync(0xffffffffu, row[u], gi * G + s0);
+            if (len > 0) {
 #pragma unroll
-            for (int b = 0; b < BATCH; b++) {
-              if (i0 + b < nh_u) {
+              for (int q = 0; q < QW; q++) {
+                const int w0 = (q * G + gl) * 4;
+                const uint4 w = ldg16(a.rows + (size_t)rr * RW + w0);
+                if (w.x | w.y | w.z | w.w) {                     // res[server] += len for every server in the set
+                  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                for (int q = 0; q < QW; q++) {
-                  const uint4 w = wb[b][q];
-                  any[q][0] |= w.x;
-                  any[q][1] |= w.y;
-                  any[q][2] |= w.z;
-                  any[q][3] |= w.w;
-                  if (w.x == prevw[q].x && w.y == prevw[q].y && w.z == prevw[q].z && w.w == prevw[q].w) {
-                    run[q]++;
-                  } else {
-                    flush(q);
-                    prevw[q] = w;
-                    run[q] = 1;
+                  for (int t = 0; t < 4; t++) {
+                    uint32_t x = ww[t];
+                    any[q][t] |= x;
+                    while (x) {
+                      const int k = __ffs(x) - 1;
+                      x &= x - 1;
+                      cnt[(w0 + t) * 32 + k] += (CNT)len;
+                    }
                   }
                 }
               }
@@ -202,8 +181,6 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
         c0 += U * G;
         if (nh_total < U * G || c0 >= n) stop = true;
       }
-#pragma unroll
-      for (int q = 0; q < QW; q++) flush(q);
     }
 
     // ---------------- exceptions: endpoints with a non-zero match count ----------------

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "xxh64.cuh"
 
 namespace eppscore {
 
@@ -178,14 +179,19 @@ class PrefixIndex {
     slots_.assign(c, Slot{~0ULL, kEmptyRow, 0u});
     slot_mask_ = c - 1;
     slot_dirty_flag_.assign(c, 0);
+    // row 0 is the permanent empty set: every new hash starts there (and returns there when emptied)
+    rows_.assign((size_t)geo_.row_words, 0u);
+    row_ref_.assign(1, 1u);
+    n_rows_ = 1;
+    word_dirty_flag_.assign((rows_.size() + 7) / 8, 0);
   }
 
   const Geo& geo() const { return geo_; }
   const std::vector<Slot>& slots() const { return slots_; }
   const std::vector<uint32_t>& rows() const { return rows_; }
   uint64_t slot_mask() const { return slot_mask_; }
-  int64_t n_rows() const { return n_rows_; }
-  int64_t n_keys() const { return n_rows_; }
+  int64_t n_rows() const { return n_rows_; }  // rows ever allocated (high-water mark; row 0 = the empty set)
+  int64_t n_keys() const { return n_keys_; }  // distinct block hashes with a slot
   int64_t n_live() const { return n_live_; }
   int64_t capacity_rows() const { return cap_rows_; }
   int64_t lru_entries() const {
@@ -283,27 +289,97 @@ class PrefixIndex {
       dirty_words_.push_back((uint32_t)wi);
     }
   }
+  // ---- row interning: hashes whose endpoint SETS are identical share one bitset row, so the pick kernel can
+  // run-length merge a request's consecutive matched blocks by row id and read each distinct set once.
+  // (Consecutive blocks of a prompt are normally cached on exactly the same endpoints.)
+  static uint64_t content_hash(const uint32_t* w, int nwords) { return xxh64_host(w, (size_t)nwords * 4, 0x5eed); }
+  bool same_content(uint32_t row, const uint32_t* w) const {
+    return std::memcmp(&rows_[(size_t)row * geo_.row_words], w, (size_t)geo_.row_words * 4) == 0;
+  }
+  void release_row(uint32_t row) {
+    if (row == 0) return;
+    if (--row_ref_[row] == 0) {
+      const uint64_t ch = content_hash(&rows_[(size_t)row * geo_.row_words], geo_.row_words);
+      uint32_t r;
+      if (intern_.get(ch, &r) && r == row) intern_.erase(ch);
+      free_rows_.push_back(row);
+    }
+  }
+  // point slot i at a row holding `content` (the slot's set just changed by one endpoint: bit `pos`)
+  bool assign_content(uint64_t i, const uint32_t* content, uint32_t pos, bool now_empty) {
+    const uint32_t old = slots_[i].row;
+    const int RW = geo_.row_words;
+    if (now_empty) {
+      slots_[i].row = 0;
+      release_row(old);
+      return true;
+    }
+    const uint64_t ch = content_hash(content, RW);
+    uint32_t r;
+    if (intern_.get(ch, &r) && same_content(r, content)) {  // an identical set already has a row: share it
+      row_ref_[r]++;
+      slots_[i].row = r;
+      release_row(old);
+      return true;
+    }
+    const bool clash = intern_.get(ch, &r);  // (64-bit content-hash collision: keep this row un-interned)
+    if (old != 0 && row_ref_[old] == 1) {    // sole owner: mutate in place, only one word changes
+      const uint64_t och = content_hash(&rows_[(size_t)old * RW], RW);
+      uint32_t t;
+      if (intern_.get(och, &t) && t == old) intern_.erase(och);
+      const uint64_t wi = (uint64_t)old * RW + (pos >> 5);
+      rows_[wi] = content[pos >> 5];
+      touch_word(wi);
+      if (!clash) intern_.put(ch, old);
+      return true;
+    }
+    uint32_t nr;
+    if (!free_rows_.empty()) {
+      nr = free_rows_.back();
+      free_rows_.pop_back();
+    } else {
+      if (n_rows_ > cap_rows_) return false;  // live rows <= live hashes <= capacity (+ row 0): cannot happen
+      nr = (uint32_t)n_rows_++;
+      rows_.resize((size_t)n_rows_ * RW, 0u);
+      row_ref_.resize((size_t)n_rows_, 0u);
+      word_dirty_flag_.resize((rows_.size() + 7) / 8, 0);
+    }
+    row_ref_[nr] = 1;
+    for (int w = 0; w < RW; w++) {
+      const uint64_t wi = (uint64_t)nr * RW + w;
+      if (rows_[wi] != content[w]) {
+        rows_[wi] = content[w];
+        touch_word(wi);
+      }
+    }
+    if (!clash) intern_.put(ch, nr);
+    slots_[i].row = nr;
+    release_row(old);
+    return true;
+  }
   bool set_bit(uint64_t h, int32_t endpoint) {
     uint64_t i = h & slot_mask_;
     for (;; i = (i + 1) & slot_mask_) {
-      if (slots_[i].row == kEmptyRow) {  // new hash: claim slot + row
-        if (n_rows_ >= cap_rows_) return false;
+      if (slots_[i].row == kEmptyRow) {  // new hash: claim the slot, start from the empty set
+        if (n_keys_ >= cap_rows_) return false;
         slots_[i].key = h;
-        slots_[i].row = (uint32_t)n_rows_++;
+        slots_[i].row = 0;
         slots_[i].cnt = 0;
-        rows_.resize((size_t)n_rows_ * geo_.row_words, 0u);
-        word_dirty_flag_.resize((rows_.size() + 7) / 8, 0);
+        n_keys_++;
         break;
       }
       if (slots_[i].key == h) break;
     }
+    const int RW = geo_.row_words;
     const uint32_t pos = perm_bitpos((uint32_t)endpoint, geo_.log_epl);
-    const uint64_t wi = (uint64_t)slots_[i].row * geo_.row_words + (pos >> 5);
     const uint32_t bit = 1u << (pos & 31);
-    if (!(rows_[wi] & bit)) {
-      rows_[wi] |= bit;
+    const uint32_t* cur = &rows_[(size_t)slots_[i].row * RW];
+    if (!(cur[pos >> 5] & bit)) {
+      uint32_t tmp[256];
+      std::memcpy(tmp, cur, (size_t)RW * 4);
+      tmp[pos >> 5] |= bit;
+      if (!assign_content(i, tmp, pos, false)) return false;
       if (slots_[i].cnt++ == 0) n_live_++;
-      touch_word(wi);
     }
     touch_slot(i);
     return true;
@@ -311,23 +387,30 @@ class PrefixIndex {
   void clear_bit(uint64_t h, int32_t endpoint) {
     const int64_t i = find(h);
     if (i < 0) return;
+    const int RW = geo_.row_words;
     const uint32_t pos = perm_bitpos((uint32_t)endpoint, geo_.log_epl);
-    const uint64_t wi = (uint64_t)slots_[i].row * geo_.row_words + (pos >> 5);
     const uint32_t bit = 1u << (pos & 31);
-    if (rows_[wi] & bit) {
-      rows_[wi] &= ~bit;
+    const uint32_t* cur = &rows_[(size_t)slots_[i].row * RW];
+    if (cur[pos >> 5] & bit) {
+      uint32_t tmp[256];
+      std::memcpy(tmp, cur, (size_t)RW * 4);
+      tmp[pos >> 5] &= ~bit;
+      const bool now_empty = slots_[i].cnt == 1;
+      assign_content((uint64_t)i, tmp, pos, now_empty);  // cannot fail: the row pool holds capacity + 1 rows
       if (--slots_[i].cnt == 0) n_live_--;
-      touch_word(wi);
       touch_slot((uint64_t)i);
     }
   }
 
   Geo geo_;
   int32_t default_lru_;
-  int64_t cap_rows_ = 0, n_rows_ = 0, n_live_ = 0;
+  int64_t cap_rows_ = 0, n_rows_ = 0, n_keys_ = 0, n_live_ = 0;
   uint64_t slot_mask_ = 0;
   std::vector<Slot> slots_;
   std::vector<uint32_t> rows_;
+  std::vector<uint32_t> row_ref_;    // slots pointing at each row
+  std::vector<uint32_t> free_rows_;
+  FlatMap64 intern_{1024};           // content hash -> row id
   std::vector<std::unique_ptr<LruSet>> lru_;
   std::vector<uint32_t> dirty_slots_, dirty_words_;
   std::vector<uint8_t> slot_dirty_flag_, word_dirty_flag_;
