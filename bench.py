@@ -451,7 +451,14 @@ def run_gpu(args):
             (e or eng).schedule(R, hashes_in=hh, n_hashes_in=nn, hash_stride=MAX_BLOCKS, adapter_id=dsets[i % NSETS]["adapters"],
                                 request_base=rank * R, device=True, stream=sptr, out=out)
 
-        t_hash = time_kernel(hash_only)
+        eng.set_debug(2, 1)                     # diagnostics knob: body kernel only
+        t_bodies = time_kernel(hash_only)
+        eng.set_debug(2, 2)                     # chain kernel only (re-chains the buffer in place: same work)
+        t_chain = time_kernel(hash_only)
+        eng.set_debug(2, 3)
+        for i in range(NSETS):                  # restore real hashes for the pick-only timing below
+            hash_only(i)
+            hsets_dev[i] = (hashes.clone(), nh.clone())
         t_pick = time_kernel(pick_only)
         t_prep = time_kernel(lambda i: apply_snapshot(eng))
         nhv = hsets_dev[0][1].cpu().numpy().astype(np.int64)
@@ -461,29 +468,32 @@ def run_gpu(args):
         hits = float(res_m["match_blocks"].max(axis=1).mean())
         exc = float((res_m["match_blocks"] > 0).sum(axis=1).mean())
         row_bytes = eng.cfg.max_endpoints // 8  # one bitset row (M bits)
-        # algorithmic bytes: hashes + slot probes + matched rows + adapter + summary + outputs
-        bytes_pick = R * (B * 8 + min(B, hits + 1) * 16 + hits * row_bytes + 2 + 4 + 16 + 16)
-        bytes_hash = float(sets[0]["off"][R]) + R * (8 + 8 + B * 8 + 2)
+        runs = float(np.ceil(hits / 8.0))       # identical consecutive sets are interned: one row read per run of <= 8 hits
+        # algorithmic bytes per launch
+        plen = float(sets[0]["off"][R])
+        bytes_bodies = plen + R * 16 + R * B * 8                       # prompts + offsets in, body states out
+        bytes_chain = R * (2 * B * 8 + 8 + 16 + 2)                     # body states in, hashes out, seed, offsets, count
+        bytes_pick = R * (B * 8 + B * 16 + runs * row_bytes + 2 + 4 + 16 + 16)  # hashes, slot probes, set rows, adapter, summary, outputs
         bytes_prep = M * (8 + 8 + 8 + 8 + 8 + 4 + 4) + M * 8 * 3 + (A + 1) * (2 * row_bytes + 16 + row_bytes)
-        kern = {"hash_prompts_kernel": (t_hash, bytes_hash), "pick_sparse_kernel": (t_pick, bytes_pick),
-                "prepare_snapshot (2 kernels)": (t_prep, bytes_prep)}
-        extra["kernels"] = {k: {"us": t * 1e6, "algorithmic_bytes": b, "gbs": b / t / 1e9, "frac_of_peak": b / t / 1e9 / peak}
+        kern = {"hash_bodies_kernel": (t_bodies, bytes_bodies), "hash_chain_kernel": (t_chain, bytes_chain),
+                "pick_sparse_kernel": (t_pick, bytes_pick), "prepare_snapshot (2 kernels, side stream)": (t_prep, bytes_prep)}
+        extra["kernels"] = {k: {"us": t * 1e6, "algorithmic_bytes": b, "gbs": b / t / 1e9, "frac_of_peak": b / t / 1e9 / peak,
+                                "traffic": traffic.get(k.split(" ")[0])}
                             for k, (t, b) in kern.items()}
         extra["kernels"]["avg_blocks_per_request"] = B
         extra["kernels"]["avg_matched_blocks"] = hits
         extra["kernels"]["avg_endpoints_with_match"] = exc
-        dom = max(("hash_prompts_kernel", "pick_sparse_kernel"), key=lambda k: kern[k][0])
+        dom = max(("hash_bodies_kernel", "hash_chain_kernel", "pick_sparse_kernel"), key=lambda k: kern[k][0])
         t_dom, b_dom = kern[dom]
         extra["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": b_dom / t_dom / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": b_dom / t_dom / 1e9 / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": b_dom, "us_per_launch": t_dom * 1e6,
-                             "share_of_step": t_dom / (t_hash + t_pick + t_prep)}
+                             "share_of_step": t_dom / (t_bodies + t_chain + t_pick)}
 
         # ---- the fully general R x M evaluation (every pair scored; what masks / diagnostics use) ----
         try:
-            os.environ["EPPSCORE_FORCE_GENERIC"] = "1"
             eng_g = make_engine()
-            os.environ.pop("EPPSCORE_FORCE_GENERIC")
+            eng_g.set_debug(1, 1)               # diagnostics knob: always the fully general kernels
             apply_snapshot(eng_g)
             eng_g.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
             t_gen = time_kernel(lambda i: pick_only(i, eng_g), iters=10)
@@ -492,7 +502,6 @@ def run_gpu(args):
             eng_g.close()
         except Exception as ex:  # noqa: BLE001
             extra["generic_full_matrix"] = {"error": str(ex)}
-            os.environ.pop("EPPSCORE_FORCE_GENERIC", None)
 
         # ---- dense-row mode (R x M float4 feature rows streamed from HBM): reported beside the headline ----
         try:

@@ -62,6 +62,7 @@ ABI_SYMBOLS = [
     ("eppscore_destroy", None, [_P]),
     ("eppscore_last_error", C.c_char_p, [_P]),
     ("eppscore_get_stats", C.c_int32, [_P, C.POINTER(Stats)]),
+    ("eppscore_set_debug", C.c_int32, [_P, C.c_int32, C.c_int64]),
     ("eppscore_set_snapshot", C.c_int32, [_P, C.POINTER(Snapshot)]),
     ("eppscore_schedule_batch", C.c_int32, [_P, C.POINTER(Batch)]),
     ("eppscore_hash_prompts", C.c_int32, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),

@@ -63,7 +63,8 @@ struct eppscore_engine {
   unsigned long long snapshot_capture_id = 0;    // != 0: ev_snapshot was recorded inside that CUDA-graph capture
   std::string err;
   uint64_t launches = 0;
-  bool force_generic = false;  // EPPSCORE_FORCE_GENERIC=1: skip the specialised kernels (A/B tests, profiling)
+  bool force_generic = false;  // EPPSCORE_FORCE_GENERIC=1 / eppscore_set_debug(1): skip the specialised kernels
+  int32_t hash_stage_mask = 3;  // eppscore_set_debug(2): profiling only
 
   // snapshot
   bool have_snapshot = false;
@@ -83,6 +84,7 @@ struct eppscore_engine {
   Slot* d_slots = nullptr;
   uint32_t* d_rows = nullptr;
   bool table_adopted = false;
+  int64_t dev_capacity = 0;  // capacity (hashes) the device slot/row buffers were allocated for
   DevBuf st_idx, st_val, st_slot;
   DevBuf probe_out;
 
@@ -187,6 +189,19 @@ int32_t flush_table(eppscore_engine* e) {
   PrefixIndex* ix = e->index.get();
   if (!ix || e->table_adopted) return EPPSCORE_OK;
   if (!ix->full_upload_needed() && ix->dirty_slots().empty() && ix->dirty_words().empty()) return EPPSCORE_OK;
+  if (ix->capacity_rows() != e->dev_capacity) {  // the host index grew: reallocate the device table, then upload it all
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (e->d_slots) cudaFree(e->d_slots);
+    if (e->d_rows) cudaFree(e->d_rows);
+    e->d_slots = nullptr;
+    e->d_rows = nullptr;
+    const size_t rb = ((size_t)ix->capacity_rows() + 1) * e->geo.row_words * 4;
+    CK(e, cudaMalloc(&e->d_slots, ix->slots().size() * sizeof(Slot)));
+    CK(e, cudaMalloc(&e->d_rows, rb));
+    CK(e, cudaMemsetAsync(e->d_rows, 0, rb, e->stream));
+    e->dev_capacity = ix->capacity_rows();
+    ix->mark_full_upload();
+  }
   const size_t nrow_words = ix->rows().size();
   const size_t nds = ix->dirty_slots().size(), ndw = ix->dirty_words().size();
   const bool full = ix->full_upload_needed() || (nds + ndw) * 8 > ix->slots().size() + nrow_words;
@@ -328,6 +343,7 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
         h.hashes = hashes;
         h.stride = mb;
         h.n_hashes = e->s_nh.as<uint16_t>();
+        h.stage_mask = e->hash_stage_mask;
         e->launches += launch_hash_prompts(h, s, e->sm_count);
         a.hashes = hashes;
         a.n_hashes = h.n_hashes;
@@ -481,6 +497,7 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   CK(nullptr, cudaMalloc(&ep->d_rows, ((size_t)ep->cfg.prefix_capacity + 1) * ep->geo.row_words * 4));
   CK(nullptr, cudaMemsetAsync(ep->d_slots, 0xFF, nslots * sizeof(Slot), ep->stream));
   CK(nullptr, cudaMemsetAsync(ep->d_rows, 0, ((size_t)ep->cfg.prefix_capacity + 1) * ep->geo.row_words * 4, ep->stream));
+  ep->dev_capacity = ep->index->capacity_rows();
   CK(nullptr, ep->probe_out.reserve((size_t)(2 + ep->geo.row_words) * 4));
   CK(nullptr, cudaEventRecord(ep->ev_table, ep->stream));
   CK(nullptr, cudaEventRecord(ep->ev_snapshot, ep->stream));
@@ -525,6 +542,19 @@ int32_t eppscore_get_stats(const eppscore_engine* e, eppscore_stats* out) {
                             (int64_t)e->index->n_rows() * e->geo.row_words * 4;
   out->lru_entries = e->index->lru_entries();
   return EPPSCORE_OK;
+}
+
+int32_t eppscore_set_debug(eppscore_engine* e, int32_t key, int64_t value) {
+  if (!e) return EPPSCORE_ERR_INVALID;
+  if (key == 1) {
+    e->force_generic = value != 0;
+    return EPPSCORE_OK;
+  }
+  if (key == 2) {
+    e->hash_stage_mask = (int32_t)(value & 3);
+    return EPPSCORE_OK;
+  }
+  return fail(e, EPPSCORE_ERR_INVALID, "unknown debug key");
 }
 
 int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
@@ -735,6 +765,7 @@ int32_t eppscore_hash_prompts(eppscore_engine* e, int32_t R, int32_t location, c
   h.block_chars = bc;
   h.max_blocks = mb;
   h.stride = mb;
+  h.stage_mask = e->hash_stage_mask;
   if (location == 1) {
     h.bytes = prompt_bytes;
     h.off = prompt_off;
@@ -793,7 +824,7 @@ int32_t eppscore_commit_picks(eppscore_engine* e, int32_t R, const int32_t* pick
     if (ep >= e->geo.Mpad) return fail(e, EPPSCORE_ERR_INVALID, "pick out of range");
     const int32_t cap = lru_capacity ? lru_capacity[ep] : 0;  // makeserver, plugin.go:207-216
     if (!e->index->add(hashes + (size_t)r * hash_stride, n_hashes[r], ep, cap))
-      return fail(e, EPPSCORE_ERR_CAPACITY, "prefix table full (raise config.prefix_capacity)");
+      return fail(e, EPPSCORE_ERR_CAPACITY, "prefix table cannot grow further (row index space exhausted)");
   }
   return EPPSCORE_OK;
 }

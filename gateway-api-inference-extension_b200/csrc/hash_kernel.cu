@@ -88,63 +88,80 @@ __global__ void __launch_bounds__(kBodyWarps * 32) hash_bodies_kernel(HashArgs a
   }
 }
 
+// One CTA (4 warps) per tile of 64 requests: all warps move the tile in and out (16 requests each, loads
+// batched), warps 0 and 1 run the 64 serial chains (lane = request).  The kernel is latency bound (each
+// link is ~35 dependent integer instructions), so the point is to keep many independent chains in flight
+// per SM while keeping each tile's critical path short.
+constexpr int kChainWarps = 2;                  // warps that run chains
+constexpr int kTileReq = 32 * kChainWarps;      // requests per tile
+constexpr int kMoveReq = kTileReq / kHashWarps; // requests each warp moves
+
 __global__ void __launch_bounds__(kHashWarps * 32) hash_chain_kernel(HashArgs a) {
-  __shared__ uint64_t s_body[kHashWarps][32][33];
+  __shared__ uint64_t body[kTileReq][33];
+  __shared__ int s_nfull[kTileReq], s_fast[kTileReq], s_maxfull[kChainWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bc = a.block_chars;
-  const int ntiles = (a.R + 31) >> 5;
-  uint64_t(*body)[33] = s_body[warp];
-  for (int tile = blockIdx.x * kHashWarps + warp; tile < ntiles; tile += gridDim.x * kHashWarps) {
-    const int r = tile * 32 + lane;
+  const int ntiles = (a.R + kTileReq - 1) / kTileReq;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int base = tile * kTileReq;
+    const int r = base + warp * 32 + lane;  // meaningful for the chain warps only
     ReqDesc d;
     d.p = nullptr;
     d.seed = 0;
     d.nfull = 0;
     d.rem = 0;
     d.fast = false;
-    if (r < a.R) d = load_desc(a, r, bc);
-    uint64_t prev = d.seed;
-    int maxfull = d.nfull;
+    if (warp < kChainWarps) {
+      if (r < a.R) d = load_desc(a, r, bc);
+      int maxfull = d.nfull;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) maxfull = max(maxfull, __shfl_xor_sync(0xffffffffu, maxfull, o));
+      for (int o = 16; o; o >>= 1) maxfull = max(maxfull, __shfl_xor_sync(0xffffffffu, maxfull, o));
+      s_nfull[warp * 32 + lane] = d.nfull;
+      s_fast[warp * 32 + lane] = d.fast ? 1 : 0;
+      if (lane == 0) s_maxfull[warp] = maxfull;
+    }
+    __syncthreads();
+    uint64_t prev = d.seed;
+    int maxfull = 0;
+#pragma unroll
+    for (int w = 0; w < kChainWarps; w++) maxfull = max(maxfull, s_maxfull[w]);
     for (int c0 = 0; c0 < maxfull; c0 += 32) {
-      // body states in (coalesced: lanes = blocks of one request); 8 independent loads in flight per lane
-      for (int q0 = 0; q0 < 32; q0 += 8) {
+      // body states in (coalesced: lanes = blocks of one request); this warp's requests, 8 loads in flight
+#pragma unroll
+      for (int u0 = 0; u0 < kMoveReq; u0 += 8) {
         uint64_t v[8];
         bool on[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-          const int q = q0 + u;
-          const int nf_q = __shfl_sync(0xffffffffu, d.nfull, q);
-          const int fast_q = __shfl_sync(0xffffffffu, (int)d.fast, q);
-          const int b = c0 + lane;
-          on[u] = fast_q && b < nf_q;
-          v[u] = on[u] ? a.hashes[(size_t)(tile * 32 + q) * a.stride + b] : 0ULL;
+          const int q = warp + (u0 + u) * kHashWarps, b = c0 + lane;
+          on[u] = s_fast[q] && b < s_nfull[q];
+          v[u] = on[u] ? a.hashes[(size_t)(base + q) * a.stride + b] : 0ULL;
         }
 #pragma unroll
         for (int u = 0; u < 8; u++)
-          if (on[u]) body[q0 + u][lane] = v[u];
+          if (on[u]) body[warp + (u0 + u) * kHashWarps][lane] = v[u];
       }
-      __syncwarp();
-      // the chain (lanes = requests)
-      const int nb = min(32, d.nfull - c0);
-      for (int i = 0; i < nb; i++) {
-        if (d.fast)
-          prev = xchain_aligned(body[lane][i], prev);
-        else
-          prev = xxh64_link<false>(d.p + (size_t)(c0 + i) * bc, (uint32_t)bc, prev);  // hashing.go:80-87
-        body[lane][i] = prev;
+      __syncthreads();
+      if (warp < kChainWarps) {  // the chain (lanes = requests)
+        uint64_t(*mine)[33] = body + warp * 32;
+        const int nb = min(32, d.nfull - c0);
+        for (int i = 0; i < nb; i++) {
+          if (d.fast)
+            prev = xchain_aligned(mine[lane][i], prev);
+          else
+            prev = xxh64_link<false>(d.p + (size_t)(c0 + i) * bc, (uint32_t)bc, prev);  // hashing.go:80-87
+          mine[lane][i] = prev;
+        }
       }
-      __syncwarp();
-      // hashes out (coalesced)
-      for (int q = 0; q < 32; q++) {
-        const int nf_q = __shfl_sync(0xffffffffu, d.nfull, q);
-        const int b = c0 + lane;
-        if (tile * 32 + q < a.R && b < nf_q) a.hashes[(size_t)(tile * 32 + q) * a.stride + b] = body[q][lane];
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < kMoveReq; u++) {  // hashes out (coalesced)
+        const int q = warp + u * kHashWarps, b = c0 + lane;
+        if (base + q < a.R && b < s_nfull[q]) a.hashes[(size_t)(base + q) * a.stride + b] = body[q][lane];
       }
-      __syncwarp();
+      __syncthreads();
     }
-    if (r < a.R) {
+    if (warp < kChainWarps && r < a.R) {
       if (d.rem > 0) {                                   // trailing partial block, hashing.go:89-95
         const uint8_t* t = d.p + (size_t)d.nfull * bc;
         const uint64_t h = ((reinterpret_cast<uintptr_t>(t) & 7) == 0) ? xxh64_link<true>(t, (uint32_t)d.rem, prev)
@@ -153,13 +170,15 @@ __global__ void __launch_bounds__(kHashWarps * 32) hash_chain_kernel(HashArgs a)
       }
       a.n_hashes[r] = (uint16_t)(d.nfull + (d.rem > 0 ? 1 : 0));
     }
+    __syncthreads();  // the tile descriptors are rewritten by the next tile
   }
 }
 
 int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
   int launched = 0;
-  if (a.block_chars > 0 && (a.block_chars & 31) == 0) {
+  const int stages = a.stage_mask ? a.stage_mask : 3;
+  if ((stages & 1) && a.block_chars > 0 && (a.block_chars & 31) == 0) {
     long long blocks = ((long long)a.R + kBodyWarps - 1) / kBodyWarps;
     const long long cap = (long long)sm_count * 64;      // grid-stride beyond a few waves
     if (blocks > cap) blocks = cap;
@@ -169,8 +188,9 @@ int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
       hash_bodies_kernel<0><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
     launched++;
   }
-  const int ntiles = (a.R + 31) / 32;
-  hash_chain_kernel<<<(ntiles + kHashWarps - 1) / kHashWarps, kHashWarps * 32, 0, s>>>(a);
+  if (!(stages & 2)) return launched;
+  const int ntiles = (a.R + kTileReq - 1) / kTileReq;
+  hash_chain_kernel<<<ntiles, kHashWarps * 32, 0, s>>>(a);
   return launched + 1;
 }
 

@@ -136,6 +136,7 @@ struct HashArgs {
   uint64_t* hashes;         // [R][stride]
   int32_t stride;
   uint16_t* n_hashes;       // [R]
+  int32_t stage_mask;       // diagnostics: bit 0 body kernel, bit 1 chain kernel (0 => both)
 };
 
 struct PrepareArgs {

@@ -289,6 +289,28 @@ class PrefixIndex {
       dirty_words_.push_back((uint32_t)wi);
     }
   }
+  // Double the capacity: re-insert every slot into a table twice the size (rows keep their ids); the engine
+  // notices the new capacity, reallocates the device buffers and uploads the whole mirror.
+  bool grow() {
+    if (((uint64_t)cap_rows_ * 2 + 1) * (uint64_t)geo_.row_words >= (1ULL << 32)) return false;  // 32-bit word indices
+    std::vector<Slot> old;
+    old.swap(slots_);
+    const uint64_t c = (slot_mask_ + 1) * 2;
+    slots_.assign(c, Slot{~0ULL, kEmptyRow, 0u});
+    slot_mask_ = c - 1;
+    slot_dirty_flag_.assign(c, 0);
+    dirty_slots_.clear();
+    for (const Slot& sl : old) {
+      if (sl.row == kEmptyRow) continue;
+      uint64_t i = sl.key & slot_mask_;
+      while (slots_[i].row != kEmptyRow) i = (i + 1) & slot_mask_;
+      slots_[i] = sl;
+    }
+    cap_rows_ *= 2;
+    full_upload_ = true;
+    return true;
+  }
+
   // ---- row interning: hashes whose endpoint SETS are identical share one bitset row, so the pick kernel can
   // run-length merge a request's consecutive matched blocks by row id and read each distinct set once.
   // (Consecutive blocks of a prompt are normally cached on exactly the same endpoints.)
@@ -361,7 +383,10 @@ class PrefixIndex {
     uint64_t i = h & slot_mask_;
     for (;; i = (i + 1) & slot_mask_) {
       if (slots_[i].row == kEmptyRow) {  // new hash: claim the slot, start from the empty set
-        if (n_keys_ >= cap_rows_) return false;
+        if (n_keys_ >= cap_rows_) {
+          if (!grow()) return false;
+          return set_bit(h, endpoint);  // re-probe in the doubled table
+        }
         slots_[i].key = h;
         slots_[i].row = 0;
         slots_[i].cnt = 0;

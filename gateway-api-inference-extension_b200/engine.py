@@ -94,6 +94,9 @@ class Engine:
         self._check(self._lib.eppscore_get_stats(self._h, C.byref(s)))
         return s
 
+    def set_debug(self, key: int, value: int):
+        self._check(self._lib.eppscore_set_debug(self._h, key, value))
+
     # ------------------------------------------------------------------ snapshot
     def set_snapshot(self, kv_usage, queue, running=None, lora_active=None, lora_waiting=None, lora_nmodels=None,
                      lora_max=None, endpoint_cols=(), epoch=0, device=False, stream=None, M=None, lora_words=None):

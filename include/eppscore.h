@@ -86,7 +86,7 @@ typedef struct eppscore_config {
   uint64_t tie_seed;
   int32_t max_endpoints;   /* capacity for M (rounded up internally); default 1024 */
   int32_t max_adapters;    /* capacity for the LoRA adapter dictionary A; default 64 */
-  int64_t prefix_capacity; /* max distinct block hashes resident in the device table; default 1<<20 */
+  int64_t prefix_capacity; /* INITIAL capacity (distinct block hashes) of the device table; it doubles on demand. default 1<<18 */
   int32_t lru_capacity_default; /* defaultLRUCapacityPerServer = 31250 (types.go:109) */
 } eppscore_config;
 
@@ -168,6 +168,10 @@ int32_t eppscore_create(int32_t device, const eppscore_config *cfg, struct eppsc
 void eppscore_destroy(struct eppscore_engine *e);
 const char *eppscore_last_error(const struct eppscore_engine *e); /* e may be NULL: last create() error */
 int32_t eppscore_get_stats(const struct eppscore_engine *e, eppscore_stats *out);
+/* Diagnostics knobs (profiling / A-B runs only; never needed for correct operation):
+ *   key 1: 1 = always use the fully general kernels (same as env EPPSCORE_FORCE_GENERIC=1), 0 = normal dispatch;
+ *   key 2: hash stage mask — bit 0 run the body kernel, bit 1 run the chain kernel (default 3 = both). */
+int32_t eppscore_set_debug(struct eppscore_engine *e, int32_t key, int64_t value);
 
 /* ---- snapshot (replaces the per-request deep clone, director.go:342-349) ---- */
 int32_t eppscore_set_snapshot(struct eppscore_engine *e, const eppscore_snapshot *s);

@@ -512,6 +512,31 @@ def test_sparse_path_full_256_block_match(pkg):
     eng.close()
 
 
+def test_prefix_table_grows_on_device(pkg):
+    """prefix_capacity is only the INITIAL size: the table doubles (host mirror re-hashed, device buffers
+    reallocated and re-uploaded) and results stay identical to the oracle."""
+    M, R = 200, 1500
+    scorers = [("queue", 2), ("kv", 2), ("prefix", 3)]
+    eng = make_engine(pkg, scorers, M, prefix_capacity=32)
+    sd = synth_snapshot(M, seed=21)
+    eng.set_snapshot(**sd)
+    snap, prof, idx = o.SnapshotData(**sd), profile_of(pkg, scorers), o.Index()
+    prompts, off, _ = synth_prompts(R, prompt_len=1024, groups=12, shared=512, seed=21)
+    seeds = np.full(R, eng.model_seed("grow"), np.uint64)
+    kw = dict(prompt_bytes=prompts, prompt_off=off, model_seed=seeds)
+    for rnd in range(2):
+        got = eng.schedule(R, want_hashes=True, **kw)
+        want = o.schedule_batch(snap, prof, idx, R, want_hashes=True, n_threads=8, **kw)
+        assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks"))
+        eng.commit_picks(got["pick"], got["hashes_out"], got["total_blocks"])
+        idx.commit(want["pick"], want["hashes_out"], want["total_blocks"])
+    st = eng.stats()
+    assert st.prefix_capacity >= 8192 and st.prefix_live_hashes == idx.num_hashes() > 32
+    h0 = int(got["hashes_out"][5, 0])
+    assert eng.prefix_get(h0) == idx.get(h0) and len(idx.get(h0)) >= 1
+    eng.close()
+
+
 def test_hashes_in_path_and_small_blocks(pkg):
     """Pre-hashed input (a host that hashes itself) and the generic (block_chars=4, unaligned) hash path."""
     M, R = 128, 600
