@@ -497,11 +497,29 @@ def run_gpu(args):
             apply_snapshot(eng_g)
             eng_g.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
             t_gen = time_kernel(lambda i: pick_only(i, eng_g), iters=10)
-            extra["generic_full_matrix"] = {"kernel": "score_pick_fused_kernel", "us": t_gen * 1e6, "picks_per_s": R / t_gen,
+            extra["generic_full_matrix"] = {"kernel": "score_matrix_kernel<E,P,L>", "us": t_gen * 1e6, "picks_per_s": R / t_gen,
                                             "pairs_per_s": R * M / t_gen}
             eng_g.close()
         except Exception as ex:  # noqa: BLE001
             extra["generic_full_matrix"] = {"error": str(ex)}
+
+        # ---- candidate masks (the Filter chain's result): every pair scored, per-row queue min/max ----
+        try:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(5)
+            cmask = torch.randint(0, 2 ** 31 - 1, (R, M // 32), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+            cmask = (cmask ^ (cmask << 1)).contiguous()  # ~50 % of the endpoints are candidates of each request
+
+            def masked_only(i):
+                hh, nn = hsets_dev[i % NSETS]
+                eng.schedule(R, hashes_in=hh, n_hashes_in=nn, hash_stride=MAX_BLOCKS, adapter_id=dsets[i % NSETS]["adapters"],
+                             cand_mask=cmask, request_base=rank * R, device=True, stream=sptr, out=out)
+
+            t_msk = time_kernel(masked_only, iters=10)
+            extra["masked_full_matrix"] = {"kernel": "score_matrix_kernel<Q,E,P,L; masked>", "us": t_msk * 1e6, "picks_per_s": R / t_msk,
+                                           "pairs_per_s": R * M / t_msk, "candidates_per_request": "~50 % random"}
+        except Exception as ex:  # noqa: BLE001
+            extra["masked_full_matrix"] = {"error": str(ex)}
 
         # ---- dense-row mode (R x M float4 feature rows streamed from HBM): reported beside the headline ----
         try:

@@ -174,6 +174,7 @@ struct PrepareArgs {
 int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count);
 int launch_prepare_snapshot(const PrepareArgs& a, cudaStream_t s);
 int launch_score_pick(const ScoreArgs& a, bool dense, cudaStream_t s, int sm_count);   // generic (any plan, masks, diagnostics)
+int launch_score_matrix(const ScoreArgs& a, cudaStream_t s, int sm_count);             // every pair scored (masks, diagnostics)
 int launch_score_dense_fast(const ScoreArgs& a, cudaStream_t s, int sm_count);         // 0 if no specialisation applies
 int launch_pick_sparse(const ScoreArgs& a, cudaStream_t s, int sm_count);              // 0 if not applicable
 int launch_scatter_u32(uint32_t* dst, const uint32_t* idx, const uint32_t* val, int64_t n, cudaStream_t s);

@@ -1,8 +1,6 @@
-// score_generic.cu — the fully general Score+Pick kernels: any scorer order, candidate masks, pair
-// columns, diagnostics outputs (match_out / scores_out).  One warp per request; every (request,
-// endpoint) pair is evaluated.  The specialised fast paths live in score_dense.cu (streaming float4
-// rows) and pick_sparse.cu (per-adapter summaries + per-request exceptions); this file is their
-// fallback and the reference point the fast paths are tested against.
+// score_generic.cu — the fully general DENSE-ROW Score+Pick kernel: any scorer order, candidate masks,
+// pair columns, diagnostics outputs, runtime step dispatch.  It is the fallback of score_dense.cu's
+// specialised streaming kernels; the full-matrix kernel for prompt-driven batches is score_matrix.cu.
 //   matchLongestPrefix  approximateprefix/plugin.go:219-235
 //   scorers + sum       scheduler_profile.go:151-174 (+ the four Score bodies)
 //   picker              maxscore/picker.go:87-115
@@ -14,208 +12,6 @@ namespace eppscore {
 // Score + Pick
 // ---------------------------------------------------------------------------------------------
 constexpr int kScoreWarps = 8;
-
-template <int LOG_EPL, int J, int NP, bool MASKED>
-__global__ void __launch_bounds__(kScoreWarps * 32) score_pick_fused_kernel(const __grid_constant__ ScoreArgs a) {
-  constexpr int EPL = 1 << LOG_EPL;
-  constexpr int MPAD = J * 32 * EPL;
-  constexpr int RW = J * 32;
-  constexpr int MASKW = (J * EPL + 31) / 32;  // registers holding this row's candidate mask words
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Plan& plan = a.plan;
-  double* s_term = reinterpret_cast<double*>(smem_raw);                       // [n_terms][MPAD]
-  long long* s_q = reinterpret_cast<long long*>(s_term + (size_t)plan.n_terms * MPAD);  // MASKED: [2][MPAD]
-  double* s_lut = reinterpret_cast<double*>(s_q + (MASKED ? 2 * MPAD : 0));   // [warps][kLutMax+1]
-  const int M = a.geo.M;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  // stage the endpoint tile once per CTA
-  for (int t = 0; t < plan.n_terms; t++)
-    for (int m = threadIdx.x; m < MPAD; m += blockDim.x) s_term[(size_t)t * MPAD + m] = a.term[t][m];
-  if (MASKED) {
-    for (int which = 0; which < 2; which++)
-      for (int m = threadIdx.x; m < MPAD; m += blockDim.x)
-        s_q[which * MPAD + m] = (a.minmax_q[which] && m < M) ? a.minmax_q[which][m] : 0;
-  }
-  __syncthreads();
-
-  double* lut = s_lut + warp * (kLutMax + 1);
-  int lut_total = -1;
-  int prefix_step = -1;
-  bool has_minmax[2] = {false, false};
-  for (int s = 0; s < plan.n_steps; s++) {
-    if (plan.kind[s] == STEP_PREFIX && prefix_step < 0) prefix_step = s;
-    if (plan.kind[s] == STEP_MINMAX) has_minmax[plan.arg[s]] = true;
-  }
-  const bool want_prefix = prefix_step >= 0 || a.match_out != nullptr;
-  const int tie_mode = plan.tie_mode;
-
-  const int gw = blockIdx.x * kScoreWarps + warp, nw = gridDim.x * kScoreWarps;
-  for (int r = gw; r < a.R; r += nw) {
-    // ---------------- matchLongestPrefix (plugin.go:219-235) into bit-sliced counters ----------------
-    uint32_t P[J][NP];
-#pragma unroll
-    for (int j = 0; j < J; j++)
-#pragma unroll
-      for (int p = 0; p < NP; p++) P[j][p] = 0;
-    int total = 0;
-    if (want_prefix && a.hashes) {
-      const int n = a.n_hashes[r];
-      total = n;
-      bool stop = false;
-      for (int c0 = 0; c0 < n && !stop; c0 += 32) {
-        const int i = c0 + lane;
-        uint32_t row = kEmptyRow;
-        if (i < n && a.slots) {
-          const uint64_t h = a.hashes[(size_t)r * a.hash_stride + i];
-          uint64_t idx = h & a.slot_mask;
-          for (;;) {                                        // indexer.Get, indexer.go:86-102
-            const uint4 sv = ldg16(&a.slots[idx]);
-            if (sv.z == kEmptyRow) break;                   // never-used slot: hash unknown
-            if ((((uint64_t)sv.y << 32) | sv.x) == h) {
-              if (sv.w != 0) row = sv.z;                    // cnt==0: emptied set == deleted key
-              break;
-            }
-            idx = (idx + 1) & a.slot_mask;
-          }
-        }
-        const uint32_t miss = __ballot_sync(0xffffffffu, row == kEmptyRow);
-        const int nh = miss ? (__ffs(miss) - 1) : 32;       // blocks matched before the first global miss
-        if (nh < 32) stop = true;
-        for (int i2 = 0; i2 < nh; i2++) {
-          const uint32_t rr = __shfl_sync(0xffffffffu, row, i2);
-          const uint32_t* rp = a.rows + (size_t)rr * RW + lane;
-#pragma unroll
-          for (int j = 0; j < J; j++) {
-            uint32_t carry = __ldg(rp + j * 32);            // res[server]++ for every server in the set
-#pragma unroll
-            for (int p = 0; p < NP; p++) {
-              const uint32_t t = P[j][p] & carry;
-              P[j][p] ^= carry;
-              carry = t;
-            }
-          }
-        }
-      }
-    }
-    if (prefix_step >= 0 && total != lut_total) {
-      const double w = plan.weight[prefix_step];
-      const int top = total < kLutMax ? total : kLutMax;
-      __syncwarp();
-      for (int c = lane; c <= top; c += 32) lut[c] = prefix_term_direct(c, total, w);
-      lut_total = total;
-      __syncwarp();
-    }
-
-    // ---------------- per-request scorer inputs ----------------
-    int ad = a.adapter_id ? a.adapter_id[r] : -1;
-    if (ad < 0 || ad >= a.A) ad = a.A;
-    uint32_t maskw[MASKW];
-    if (MASKED) {
-#pragma unroll
-      for (int q = 0; q < MASKW; q++) {
-        const int wi = q * 32 + lane;
-        maskw[q] = wi < a.mask_words ? a.cand_mask[(size_t)r * a.mask_words + wi] : 0u;
-      }
-    }
-    // candidate-set min/max for STEP_MINMAX (queue.go:79-91 over the FILTERED endpoints)
-    long long mn[2] = {0, 0}, mx[2] = {0, 0};
-    if (MASKED && (has_minmax[0] || has_minmax[1])) {
-      mn[0] = mn[1] = 0x7fffffffffffffffLL;
-      mx[0] = mx[1] = (long long)0x8000000000000000ULL;
-#pragma unroll
-      for (int j = 0; j < J; j++)
-#pragma unroll 4
-        for (int k = 0; k < EPL; k++) {
-          const int t = j * EPL + k, m = t * 32 + lane;
-          const uint32_t mwv = __shfl_sync(0xffffffffu, maskw[t >> 5], t & 31);
-          if (((mwv >> lane) & 1u) && m < M) {
-#pragma unroll
-            for (int which = 0; which < 2; which++) {
-              const long long v = s_q[which * MPAD + m];
-              mn[which] = v < mn[which] ? v : mn[which];
-              mx[which] = v > mx[which] ? v : mx[which];
-            }
-          }
-        }
-#pragma unroll
-      for (int o = 16; o; o >>= 1)
-#pragma unroll
-        for (int which = 0; which < 2; which++) {
-          const long long omn = shfl_xor_i64(mn[which], o), omx = shfl_xor_i64(mx[which], o);
-          mn[which] = omn < mn[which] ? omn : mn[which];
-          mx[which] = omx > mx[which] ? omx : mx[which];
-        }
-    }
-
-    const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
-    Best best = best_none();
-
-    // ---------------- Score (scheduler_profile.go:151-174) + Pick (maxscore/picker.go:87-115) ----------------
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      uint32_t any = 0;
-#pragma unroll
-      for (int p = 0; p < NP; p++) any |= P[j][p];
-      uint32_t clo = 0, chi = 0;
-      if (a.cls_lo) {
-        clo = __ldg(a.cls_lo + (size_t)ad * RW + j * 32 + lane);
-        chi = __ldg(a.cls_hi + (size_t)ad * RW + j * 32 + lane);
-      }
-#pragma unroll 4
-      for (int k = 0; k < EPL; k++) {
-        const int t = j * EPL + k, m = t * 32 + lane;
-        bool cand = m < M;
-        if (MASKED) {
-          const uint32_t mwv = __shfl_sync(0xffffffffu, maskw[t >> 5], t & 31);
-          cand = cand && ((mwv >> lane) & 1u);
-        }
-        int c = 0;
-        if ((any >> k) & 1u) {
-#pragma unroll
-          for (int p = 0; p < NP; p++) c |= (int)((P[j][p] >> k) & 1u) << p;
-        }
-        if (a.match_out && m < M) a.match_out[(size_t)r * M + m] = (uint16_t)c;
-        const int cls = (int)((clo >> k) & 1u) | ((int)((chi >> k) & 1u) << 1);
-        double acc = 0.0;  // weightedScorePerEndpoint[endpoint] = float64(0), scheduler_profile.go:156-158
-        for (int s = 0; s < plan.n_steps; s++) {
-          double term;
-          switch (plan.kind[s]) {
-            case STEP_EP_TERM: term = s_term[(size_t)plan.arg[s] * MPAD + m]; break;
-            case STEP_PREFIX:
-              term = (s == prefix_step && total <= kLutMax) ? lut[c] : prefix_term_direct(c, total, plan.weight[s]);
-              break;
-            case STEP_LORA: {
-              const double* lt = plan.lora_term[s];
-              term = cls == 3 ? lt[3] : (cls == 2 ? lt[2] : (cls == 1 ? lt[1] : lt[0]));
-              break;
-            }
-            case STEP_MINMAX: {
-              const int which = plan.arg[s];
-              double sc = 1.0;                               // queue.go:95-98
-              if (MASKED && mx[which] != mn[which])
-                sc = __ddiv_rn(__ll2double_rn(mx[which] - s_q[which * MPAD + m]),
-                               __ll2double_rn(mx[which] - mn[which]));        // queue.go:99
-              term = __dmul_rn(clamp01(sc), plan.weight[s]);
-              break;
-            }
-            default: term = __dmul_rn(0.0, plan.weight[s]); break;  // pair columns absent: score 0
-          }
-          acc = __dadd_rn(acc, term);  // += enforceScoreRange(score) * weight, scheduler_profile.go:168
-        }
-        if (a.scores_out && m < M) a.scores_out[(size_t)r * M + m] = cand ? acc : nan64();
-        if (cand) best_update(best, acc, m, tie_mode, areq, plan.seed_hi);
-      }
-    }
-    best_group_reduce<32>(best, tie_mode);
-    if (lane == 0) {
-      a.pick[r] = best.m;
-      a.pick_score[r] = best.m >= 0 ? best.score : 0.0;
-      a.tie_count[r] = best.cnt;
-      if (a.total_out) a.total_out[r] = (uint16_t)total;
-    }
-  }
-}
 
 // Dense rows: float4 {matchBlocks, lora class, pair0, pair1} per (request, endpoint), streamed with
 // coalesced 128-bit loads (lane l reads endpoint i*32+l); endpoint tile in shared memory.
@@ -354,23 +150,6 @@ static int launch_with_smem(K kernel, const ScoreArgs& a, size_t smem, cudaStrea
   return 1;
 }
 
-template <int LOG_EPL, int J>
-static int launch_fused_geo(const ScoreArgs& a, int np_class, bool masked, cudaStream_t s, int sm_count) {
-  constexpr int MPAD = J * 32 * (1 << LOG_EPL);
-  size_t smem = (size_t)a.plan.n_terms * MPAD * 8 + (masked ? 2 * (size_t)MPAD * 8 : 0) +
-                (size_t)kScoreWarps * (kLutMax + 1) * 8;
-  if (np_class == 0) {
-    if (masked) return launch_with_smem(score_pick_fused_kernel<LOG_EPL, J, 6, true>, a, smem, s, sm_count);
-    return launch_with_smem(score_pick_fused_kernel<LOG_EPL, J, 6, false>, a, smem, s, sm_count);
-  }
-  if (np_class == 1) {
-    if (masked) return launch_with_smem(score_pick_fused_kernel<LOG_EPL, J, 9, true>, a, smem, s, sm_count);
-    return launch_with_smem(score_pick_fused_kernel<LOG_EPL, J, 9, false>, a, smem, s, sm_count);
-  }
-  if (masked) return launch_with_smem(score_pick_fused_kernel<LOG_EPL, J, 16, true>, a, smem, s, sm_count);
-  return launch_with_smem(score_pick_fused_kernel<LOG_EPL, J, 16, false>, a, smem, s, sm_count);
-}
-
 int launch_score_pick(const ScoreArgs& a, bool dense, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
   const bool masked = a.cand_mask != nullptr;
@@ -381,18 +160,7 @@ int launch_score_pick(const ScoreArgs& a, bool dense, cudaStream_t s, int sm_cou
     if (masked) return launch_with_smem(score_pick_dense_kernel<true>, a, smem, s, sm_count);
     return launch_with_smem(score_pick_dense_kernel<false>, a, smem, s, sm_count);
   }
-  // counter planes must hold counts up to the largest possible number of hashes per request
-  const int maxn = a.hashes ? a.hash_stride : 0;
-  const int np_class = maxn <= 63 ? 0 : (maxn <= 511 ? 1 : 2);
-  const Geo& g = a.geo;
-  if (g.log_epl == 3) return launch_fused_geo<3, 1>(a, np_class, masked, s, sm_count);
-  if (g.log_epl == 4) return launch_fused_geo<4, 1>(a, np_class, masked, s, sm_count);
-  switch (g.J) {
-    case 1: return launch_fused_geo<5, 1>(a, np_class, masked, s, sm_count);
-    case 2: return launch_fused_geo<5, 2>(a, np_class, masked, s, sm_count);
-    case 4: return launch_fused_geo<5, 4>(a, np_class, masked, s, sm_count);
-    default: return launch_fused_geo<5, 8>(a, np_class, masked, s, sm_count);
-  }
+  return launch_score_matrix(a, s, sm_count);  // score_matrix.cu
 }
 
 }  // namespace eppscore

@@ -1,0 +1,320 @@
+// score_matrix.cu — the full-matrix Score+Pick kernel: every (request, endpoint) pair is scored, nothing is
+// assumed about the batch.  It is what candidate masks (the Filter chain's result), negative prefix weights
+// and the diagnostics outputs (match_out / scores_out) run on, and the reference point the sparse path is
+// tested against.  One warp per request; the R x M score matrix is never materialised.
+//
+//   matchLongestPrefix  approximateprefix/plugin.go:219-235   probe → run-length merge by interned row id →
+//                                                             per-endpoint match counters in shared memory
+//   queue scorer        scorer/queuedepth/queue.go:78-108     min/max over the FILTERED endpoints of the row,
+//                                                             then a per-row LUT lut[d] = clamp(d/(max-min))*w
+//   scorers + sum       scheduler_profile.go:151-174          float64, profile order, from 0.0
+//   picker              maxscore/picker.go:87-115             branch-free arg-max + warp-shuffle reduce
+// The scorer sequence is a template parameter (SEQ packs kind+1 per step, 4 bits each; 0 = runtime loop).
+#include "device_common.cuh"
+
+namespace eppscore {
+
+constexpr int kMatrixWarps = 8;
+constexpr int kMaxJ = 8;
+
+template <uint32_t SEQ, bool MASKED, bool DIAG>
+__global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const __grid_constant__ ScoreArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Plan& plan = a.plan;
+  const int M = a.geo.M, MPAD = a.geo.Mpad, J = a.geo.J, LOG_EPL = a.geo.log_epl, EPL = 1 << LOG_EPL;
+  const int RW = a.geo.row_words;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool wide_cnt = a.hash_stride > 256;  // counters: 8-bit (0 decodes as 256 for touched slots) or 16-bit
+
+  // ---- shared memory carve-up ----
+  double* s_term = reinterpret_cast<double*>(smem_raw);
+  long long* s_q = reinterpret_cast<long long*>(s_term + (size_t)plan.n_terms * MPAD);
+  double* s_lora = reinterpret_cast<double*>(s_q + (MASKED ? 2 * MPAD : 0));
+  double* s_lut = s_lora + kMaxSteps * 4;
+  double* lut_p = s_lut + (size_t)warp * 2 * (kLutMax + 1);
+  double* lut_q = lut_p + (kLutMax + 1);
+  unsigned char* s_cnt_all = reinterpret_cast<unsigned char*>(s_lut + (size_t)kMatrixWarps * 2 * (kLutMax + 1));
+  const int cnt_bytes = MPAD * (wide_cnt ? 2 : 1);
+  unsigned char* cnt_raw = s_cnt_all + (size_t)warp * cnt_bytes;
+  uint8_t* cnt8 = cnt_raw;
+  uint16_t* cnt16 = reinterpret_cast<uint16_t*>(cnt_raw);
+
+  for (int t = 0; t < plan.n_terms; t++)
+    for (int m = threadIdx.x; m < MPAD; m += blockDim.x) s_term[(size_t)t * MPAD + m] = a.term[t][m];
+  if (MASKED)
+    for (int which = 0; which < 2; which++)
+      for (int m = threadIdx.x; m < MPAD; m += blockDim.x)
+        s_q[which * MPAD + m] = (a.minmax_q[which] && m < M) ? a.minmax_q[which][m] : 0;
+  if (threadIdx.x < kMaxSteps * 4) s_lora[threadIdx.x] = plan.lora_term[threadIdx.x >> 2][threadIdx.x & 3];
+  for (int i = threadIdx.x; i < (kMatrixWarps * cnt_bytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_cnt_all)[i] = 0;
+  __syncthreads();
+
+  // ---- plan facts (warp-uniform) ----
+  int prefix_step = -1, q_step = -1;
+  bool has_minmax[2] = {false, false};
+  for (int s = 0; s < plan.n_steps; s++) {
+    if (plan.kind[s] == STEP_PREFIX && prefix_step < 0) prefix_step = s;
+    if (plan.kind[s] == STEP_MINMAX) {
+      has_minmax[plan.arg[s]] = true;
+      if (q_step < 0) q_step = s;  // the first min/max scorer gets the per-row LUT
+    }
+  }
+  const bool want_prefix = prefix_step >= 0 || a.match_out != nullptr || a.total_out != nullptr;
+  const int tie_mode = plan.tie_mode;
+  int lut_total = -1;
+
+  const int gw = blockIdx.x * kMatrixWarps + warp, nw = gridDim.x * kMatrixWarps;
+  for (int r = gw; r < a.R; r += nw) {
+    // ---------------- matchLongestPrefix into the shared-memory counters ----------------
+    uint32_t any[kMaxJ];
+#pragma unroll
+    for (int j = 0; j < kMaxJ; j++) any[j] = 0;
+    int total = 0;
+    if (want_prefix && a.hashes) {
+      const int n = a.n_hashes[r];
+      total = n;
+      bool stop = n == 0 || a.slots == nullptr;
+      for (int c0 = 0; !stop; c0 += 32) {
+        const int i = c0 + lane;
+        uint32_t row = kEmptyRow;
+        if (i < n) {
+          const uint64_t h = a.hashes[(size_t)r * a.hash_stride + i];
+          uint64_t idx = h & a.slot_mask;
+          for (;;) {                                        // indexer.Get, indexer.go:86-102
+            const uint4 sv = ldg16(&a.slots[idx]);
+            if (sv.z == kEmptyRow) break;                   // never-used slot: hash unknown
+            if ((((uint64_t)sv.y << 32) | sv.x) == h) {
+              if (sv.w != 0) row = sv.z;                    // emptied set == deleted key
+              break;
+            }
+            idx = (idx + 1) & a.slot_mask;
+          }
+        }
+        const uint32_t miss = __ballot_sync(0xffffffffu, row == kEmptyRow);
+        const int nh = miss ? (__ffs(miss) - 1) : 32;       // blocks matched before the first global miss
+        // identical sets are interned to one row id: read each run of equal ids once
+        const uint32_t prev_rr = __shfl_up_sync(0xffffffffu, row, 1);
+        uint32_t bm = __ballot_sync(0xffffffffu, lane < nh && (lane == 0 || row != prev_rr));
+        while (bm) {
+          const int s0 = __ffs(bm) - 1;
+          bm &= bm - 1;
+          const int len = (bm ? (__ffs(bm) - 1) : nh) - s0;
+          const uint32_t rr = __shfl_sync(0xffffffffu, row, s0);
+#pragma unroll
+          for (int j = 0; j < kMaxJ; j++) {
+            if (j < J) {
+              uint32_t x = __ldg(a.rows + (size_t)rr * RW + j * 32 + lane);  // res[server] += len for the set's members
+              any[j] |= x;
+              const int base = (j * 32 + lane) << LOG_EPL;  // compact counter index: EPL slots per lane-word
+              while (x) {
+                const int k = __ffs(x) - 1;
+                x &= x - 1;
+                if (wide_cnt) cnt16[base + k] += (uint16_t)len;
+                else cnt8[base + k] += (uint8_t)len;
+              }
+            }
+          }
+        }
+        if (nh < 32 || c0 + 32 >= n) stop = true;
+      }
+    }
+    if (prefix_step >= 0 && total != lut_total && total <= kLutMax) {
+      const double w = plan.weight[prefix_step];
+      __syncwarp();
+      for (int c = lane; c <= total; c += 32) lut_p[c] = prefix_term_direct(c, total, w);
+      lut_total = total;
+      __syncwarp();
+    }
+    const bool plut_ok = total <= kLutMax;
+
+    // ---------------- per-request scorer inputs ----------------
+    int ad = a.adapter_id ? a.adapter_id[r] : -1;
+    if (ad < 0 || ad >= a.A) ad = a.A;
+    const uint32_t* mrow = MASKED ? a.cand_mask + (size_t)r * a.mask_words : nullptr;
+    // candidate-set min/max (queue.go:79-91 over the FILTERED endpoints), then the first such scorer's LUT
+    long long mn[2] = {0, 0}, mx[2] = {0, 0};
+    bool qlut_ok = false;
+    if (MASKED && (has_minmax[0] || has_minmax[1])) {
+      mn[0] = mn[1] = 0x7fffffffffffffffLL;
+      mx[0] = mx[1] = (long long)0x8000000000000000ULL;
+      for (int t = 0; t < J * EPL; t++) {
+        const int m = t * 32 + lane;
+        if (m < M && ((__ldg(mrow + t) >> lane) & 1u)) {
+#pragma unroll
+          for (int which = 0; which < 2; which++) {
+            const long long v = s_q[which * MPAD + m];
+            mn[which] = v < mn[which] ? v : mn[which];
+            mx[which] = v > mx[which] ? v : mx[which];
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1)
+#pragma unroll
+        for (int which = 0; which < 2; which++) {
+          const long long omn = shfl_xor_i64(mn[which], o), omx = shfl_xor_i64(mx[which], o);
+          mn[which] = omn < mn[which] ? omn : mn[which];
+          mx[which] = omx > mx[which] ? omx : mx[which];
+        }
+      if (q_step >= 0) {
+        const int which = plan.arg[q_step];
+        const long long range = mx[which] >= mn[which] ? mx[which] - mn[which] : 0;  // (no candidates: nothing to score)
+        if (range > 0 && range <= kLutMax) {  // lut_q[d] = clamp(d / range) * w, d = max - q  (queue.go:99)
+          const double w = plan.weight[q_step];
+          __syncwarp();
+          for (int d = lane; d <= (int)range; d += 32)
+            lut_q[d] = __dmul_rn(clamp01(__ddiv_rn(__ll2double_rn((long long)d), __ll2double_rn(range))), w);
+          __syncwarp();
+          qlut_ok = true;
+        }
+      }
+    }
+
+    const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
+    Best best = best_none();
+
+    // ---------------- Score (scheduler_profile.go:151-174) + Pick (maxscore/picker.go:87-115) ----------------
+    // per-step constants hoisted out of the pair loop (compile-time step index when SEQ != 0)
+    const double* tptr[8];
+    double wq[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      tptr[s] = s_term + (size_t)(s < plan.n_steps && plan.kind[s] == STEP_EP_TERM ? plan.arg[s] : 0) * MPAD;
+      wq[s] = s < plan.n_steps ? plan.weight[s] : 0.0;
+    }
+    const bool q_flat = !MASKED || q_step < 0 || mx[plan.arg[q_step < 0 ? 0 : q_step]] == mn[plan.arg[q_step < 0 ? 0 : q_step]];
+#pragma unroll
+    for (int j = 0; j < kMaxJ; j++) {
+      if (j >= J) break;
+      uint32_t clo = 0, chi = 0;
+      if (a.cls_lo) {
+        clo = __ldg(a.cls_lo + (size_t)ad * RW + j * 32 + lane);
+        chi = __ldg(a.cls_hi + (size_t)ad * RW + j * 32 + lane);
+      }
+      const uint32_t anyj = any[j];
+      const int cbase = (j * 32 + lane) << LOG_EPL;
+#pragma unroll 4
+      for (int k = 0; k < EPL; k++) {
+        const int t = j * EPL + k, m = t * 32 + lane;
+        bool cand = m < M;
+        if (MASKED) cand = cand && ((__ldg(mrow + t) >> lane) & 1u);
+        // match count: untouched slots hold 0; a touched slot holds the count modulo 2^bits (never 0 modulo)
+        int c = wide_cnt ? (int)cnt16[cbase + k] : (int)cnt8[cbase + k];
+        c = (c == 0 && ((anyj >> k) & 1u)) ? (wide_cnt ? 65536 : 256) : c;
+        if (DIAG && a.match_out && m < M) a.match_out[(size_t)r * M + m] = (uint16_t)c;
+        const int cls = (int)((clo >> k) & 1u) | ((int)((chi >> k) & 1u) << 1);
+        double acc = 0.0;  // weightedScorePerEndpoint[endpoint] = float64(0), scheduler_profile.go:156-158
+        auto step = [&](int s, int kind) {
+          double term;
+          if (kind == STEP_EP_TERM) {
+            term = tptr[s][m];
+          } else if (kind == STEP_PREFIX) {
+            term = (s == prefix_step && plut_ok) ? lut_p[c] : prefix_term_direct(c, total, wq[s]);
+          } else if (kind == STEP_LORA) {
+            term = s_lora[s * 4 + cls];
+          } else if (kind == STEP_MINMAX) {
+            const int which = plan.arg[s];
+            if (s == q_step ? q_flat : (!MASKED || mx[which] == mn[which])) {
+              term = __dmul_rn(1.0, wq[s]);                                  // queue.go:95-98
+            } else if (s == q_step && qlut_ok) {
+              long long d = mx[which] - s_q[which * MPAD + m];
+              d = d < 0 ? 0 : (d > kLutMax ? kLutMax : d);                   // (non-candidates only)
+              term = lut_q[(int)d];
+            } else {
+              const double sc = __ddiv_rn(__ll2double_rn(mx[which] - s_q[which * MPAD + m]),
+                                          __ll2double_rn(mx[which] - mn[which]));  // queue.go:99
+              term = __dmul_rn(clamp01(sc), wq[s]);
+            }
+          } else {
+            term = __dmul_rn(0.0, wq[s]);                                    // pair columns absent: score 0
+          }
+          acc = __dadd_rn(acc, term);  // += enforceScoreRange(score) * weight, scheduler_profile.go:168
+        };
+        if (SEQ == 0) {
+          for (int s = 0; s < plan.n_steps; s++) step(s, plan.kind[s]);
+        } else {
+#pragma unroll
+          for (int s = 0; s < 8; s++) {
+            const int kind = (int)((SEQ >> (4 * s)) & 15u) - 1;
+            if (kind >= 0) step(s, kind);
+          }
+        }
+        if (DIAG && a.scores_out && m < M) a.scores_out[(size_t)r * M + m] = cand ? acc : nan64();
+        if (cand) best_update(best, acc, m, tie_mode, areq, plan.seed_hi);
+      }
+      // re-zero exactly the counters this request touched
+      uint32_t x = anyj;
+      while (x) {
+        const int k = __ffs(x) - 1;
+        x &= x - 1;
+        if (wide_cnt) cnt16[cbase + k] = 0;
+        else cnt8[cbase + k] = 0;
+      }
+    }
+    best_group_reduce<32>(best, tie_mode);
+    if (lane == 0) {
+      a.pick[r] = best.m;
+      a.pick_score[r] = best.m >= 0 ? best.score : 0.0;
+      a.tie_count[r] = best.cnt;
+      if (a.total_out) a.total_out[r] = (uint16_t)total;
+    }
+    __syncwarp();
+  }
+}
+
+template <typename K>
+static int launch_matrix(K kernel, const ScoreArgs& a, bool masked, cudaStream_t s, int sm_count) {
+  const int MPAD = a.geo.Mpad;
+  const bool wide = a.hash_stride > 256;
+  const size_t smem = (size_t)a.plan.n_terms * MPAD * 8 + (masked ? 2 * (size_t)MPAD * 8 : 0) + kMaxSteps * 4 * 8 +
+                      (size_t)kMatrixWarps * 2 * (kLutMax + 1) * 8 + (size_t)kMatrixWarps * MPAD * (wide ? 2 : 1);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kMatrixWarps * 32, smem);
+  if (occ < 1) occ = 1;
+  const int need = (a.R + kMatrixWarps - 1) / kMatrixWarps;
+  int blocks = sm_count * occ;  // persistent: one wave, warps stride over requests
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  kernel<<<blocks, kMatrixWarps * 32, smem, s>>>(a);
+  return 1;
+}
+
+constexpr uint32_t mseq() { return 0; }
+template <typename... Rest>
+constexpr uint32_t mseq(int k, Rest... rest) {
+  return (uint32_t)(k + 1) | (mseq(rest...) << 4);
+}
+
+#define E STEP_EP_TERM
+#define P STEP_PREFIX
+#define L STEP_LORA
+#define Q STEP_MINMAX
+template <bool MASKED, bool DIAG>
+static int launch_matrix_seq(const ScoreArgs& a, cudaStream_t s, int sm_count) {
+  switch (a.plan.seq) {
+    case mseq(E): return launch_matrix(score_matrix_kernel<mseq(E), MASKED, DIAG>, a, MASKED, s, sm_count);
+    case mseq(E, P): return launch_matrix(score_matrix_kernel<mseq(E, P), MASKED, DIAG>, a, MASKED, s, sm_count);
+    case mseq(E, P, L): return launch_matrix(score_matrix_kernel<mseq(E, P, L), MASKED, DIAG>, a, MASKED, s, sm_count);
+    case mseq(E, L): return launch_matrix(score_matrix_kernel<mseq(E, L), MASKED, DIAG>, a, MASKED, s, sm_count);
+    case mseq(Q, E): return launch_matrix(score_matrix_kernel<mseq(Q, E), MASKED, DIAG>, a, MASKED, s, sm_count);
+    case mseq(Q, E, P): return launch_matrix(score_matrix_kernel<mseq(Q, E, P), MASKED, DIAG>, a, MASKED, s, sm_count);
+    case mseq(Q, E, P, L): return launch_matrix(score_matrix_kernel<mseq(Q, E, P, L), MASKED, DIAG>, a, MASKED, s, sm_count);
+    case mseq(E, Q, P, L): return launch_matrix(score_matrix_kernel<mseq(E, Q, P, L), MASKED, DIAG>, a, MASKED, s, sm_count);
+    default: return launch_matrix(score_matrix_kernel<0, MASKED, DIAG>, a, MASKED, s, sm_count);
+  }
+}
+#undef E
+#undef P
+#undef L
+#undef Q
+
+// every (request, endpoint) pair scored; any plan without pair columns
+int launch_score_matrix(const ScoreArgs& a, cudaStream_t s, int sm_count) {
+  if (a.R <= 0) return 0;
+  const bool diag = a.match_out != nullptr || a.scores_out != nullptr;  // diagnostics variants keep the R x M stores out of the hot loop
+  if (a.cand_mask) return diag ? launch_matrix_seq<true, true>(a, s, sm_count) : launch_matrix_seq<true, false>(a, s, sm_count);
+  return diag ? launch_matrix_seq<false, true>(a, s, sm_count) : launch_matrix_seq<false, false>(a, s, sm_count);
+}
+
+}  // namespace eppscore
