@@ -3,8 +3,9 @@
 scorers (queue 2, kv 2, prefix 3, lora 1), 2 KB shared-prefix prompts, on N B200s of one node.
 
 A "step" = one pass of the hot path over one batch of R requests per GPU:
-    hash_prompts_kernel (chained XXH64 of every prompt)  →  score_pick_fused_kernel (table probe,
-    4 scorers, weighted float64 sum, arg-max pick)        — 2 kernel launches, nothing else.
+    prepare_endpoints + prepare_adapters (side stream) ‖ hash_bodies + hash_chain (chained XXH64 of
+    every prompt)  →  pick_sparse (table probe, 4 scorers, weighted float64 sum, arg-max pick)
+    — 5 kernel launches replayed as one CUDA graph, nothing else.
 `value`  : whole-job picks/s with the inputs already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same metric through the C ABI with HOST (pinned) buffers: H2D of prompts/seeds/adapters
            and D2H of picks/scores/tie counts inside the timed region.
