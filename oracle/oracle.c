@@ -9,6 +9,7 @@
 #define _GNU_SOURCE
 #include "oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
@@ -581,6 +582,272 @@ void orc_score_prefix(int32_t M, const uint32_t *mask, const uint16_t *match, in
   }
 }
 
+
+/* token_load.go:83-111: 1.0 when no in-flight tokens, else 1 - min(tokens, thr)/thr */
+void orc_score_token_load(const orc_snapshot *s, const uint32_t *mask, double threshold, double *out) {
+  if (threshold <= 0) threshold = 4194304.0; /* tokenQueueThresholdDefault, token_load.go:33,57-61 */
+  for (int32_t m = 0; m < s->M; m++) {
+    if (!is_cand(mask, m)) continue;
+    double load = s->inflight_tokens ? (double)s->inflight_tokens[m] : 0.0;
+    double score;
+    if (load <= 0) {
+      score = 1.0;
+    } else {
+      if (load > threshold) load = threshold;
+      score = 1.0 - (load / threshold);
+    }
+    out[m] = score;
+  }
+}
+
+/* =====================================================================================
+ * Latency-predictor fold-in: predicted-latency producer + latency-scorer
+ * ===================================================================================== */
+/* sidecars/latencypredictorasync/prediction.go:164-194 (left-to-right float64, no fusing) */
+void orc_latency_predict(const orc_latency_params *lp, double kv, int64_t input_tokens, int64_t waiting,
+                         int64_t running, int64_t generated, double prefix_score, double *ttft, double *tpot) {
+  *ttft = lp->ttft_intercept + lp->ttft_kv * kv + lp->ttft_input * (double)input_tokens +
+          lp->ttft_waiting * (double)waiting + lp->ttft_running * (double)running + lp->ttft_prefix * prefix_score;
+  *tpot = lp->tpot_intercept + lp->tpot_kv * kv + lp->tpot_input * (double)input_tokens +
+          lp->tpot_waiting * (double)waiting + lp->tpot_running * (double)running +
+          lp->tpot_generated * (double)generated;
+}
+
+/* predictedlatency/prediction.go:137-166, then :100-104 */
+void orc_latency_validate(const orc_latency_params *lp, double ttft, double tpot, double ttft_slo, double tpot_slo,
+                          double pod_min, int32_t neutralize, int32_t *ok_out, double *headroom_out) {
+  int ttft_ok = ttft < ttft_slo;
+  double ttft_headroom = ttft_slo - ttft;
+  int tpot_ok = 1;
+  double headroom = 0.0;
+  if (lp->streaming_mode) {
+    double buffered = tpot_slo * lp->slo_buffer_factor;
+    if (pod_min > 0) {
+      double alt = pod_min * lp->slo_buffer_factor;
+      if (alt < buffered) buffered = alt; /* min(bufferedTPOT, podMinTPOTSLO*factor) */
+    }
+    tpot_ok = tpot < buffered;
+    headroom = buffered - tpot;
+  }
+  int valid = ttft_ok && tpot_ok;
+  if (neutralize) { /* !StreamingMode || hasPrefillRole */
+    tpot_ok = 1;
+    headroom = 0;
+    valid = ttft_ok;
+  }
+  if (ok_out) {
+    ok_out[0] = ttft_ok;
+    ok_out[1] = tpot_ok;
+    ok_out[2] = valid;
+  }
+  headroom_out[0] = headroom;
+  headroom_out[1] = ttft_headroom;
+}
+
+typedef struct {
+  int32_t m;
+  int has_info;
+  double th, ph; /* ttftHeadroom, tpotHeadroom */
+  int32_t dispatched;
+} lat_ep;
+
+/* scorer/latency/plugin.go:246-318 */
+static void lat_score_bucket(const orc_latency_params *lp, const lat_ep *d, int32_t n, double *scores, int force_least) {
+  double alpha, beta; /* normalizedWeights :373-379 */
+  {
+    double sum = lp->ttft_weight + lp->tpot_weight;
+    if (sum <= 0) {
+      alpha = 1.0;
+      beta = 0.0;
+    } else {
+      alpha = lp->ttft_weight / sum;
+      beta = lp->tpot_weight / sum;
+    }
+  }
+  double min_t = DBL_MAX, max_t = -DBL_MAX, min_p = DBL_MAX, max_p = -DBL_MAX;
+  for (int32_t i = 0; i < n; i++) {
+    double h = fabs(d[i].th);
+    if (h < min_t) min_t = h;
+    if (h > max_t) max_t = h;
+    h = fabs(d[i].ph);
+    if (h < min_p) min_p = h;
+    if (h > max_p) max_p = h;
+  }
+  const double eps = 1e-9;
+  double range_t = max_t - min_t, range_p = max_p - min_p;
+  if (range_t <= eps && range_p > eps) {
+    alpha = 0.0;
+    beta = 1.0;
+  } else if (range_p <= eps && range_t > eps) {
+    alpha = 1.0;
+    beta = 0.0;
+  }
+  for (int32_t i = 0; i < n; i++) {
+    double nt, np;
+    if (range_t > eps)
+      nt = (fabs(d[i].th) - min_t) / range_t;
+    else
+      nt = 0.5;
+    if (range_p > eps)
+      np = (fabs(d[i].ph) - min_p) / range_p;
+    else
+      np = 0.5;
+    double combined = alpha * nt + beta * np;
+    double w;
+    if (lp->strategy_most && !force_least)
+      w = (double)((int64_t)(combined * 100.0) + 0 + 1); /* int() truncates toward zero */
+    else
+      w = (double)((int64_t)((1.0 - combined) * 100.0) + 0 + 1);
+    scores[d[i].m] = w / 100.0;
+  }
+}
+
+/* scorer/latency/plugin.go:323-367 */
+static void lat_composite(const orc_latency_params *lp, const orc_snapshot *s, const uint32_t *mask,
+                          const uint16_t *match, int32_t total, double *out) {
+  double wkv = lp->composite_kv, wq = lp->composite_queue, wpref = lp->composite_prefix;
+  double sumw = wkv + wq + wpref;
+  if (sumw <= 0) {
+    wkv = 1;
+    wq = 0;
+    wpref = 0;
+    sumw = 1;
+  }
+  wkv /= sumw;
+  wq /= sumw;
+  wpref /= sumw;
+  int64_t max_q = 0;
+  for (int32_t m = 0; m < s->M; m++)
+    if (is_cand(mask, m) && s->queue[m] > max_q) max_q = s->queue[m];
+  double q_range = (double)max_q;
+  for (int32_t m = 0; m < s->M; m++) {
+    if (!is_cand(mask, m)) continue;
+    double rel = 1.0;
+    if (q_range > 0) rel = (double)(max_q - s->queue[m]) / q_range;
+    double kv_free = 1.0 - s->kv_usage[m];
+    double prefix = 0; /* prefixCacheScore :381-392 */
+    if (match && total > 0) {
+      double sc = (double)match[m] / (double)total;
+      if (!isnan(sc)) prefix = sc;
+    }
+    double composite = wkv * kv_free + wq * rel + wpref * prefix;
+    int64_t w = (int64_t)round(0.0 + 100.0 * composite); /* math.Round: half away from zero */
+    out[m] = (double)w / 100.0;
+  }
+}
+
+void orc_score_latency_info(const orc_latency_params *lp, const orc_snapshot *s, const uint32_t *mask,
+                            const uint8_t *have_info, const double *ttft_headroom, const double *tpot_headroom,
+                            const int32_t *dispatched, const uint16_t *match, int32_t total, double *out) {
+  const int32_t M = s->M;
+  lat_ep *data = (lat_ep *)malloc(sizeof(lat_ep) * (size_t)(M > 0 ? M : 1) * 2);
+  lat_ep *tmp = data + (M > 0 ? M : 1);
+  int32_t n = 0;
+  int has_predictions = 0;
+  for (int32_t m = 0; m < M; m++) { /* :147-166 */
+    if (!is_cand(mask, m)) continue;
+    out[m] = 0;
+    lat_ep d = {m, 0, 0.0, 0.0, 0};
+    if (have_info && have_info[m]) {
+      d.has_info = 1;
+      d.th = ttft_headroom[m];
+      d.ph = tpot_headroom[m];
+      d.dispatched = dispatched ? dispatched[m] : 0;
+      has_predictions = 1;
+    }
+    data[n++] = d;
+  }
+  if (!has_predictions) { /* :169-172 */
+    lat_composite(lp, s, mask, match, total, out);
+    free(data);
+    return;
+  }
+  /* :177-189 positive bucket first */
+  int32_t k = 0;
+  for (int32_t i = 0; i < n; i++)
+    if (!(data[i].has_info && (data[i].th < 0 || data[i].ph < 0))) tmp[k++] = data[i];
+  if (k > 0) {
+    lat_score_bucket(lp, tmp, k, out, 0);
+    free(data);
+    return;
+  }
+  /* all negative: idle preference :193-204 */
+  k = 0;
+  for (int32_t i = 0; i < n; i++)
+    if (data[i].has_info && data[i].dispatched == 0) tmp[k++] = data[i];
+  if (k > 0) {
+    lat_score_bucket(lp, tmp, k, out, 1);
+    free(data);
+    return;
+  }
+  /* deficit buckets :209-238, order negTPOTonly, negTTFTonly, bothNeg */
+  for (int pass = 0; pass < 3; pass++) {
+    k = 0;
+    for (int32_t i = 0; i < n; i++) {
+      int bucket;
+      if (!data[i].has_info) {
+        bucket = 2;
+      } else {
+        int tn = data[i].th < 0, pn = data[i].ph < 0;
+        bucket = (tn && pn) ? 2 : (tn ? 1 : (pn ? 0 : 2));
+      }
+      if (bucket == pass) tmp[k++] = data[i];
+    }
+    if (k > 0) {
+      lat_score_bucket(lp, tmp, k, out, 1);
+      free(data);
+      return;
+    }
+  }
+  lat_score_bucket(lp, data, n, out, 1); /* :241 (n == 0 here) */
+  free(data);
+}
+
+void orc_score_latency(const orc_latency_params *lp, const orc_snapshot *s, const uint32_t *mask,
+                       const uint16_t *match, int32_t total, const orc_latency_request *lr, double *out,
+                       double *pred_out) {
+  const int32_t M = s->M;
+  orc_latency_request zero = {0, 0.0, 0.0};
+  if (!lr) lr = &zero;
+  if (!lp->has_predictions) {
+    orc_score_latency_info(lp, s, mask, NULL, NULL, NULL, NULL, match, total, out);
+    if (pred_out)
+      for (int32_t m = 0; m < 2 * M; m++) pred_out[m] = NAN;
+    return;
+  }
+  uint8_t *have = (uint8_t *)malloc((size_t)(M > 0 ? M : 1));
+  double *th = (double *)malloc(sizeof(double) * (size_t)(M > 0 ? M : 1) * 2);
+  double *ph = th + (M > 0 ? M : 1);
+  int32_t *disp = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M > 0 ? M : 1));
+  /* PrepareRequestData runs over every endpoint handed to the scheduler, before the filters */
+  for (int32_t m = 0; m < M; m++) {
+    double prefix = 0.0; /* preparedata_hooks.go:44-58: match/total, NaN => 0, attribute absent => 0 */
+    if (match) {
+      prefix = (double)match[m] / (double)total;
+      if (isnan(prefix)) prefix = 0.0;
+    }
+    double ttft, tpot; /* training.go:35-57: generatedTokens = 1 (prediction.go:69) */
+    orc_latency_predict(lp, s->kv_usage[m], lr->input_tokens, s->queue[m], s->running ? s->running[m] : 0, 1, prefix,
+                        &ttft, &tpot);
+    int neutralize = !lp->streaming_mode || (s->prefill_role && s->prefill_role[m]);
+    double hr[2];
+    orc_latency_validate(lp, ttft, tpot, lr->ttft_slo, lr->tpot_slo, s->min_tpot_slo ? s->min_tpot_slo[m] : 0.0,
+                         neutralize, NULL, hr);
+    have[m] = 1;
+    th[m] = hr[1];
+    ph[m] = hr[0];
+    disp[m] = s->dispatched ? s->dispatched[m] : 0;
+    if (pred_out) {
+      pred_out[2 * m] = ttft;
+      pred_out[2 * m + 1] = tpot;
+    }
+  }
+  orc_score_latency_info(lp, s, mask, have, th, ph, disp, match, total, out);
+  free(have);
+  free(th);
+  free(disp);
+}
+
 static inline uint32_t lowbias32(uint32_t x) {
   x ^= x >> 16;
   x *= 0x7feb352dU;
@@ -602,6 +869,15 @@ int32_t orc_schedule_one(const orc_snapshot *s, const orc_profile *p, int64_t re
                          int32_t adapter_id, const uint32_t *mask, const uint16_t *match,
                          int32_t total, const float *pair_col, int32_t *pick_out, double *score_out,
                          int32_t *tie_count_out, uint32_t *tie_set_out, double *weighted_out) {
+  return orc_schedule_one_lat(s, p, request_index, adapter_id, mask, match, total, pair_col, NULL, pick_out,
+                              score_out, tie_count_out, tie_set_out, weighted_out, NULL);
+}
+
+int32_t orc_schedule_one_lat(const orc_snapshot *s, const orc_profile *p, int64_t request_index,
+                             int32_t adapter_id, const uint32_t *mask, const uint16_t *match,
+                             int32_t total, const float *pair_col, const orc_latency_request *lat,
+                             int32_t *pick_out, double *score_out, int32_t *tie_count_out,
+                             uint32_t *tie_set_out, double *weighted_out, double *pred_out) {
   const int32_t M = s->M;
   /* runFilterPlugins (scheduler_profile.go:130-149) is modelled as the candidate mask */
   int32_t ncand = 0;
@@ -625,6 +901,13 @@ int32_t orc_schedule_one(const orc_snapshot *s, const orc_profile *p, int64_t re
       case ORC_SCORER_QUEUE: orc_score_queue(s, mask, sc); break;
       case ORC_SCORER_KV_CACHE: orc_score_kv(s, mask, sc); break;
       case ORC_SCORER_RUNNING: orc_score_running(s, mask, sc); break;
+      case ORC_SCORER_TOKEN_LOAD: orc_score_token_load(s, mask, p->token_load_threshold, sc); break;
+      case ORC_SCORER_LATENCY:
+        if (p->latency)
+          orc_score_latency(p->latency, s, mask, match, total, lat, sc, pred_out);
+        else
+          for (int32_t m = 0; m < M; m++) sc[m] = 0.0;
+        break;
       case ORC_SCORER_PREFIX:
         if (pair_col && match == NULL) { /* dense rows carry match in column x */
           for (int32_t m = 0; m < M; m++) {
@@ -719,7 +1002,7 @@ static void *batch_worker(void *arg) {
   const orc_batch *b = j->b;
   const int32_t M = j->s->M;
   const int32_t mw = (M + 31) / 32;
-  const int need_prefix = profile_has(j->p, ORC_SCORER_PREFIX) || b->match_blocks || b->total_blocks || b->hashes_out;
+  const int need_prefix = profile_has(j->p, ORC_SCORER_PREFIX) || profile_has(j->p, ORC_SCORER_LATENCY) || b->match_blocks || b->total_blocks || b->hashes_out;
   int32_t hcap = b->max_blocks > 0 ? b->max_blocks : 1;
   if (b->hashes_in && b->hash_stride > hcap) hcap = b->hash_stride;
   uint64_t *hashes = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)hcap);
@@ -755,10 +1038,13 @@ static void *batch_worker(void *arg) {
             pair ? (uint16_t)pair[(size_t)m * 4] : (match_p ? match_p[m] : 0);
     }
     const uint32_t *mask = b->cand_mask ? b->cand_mask + (size_t)r * mw : NULL;
-    orc_schedule_one(j->s, j->p, b->request_base + r, b->adapter_id ? b->adapter_id[r] : -1, mask, match_p, total,
-                     pair, &b->pick[r], &b->pick_score[r], &b->tie_count[r],
-                     b->tie_set ? b->tie_set + (size_t)r * mw : NULL,
-                     b->weighted_out ? b->weighted_out + (size_t)r * M : NULL);
+    orc_latency_request lr = {b->input_tokens ? b->input_tokens[r] : 0, b->ttft_slo ? b->ttft_slo[r] : 0.0,
+                              b->tpot_slo ? b->tpot_slo[r] : 0.0};
+    orc_schedule_one_lat(j->s, j->p, b->request_base + r, b->adapter_id ? b->adapter_id[r] : -1, mask, match_p, total,
+                         pair, &lr, &b->pick[r], &b->pick_score[r], &b->tie_count[r],
+                         b->tie_set ? b->tie_set + (size_t)r * mw : NULL,
+                         b->weighted_out ? b->weighted_out + (size_t)r * M : NULL,
+                         b->pred_out ? b->pred_out + (size_t)r * M * 2 : NULL);
   }
   free(hashes);
   free(match);

@@ -38,11 +38,31 @@ enum {
   ORC_SCORER_PREFIX = 2,     /* scorer/prefix/plugin.go:95-117 */
   ORC_SCORER_LORA = 3,       /* scorer/loraaffinity/lora_affinity.go:76-102 */
   ORC_SCORER_RUNNING = 4,    /* scorer/runningrequests/runningrequest.go:78-108 (same form as queue) */
+  ORC_SCORER_LATENCY = 5,    /* scorer/latency/plugin.go:144-318 fed by the predicted-latency producer */
+  ORC_SCORER_TOKEN_LOAD = 6, /* scorer/tokenload/token_load.go:83-111 */
   ORC_SCORER_ENDPOINT_COL0 = 8,  /* +k: caller-supplied per-endpoint float64 score column k (0..3) */
   ORC_SCORER_PAIR_COL0 = 16      /* +k: caller-supplied per-(request,endpoint) float32 column k (0..1) */
 };
 
 enum { ORC_TIE_LOWEST_INDEX = 0, ORC_TIE_SEEDED_RANDOM = 1 };
+
+/*
+ * Latency-predictor fold-in: the Bayesian-ridge linear model the Go client evaluates from
+ * cached coefficients (sidecars/latencypredictorasync/prediction.go:164-194), the producer's validity /
+ * headroom rules (requestcontrol/dataproducer/predictedlatency/prediction.go:46-166) and the
+ * latency-scorer's configuration (scheduling/scorer/latency/plugin.go:59-90).
+ */
+typedef struct orc_latency_params {
+  double ttft_intercept, ttft_kv, ttft_input, ttft_waiting, ttft_running, ttft_prefix;
+  double tpot_intercept, tpot_kv, tpot_input, tpot_waiting, tpot_running, tpot_generated;
+  double slo_buffer_factor;  /* Config.SLOBufferFactor, default 1 (plugin.go:132) */
+  int32_t streaming_mode;    /* Config.StreamingMode, default false (plugin.go:134) */
+  int32_t has_predictions;   /* 0: no LatencyPredictionInfo on any endpoint (sidecar down) => composite fallback */
+  double ttft_weight, tpot_weight; /* scorer Config, defaults 0.8 / 0.2 */
+  int32_t strategy_most;     /* HeadroomSelectionStrategy: 0 "least" (default), 1 "most" */
+  int32_t reserved;
+  double composite_kv, composite_queue, composite_prefix; /* defaults 1,1,1 */
+} orc_latency_params;
 
 typedef struct orc_profile {
   int32_t n_scorers;
@@ -50,6 +70,8 @@ typedef struct orc_profile {
   double scorer_weight[ORC_MAX_SCORERS];
   int32_t tie_mode;
   uint64_t tie_seed;
+  const orc_latency_params *latency; /* required by ORC_SCORER_LATENCY */
+  double token_load_threshold;       /* queueThresholdTokens (token_load.go:33,57-61); <= 0 => 4194304 */
 } orc_profile;
 
 /* One immutable metrics snapshot (interface/datalayer/metrics.go:26-42 fields the path reads). */
@@ -64,6 +86,11 @@ typedef struct orc_snapshot {
   const int32_t *lora_nmodels;   /* len(ActiveModels)+len(WaitingModels) */
   const int32_t *lora_max;       /* MaxActiveModels */
   const double *endpoint_col[4]; /* optional generic per-endpoint score columns */
+  /* predicted-latency producer state per endpoint (plugin.go:347-363) and role label; NULL => 0 */
+  const double *min_tpot_slo;    /* getEndpointMinTPOTSLO */
+  const int32_t *dispatched;     /* getEndpointRunningRequestCount */
+  const uint8_t *prefill_role;   /* hasPrefillRole(EndpointRoleLabel, endpoint) (prediction.go:168-175) */
+  const int64_t *inflight_tokens;/* InFlightLoad.Tokens attribute (token_load.go:91-95); NULL => attribute absent */
 } orc_snapshot;
 
 /* ---- XXH64 (third-party cespare/xxhash v2.3.0 == canonical XXH64, seed 0) ---- */
@@ -102,6 +129,32 @@ void orc_score_prefix(int32_t M, const uint32_t *cand_mask, const uint16_t *matc
                       int32_t have_info, double *out);
 double orc_enforce_score_range(double s); /* scheduler_profile.go:194-202 */
 
+void orc_score_token_load(const orc_snapshot *, const uint32_t *cand_mask, double threshold, double *out);
+
+/* per-request inputs of the latency path */
+typedef struct orc_latency_request {
+  int64_t input_tokens; /* len(strings.Fields(prompt)), training.go:51 */
+  double ttft_slo;      /* x-slo-ttft-ms header or 0 (plugin.go:330-343) */
+  double tpot_slo;      /* x-slo-tpot-ms header or 0 */
+} orc_latency_request;
+/* prediction.go:164-194 with NumTokensGenerated = generated */
+void orc_latency_predict(const orc_latency_params *, double kv, int64_t input_tokens, int64_t waiting,
+                         int64_t running, int64_t generated, double prefix_score, double *ttft, double *tpot);
+/* predictedlatency/prediction.go:137-166 (+ the neutralisation of :100-104 when neutralize != 0);
+ * out = {ttftOk, tpotOk, isValid}, headrooms = {tpot headroom, ttft headroom} */
+void orc_latency_validate(const orc_latency_params *, double ttft, double tpot, double ttft_slo, double tpot_slo,
+                          double pod_min_tpot_slo, int32_t neutralize, int32_t *ok_out, double *headroom_out);
+/* scorer/latency/plugin.go:144-318 over caller-supplied LatencyPredictionInfo (for the scorer's own tests):
+ * have_info[m]==0 => attribute absent. Non-candidates are left untouched. */
+void orc_score_latency_info(const orc_latency_params *, const orc_snapshot *, const uint32_t *cand_mask,
+                            const uint8_t *have_info, const double *ttft_headroom, const double *tpot_headroom,
+                            const int32_t *dispatched, const uint16_t *match, int32_t total, double *out);
+/* producer + scorer for one request: PrepareRequestData (preparedata_hooks.go:36-104) over all M endpoints,
+ * then Score over the candidates. pred_out: optional M x 2 {ttft, tpot}. */
+void orc_score_latency(const orc_latency_params *, const orc_snapshot *, const uint32_t *cand_mask,
+                       const uint16_t *match, int32_t total, const orc_latency_request *, double *out,
+                       double *pred_out);
+
 /* counter-based tie priority shared (by specification) with the CUDA engine */
 uint32_t orc_tie_priority(uint64_t seed, int64_t request_index, int32_t endpoint);
 
@@ -118,6 +171,12 @@ int32_t orc_schedule_one(const orc_snapshot *, const orc_profile *, int64_t requ
                          int32_t adapter_id, const uint32_t *cand_mask, const uint16_t *match,
                          int32_t total, const float *pair_col, int32_t *pick_out, double *score_out,
                          int32_t *tie_count_out, uint32_t *tie_set_out, double *weighted_out);
+/* the same with the latency path's per-request inputs (NULL => zeros) and optional M x 2 prediction output */
+int32_t orc_schedule_one_lat(const orc_snapshot *, const orc_profile *, int64_t request_index,
+                             int32_t adapter_id, const uint32_t *cand_mask, const uint16_t *match,
+                             int32_t total, const float *pair_col, const orc_latency_request *lat,
+                             int32_t *pick_out, double *score_out, int32_t *tie_count_out,
+                             uint32_t *tie_set_out, double *weighted_out, double *pred_out);
 
 /* Batch description; mirrors eppscore_batch (host pointers only). */
 typedef struct orc_batch {
@@ -143,6 +202,11 @@ typedef struct orc_batch {
   uint16_t *total_blocks;        /* optional R */
   uint64_t *hashes_out;          /* optional R x max_blocks */
   double *weighted_out;          /* optional R x M: weightedScorePerEndpoint, NaN for non-candidates */
+  /* latency path (all optional) */
+  const int32_t *input_tokens;   /* R */
+  const double *ttft_slo;        /* R */
+  const double *tpot_slo;        /* R */
+  double *pred_out;              /* R x M x 2 {ttft, tpot} */
 } orc_batch;
 
 /* Whole hot path for a batch (hash → match → score → pick), requests partitioned over n_threads

@@ -16,6 +16,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
 MAX_SCORERS = 8
 SCORER_QUEUE, SCORER_KV_CACHE, SCORER_PREFIX, SCORER_LORA, SCORER_RUNNING = 0, 1, 2, 3, 4
+SCORER_LATENCY, SCORER_TOKEN_LOAD = 5, 6
 SCORER_ENDPOINT_COL0 = 8
 SCORER_PAIR_COL0 = 16
 TIE_LOWEST_INDEX, TIE_SEEDED_RANDOM = 0, 1
@@ -30,17 +31,53 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+class LatencyParams(C.Structure):
+    _fields_ = [("ttft_intercept", C.c_double), ("ttft_kv", C.c_double), ("ttft_input", C.c_double),
+                ("ttft_waiting", C.c_double), ("ttft_running", C.c_double), ("ttft_prefix", C.c_double),
+                ("tpot_intercept", C.c_double), ("tpot_kv", C.c_double), ("tpot_input", C.c_double),
+                ("tpot_waiting", C.c_double), ("tpot_running", C.c_double), ("tpot_generated", C.c_double),
+                ("slo_buffer_factor", C.c_double), ("streaming_mode", C.c_int32), ("has_predictions", C.c_int32),
+                ("ttft_weight", C.c_double), ("tpot_weight", C.c_double), ("strategy_most", C.c_int32),
+                ("reserved", C.c_int32), ("composite_kv", C.c_double), ("composite_queue", C.c_double),
+                ("composite_prefix", C.c_double)]
+
+
+LATENCY_FIELDS = [f for f, _ in LatencyParams._fields_ if f != "reserved"]
+
+
+def make_latency_params(**kw) -> LatencyParams:
+    """Defaults: predictedlatency DefaultConfig (plugin.go:128-136) + latency-scorer DefaultConfig (plugin.go:83-90)."""
+    lp = LatencyParams()
+    lp.slo_buffer_factor = 1.0
+    lp.streaming_mode = 0
+    lp.has_predictions = 1
+    lp.ttft_weight, lp.tpot_weight = 0.8, 0.2
+    lp.strategy_most = 0
+    lp.composite_kv = lp.composite_queue = lp.composite_prefix = 1.0
+    for k, v in kw.items():
+        if k not in LATENCY_FIELDS:
+            raise KeyError(k)
+        setattr(lp, k, v)
+    return lp
+
+
+class LatencyRequest(C.Structure):
+    _fields_ = [("input_tokens", C.c_int64), ("ttft_slo", C.c_double), ("tpot_slo", C.c_double)]
+
+
 class Profile(C.Structure):
     _fields_ = [("n_scorers", C.c_int32), ("scorer_kind", C.c_int32 * MAX_SCORERS),
                 ("scorer_weight", C.c_double * MAX_SCORERS), ("tie_mode", C.c_int32),
-                ("tie_seed", C.c_uint64)]
+                ("tie_seed", C.c_uint64), ("latency", C.POINTER(LatencyParams)),
+                ("token_load_threshold", C.c_double)]
 
 
 class Snapshot(C.Structure):
     _fields_ = [("M", C.c_int32), ("lora_words", C.c_int32), ("kv_usage", C.c_void_p),
                 ("queue", C.c_void_p), ("running", C.c_void_p), ("lora_active", C.c_void_p),
                 ("lora_waiting", C.c_void_p), ("lora_nmodels", C.c_void_p), ("lora_max", C.c_void_p),
-                ("endpoint_col", C.c_void_p * 4)]
+                ("endpoint_col", C.c_void_p * 4), ("min_tpot_slo", C.c_void_p), ("dispatched", C.c_void_p),
+                ("prefill_role", C.c_void_p), ("inflight_tokens", C.c_void_p)]
 
 
 class Batch(C.Structure):
@@ -51,7 +88,8 @@ class Batch(C.Structure):
                 ("block_chars", C.c_int32), ("max_blocks", C.c_int32), ("pick", C.c_void_p),
                 ("pick_score", C.c_void_p), ("tie_count", C.c_void_p), ("tie_set", C.c_void_p),
                 ("match_blocks", C.c_void_p), ("total_blocks", C.c_void_p), ("hashes_out", C.c_void_p),
-                ("weighted_out", C.c_void_p)]
+                ("weighted_out", C.c_void_p), ("input_tokens", C.c_void_p), ("ttft_slo", C.c_void_p),
+                ("tpot_slo", C.c_void_p), ("pred_out", C.c_void_p)]
 
 
 _lib = None
@@ -97,6 +135,20 @@ def lib():
         L.orc_schedule_one.argtypes = [C.POINTER(Snapshot), C.POINTER(Profile), C.c_int64, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
+        L.orc_schedule_one_lat.restype = C.c_int32
+        L.orc_schedule_one_lat.argtypes = [C.POINTER(Snapshot), C.POINTER(Profile), C.c_int64, C.c_int32, C.c_void_p,
+                                           C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(LatencyRequest),
+                                           C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_score_token_load.argtypes = [C.POINTER(Snapshot), C.c_void_p, C.c_double, C.c_void_p]
+        L.orc_latency_predict.argtypes = [C.POINTER(LatencyParams), C.c_double, C.c_int64, C.c_int64, C.c_int64,
+                                          C.c_int64, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_latency_validate.argtypes = [C.POINTER(LatencyParams), C.c_double, C.c_double, C.c_double, C.c_double,
+                                           C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
+        L.orc_score_latency_info.argtypes = [C.POINTER(LatencyParams), C.POINTER(Snapshot), C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_score_latency.argtypes = [C.POINTER(LatencyParams), C.POINTER(Snapshot), C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.POINTER(LatencyRequest), C.c_void_p, C.c_void_p]
         L.orc_schedule_batch.restype = C.c_int32
         L.orc_schedule_batch.argtypes = [C.POINTER(Snapshot), C.POINTER(Profile), C.c_void_p, C.POINTER(Batch), C.c_int32]
         L.orc_commit_picks.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
@@ -135,9 +187,14 @@ def hash_prompt(prompt: bytes, seed: int, block_chars: int, max_blocks: int) -> 
     return out[:n].copy()
 
 
-def make_profile(scorers, tie_mode=TIE_LOWEST_INDEX, tie_seed=0) -> Profile:
+def make_profile(scorers, tie_mode=TIE_LOWEST_INDEX, tie_seed=0, latency: LatencyParams | None = None,
+                 token_load_threshold: float = 0.0) -> Profile:
     """scorers: list of (kind, weight) in profile order."""
     p = Profile()
+    if latency is not None:
+        p._latency_keep = latency  # keep the pointee alive with the struct
+        p.latency = C.pointer(latency)
+    p.token_load_threshold = token_load_threshold
     p.n_scorers = len(scorers)
     for i, (k, w) in enumerate(scorers):
         p.scorer_kind[i] = int(k)
@@ -151,7 +208,8 @@ class SnapshotData:
     """Owns the numpy arrays a Snapshot struct points at."""
 
     def __init__(self, kv_usage, queue, running=None, lora_active=None, lora_waiting=None,
-                 lora_nmodels=None, lora_max=None, lora_words=None, endpoint_cols=()):
+                 lora_nmodels=None, lora_max=None, lora_words=None, endpoint_cols=(), min_tpot_slo=None,
+                 dispatched=None, prefill_role=None, inflight_tokens=None):
         self.M = len(kv_usage)
         M = self.M
         self.kv_usage = _arr(kv_usage, np.float64)
@@ -180,6 +238,14 @@ class SnapshotData:
         s.lora_max = _ptr(self.lora_max)
         for i, c in enumerate(self.endpoint_cols):
             s.endpoint_col[i] = _ptr(c)
+        self.min_tpot_slo = _arr(min_tpot_slo, np.float64)
+        self.dispatched = _arr(dispatched, np.int32)
+        self.prefill_role = _arr(prefill_role, np.uint8)
+        self.inflight_tokens = _arr(inflight_tokens, np.int64)
+        s.min_tpot_slo = _ptr(self.min_tpot_slo)
+        s.dispatched = _ptr(self.dispatched)
+        s.prefill_role = _ptr(self.prefill_role)
+        s.inflight_tokens = _ptr(self.inflight_tokens)
         self.struct = s
 
 
@@ -248,10 +314,51 @@ class Index:
         lib().orc_commit_picks(self._h, len(pick), _ptr(pick), _ptr(hashes), _ptr(n_hashes), stride, _ptr(gb))
 
 
-def score_single(kind: str, snap: SnapshotData, mask=None, adapter_id: int = -1):
+def latency_predict(lp: LatencyParams, kv, input_tokens, waiting, running, prefix_score, generated=1):
+    t, p = C.c_double(), C.c_double()
+    lib().orc_latency_predict(C.byref(lp), kv, input_tokens, waiting, running, generated, prefix_score, C.byref(t),
+                              C.byref(p))
+    return t.value, p.value
+
+
+def latency_validate(lp: LatencyParams, ttft, tpot, ttft_slo, tpot_slo, pod_min_tpot_slo=0.0, neutralize=False):
+    ok = np.zeros(3, np.int32)
+    hr = np.zeros(2, np.float64)
+    lib().orc_latency_validate(C.byref(lp), ttft, tpot, ttft_slo, tpot_slo, pod_min_tpot_slo, 1 if neutralize else 0,
+                               _ptr(ok), _ptr(hr))
+    return dict(ttft_ok=bool(ok[0]), tpot_ok=bool(ok[1]), valid=bool(ok[2]), headroom=float(hr[0]),
+                ttft_headroom=float(hr[1]))
+
+
+def score_latency_info(lp: LatencyParams, snap: SnapshotData, have_info, ttft_headroom, tpot_headroom, dispatched=None,
+                       mask=None, match=None, total=0):
+    out = np.full(snap.M, np.nan)
+    hv = _arr(have_info, np.uint8)
+    th, ph = _arr(ttft_headroom, np.float64), _arr(tpot_headroom, np.float64)
+    dp = _arr(dispatched, np.int32)
+    m, mt = _arr(mask, np.uint32), _arr(match, np.uint16)
+    lib().orc_score_latency_info(C.byref(lp), C.byref(snap.struct), _ptr(m), _ptr(hv), _ptr(th), _ptr(ph), _ptr(dp),
+                                 _ptr(mt), total, _ptr(out))
+    return out
+
+
+def score_latency(lp: LatencyParams, snap: SnapshotData, input_tokens=0, ttft_slo=0.0, tpot_slo=0.0, mask=None,
+                  match=None, total=0):
+    out = np.full(snap.M, np.nan)
+    pred = np.zeros((max(snap.M, 1), 2))
+    lr = LatencyRequest(input_tokens, ttft_slo, tpot_slo)
+    m, mt = _arr(mask, np.uint32), _arr(match, np.uint16)
+    lib().orc_score_latency(C.byref(lp), C.byref(snap.struct), _ptr(m), _ptr(mt), total, C.byref(lr), _ptr(out),
+                            _ptr(pred))
+    return out, pred[:snap.M]
+
+
+def score_single(kind: str, snap: SnapshotData, mask=None, adapter_id: int = -1, threshold: float = 0.0):
     out = np.full(snap.M, np.nan)
     m = _arr(mask, np.uint32)
-    if kind == "lora":
+    if kind == "token_load":
+        lib().orc_score_token_load(C.byref(snap.struct), _ptr(m), threshold, _ptr(out))
+    elif kind == "lora":
         lib().orc_score_lora(C.byref(snap.struct), _ptr(m), adapter_id, _ptr(out))
     else:
         getattr(lib(), f"orc_score_{kind}")(C.byref(snap.struct), _ptr(m), _ptr(out))
@@ -286,7 +393,7 @@ def schedule_batch(snap: SnapshotData, profile: Profile, index: Index | None, R:
                    prompt_off=None, model_seed=None, hashes_in=None, n_hashes_in=None, adapter_id=None,
                    cand_mask=None, dense_feat=None, dense_total=None, block_chars=64, max_blocks=256,
                    request_base=0, n_threads=1, want_match=False, want_hashes=False, want_tie_set=False,
-                   want_scores=False):
+                   want_scores=False, input_tokens=None, ttft_slo=None, tpot_slo=None, want_pred=False):
     M = snap.M
     mw = (M + 31) // 32
     b = Batch()
@@ -310,6 +417,9 @@ def schedule_batch(snap: SnapshotData, profile: Profile, index: Index | None, R:
     put("cand_mask", cand_mask, np.uint32)
     put("dense_feat", dense_feat, np.float32)
     put("dense_total", dense_total, np.uint16)
+    put("input_tokens", input_tokens, np.int32)
+    put("ttft_slo", ttft_slo, np.float64)
+    put("tpot_slo", tpot_slo, np.float64)
     b.block_chars = block_chars
     b.max_blocks = max_blocks
     out = dict(pick=np.zeros(R, np.int32), pick_score=np.zeros(R, np.float64), tie_count=np.zeros(R, np.int32),
@@ -322,6 +432,8 @@ def schedule_batch(snap: SnapshotData, profile: Profile, index: Index | None, R:
         out["tie_set"] = np.zeros((R, mw), np.uint32)
     if want_scores:
         out["weighted_out"] = np.zeros((R, M), np.float64)
+    if want_pred:
+        out["pred_out"] = np.zeros((R, M, 2), np.float64)
     for k, v in out.items():
         setattr(b, k, _ptr(v))
     lib().orc_schedule_batch(C.byref(snap.struct), C.byref(profile), index._h if index is not None else None,

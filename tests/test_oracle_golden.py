@@ -296,3 +296,83 @@ def test_batch_matches_single_and_threads_agree():
                              total=int(a["total_blocks"][r]))
         assert one["pick"] == a["pick"][r] and one["score"] == a["pick_score"][r]
         assert one["tie_count"] == a["tie_count"][r]
+
+
+# ---------------------------------------------------------------- token-load scorer, latency fold-in
+def test_token_load_scorer(golden):
+    g = golden["token_load_scorer"]
+    snap = o.SnapshotData([0.0] * 3, [0] * 3, inflight_tokens=g["tokens"])
+    got = o.score_single("token_load", snap, threshold=g["threshold"])
+    assert np.allclose(got, g["want"], atol=g["tolerance"])
+    # attribute absent => tokenLoad 0 => 1.0 (token_load.go:89-100); threshold <= 0 => default 4194304 (:57-61)
+    assert np.array_equal(o.score_single("token_load", o.SnapshotData([0.0] * 2, [0] * 2), threshold=10.0), [1.0, 1.0])
+    snap2 = o.SnapshotData([0.0] * 3, [0] * 3, inflight_tokens=[-5, 2097152, 1 << 40])
+    assert np.array_equal(o.score_single("token_load", snap2, threshold=0.0), [1.0, 0.5, 0.0])
+
+
+def test_latency_validate(golden):
+    for c in golden["latency_validate"]["cases"]:
+        lp = o.make_latency_params(streaming_mode=c["streaming"])
+        neutral = bool(c.get("neutralize", 0)) or not c["streaming"]
+        got = o.latency_validate(lp, c["ttft"], c["tpot"], c["ttft_slo"], c["tpot_slo"], c["pod_min"], neutral)
+        assert got["ttft_ok"] == c["want_ttft_ok"], c["name"]
+        assert got["tpot_ok"] == c["want_tpot_ok"], c["name"]
+        assert got["valid"] == c["want_valid"], c["name"]
+        if c.get("want_ttft_headroom_pos"):
+            assert got["ttft_headroom"] > 0, c["name"]
+        if "want_headroom_pos" in c:
+            assert (got["headroom"] > 0) == c["want_headroom_pos"], c["name"]
+        if "want_headroom" in c:
+            assert got["headroom"] == c["want_headroom"], c["name"]
+
+
+def test_latency_scorer(golden):
+    lp = o.make_latency_params()
+    for c in golden["latency_scorer"]["cases"]:
+        eps = c["endpoints"]
+        snap = o.SnapshotData([e[0] for e in eps], [e[1] for e in eps], [e[2] for e in eps])
+        if c["info"] is None:
+            got = o.score_latency_info(lp, snap, None, None, None)
+        else:
+            got = o.score_latency_info(lp, snap, [1] * len(eps), [i[0] for i in c["info"]], [i[1] for i in c["info"]],
+                                       [i[2] for i in c["info"]])
+        a = c["assert"]
+        for i in a.get("nonzero", []):
+            assert got[i] != 0, c["name"]
+        for i in a.get("zero", []):
+            assert got[i] == 0, c["name"]
+        for hi, lo in a.get("greater", []):
+            assert got[hi] > got[lo], c["name"]
+        assert np.allclose(got, c["derived"], atol=1e-12), (c["name"], got)
+
+
+def test_latency_predict_and_pipeline():
+    # prediction.go:164-194, left-to-right float64; exact against the same expression in Python floats
+    lp = o.make_latency_params(ttft_intercept=12.5, ttft_kv=80.0, ttft_input=0.031, ttft_waiting=7.25, ttft_running=1.5,
+                               ttft_prefix=-40.0, tpot_intercept=9.0, tpot_kv=11.0, tpot_input=0.0007,
+                               tpot_waiting=0.9, tpot_running=0.35, tpot_generated=0.01, streaming_mode=1)
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        kv, inp, w, r, pf = rng.random(), int(rng.integers(0, 5000)), int(rng.integers(0, 50)), int(rng.integers(0, 90)), rng.random()
+        t, p = o.latency_predict(lp, kv, inp, w, r, pf)
+        assert t == ((((12.5 + 80.0 * kv) + 0.031 * float(inp)) + 7.25 * float(w)) + 1.5 * float(r)) + -40.0 * pf
+        assert p == ((((9.0 + 11.0 * kv) + 0.0007 * float(inp)) + 0.9 * float(w)) + 0.35 * float(r)) + 0.01 * 1.0
+    # producer + scorer == scorer over the producer's headrooms, candidates only
+    M = 37
+    kvs, q, run = rng.random(M), rng.integers(0, 20, M), rng.integers(0, 30, M)
+    snap = o.SnapshotData(kvs, q, run, min_tpot_slo=rng.choice([0.0, 25.0, 60.0], M), dispatched=rng.integers(0, 3, M),
+                          prefill_role=(rng.random(M) < 0.2).astype(np.uint8))
+    match = rng.integers(0, 9, M).astype(np.uint16)
+    mask = mask_from_list(M, [m for m in range(M) if m % 3])
+    for ttft_slo, tpot_slo in [(0.0, 0.0), (150.0, 30.0), (400.0, 50.0), (1e6, 1e6)]:
+        got, pred = o.score_latency(lp, snap, 700, ttft_slo, tpot_slo, mask, match, 8)
+        th, ph, have = np.zeros(M), np.zeros(M), np.ones(M, np.uint8)
+        for m in range(M):
+            t, p = o.latency_predict(lp, kvs[m], 700, int(q[m]), int(run[m]), match[m] / 8)
+            assert (t, p) == tuple(pred[m])
+            v = o.latency_validate(lp, t, p, ttft_slo, tpot_slo, snap.min_tpot_slo[m], bool(snap.prefill_role[m]))
+            th[m], ph[m] = v["ttft_headroom"], v["headroom"]
+        want = o.score_latency_info(lp, snap, have, th, ph, snap.dispatched, mask)
+        assert np.array_equal(got, want, equal_nan=True)
+        cand = ~np.isnan(got)
+        assert cand.sum() == sum(1 for m in range(M) if m % 3) and (got[cand] >= 0).all() and (got[cand] <= 1.01).all()
