@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 MAX_SCORERS = 8
 MAX_ENDPOINT_COLS = 4
 
-SCORER = {"queue": 0, "kv": 1, "prefix": 2, "lora": 3, "running": 4,
+SCORER = {"queue": 0, "kv": 1, "prefix": 2, "lora": 3, "running": 4, "latency": 5, "token_load": 6,
           "col0": 8, "col1": 9, "col2": 10, "col3": 11, "pair0": 16, "pair1": 17}
 TIE_LOWEST_INDEX, TIE_SEEDED_RANDOM = 0, 1
 
@@ -25,14 +25,28 @@ class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_scorers", C.c_int32), ("scorer_kind", C.c_int32 * MAX_SCORERS),
                 ("scorer_weight", C.c_double * MAX_SCORERS), ("block_chars", C.c_int32), ("max_blocks", C.c_int32),
                 ("tie_mode", C.c_int32), ("tie_seed", C.c_uint64), ("max_endpoints", C.c_int32),
-                ("max_adapters", C.c_int32), ("prefix_capacity", C.c_int64), ("lru_capacity_default", C.c_int32)]
+                ("max_adapters", C.c_int32), ("prefix_capacity", C.c_int64), ("lru_capacity_default", C.c_int32),
+                ("token_load_threshold", C.c_double)]
+
+
+class LatencyParams(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("has_predictions", C.c_int32),
+                ("ttft_intercept", C.c_double), ("ttft_kv", C.c_double), ("ttft_input", C.c_double),
+                ("ttft_waiting", C.c_double), ("ttft_running", C.c_double), ("ttft_prefix", C.c_double),
+                ("tpot_intercept", C.c_double), ("tpot_kv", C.c_double), ("tpot_input", C.c_double),
+                ("tpot_waiting", C.c_double), ("tpot_running", C.c_double), ("tpot_generated", C.c_double),
+                ("slo_buffer_factor", C.c_double), ("streaming_mode", C.c_int32), ("strategy_most", C.c_int32),
+                ("ttft_weight", C.c_double), ("tpot_weight", C.c_double), ("composite_kv", C.c_double),
+                ("composite_queue", C.c_double), ("composite_prefix", C.c_double)]
 
 
 class Snapshot(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("M", C.c_int32), ("lora_words", C.c_int32), ("location", C.c_int32),
                 ("kv_usage", C.c_void_p), ("queue", C.c_void_p), ("running", C.c_void_p), ("lora_active", C.c_void_p),
                 ("lora_waiting", C.c_void_p), ("lora_nmodels", C.c_void_p), ("lora_max", C.c_void_p),
-                ("endpoint_col", C.c_void_p * MAX_ENDPOINT_COLS), ("epoch", C.c_uint64), ("stream", C.c_void_p)]
+                ("endpoint_col", C.c_void_p * MAX_ENDPOINT_COLS), ("epoch", C.c_uint64), ("stream", C.c_void_p),
+                ("min_tpot_slo", C.c_void_p), ("dispatched", C.c_void_p), ("prefill_role", C.c_void_p),
+                ("inflight_tokens", C.c_void_p)]
 
 
 class Batch(C.Structure):
@@ -44,7 +58,8 @@ class Batch(C.Structure):
                 ("cand_mask", C.c_void_p), ("dense_feat", C.c_void_p), ("dense_total", C.c_void_p),
                 ("pick", C.c_void_p), ("pick_score", C.c_void_p), ("tie_count", C.c_void_p),
                 ("match_blocks", C.c_void_p), ("total_blocks", C.c_void_p), ("hashes_out", C.c_void_p),
-                ("scores_out", C.c_void_p), ("stream", C.c_void_p)]
+                ("scores_out", C.c_void_p), ("stream", C.c_void_p), ("input_tokens", C.c_void_p),
+                ("ttft_slo", C.c_void_p), ("tpot_slo", C.c_void_p), ("pred_out", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -64,6 +79,8 @@ ABI_SYMBOLS = [
     ("eppscore_get_stats", C.c_int32, [_P, C.POINTER(Stats)]),
     ("eppscore_set_debug", C.c_int32, [_P, C.c_int32, C.c_int64]),
     ("eppscore_set_snapshot", C.c_int32, [_P, C.POINTER(Snapshot)]),
+    ("eppscore_latency_params_default", None, [C.POINTER(LatencyParams)]),
+    ("eppscore_set_latency_params", C.c_int32, [_P, C.POINTER(LatencyParams)]),
     ("eppscore_schedule_batch", C.c_int32, [_P, C.POINTER(Batch)]),
     ("eppscore_hash_prompts", C.c_int32, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     ("eppscore_model_seed", C.c_uint64, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),

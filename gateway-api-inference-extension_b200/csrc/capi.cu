@@ -71,6 +71,9 @@ struct eppscore_engine {
   int32_t M = 0, A = 0, lora_words = 0;
   uint64_t epoch = 0;
   DevBuf raw_kv, raw_queue, raw_running, raw_act, raw_wait, raw_nmodels, raw_max, raw_col[4];
+  DevBuf raw_min_tpot, raw_dispatched, raw_prefill, raw_tokens, lat_ep, lat_flags;
+  eppscore_latency_params lat_params{};  // pending: applied by the next set_snapshot
+  LatArgs lat_args{};                    // what the current snapshot was prepared with
   bool have_col[4] = {false, false, false, false};
   bool have_running = false;
   const int64_t* cur_queue = nullptr;    // raw WaitingQueueSize / RunningRequestsSize of the current snapshot
@@ -90,7 +93,7 @@ struct eppscore_engine {
 
   // scratch for host-location batches and internal hashes
   DevBuf s_prompts, s_off, s_len, s_seed, s_hashes, s_nh, s_adapter, s_mask, s_dense, s_dtotal, s_pick, s_score,
-      s_tie, s_match, s_total, s_scores;
+      s_tie, s_match, s_total, s_scores, s_intok, s_tslo, s_pslo, s_pred;
 };
 
 namespace {
@@ -110,7 +113,7 @@ int32_t cuda_fail(eppscore_engine* e, cudaError_t c, const char* what) {
   } while (0)
 
 bool is_endpoint_term_kind(int k, bool masked) {
-  if (k == EPPSCORE_SCORER_KV_CACHE) return true;
+  if (k == EPPSCORE_SCORER_KV_CACHE || k == EPPSCORE_SCORER_TOKEN_LOAD) return true;
   if (k >= EPPSCORE_SCORER_ENDPOINT_COL0 && k < EPPSCORE_SCORER_ENDPOINT_COL0 + EPPSCORE_MAX_ENDPOINT_COLS) return true;
   if (!masked && (k == EPPSCORE_SCORER_QUEUE || k == EPPSCORE_SCORER_RUNNING)) return true;
   return false;
@@ -151,6 +154,8 @@ void build_plan(eppscore_engine* e, bool masked, PlanSet* ps) {
       p.arg[ns] = k == EPPSCORE_SCORER_QUEUE ? 0 : 1;
     } else if (k == EPPSCORE_SCORER_PREFIX) {
       p.kind[ns] = STEP_PREFIX;
+    } else if (k == EPPSCORE_SCORER_LATENCY) {
+      p.kind[ns] = STEP_LATENCY;
     } else if (k == EPPSCORE_SCORER_LORA) {
       p.kind[ns] = STEP_LORA;
       static const double cls_score[4] = {0.0, 0.6, 0.8, 1.0};  // lora_affinity.go:84-99
@@ -256,6 +261,10 @@ struct DevBatch {  // all device pointers
   const uint32_t* cand_mask;
   const float* dense_feat;
   const uint16_t* dense_total;
+  const int32_t* input_tokens;
+  const double* ttft_slo;
+  const double* tpot_slo;
+  double* pred_out;
   int32_t* pick;
   double* pick_score;
   int32_t* tie_count;
@@ -312,9 +321,19 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
   a.match_out = b.match_blocks;
   a.total_out = b.total_blocks;
   a.scores_out = b.scores_out;
+  if (cfg_has(e->cfg, EPPSCORE_SCORER_LATENCY)) {
+    if (dense) return fail(e, EPPSCORE_ERR_INVALID, "the latency scorer is not available on dense feature rows");
+    if (!e->lat_args.enabled) return fail(e, EPPSCORE_ERR_INVALID, "latency scorer configured but the snapshot was prepared without latency params");
+    a.lat = e->lat_args;
+    a.lat.input_tokens = b.input_tokens;
+    a.lat.ttft_slo = b.ttft_slo;
+    a.lat.tpot_slo = b.tpot_slo;
+    a.lat.pred_out = b.pred_out;
+  }
 
   if (!dense) {
-    const bool want_prefix = cfg_has(e->cfg, EPPSCORE_SCORER_PREFIX) || b.match_blocks || b.total_blocks || b.hashes_out;
+    const bool want_prefix = cfg_has(e->cfg, EPPSCORE_SCORER_PREFIX) || cfg_has(e->cfg, EPPSCORE_SCORER_LATENCY) ||
+                             b.match_blocks || b.total_blocks || b.hashes_out;
     if (want_prefix && (b.hashes_in || b.prompt_bytes)) {
       if (b.hashes_in) {
         if (!b.n_hashes_in || b.hash_stride <= 0) return fail(e, EPPSCORE_ERR_INVALID, "hashes_in needs n_hashes_in and hash_stride");
@@ -404,6 +423,27 @@ void eppscore_config_default(eppscore_config* c) {
   c->max_adapters = 64;
   c->prefix_capacity = 1 << 18;
   c->lru_capacity_default = 31250;  // types.go:109
+  c->token_load_threshold = 4194304.0;  // tokenQueueThresholdDefault, token_load.go:33
+}
+
+void eppscore_latency_params_default(eppscore_latency_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->struct_size = sizeof(*p);
+  p->has_predictions = 1;
+  p->slo_buffer_factor = 1.0;  // predictedlatency/plugin.go:132
+  p->streaming_mode = 0;       // :134
+  p->strategy_most = 0;        // scorer/latency/plugin.go:86 "least"
+  p->ttft_weight = 0.8;        // :84-85
+  p->tpot_weight = 0.2;
+  p->composite_kv = p->composite_queue = p->composite_prefix = 1.0;  // :87-89
+}
+
+int32_t eppscore_set_latency_params(eppscore_engine* e, const eppscore_latency_params* p) {
+  if (!e) return EPPSCORE_ERR_INVALID;
+  if (!p || p->struct_size != sizeof(eppscore_latency_params)) return fail(e, EPPSCORE_ERR_INVALID, "latency params NULL or struct_size mismatch");
+  if (!(p->slo_buffer_factor > 0)) return fail(e, EPPSCORE_ERR_INVALID, "sloBufferFactor must be > 0");  // predictedlatency/plugin.go:169
+  e->lat_params = *p;
+  return EPPSCORE_OK;
 }
 
 int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_engine** out) {
@@ -414,8 +454,13 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   if (cfg->n_scorers < 0 || cfg->n_scorers > EPPSCORE_MAX_SCORERS) return fail(nullptr, EPPSCORE_ERR_INVALID, "n_scorers out of range");
   for (int i = 0; i < cfg->n_scorers; i++) {
     const int k = cfg->scorer_kind[i];
-    const bool ok = (k >= 0 && k <= 4) || (k >= 8 && k < 12) || (k >= 16 && k < 18);
+    const bool ok = (k >= 0 && k <= 6) || (k >= 8 && k < 12) || (k >= 16 && k < 18);
     if (!ok) return fail(nullptr, EPPSCORE_ERR_INVALID, "unknown scorer kind");
+  }
+  {
+    int nlat = 0;
+    for (int i = 0; i < cfg->n_scorers; i++) nlat += cfg->scorer_kind[i] == EPPSCORE_SCORER_LATENCY;
+    if (nlat > 1) return fail(nullptr, EPPSCORE_ERR_INVALID, "at most one latency scorer per profile");
   }
   if (cfg->max_endpoints < 1 || cfg->max_endpoints > 8192)
     return fail(nullptr, EPPSCORE_ERR_CAPACITY, "max_endpoints must be in [1, 8192]");
@@ -434,6 +479,8 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   if (e->cfg.max_adapters < 1) e->cfg.max_adapters = 64;
   if (e->cfg.prefix_capacity <= 0) e->cfg.prefix_capacity = 1 << 18;
   if (e->cfg.lru_capacity_default <= 0) e->cfg.lru_capacity_default = 31250;
+  if (!(e->cfg.token_load_threshold > 0)) e->cfg.token_load_threshold = 4194304.0;  // token_load.go:57-61
+  eppscore_latency_params_default(&e->lat_params);
   e->geo = make_geo(e->cfg.max_endpoints);
   e->A_cap = (e->cfg.max_adapters + 63) / 64 * 64;
   if (((uint64_t)e->cfg.prefix_capacity + 1) * (uint64_t)e->geo.row_words >= (1ULL << 32))
@@ -462,6 +509,14 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   CK(nullptr, ep->raw_nmodels.reserve(mp * 4));
   CK(nullptr, ep->raw_max.reserve(mp * 4));
   for (int i = 0; i < 4; i++) CK(nullptr, ep->raw_col[i].reserve(mp * 8));
+  CK(nullptr, ep->raw_tokens.reserve(mp * 8));
+  if (cfg_has(ep->cfg, EPPSCORE_SCORER_LATENCY)) {
+    CK(nullptr, ep->raw_min_tpot.reserve(mp * 8));
+    CK(nullptr, ep->raw_dispatched.reserve(mp * 4));
+    CK(nullptr, ep->raw_prefill.reserve(mp));
+    CK(nullptr, ep->lat_ep.reserve(mp * 8 * kLatArrays));
+    CK(nullptr, ep->lat_flags.reserve(mp * 4));
+  }
   for (int i = 0; i < kMaxSteps; i++) CK(nullptr, ep->term[i].reserve(mp * 8));
   CK(nullptr, ep->fold_unmasked.reserve(mp * 8));
   CK(nullptr, ep->fold_masked.reserve(mp * 8));
@@ -511,7 +566,8 @@ void eppscore_destroy(eppscore_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
+  DevBuf* bufs[] = {&e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep, &e->lat_flags,
+                    &e->s_intok, &e->s_tslo, &e->s_pslo, &e->s_pred, &e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
                     &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->prefix_lut2d, &e->st_idx, &e->st_val, &e->st_slot,
                     &e->probe_out, &e->s_prompts, &e->s_off, &e->s_len, &e->s_seed, &e->s_hashes, &e->s_nh, &e->s_adapter,
                     &e->s_mask, &e->s_dense, &e->s_dtotal, &e->s_pick, &e->s_score, &e->s_tie, &e->s_match, &e->s_total, &e->s_scores};
@@ -585,6 +641,12 @@ int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
     CK(e, cp(e->raw_nmodels, s->lora_nmodels, M * 4));
     CK(e, cp(e->raw_max, s->lora_max, M * 4));
     for (int i = 0; i < 4; i++) CK(e, cp(e->raw_col[i], s->endpoint_col[i], M * 8));
+    CK(e, cp(e->raw_tokens, s->inflight_tokens, M * 8));
+    if (e->lat_ep.p) {
+      CK(e, cp(e->raw_min_tpot, s->min_tpot_slo, M * 8));
+      CK(e, cp(e->raw_dispatched, s->dispatched, M * 4));
+      CK(e, cp(e->raw_prefill, s->prefill_role, M));
+    }
   }
   e->cur_queue = on_device ? s->queue : e->raw_queue.as<int64_t>();
   e->cur_running = s->running ? (on_device ? s->running : e->raw_running.as<int64_t>()) : nullptr;
@@ -611,6 +673,60 @@ int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
   pa.maxm = s->lora_max ? (on_device ? s->lora_max : e->raw_max.as<int32_t>()) : nullptr;
   for (int i = 0; i < 4; i++)
     pa.col[i] = s->endpoint_col[i] ? (on_device ? s->endpoint_col[i] : e->raw_col[i].as<double>()) : nullptr;
+  pa.tokens = s->inflight_tokens ? (on_device ? s->inflight_tokens : e->raw_tokens.as<int64_t>()) : nullptr;
+  pa.token_threshold = e->cfg.token_load_threshold;
+  e->lat_args = LatArgs{};
+  if (e->lat_ep.p) {
+    // latency fold-in: split the linear forms into endpoint-only arrays (prepared on the device) and
+    // per-request / per-pair terms (LatArgs); the weight normalisations are single IEEE divides
+    // (scorer/latency/plugin.go:325-333,373-379) done here on the host (-ffp-contract=off).
+    const eppscore_latency_params& lp = e->lat_params;
+    pa.min_tpot = s->min_tpot_slo ? (on_device ? s->min_tpot_slo : e->raw_min_tpot.as<double>()) : nullptr;
+    pa.dispatched = s->dispatched ? (on_device ? s->dispatched : e->raw_dispatched.as<int32_t>()) : nullptr;
+    pa.prefill = s->prefill_role ? (on_device ? s->prefill_role : e->raw_prefill.as<uint8_t>()) : nullptr;
+    const double coef[8] = {lp.ttft_intercept, lp.ttft_kv, lp.ttft_waiting, lp.ttft_running,
+                            lp.tpot_intercept, lp.tpot_kv, lp.tpot_waiting, lp.tpot_running};
+    for (int i = 0; i < 8; i++) pa.lat_coef[i] = coef[i];
+    pa.lat_buffer = lp.slo_buffer_factor;
+    pa.lat_streaming = lp.streaming_mode;
+    volatile double wkv = lp.composite_kv, wq = lp.composite_queue, wpref = lp.composite_prefix;
+    volatile double sumw = wkv + wq;
+    sumw = sumw + wpref;
+    if (sumw <= 0) {
+      wkv = 1;
+      wq = 0;
+      wpref = 0;
+      sumw = 1;
+    }
+    wkv = wkv / sumw;
+    wq = wq / sumw;
+    wpref = wpref / sumw;
+    pa.lat_ckv = wkv;
+    pa.lat_ep = e->lat_ep.as<double>();
+    pa.lat_flags = e->lat_flags.as<int32_t>();
+    LatArgs& L = e->lat_args;
+    L.enabled = 1;
+    L.has_predictions = lp.has_predictions;
+    L.strategy_most = lp.strategy_most;
+    L.ttft_input = lp.ttft_input;
+    L.ttft_prefix = lp.ttft_prefix;
+    L.tpot_input = lp.tpot_input;
+    L.tpot_generated = lp.tpot_generated;  // * float64(NumTokensGenerated = 1) is exact
+    L.buffer = lp.slo_buffer_factor;
+    volatile double wsum = lp.ttft_weight + lp.tpot_weight;
+    if (wsum <= 0) {
+      L.alpha = 1.0;
+      L.beta = 0.0;
+    } else {
+      volatile double al = lp.ttft_weight / wsum, be = lp.tpot_weight / wsum;
+      L.alpha = al;
+      L.beta = be;
+    }
+    L.wq = wq;
+    L.wpref = wpref;
+    L.ep = pa.lat_ep;
+    L.flags = pa.lat_flags;
+  }
   pa.lora_words = e->lora_words;
   pa.A = e->A;
   int lead_u = 0, lead_m = 0;
@@ -671,6 +787,10 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
     d.cand_mask = b->cand_mask;
     d.dense_feat = b->dense_feat;
     d.dense_total = b->dense_total;
+    d.input_tokens = b->input_tokens;
+    d.ttft_slo = b->ttft_slo;
+    d.tpot_slo = b->tpot_slo;
+    d.pred_out = b->pred_out;
     d.pick = b->pick;
     d.pick_score = b->pick_score;
     d.tie_count = b->tie_count;
@@ -710,6 +830,9 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
   H2D(e->s_mask, cand_mask, R * mw)
   H2D(e->s_dense, dense_feat, R * M * 4)
   H2D(e->s_dtotal, dense_total, R)
+  H2D(e->s_intok, input_tokens, R)
+  H2D(e->s_tslo, ttft_slo, R)
+  H2D(e->s_pslo, tpot_slo, R)
 #undef H2D
   CK(e, e->s_pick.reserve(R * 4));
   CK(e, e->s_score.reserve(R * 8));
@@ -729,6 +852,10 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
     CK(e, e->s_scores.reserve(R * M * 8));
     d.scores_out = e->s_scores.as<double>();
   }
+  if (b->pred_out) {
+    CK(e, e->s_pred.reserve(R * M * 16));
+    d.pred_out = e->s_pred.as<double>();
+  }
   uint64_t* hashes_dev = nullptr;
   if (b->hashes_out && !b->hashes_in) {
     // reuse the internal hash scratch as the device-side hashes_out
@@ -744,6 +871,7 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
   if (b->match_blocks) CK(e, cudaMemcpyAsync(b->match_blocks, d.match_blocks, R * M * 2, cudaMemcpyDeviceToHost, e->stream));
   if (b->total_blocks) CK(e, cudaMemcpyAsync(b->total_blocks, d.total_blocks, R * 2, cudaMemcpyDeviceToHost, e->stream));
   if (b->scores_out) CK(e, cudaMemcpyAsync(b->scores_out, d.scores_out, R * M * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (b->pred_out) CK(e, cudaMemcpyAsync(b->pred_out, d.pred_out, R * M * 16, cudaMemcpyDeviceToHost, e->stream));
   if (hashes_dev) CK(e, cudaMemcpyAsync(b->hashes_out, hashes_dev, R * (size_t)mb * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
   return EPPSCORE_OK;

@@ -33,7 +33,31 @@ enum StepKind : int32_t {
   STEP_PREFIX = 1,   // + clamp(match/total)*w          (scorer/prefix/plugin.go:95-117)
   STEP_LORA = 2,     // + clamp(class score)*w          (scorer/loraaffinity/lora_affinity.go:76-102)
   STEP_PAIR = 3,     // + clamp(double(feat[arg]))*w    (dense per-pair column)
-  STEP_MINMAX = 4    // + clamp((max-q)/(max-min))*w over the candidate set (queue.go:78-108), arg: 0 queue 1 running
+  STEP_MINMAX = 4,   // + clamp((max-q)/(max-min))*w over the candidate set (queue.go:78-108), arg: 0 queue 1 running
+  STEP_LATENCY = 5   // + clamp(latency-scorer)*w: prediction + headroom + tier/bucket logic (scorer/latency/plugin.go:144-318)
+};
+
+// Latency fold-in (score_matrix.cu).  Per-endpoint arrays are prepared once per snapshot (prepare_kernel.cu):
+//   ep[0] tA = ttft_intercept + ttft_kv*kv      ep[1] tW = ttft_waiting*waiting   ep[2] tR = ttft_running*running
+//   ep[3] pA = tpot_intercept + tpot_kv*kv      ep[4] pW = tpot_waiting*waiting   ep[5] pR = tpot_running*running
+//   ep[6] lim = podMinTPOTSLO > 0 ? podMinTPOTSLO*buffer : +inf                   ep[7] cK = composite_kv*(1-kv)
+//   flags bit 0: dispatched == 0 (idle), bit 1: TPOT neutralised (!streaming || prefill role)
+constexpr int kLatArrays = 8;
+struct LatArgs {
+  int32_t enabled;
+  int32_t has_predictions;
+  int32_t strategy_most;
+  int32_t pad;
+  double ttft_input, ttft_prefix, tpot_input, tpot_generated;
+  double buffer;            // SLOBufferFactor
+  double alpha, beta;       // normalizedWeights(ttftWeight, tpotWeight), plugin.go:373-379
+  double wq, wpref;         // normalised composite weights (queue, prefix); the kv one is folded into ep[7]
+  const double* ep;         // [kLatArrays][Mpad]
+  const int32_t* flags;     // [Mpad]
+  const int32_t* input_tokens;  // [R] or null
+  const double* ttft_slo;   // [R] or null
+  const double* tpot_slo;   // [R] or null
+  double* pred_out;         // [R][M][2] or null
 };
 
 struct Plan {
@@ -123,6 +147,7 @@ struct ScoreArgs {
   uint16_t* match_out;          // [R][M] or null
   uint16_t* total_out;          // [R] or null
   double* scores_out;           // [R][M] or null (diagnostics)
+  LatArgs lat;
 };
 
 struct HashArgs {
@@ -153,8 +178,19 @@ struct PrepareArgs {
   const int32_t* nmodels;
   const int32_t* maxm;
   const double* col[4];
+  const int64_t* tokens;        // InFlightLoad.Tokens or null
+  double token_threshold;
   int32_t lora_words;
   int32_t A;
+  // latency fold-in inputs (null lat_ep: not configured)
+  const double* min_tpot;
+  const int32_t* dispatched;
+  const uint8_t* prefill;
+  double lat_coef[8];           // ttft {intercept, kv, waiting, running}, tpot {intercept, kv, waiting, running}
+  double lat_buffer, lat_ckv;
+  int32_t lat_streaming;
+  double* lat_ep;               // [kLatArrays][Mpad]
+  int32_t* lat_flags;           // [Mpad]
   // outputs of the endpoint kernel
   double* term[kMaxSteps];      // per scorer (null where not an endpoint term)
   double* fold_unmasked;        // leading run folded (or null)

@@ -68,6 +68,14 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const __grid_co
             sc = 1.0;                                                               // queue.go:95-98
           else
             sc = __ddiv_rn(__ll2double_rn(mx - q[m]), __ll2double_rn(mx - mn));    // queue.go:99
+        } else if (kind == 6) {                                                      // token_load.go:96-106
+          double load = a.tokens ? __ll2double_rn(a.tokens[m]) : 0.0;
+          if (load <= 0.0) {
+            sc = 1.0;
+          } else {
+            if (load > a.token_threshold) load = a.token_threshold;
+            sc = __dsub_rn(1.0, __ddiv_rn(load, a.token_threshold));
+          }
         } else {
           const double* col = a.col[kind - 8];
           sc = col ? col[m] : 0.0;
@@ -81,6 +89,25 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const __grid_co
     }
     if (a.fold_unmasked) a.fold_unmasked[m] = fold_u;
     if (a.fold_masked) a.fold_masked[m] = fold_m;
+    // latency fold-in: the endpoint-only prefixes of the two linear forms (prediction.go:171-185 evaluates
+    // left to right, so "intercept + c_kv*kv" is a rounded partial sum and the products are rounded terms)
+    if (a.lat_ep) {
+      const double kv = m < M ? a.kv[m] : 0.0;
+      const double wt = (m < M && a.queue) ? __ll2double_rn(a.queue[m]) : 0.0;
+      const double rn = (m < M && a.running) ? __ll2double_rn(a.running[m]) : 0.0;
+      const double pod_min = (m < M && a.min_tpot) ? a.min_tpot[m] : 0.0;
+      a.lat_ep[0 * Mpad + m] = __dadd_rn(a.lat_coef[0], __dmul_rn(a.lat_coef[1], kv));
+      a.lat_ep[1 * Mpad + m] = __dmul_rn(a.lat_coef[2], wt);
+      a.lat_ep[2 * Mpad + m] = __dmul_rn(a.lat_coef[3], rn);
+      a.lat_ep[3 * Mpad + m] = __dadd_rn(a.lat_coef[4], __dmul_rn(a.lat_coef[5], kv));
+      a.lat_ep[4 * Mpad + m] = __dmul_rn(a.lat_coef[6], wt);
+      a.lat_ep[5 * Mpad + m] = __dmul_rn(a.lat_coef[7], rn);
+      a.lat_ep[6 * Mpad + m] = pod_min > 0.0 ? __dmul_rn(pod_min, a.lat_buffer) : __longlong_as_double(0x7ff0000000000000LL);
+      a.lat_ep[7 * Mpad + m] = __dmul_rn(a.lat_ckv, __dsub_rn(1.0, kv));         // plugin.go:351,355
+      const bool idle = !(m < M && a.dispatched) || a.dispatched[m] == 0;
+      const bool neutral = !a.lat_streaming || (m < M && a.prefill && a.prefill[m]);
+      a.lat_flags[m] = (idle ? 1 : 0) | (neutral ? 2 : 0);
+    }
   }
 }
 

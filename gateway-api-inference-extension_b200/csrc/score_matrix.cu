@@ -9,6 +9,10 @@
 //                                                             then a per-row LUT lut[d] = clamp(d/(max-min))*w
 //   scorers + sum       scheduler_profile.go:151-174          float64, profile order, from 0.0
 //   picker              maxscore/picker.go:87-115             branch-free arg-max + warp-shuffle reduce
+//   latency fold-in     latencypredictorasync/prediction.go:164-194, predictedlatency/prediction.go:137-166,
+//   (LAT variants)      scorer/latency/plugin.go:144-367      per pair: both linear predictions and the headrooms;
+//                                                             per row: tier/bucket selection + min/max over the
+//                                                             candidates in one pass, then the normalised score
 // The scorer sequence is a template parameter (SEQ packs kind+1 per step, 4 bits each; 0 = runtime loop).
 #include "device_common.cuh"
 
@@ -17,7 +21,34 @@ namespace eppscore {
 constexpr int kMatrixWarps = 8;
 constexpr int kMaxJ = 8;
 
-template <uint32_t SEQ, bool MASKED, bool DIAG>
+constexpr int kLatW = 128;  // latency-scorer weights w/100 are tabulated for w in [0, 128) (plugin.go:301-306: w in [1,101])
+
+// One (request, endpoint) pair of the predicted-latency producer: TTFT/TPOT (prediction.go:171-185, left to right),
+// headrooms (predictedlatency/prediction.go:143-161, :100-104) and the endpoint's tier:
+//   0 positive, 1 negative & idle, 2 only TPOT negative, 3 only TTFT negative, 4 both negative
+// (plugin.go:177-238: the scorer scores the lowest non-empty tier only).
+struct LatPair {
+  double ttft, tpot, hT, hP;
+  int rank;
+};
+__device__ __forceinline__ LatPair lat_pair(const LatArgs& L, int MPAD, int m, double pref_term, double x_in, double y_in,
+                                            double ttft_slo, double buf_tpot) {
+  LatPair o;
+  const double* ep = L.ep + m;
+  o.ttft = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__ldg(ep), x_in), __ldg(ep + MPAD)), __ldg(ep + 2 * MPAD)), pref_term);
+  o.tpot = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__ldg(ep + 3 * MPAD), y_in), __ldg(ep + 4 * MPAD)), __ldg(ep + 5 * MPAD)),
+                     L.tpot_generated);                      // NumTokensGenerated = 1 (prediction.go:69)
+  o.hT = __dsub_rn(ttft_slo, o.ttft);
+  const int fl = __ldg(L.flags + m);
+  const double lim = __ldg(ep + 6 * MPAD);
+  const double buffered = lim < buf_tpot ? lim : buf_tpot;   // min(bufferedTPOT, podMinTPOTSLO*factor)
+  o.hP = (fl & 2) ? 0.0 : __dsub_rn(buffered, o.tpot);
+  const bool tn = o.hT < 0.0, pn = o.hP < 0.0;
+  o.rank = !(tn || pn) ? 0 : ((fl & 1) ? 1 : (tn && pn ? 4 : (tn ? 3 : 2)));
+  return o;
+}
+
+template <uint32_t SEQ, bool MASKED, bool DIAG, bool LAT>
 __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const __grid_constant__ ScoreArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Plan& plan = a.plan;
@@ -30,10 +61,13 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
   double* s_term = reinterpret_cast<double*>(smem_raw);
   long long* s_q = reinterpret_cast<long long*>(s_term + (size_t)plan.n_terms * MPAD);
   double* s_lora = reinterpret_cast<double*>(s_q + (MASKED ? 2 * MPAD : 0));
-  double* s_lut = s_lora + kMaxSteps * 4;
-  double* lut_p = s_lut + (size_t)warp * 2 * (kLutMax + 1);
+  double* s_latw = s_lora + kMaxSteps * 4;
+  double* s_lut = s_latw + (LAT ? kLatW : 0);
+  constexpr int NLUT = LAT ? 3 : 2;
+  double* lut_p = s_lut + (size_t)warp * NLUT * (kLutMax + 1);
   double* lut_q = lut_p + (kLutMax + 1);
-  unsigned char* s_cnt_all = reinterpret_cast<unsigned char*>(s_lut + (size_t)kMatrixWarps * 2 * (kLutMax + 1));
+  double* lut_l = lut_q + (LAT ? (kLutMax + 1) : 0);  // coef * (c/total) of the prediction / composite
+  unsigned char* s_cnt_all = reinterpret_cast<unsigned char*>(s_lut + (size_t)kMatrixWarps * NLUT * (kLutMax + 1));
   const int cnt_bytes = MPAD * (wide_cnt ? 2 : 1);
   unsigned char* cnt_raw = s_cnt_all + (size_t)warp * cnt_bytes;
   uint8_t* cnt8 = cnt_raw;
@@ -46,6 +80,14 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
       for (int m = threadIdx.x; m < MPAD; m += blockDim.x)
         s_q[which * MPAD + m] = (a.minmax_q[which] && m < M) ? a.minmax_q[which][m] : 0;
   if (threadIdx.x < kMaxSteps * 4) s_lora[threadIdx.x] = plan.lora_term[threadIdx.x >> 2][threadIdx.x & 3];
+  int lat_step = -1;
+  if (LAT) {
+    for (int s = 0; s < plan.n_steps; s++)
+      if (plan.kind[s] == STEP_LATENCY && lat_step < 0) lat_step = s;
+    // scores[ep] = w / wMax (plugin.go:306, :360), clamped and weighted like any scorer (scheduler_profile.go:168)
+    if (threadIdx.x < kLatW)
+      s_latw[threadIdx.x] = __dmul_rn(clamp01(__ddiv_rn((double)threadIdx.x, 100.0)), plan.weight[lat_step < 0 ? 0 : lat_step]);
+  }
   for (int i = threadIdx.x; i < (kMatrixWarps * cnt_bytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_cnt_all)[i] = 0;
   __syncthreads();
 
@@ -59,9 +101,9 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
       if (q_step < 0) q_step = s;  // the first min/max scorer gets the per-row LUT
     }
   }
-  const bool want_prefix = prefix_step >= 0 || a.match_out != nullptr || a.total_out != nullptr;
+  const bool want_prefix = prefix_step >= 0 || a.match_out != nullptr || a.total_out != nullptr || (LAT && lat_step >= 0);
   const int tie_mode = plan.tie_mode;
-  int lut_total = -1;
+  int lut_total = -1, lutl_total = -1;
 
   const int gw = blockIdx.x * kMatrixWarps + warp, nw = gridDim.x * kMatrixWarps;
   for (int r = gw; r < a.R; r += nw) {
@@ -170,6 +212,110 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
       }
     }
 
+    // ---------------- latency fold-in: per-request inputs and tier selection (plugin.go:174-243) ----------------
+    double l_x = 0.0, l_y = 0.0, l_tslo = 0.0, l_buf = 0.0;
+    double l_mnT = 0.0, l_rgT = 0.0, l_mnP = 0.0, l_rgP = 0.0, l_alpha = 0.0, l_beta = 0.0, l_qrange = 0.0;
+    long long l_maxq = 0;
+    int l_sel = 5;
+    bool l_tok = false, l_pok = false;
+    const bool llut_ok = total <= kLutMax;
+    if (LAT && lat_step >= 0) {
+      const LatArgs& L = a.lat;
+      const double in_tok = (double)(L.input_tokens ? L.input_tokens[r] : 0);  // len(strings.Fields(prompt)), training.go:51
+      l_x = __dmul_rn(L.ttft_input, in_tok);
+      l_y = __dmul_rn(L.tpot_input, in_tok);
+      l_tslo = L.ttft_slo ? L.ttft_slo[r] : 0.0;
+      l_buf = __dmul_rn(L.tpot_slo ? L.tpot_slo[r] : 0.0, L.buffer);            // prediction.go:150
+      const double pcoef = L.has_predictions ? L.ttft_prefix : L.wpref;
+      if (llut_ok && total != lutl_total) {  // match/total with NaN (0/0) => 0: preparedata_hooks.go:44-58, plugin.go:381-392
+        __syncwarp();
+        for (int c = lane; c <= total; c += 32)
+          lut_l[c] = __dmul_rn(pcoef, total ? __ddiv_rn((double)c, (double)total) : 0.0);
+        lutl_total = total;
+        __syncwarp();
+      }
+      if (L.has_predictions) {
+        // one pass: every lane tracks the best (lowest) tier it has seen and the |headroom| min/max inside it
+        int rank_l = 5;
+        double mnT = 1.7976931348623157e308, mxT = -1.7976931348623157e308, mnP = mnT, mxP = mxT;
+#pragma unroll
+        for (int j = 0; j < kMaxJ; j++) {
+          if (j >= J) break;
+          const uint32_t anyj = any[j];
+          const int cbase = (j * 32 + lane) << LOG_EPL;
+          for (int k = 0; k < EPL; k++) {
+            const int t = j * EPL + k, m = t * 32 + lane;
+            bool cand = m < M;
+            if (MASKED) cand = cand && ((__ldg(mrow + t) >> lane) & 1u);
+            if (!cand) continue;
+            int c = wide_cnt ? (int)cnt16[cbase + k] : (int)cnt8[cbase + k];
+            c = (c == 0 && ((anyj >> k) & 1u)) ? (wide_cnt ? 65536 : 256) : c;
+            const double pt = llut_ok ? lut_l[c] : __dmul_rn(pcoef, total ? __ddiv_rn((double)c, (double)total) : 0.0);
+            const LatPair lp = lat_pair(L, MPAD, m, pt, l_x, l_y, l_tslo, l_buf);
+            const double aT = fabs(lp.hT), aP = fabs(lp.hP);
+            if (lp.rank < rank_l) {
+              rank_l = lp.rank;
+              mnT = mxT = aT;
+              mnP = mxP = aP;
+            } else if (lp.rank == rank_l) {
+              mnT = aT < mnT ? aT : mnT;
+              mxT = aT > mxT ? aT : mxT;
+              mnP = aP < mnP ? aP : mnP;
+              mxP = aP > mxP ? aP : mxP;
+            }
+          }
+        }
+        l_sel = __reduce_min_sync(0xffffffffu, rank_l);
+        if (rank_l != l_sel) {
+          mnT = mnP = 1.7976931348623157e308;
+          mxT = mxP = -1.7976931348623157e308;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          const double a0 = shfl_xor_f64(mnT, o), a1 = shfl_xor_f64(mxT, o), a2 = shfl_xor_f64(mnP, o), a3 = shfl_xor_f64(mxP, o);
+          mnT = a0 < mnT ? a0 : mnT;
+          mxT = a1 > mxT ? a1 : mxT;
+          mnP = a2 < mnP ? a2 : mnP;
+          mxP = a3 > mxP ? a3 : mxP;
+        }
+        l_mnT = mnT;
+        l_mnP = mnP;
+        l_rgT = __dsub_rn(mxT, mnT);
+        l_rgP = __dsub_rn(mxP, mnP);
+        const double eps = 1e-9;                                                // plugin.go:41
+        l_tok = l_rgT > eps;
+        l_pok = l_rgP > eps;
+        l_alpha = L.alpha;
+        l_beta = L.beta;
+        if (!l_tok && l_pok) {                                                  // plugin.go:275-279
+          l_alpha = 0.0;
+          l_beta = 1.0;
+        } else if (!l_pok && l_tok) {
+          l_alpha = 1.0;
+          l_beta = 0.0;
+        }
+      } else {
+        // composite fallback: maxQ over the candidates, starting from 0 (plugin.go:338-344)
+        long long mq = 0;
+        for (int t = 0; t < J * EPL; t++) {
+          const int m = t * 32 + lane;
+          bool cand = m < M;
+          if (MASKED) cand = cand && ((__ldg(mrow + t) >> lane) & 1u);
+          if (cand) {
+            const long long q = __ldg(a.minmax_q[0] + m);
+            mq = q > mq ? q : mq;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          const long long oq = shfl_xor_i64(mq, o);
+          mq = oq > mq ? oq : mq;
+        }
+        l_maxq = mq;
+        l_qrange = __ll2double_rn(mq);
+      }
+    }
+
     const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
     Best best = best_none();
 
@@ -225,6 +371,37 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
                                           __ll2double_rn(mx[which] - mn[which]));  // queue.go:99
               term = __dmul_rn(clamp01(sc), wq[s]);
             }
+          } else if (LAT && kind == STEP_LATENCY) {
+            const LatArgs& L = a.lat;
+            const double pt = llut_ok ? lut_l[c] : __dmul_rn(L.has_predictions ? L.ttft_prefix : L.wpref,
+                                                             total ? __ddiv_rn((double)c, (double)total) : 0.0);
+            int w = 0;
+            if (L.has_predictions) {
+              const LatPair lp = lat_pair(L, MPAD, m < M ? m : 0, pt, l_x, l_y, l_tslo, l_buf);
+              if (DIAG && L.pred_out && m < M) {
+                L.pred_out[((size_t)r * M + m) * 2] = lp.ttft;
+                L.pred_out[((size_t)r * M + m) * 2 + 1] = lp.tpot;
+              }
+              if (lp.rank == l_sel) {                                          // scoreBucket, plugin.go:281-306
+                const double nT = l_tok ? __ddiv_rn(__dsub_rn(fabs(lp.hT), l_mnT), l_rgT) : 0.5;
+                const double nP = l_pok ? __ddiv_rn(__dsub_rn(fabs(lp.hP), l_mnP), l_rgP) : 0.5;
+                const double combined = __dadd_rn(__dmul_rn(l_alpha, nT), __dmul_rn(l_beta, nP));
+                const double v = (L.strategy_most && l_sel == 0) ? __dmul_rn(combined, 100.0)
+                                                                 : __dmul_rn(__dsub_rn(1.0, combined), 100.0);
+                w = __double2int_rz(v) + 1;                                    // float64(int(x) + minWeight + 1)
+              }
+            } else {                                                           // compositeScores, plugin.go:346-360
+              const int mm = m < M ? m : 0;
+              const long long q = __ldg(a.minmax_q[0] + mm);
+              const double rel = l_qrange > 0.0 ? __ddiv_rn(__ll2double_rn(l_maxq - q), l_qrange) : 1.0;
+              const double comp = __dadd_rn(__dadd_rn(__ldg(L.ep + 7 * MPAD + mm), __dmul_rn(L.wq, rel)), pt);
+              w = (int)__double2ll_rz(round(__dmul_rn(100.0, comp)));          // int(math.Round(0 + 100*composite))
+              if (DIAG && L.pred_out && m < M) {
+                L.pred_out[((size_t)r * M + m) * 2] = nan64();
+                L.pred_out[((size_t)r * M + m) * 2 + 1] = nan64();
+              }
+            }
+            term = (unsigned)w < (unsigned)kLatW ? s_latw[w] : __dmul_rn(clamp01(__ddiv_rn((double)w, 100.0)), wq[s]);
           } else {
             term = __dmul_rn(0.0, wq[s]);                                    // pair columns absent: score 0
           }
@@ -263,11 +440,12 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
 }
 
 template <typename K>
-static int launch_matrix(K kernel, const ScoreArgs& a, bool masked, cudaStream_t s, int sm_count) {
+static int launch_matrix(K kernel, const ScoreArgs& a, bool masked, bool lat, cudaStream_t s, int sm_count) {
   const int MPAD = a.geo.Mpad;
   const bool wide = a.hash_stride > 256;
   const size_t smem = (size_t)a.plan.n_terms * MPAD * 8 + (masked ? 2 * (size_t)MPAD * 8 : 0) + kMaxSteps * 4 * 8 +
-                      (size_t)kMatrixWarps * 2 * (kLutMax + 1) * 8 + (size_t)kMatrixWarps * MPAD * (wide ? 2 : 1);
+                      (lat ? kLatW * 8 : 0) + (size_t)kMatrixWarps * (lat ? 3 : 2) * (kLutMax + 1) * 8 +
+                      (size_t)kMatrixWarps * MPAD * (wide ? 2 : 1);
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kMatrixWarps * 32, smem);
@@ -290,20 +468,32 @@ constexpr uint32_t mseq(int k, Rest... rest) {
 #define P STEP_PREFIX
 #define L STEP_LORA
 #define Q STEP_MINMAX
+#define T STEP_LATENCY
+#define MK(...) launch_matrix(score_matrix_kernel<mseq(__VA_ARGS__), MASKED, DIAG, false>, a, MASKED, false, s, sm_count)
+#define MKL(...) launch_matrix(score_matrix_kernel<mseq(__VA_ARGS__), MASKED, DIAG, true>, a, MASKED, true, s, sm_count)
 template <bool MASKED, bool DIAG>
 static int launch_matrix_seq(const ScoreArgs& a, cudaStream_t s, int sm_count) {
+  bool lat = false;
+  for (int i = 0; i < a.plan.n_steps; i++) lat = lat || a.plan.kind[i] == STEP_LATENCY;
   switch (a.plan.seq) {
-    case mseq(E): return launch_matrix(score_matrix_kernel<mseq(E), MASKED, DIAG>, a, MASKED, s, sm_count);
-    case mseq(E, P): return launch_matrix(score_matrix_kernel<mseq(E, P), MASKED, DIAG>, a, MASKED, s, sm_count);
-    case mseq(E, P, L): return launch_matrix(score_matrix_kernel<mseq(E, P, L), MASKED, DIAG>, a, MASKED, s, sm_count);
-    case mseq(E, L): return launch_matrix(score_matrix_kernel<mseq(E, L), MASKED, DIAG>, a, MASKED, s, sm_count);
-    case mseq(Q, E): return launch_matrix(score_matrix_kernel<mseq(Q, E), MASKED, DIAG>, a, MASKED, s, sm_count);
-    case mseq(Q, E, P): return launch_matrix(score_matrix_kernel<mseq(Q, E, P), MASKED, DIAG>, a, MASKED, s, sm_count);
-    case mseq(Q, E, P, L): return launch_matrix(score_matrix_kernel<mseq(Q, E, P, L), MASKED, DIAG>, a, MASKED, s, sm_count);
-    case mseq(E, Q, P, L): return launch_matrix(score_matrix_kernel<mseq(E, Q, P, L), MASKED, DIAG>, a, MASKED, s, sm_count);
-    default: return launch_matrix(score_matrix_kernel<0, MASKED, DIAG>, a, MASKED, s, sm_count);
+    case mseq(E): return MK(E);
+    case mseq(E, P): return MK(E, P);
+    case mseq(E, P, L): return MK(E, P, L);
+    case mseq(E, L): return MK(E, L);
+    case mseq(Q, E): return MK(Q, E);
+    case mseq(Q, E, P): return MK(Q, E, P);
+    case mseq(Q, E, P, L): return MK(Q, E, P, L);
+    case mseq(E, Q, P, L): return MK(E, Q, P, L);
+    case mseq(T): return MKL(T);          // the latency profile of the reference chart (config/charts/epplib/templates/_config.yaml:66-75)
+    case mseq(T, L): return MKL(T, L);
+    default:
+      return lat ? launch_matrix(score_matrix_kernel<0, MASKED, DIAG, true>, a, MASKED, true, s, sm_count)
+                 : launch_matrix(score_matrix_kernel<0, MASKED, DIAG, false>, a, MASKED, false, s, sm_count);
   }
 }
+#undef MK
+#undef MKL
+#undef T
 #undef E
 #undef P
 #undef L
@@ -312,7 +502,7 @@ static int launch_matrix_seq(const ScoreArgs& a, cudaStream_t s, int sm_count) {
 // every (request, endpoint) pair scored; any plan without pair columns
 int launch_score_matrix(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
-  const bool diag = a.match_out != nullptr || a.scores_out != nullptr;  // diagnostics variants keep the R x M stores out of the hot loop
+  const bool diag = a.match_out != nullptr || a.scores_out != nullptr || a.lat.pred_out != nullptr;  // diagnostics variants keep the R x M stores out of the hot loop
   if (a.cand_mask) return diag ? launch_matrix_seq<true, true>(a, s, sm_count) : launch_matrix_seq<true, false>(a, s, sm_count);
   return diag ? launch_matrix_seq<false, true>(a, s, sm_count) : launch_matrix_seq<false, false>(a, s, sm_count);
 }

@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi as capi
-from ._capi import Batch, Config, EppscoreError, SCORER, Snapshot, Stats
+from ._capi import Batch, Config, EppscoreError, LatencyParams, SCORER, Snapshot, Stats
 
 
 def default_config(scorers=None, **kw) -> Config:
@@ -27,6 +27,18 @@ def default_config(scorers=None, **kw) -> Config:
             raise TypeError(f"unknown config field {k}")
         setattr(cfg, k, v)
     return cfg
+
+
+def latency_params(**kw) -> LatencyParams:
+    """eppscore_latency_params with the reference defaults (predictedlatency/plugin.go:128-136,
+    scorer/latency/plugin.go:83-90); keyword arguments override fields."""
+    p = LatencyParams()
+    capi.lib().eppscore_latency_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown latency field {k}")
+        setattr(p, k, v)
+    return p
 
 
 def _is_torch(x) -> bool:
@@ -97,9 +109,14 @@ class Engine:
     def set_debug(self, key: int, value: int):
         self._check(self._lib.eppscore_set_debug(self._h, key, value))
 
+    def set_latency_params(self, params: LatencyParams):
+        """Takes effect at the next set_snapshot."""
+        self._check(self._lib.eppscore_set_latency_params(self._h, C.byref(params)))
+
     # ------------------------------------------------------------------ snapshot
     def set_snapshot(self, kv_usage, queue, running=None, lora_active=None, lora_waiting=None, lora_nmodels=None,
-                     lora_max=None, endpoint_cols=(), epoch=0, device=False, stream=None, M=None, lora_words=None):
+                     lora_max=None, endpoint_cols=(), epoch=0, device=False, stream=None, M=None, lora_words=None,
+                     min_tpot_slo=None, dispatched=None, prefill_role=None, inflight_tokens=None):
         a = _Args(device)
         s = Snapshot()
         s.struct_size = C.sizeof(Snapshot)
@@ -125,6 +142,10 @@ class Engine:
             s.endpoint_col[i] = a.ptr(c, np.float64)
         s.epoch = epoch
         s.stream = stream
+        s.min_tpot_slo = a.ptr(min_tpot_slo, np.float64)
+        s.dispatched = a.ptr(dispatched, np.int32)
+        s.prefill_role = a.ptr(prefill_role, np.uint8)
+        s.inflight_tokens = a.ptr(inflight_tokens, np.int64)
         self._check(self._lib.eppscore_set_snapshot(self._h, C.byref(s)))
         self.M = M
 
@@ -132,7 +153,7 @@ class Engine:
     def schedule(self, R, *, prompt_bytes=None, prompt_off=None, prompt_len=None, model_seed=None, hashes_in=None,
                  n_hashes_in=None, hash_stride=0, adapter_id=None, cand_mask=None, dense_feat=None, dense_total=None,
                  block_chars=0, max_blocks=0, request_base=0, want_match=False, want_total=True, want_hashes=False,
-                 want_scores=False,
+                 want_scores=False, input_tokens=None, ttft_slo=None, tpot_slo=None, want_pred=False,
                  device=False, stream=None, out=None):
         """Host mode (device=False): numpy in, returns dict of numpy outputs (copies inside the call).
         Device mode: CUDA tensors / raw pointers in; `out` must hold preallocated CUDA tensors
@@ -159,6 +180,9 @@ class Engine:
         b.cand_mask = a.ptr(cand_mask, np.uint32)
         b.dense_feat = a.ptr(dense_feat, np.float32)
         b.dense_total = a.ptr(dense_total, np.uint16)
+        b.input_tokens = a.ptr(input_tokens, np.int32)
+        b.ttft_slo = a.ptr(ttft_slo, np.float64)
+        b.tpot_slo = a.ptr(tpot_slo, np.float64)
         b.stream = stream
         if device:
             if out is None:
@@ -170,6 +194,7 @@ class Engine:
             b.total_blocks = a.ptr(out.get("total_blocks"), None)
             b.hashes_out = a.ptr(out.get("hashes_out"), None)
             b.scores_out = a.ptr(out.get("scores_out"), None)
+            b.pred_out = a.ptr(out.get("pred_out"), None)
             self._check(self._lib.eppscore_schedule_batch(self._h, C.byref(b)))
             return out
         M = self.M
@@ -183,6 +208,8 @@ class Engine:
             res["hashes_out"] = np.zeros((R, mb), np.uint64)
         if want_scores:
             res["scores_out"] = np.zeros((R, M), np.float64)
+        if want_pred:
+            res["pred_out"] = np.zeros((R, M, 2), np.float64)
         for k, v in res.items():
             setattr(b, k, v.ctypes.data)
         self._check(self._lib.eppscore_schedule_batch(self._h, C.byref(b)))

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define EPPSCORE_ABI_VERSION 1
+#define EPPSCORE_ABI_VERSION 2
 #define EPPSCORE_MAX_SCORERS 8
 #define EPPSCORE_MAX_ENDPOINT_COLS 4
 #define EPPSCORE_MAX_BLOCKS 65535 /* match/total are uint16 (attribute/prefix/data_types.go:27-34 are Go ints) */
@@ -56,11 +56,17 @@ typedef enum eppscore_scorer_kind {
   EPPSCORE_SCORER_PREFIX = 2,   /* prefix-cache-scorer: scorer/prefix/plugin.go:95-117 (+ producer approximateprefix/) */
   EPPSCORE_SCORER_LORA = 3,     /* lora-affinity-scorer: scorer/loraaffinity/lora_affinity.go:76-102 */
   EPPSCORE_SCORER_RUNNING = 4,  /* running-requests-size-scorer: scorer/runningrequests/runningrequest.go:78-108 */
+  /* latency-scorer (scorer/latency/plugin.go:144-318) with the predicted-latency producer folded in: per
+   * (request, endpoint) the Bayesian-ridge TTFT/TPOT prediction (sidecars/latencypredictorasync/prediction.go:164-194),
+   * headroom/validity (predictedlatency/prediction.go:137-166), then the scorer's tier/bucket logic over the
+   * candidate set.  Parameters: eppscore_set_latency_params. */
+  EPPSCORE_SCORER_LATENCY = 5,
+  EPPSCORE_SCORER_TOKEN_LOAD = 6, /* token-load-scorer: scorer/tokenload/token_load.go:83-111 (snapshot.inflight_tokens) */
   /* 8+k: a host-computed, request-independent scorer supplied as float64 column k of the snapshot
    * (any custom framework.Scorer whose output does not depend on the request); clamped+weighted in-kernel. */
   EPPSCORE_SCORER_ENDPOINT_COL0 = 8,
-  /* 16+k: a per-(request,endpoint) float32 column k∈{0,1} of the dense feature rows (e.g. the
-   * latency-scorer output folded into the score matrix, scorer/latency/plugin.go:144). */
+  /* 16+k: a per-(request,endpoint) float32 column k∈{0,1} of the dense feature rows (any per-pair scorer
+   * computed elsewhere, e.g. a tree-ensemble latency model's output). */
   EPPSCORE_SCORER_PAIR_COL0 = 16
 } eppscore_scorer_kind;
 
@@ -88,7 +94,24 @@ typedef struct eppscore_config {
   int32_t max_adapters;    /* capacity for the LoRA adapter dictionary A; default 64 */
   int64_t prefix_capacity; /* INITIAL capacity (distinct block hashes) of the device table; it doubles on demand. default 1<<18 */
   int32_t lru_capacity_default; /* defaultLRUCapacityPerServer = 31250 (types.go:109) */
+  double token_load_threshold;  /* token-load-scorer queueThresholdTokens; <= 0 ⇒ 4194304 (token_load.go:33,57-61) */
 } eppscore_config;
+
+/* Latency fold-in parameters: the cached Bayesian-ridge coefficients (MetricsResponse.Coefficients,
+ * sidecars/latencypredictorasync/prediction.go:164-194), the producer's Config (predictedlatency/plugin.go:118-136)
+ * and the latency-scorer's Config (scorer/latency/plugin.go:59-90).  Takes effect at the next eppscore_set_snapshot
+ * (coefficients are refreshed on the metrics cadence, like the snapshot). */
+typedef struct eppscore_latency_params {
+  uint32_t struct_size;
+  int32_t has_predictions;   /* 0 = no LatencyPredictionInfo (sidecar down / timed out) ⇒ composite fallback (plugin.go:169-172) */
+  double ttft_intercept, ttft_kv, ttft_input, ttft_waiting, ttft_running, ttft_prefix;
+  double tpot_intercept, tpot_kv, tpot_input, tpot_waiting, tpot_running, tpot_generated;
+  double slo_buffer_factor;  /* SLOBufferFactor, default 1 */
+  int32_t streaming_mode;    /* StreamingMode, default 0: TPOT neutralised (prediction.go:100-104) */
+  int32_t strategy_most;     /* HeadroomSelectionStrategy: 0 "least" (default), 1 "most" */
+  double ttft_weight, tpot_weight;                         /* defaults 0.8, 0.2 */
+  double composite_kv, composite_queue, composite_prefix;  /* defaults 1, 1, 1 */
+} eppscore_latency_params;
 
 /* Immutable metrics snapshot: the fields of fwkdl.Metrics the path reads
  * (interface/datalayer/metrics.go:26-42), packed SoA.  LoRA maps become dictionary bitmasks:
@@ -108,6 +131,11 @@ typedef struct eppscore_snapshot {
   const double *endpoint_col[EPPSCORE_MAX_ENDPOINT_COLS]; /* optional generic score columns [M] */
   uint64_t epoch;                /* caller's snapshot generation, echoed by eppscore_stats */
   void *stream;                  /* cudaStream_t for location==1 (NULL = engine stream) */
+  /* predicted-latency producer state per endpoint (all optional, NULL ⇒ 0) */
+  const double *min_tpot_slo;    /* getEndpointMinTPOTSLO (predictedlatency/plugin.go:347-355)        [M] */
+  const int32_t *dispatched;     /* getEndpointRunningRequestCount (plugin.go:357-363)                [M] */
+  const uint8_t *prefill_role;   /* hasPrefillRole(EndpointRoleLabel, endpoint) (prediction.go:168-175) [M] */
+  const int64_t *inflight_tokens;/* InFlightLoad.Tokens attribute (token_load.go:91-95); NULL ⇒ absent [M] */
 } eppscore_snapshot;
 
 /* One batch = R concurrent Scheduler.Schedule() calls (pkg/epp/scheduling/scheduler.go:54). */
@@ -147,6 +175,11 @@ typedef struct eppscore_batch {
   double *scores_out;          /* optional [R*M]: the whole weightedScorePerEndpoint map (scheduler_profile.go:155-174),
                                   NaN for non-candidates — diagnostics / parity tests; 8*R*M bytes of HBM writes */
   void *stream;                /* cudaStream_t for location==1 (NULL = engine stream); the call is async on it */
+  /* latency fold-in, per request (optional, NULL ⇒ 0) */
+  const int32_t *input_tokens; /* [R] len(strings.Fields(prompt)) (predictedlatency/training.go:51) */
+  const double *ttft_slo;      /* [R] x-slo-ttft-ms header value or 0 (predictedlatency/plugin.go:330-343) */
+  const double *tpot_slo;      /* [R] x-slo-tpot-ms header value or 0 */
+  double *pred_out;            /* optional [R*M*2]: predicted {TTFT, TPOT} per (request, endpoint) — diagnostics */
 } eppscore_batch;
 
 typedef struct eppscore_stats {
@@ -175,6 +208,10 @@ int32_t eppscore_set_debug(struct eppscore_engine *e, int32_t key, int64_t value
 
 /* ---- snapshot (replaces the per-request deep clone, director.go:342-349) ---- */
 int32_t eppscore_set_snapshot(struct eppscore_engine *e, const eppscore_snapshot *s);
+
+/* Latency fold-in parameters (see eppscore_latency_params); applied by the next eppscore_set_snapshot. */
+void eppscore_latency_params_default(eppscore_latency_params *p);
+int32_t eppscore_set_latency_params(struct eppscore_engine *e, const eppscore_latency_params *p);
 
 /* ---- the hot path: Filter(mask) → Score → Pick for R requests ---- */
 int32_t eppscore_schedule_batch(struct eppscore_engine *e, const eppscore_batch *b);

@@ -25,14 +25,15 @@ def test_header_symbols_all_exported(pkg):
     L = pkg.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.eppscore_abi_version() == 1
+    assert L.eppscore_abi_version() == 2
 
 
 def test_struct_sizes_match_header_layout(pkg):
     # natural C layout on x86-64 (computed by hand from include/eppscore.h)
-    assert C.sizeof(pkg.Config) == 4 + 4 + 32 + 64 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4
-    assert C.sizeof(pkg.Snapshot) == 16 + 7 * 8 + 4 * 8 + 8 + 8
-    assert C.sizeof(pkg.Batch) == 16 + 8 + 6 * 8 + 16 + 4 * 8 + 7 * 8 + 8
+    assert C.sizeof(pkg.Config) == 4 + 4 + 32 + 64 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8
+    assert C.sizeof(pkg.LatencyParams) == 4 + 4 + 12 * 8 + 8 + 4 + 4 + 5 * 8
+    assert C.sizeof(pkg.Snapshot) == 16 + 7 * 8 + 4 * 8 + 8 + 8 + 4 * 8
+    assert C.sizeof(pkg.Batch) == 16 + 8 + 6 * 8 + 16 + 4 * 8 + 7 * 8 + 8 + 4 * 8
     assert C.sizeof(pkg.Stats) == 8 + 8 + 8 + 5 * 8
 
 
@@ -43,6 +44,12 @@ def test_default_config_is_reference_default(pkg):
     assert [cfg.scorer_kind[i] for i in range(3)] == [pkg.SCORER["queue"], pkg.SCORER["kv"], pkg.SCORER["prefix"]]
     assert [cfg.scorer_weight[i] for i in range(3)] == [2.0, 2.0, 3.0]
     assert cfg.block_chars == 64 and cfg.max_blocks == 256 and cfg.lru_capacity_default == 31250
+    assert cfg.token_load_threshold == 4194304.0  # token_load.go:33
+    lp = pkg.latency_params()
+    # predictedlatency/plugin.go:128-136 and scorer/latency/plugin.go:83-90
+    assert (lp.slo_buffer_factor, lp.streaming_mode, lp.has_predictions) == (1.0, 0, 1)
+    assert (lp.ttft_weight, lp.tpot_weight, lp.strategy_most) == (0.8, 0.2, 0)
+    assert (lp.composite_kv, lp.composite_queue, lp.composite_prefix) == (1.0, 1.0, 1.0)
 
 
 def test_host_helpers_match_oracle(pkg, xxh_kat):

@@ -630,3 +630,152 @@ def test_full_size_headline_parity(pkg):
                       adapter_id=ad[h:], request_base=h)
     assert np.array_equal(np.concatenate([lo["pick"], hi["pick"]]), got["pick"])
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------ latency fold-in, token load (f2)
+LAT_COEF = dict(ttft_intercept=12.5, ttft_kv=80.0, ttft_input=0.031, ttft_waiting=7.25, ttft_running=1.5,
+                ttft_prefix=-40.0, tpot_intercept=9.0, tpot_kv=11.0, tpot_input=0.0007, tpot_waiting=0.9,
+                tpot_running=0.35, tpot_generated=0.01)
+LAT_CASES = [
+    # name, M, R, scorers, latency params, options
+    ("latency_only_streaming", 1024, 1024, [("latency", 1)], dict(streaming_mode=1), dict(prefix=True)),
+    ("latency_defaults_nonstreaming", 300, 512, [("latency", 1)], {}, dict(prefix=True)),
+    ("latency_most_masked", 512, 512, [("latency", 1)], dict(streaming_mode=1, strategy_most=1), dict(prefix=True, mask=0.3)),
+    ("latency_lora_kv_buffer", 1024, 512, [("latency", 2), ("lora", 1), ("kv", 0.5)],
+     dict(streaming_mode=1, slo_buffer_factor=0.9, ttft_weight=0.5, tpot_weight=1.5), dict(prefix=True, lora=True)),
+    ("latency_after_queue_masked", 200, 512, [("queue", 1), ("latency", 3), ("prefix", 1)], dict(streaming_mode=1),
+     dict(prefix=True, mask=0.6)),
+    ("latency_composite_fallback", 700, 512, [("latency", 1)], dict(has_predictions=0, composite_kv=2.0),
+     dict(prefix=True, mask=0.5)),
+    ("latency_composite_zero_weights", 64, 256, [("latency", 1), ("kv", 1)],
+     dict(has_predictions=0, composite_kv=0.0, composite_queue=0.0, composite_prefix=0.0), {}),
+    ("latency_all_busy_buckets", 256, 512, [("latency", 1)], dict(streaming_mode=1), dict(prefix=True, busy=True)),
+    ("latency_no_prefix_info_M4096", 4096, 128, [("latency", 1)], dict(streaming_mode=1, ttft_weight=0.0, tpot_weight=0.0), {}),
+]
+
+
+@pytest.mark.parametrize("name,M,R,scorers,lkw,opt", LAT_CASES, ids=[c[0] for c in LAT_CASES])
+def test_latency_fold_in_parity(pkg, name, M, R, scorers, lkw, opt):
+    """Per (request, endpoint): Bayesian-ridge TTFT/TPOT, headrooms, tier/bucket selection over the candidates,
+    normalised latency score — picks, tie counts, weighted scores AND the predictions bit-exact vs the oracle."""
+    import zlib
+    seed = zlib.crc32(name.encode()) % 1000
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lkw = dict(LAT_COEF, **lkw)
+    eng = make_engine(pkg, scorers, M, tie_mode=1, tie_seed=5, prefix_capacity=1 << 16)
+    eng.set_latency_params(pkg.latency_params(**lkw))
+    sd = synth_snapshot(M, seed=seed)
+    sd["min_tpot_slo"] = rng.choice([0.0, 0.0, 22.0, 26.5, 60.0], M)
+    sd["dispatched"] = (rng.integers(1, 4, M) if opt.get("busy") else rng.integers(0, 3, M)).astype(np.int32)
+    sd["prefill_role"] = (rng.random(M) < 0.15).astype(np.uint8)
+    eng.set_snapshot(**sd)
+    snap = o.SnapshotData(**sd)
+    prof = o.make_profile([(pkg.SCORER[k], w) for k, w in scorers], tie_mode=1, tie_seed=5,
+                          latency=o.make_latency_params(**lkw))
+    kw = dict(input_tokens=rng.integers(0, 6000, R).astype(np.int32),
+              ttft_slo=rng.choice([0.0, 90.0, 140.0, 200.0, 400.0, 1e6], R),
+              tpot_slo=rng.choice([0.0, 18.0, 24.0, 30.0, 80.0], R))
+    idx = None
+    if opt.get("prefix"):
+        prompts, off, _ = synth_prompts(R, prompt_len=1024, groups=12, shared=512, seed=seed)
+        seeds = np.full(R, eng.model_seed("model-x"), np.uint64)
+        kw.update(prompt_bytes=prompts, prompt_off=off, model_seed=seeds)
+        idx = o.Index()
+        warm_prof = profile_of(pkg, [("kv", 1)], tie_mode=1, tie_seed=5)
+        warm = o.schedule_batch(snap, warm_prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds,
+                                want_hashes=True, n_threads=8)
+        keep = np.arange(R) % 3 != 0
+        idx.commit(warm["pick"][keep], warm["hashes_out"][keep], warm["total_blocks"][keep])
+        eng.commit_picks(warm["pick"][keep], warm["hashes_out"][keep], warm["total_blocks"][keep])
+    if opt.get("lora"):
+        kw["adapter_id"] = zipf_adapters(R, seed=seed)
+    if "mask" in opt:
+        bits = rng.random((R, M)) < opt["mask"]
+        bits[0, :] = False
+        bits[1, :] = False
+        bits[1, M // 2] = True  # a single candidate: zero ranges on both dimensions
+        mask = np.zeros((R, (M + 31) // 32), np.uint32)
+        for w in range(mask.shape[1]):
+            chunk = bits[:, w * 32:(w + 1) * 32]
+            mask[:, w] = (chunk * (1 << np.arange(chunk.shape[1], dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+        kw["cand_mask"] = mask
+    got = eng.schedule(R, want_match=True, want_scores=True, want_pred=True, **kw)
+    want = o.schedule_batch(snap, prof, idx, R, want_match=True, want_scores=True, want_pred=True, want_tie_set=True,
+                            n_threads=8, **kw)
+    assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks", "match_blocks", "scores_out"))
+    gp, wp = got["pred_out"], want["pred_out"]
+    assert np.array_equal(np.isnan(gp), np.isnan(wp))
+    assert np.array_equal(gp[~np.isnan(gp)].view(np.uint64), wp[~np.isnan(wp)].view(np.uint64))
+    fast = eng.schedule(R, **kw)   # no diagnostics: the variant without the R x M stores
+    assert_same(fast, want, ("pick", "pick_score", "tie_count", "total_blocks"))
+    ts = want["tie_set"]
+    r = np.nonzero(got["pick"] >= 0)[0]
+    assert ((ts[r, got["pick"][r] >> 5] >> (got["pick"][r] & 31).astype(np.uint32)) & 1).all()
+    if lkw.get("has_predictions", 1):
+        assert np.isfinite(gp).all()
+        if scorers == [("latency", 1)]:  # scores are w/100 with w in [1,101] inside the chosen tier, 0 outside; clamped
+            sc = got["scores_out"][~np.isnan(got["scores_out"])]
+            assert sc.min() >= 0.0 and sc.max() <= 1.0 and len(np.unique(sc)) > 3
+    if opt.get("prefix"):
+        assert got["match_blocks"].max() > 0
+    if "mask" in opt:
+        assert got["pick"][0] == -1 and got["pick"][1] == M // 2
+    eng.close()
+
+
+def test_latency_scorer_reference_cases(pkg, golden):
+    """The reference's own latency-scorer tests (plugin_test.go:52-208), driven through the engine: headrooms are
+    produced by an identity-like model (TTFT = -kv_c*kv ... ) so that the scorer sees the test's headroom values."""
+    for c in golden["latency_scorer"]["cases"]:
+        eps = c["endpoints"]
+        M = len(eps)
+        eng = make_engine(pkg, [("latency", 1)], M)
+        if c["info"] is None:
+            eng.set_latency_params(pkg.latency_params(has_predictions=0))
+            eng.set_snapshot(np.array([e[0] for e in eps]), np.array([e[1] for e in eps], np.int64),
+                             np.array([e[2] for e in eps], np.int64))
+        else:
+            # TTFT = 1*waiting, TPOT = 1*running with SLO 1000 => headroom = 1000 - value: encode the wanted headrooms
+            th = [i[0] for i in c["info"]]
+            ph = [i[1] for i in c["info"]]
+            eng.set_latency_params(pkg.latency_params(ttft_waiting=1.0, tpot_running=1.0, streaming_mode=1))
+            eng.set_snapshot(np.zeros(M), np.array([1000 - int(t) for t in th], np.int64),
+                             np.array([1000 - int(p) for p in ph], np.int64),
+                             dispatched=np.array([i[2] for i in c["info"]], np.int32))
+        got = eng.schedule(1, want_scores=True, ttft_slo=np.array([1000.0]), tpot_slo=np.array([1000.0]))
+        sc = got["scores_out"][0]
+        assert np.allclose(sc, np.clip(c["derived"], 0, 1), atol=1e-12), (c["name"], sc)
+        a = c["assert"]
+        for i in a.get("nonzero", []):
+            assert sc[i] != 0, c["name"]
+        for i in a.get("zero", []):
+            assert sc[i] == 0, c["name"]
+        for hi, lo in a.get("greater", []):
+            assert sc[hi] > sc[lo], c["name"]
+        eng.close()
+
+
+def test_token_load_scorer_parity(pkg, golden):
+    g = golden["token_load_scorer"]
+    eng = make_engine(pkg, [("token_load", 1)], 3, token_load_threshold=g["threshold"])
+    eng.set_snapshot(np.zeros(3), np.zeros(3, np.int64), inflight_tokens=np.array(g["tokens"], np.int64))
+    got = eng.schedule(1, want_scores=True)
+    assert np.allclose(got["scores_out"][0], g["want"], atol=g["tolerance"])
+    eng.close()
+    M, R = 1000, 256
+    scorers = [("token_load", 1.5), ("kv", 1), ("prefix", 2)]
+    rng = np.random.Generator(np.random.PCG64(3))
+    sd = synth_snapshot(M, seed=3)
+    sd["inflight_tokens"] = rng.choice([-3, 0, 1, 4096, 2 ** 21, 2 ** 22, 2 ** 23, 12345678], M).astype(np.int64)
+    for thr, masked in ((0.0, False), (3.0e6, True)):
+        eng = make_engine(pkg, scorers, M, token_load_threshold=thr)
+        eng.set_snapshot(**sd)
+        snap = o.SnapshotData(**sd)
+        prof = o.make_profile([(pkg.SCORER[k], w) for k, w in scorers], token_load_threshold=thr)
+        kw = {}
+        if masked:
+            kw["cand_mask"] = rng.integers(0, 2 ** 32, (R, (M + 31) // 32), dtype=np.uint64).astype(np.uint32)
+        got = eng.schedule(R, want_scores=True, **kw)
+        want = o.schedule_batch(snap, prof, None, R, want_scores=True, **kw)
+        assert_same(got, want, ("pick", "pick_score", "tie_count", "scores_out"))
+        eng.close()
