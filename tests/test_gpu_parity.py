@@ -703,7 +703,8 @@ def test_latency_fold_in_parity(pkg, name, M, R, scorers, lkw, opt):
     want = o.schedule_batch(snap, prof, idx, R, want_match=True, want_scores=True, want_pred=True, want_tie_set=True,
                             n_threads=8, **kw)
     assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks", "match_blocks", "scores_out"))
-    gp, wp = got["pred_out"], want["pred_out"]
+    ok = want["pick"] >= 0  # (the oracle returns before predicting when a request has no candidates)
+    gp, wp = got["pred_out"][ok], want["pred_out"][ok]
     assert np.array_equal(np.isnan(gp), np.isnan(wp))
     assert np.array_equal(gp[~np.isnan(gp)].view(np.uint64), wp[~np.isnan(wp)].view(np.uint64))
     fast = eng.schedule(R, **kw)   # no diagnostics: the variant without the R x M stores
