@@ -522,6 +522,63 @@ def run_gpu(args):
         except Exception as ex:  # noqa: BLE001
             extra["masked_full_matrix"] = {"error": str(ex)}
 
+        # ---- latency-predictor fold-in: the latency-scorer profile of the reference chart —
+        #      per (request, endpoint) Bayesian-ridge TTFT/TPOT, headrooms, tier selection, normalised score ----
+        try:
+            lat_coef = dict(ttft_intercept=12.5, ttft_kv=80.0, ttft_input=0.031, ttft_waiting=7.25, ttft_running=1.5,
+                            ttft_prefix=-40.0, tpot_intercept=9.0, tpot_kv=11.0, tpot_input=0.0007, tpot_waiting=0.9,
+                            tpot_running=0.35, tpot_generated=0.01, streaming_mode=1)
+            eng_l = pkg.Engine(pkg.default_config([("latency", 1.0)], max_endpoints=M, max_adapters=A, block_chars=BLOCK_CHARS,
+                                                  max_blocks=MAX_BLOCKS, prefix_capacity=1 << 19, tie_mode=1, tie_seed=11), device=local)
+            eng_l.set_latency_params(pkg.latency_params(**lat_coef))
+            lrng = np.random.Generator(np.random.PCG64(77))
+            lat_ep = dict(min_tpot_slo=lrng.choice([0.0, 0.0, 22.0, 26.5, 60.0], M),
+                          dispatched=lrng.integers(0, 3, M).astype(np.int32), prefill_role=(lrng.random(M) < 0.1).astype(np.uint8))
+            lat_ep_dev = {k: torch.from_numpy(v).to(dev) for k, v in lat_ep.items()}
+            eng_l.set_snapshot(views["kv_usage"], views["queue"], views["running"], device=True, stream=sptr, M=M, lora_words=0,
+                               **lat_ep_dev)
+            if rank == 0:
+                eng_l.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+            lat_req = dict(input_tokens=lrng.integers(16, 6000, R).astype(np.int32),
+                           ttft_slo=lrng.choice([0.0, 90.0, 140.0, 200.0, 400.0, 1e6], R),
+                           tpot_slo=lrng.choice([0.0, 18.0, 24.0, 30.0, 80.0], R))
+            lat_req_dev = {k: torch.from_numpy(v).to(dev) for k, v in lat_req.items()}
+
+            def latency_only(i):
+                hh, nn = hsets_dev[i % NSETS]
+                eng_l.schedule(R, hashes_in=hh, n_hashes_in=nn, hash_stride=MAX_BLOCKS, request_base=rank * R, device=True,
+                               stream=sptr, out=out, **lat_req_dev)
+
+            t_lat = time_kernel(latency_only, iters=10)
+            extra["latency_fold_in"] = {"kernel": "score_matrix_kernel<T>", "profile": "latency-scorer (weight 1), max-score pick",
+                                        "us": t_lat * 1e6, "picks_per_s": R / t_lat, "pairs_per_s": R * M / t_lat,
+                                        "predictions_per_s": 2.0 * R * M / t_lat,
+                                        "note": "TTFT+TPOT prediction per pair; the reference does one HTTP bulk call of <= 100 rows per request"}
+            if rank == 0:
+                # parity spot check against the oracle on the first requests of set 0
+                n_chk = 512
+                latency_only(0)
+                torch.cuda.synchronize()
+                snap_l = o.SnapshotData(snap["kv_usage"], snap["queue"], snap["running"], **lat_ep)
+                prof_l = o.make_profile([(o.SCORER_LATENCY, 1.0)], tie_mode=1, tie_seed=11, latency=o.make_latency_params(**lat_coef))
+                hh, nn = hsets_dev[0]
+                want_l = o.schedule_batch(snap_l, prof_l, idx, n_chk, hashes_in=hh[:n_chk].cpu().numpy(),
+                                          n_hashes_in=nn[:n_chk].cpu().numpy(), max_blocks=MAX_BLOCKS, n_threads=8,
+                                          **{k: v[:n_chk] for k, v in lat_req.items()})
+                ok = (np.array_equal(out["pick"][:n_chk].cpu().numpy(), want_l["pick"]) and
+                      np.array_equal(out["pick_score"][:n_chk].cpu().numpy(), want_l["pick_score"]) and
+                      np.array_equal(out["tie_count"][:n_chk].cpu().numpy(), want_l["tie_count"]))
+                extra["latency_fold_in"]["parity_vs_oracle"] = {"requests": n_chk, "bit_exact": bool(ok)}
+                # the CPU port on the same profile (all host threads), bounded sample
+                Rl = 4096
+                t0 = time.perf_counter()
+                o.schedule_batch(snap_l, prof_l, idx, Rl, hashes_in=hh[:Rl].cpu().numpy(), n_hashes_in=nn[:Rl].cpu().numpy(),
+                                 max_blocks=MAX_BLOCKS, n_threads=os.cpu_count() or 1, **{k: v[:Rl] for k, v in lat_req.items()})
+                extra["latency_fold_in"]["cpu_port_picks_per_s"] = Rl / (time.perf_counter() - t0)
+            eng_l.close()
+        except Exception as ex:  # noqa: BLE001
+            extra["latency_fold_in"] = {"error": repr(ex)}
+
         # ---- dense-row mode (R x M float4 feature rows streamed from HBM): reported beside the headline ----
         try:
             Rd = 32768

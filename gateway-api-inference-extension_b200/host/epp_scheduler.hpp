@@ -47,11 +47,14 @@ struct Metrics {
 
 struct EndpointMetadata {
   NamespacedName NamespacedName_;
+  std::map<std::string, std::string> Labels;
 };
 
 struct Endpoint {
   EndpointMetadata Metadata;
   Metrics Metrics_;
+  // attrconcurrency.InFlightLoad.Tokens (token_load.go:91-95); < 0 here = attribute absent
+  int64_t InFlightTokens = -1;
   const EndpointMetadata* GetMetadata() const { return &Metadata; }
   const Metrics* GetMetrics() const { return &Metrics_; }
 };
@@ -67,7 +70,45 @@ struct InferenceRequest {
   std::string TargetModel;
   std::string Prompt;     // getUserInputBytes() output (hashing.go:106-135): Completions prompt or marshalled messages
   std::string CacheSalt;
+  std::map<std::string, std::string> Headers;  // "x-slo-ttft-ms" / "x-slo-tpot-ms" feed the latency path
 };
+
+// len(strings.Fields(s)) (predictedlatency/plugin.go:286): runs of unicode.IsSpace separate fields.
+inline int CountFields(const std::string& s) {
+  auto is_space = [](uint32_t c) {
+    switch (c) {
+      case '\t': case '\n': case '\v': case '\f': case '\r': case ' ': case 0x85: case 0xA0: case 0x1680: case 0x2028:
+      case 0x2029: case 0x202F: case 0x205F: case 0x3000: return true;
+      default: return c >= 0x2000 && c <= 0x200A;
+    }
+  };
+  int n = 0;
+  bool in_field = false;
+  for (size_t i = 0; i < s.size();) {
+    const unsigned char b = (unsigned char)s[i];
+    uint32_t c = b;
+    size_t len = 1;
+    if (b >= 0xC2 && b < 0xE0 && i + 1 < s.size() && ((unsigned char)s[i + 1] & 0xC0) == 0x80) {
+      c = ((b & 0x1Fu) << 6) | ((unsigned char)s[i + 1] & 0x3Fu);
+      len = 2;
+    } else if (b >= 0xE0 && b < 0xF0 && i + 2 < s.size() && ((unsigned char)s[i + 1] & 0xC0) == 0x80 &&
+               ((unsigned char)s[i + 2] & 0xC0) == 0x80) {
+      c = ((b & 0x0Fu) << 12) | (((unsigned char)s[i + 1] & 0x3Fu) << 6) | ((unsigned char)s[i + 2] & 0x3Fu);
+      len = 3;
+    } else if (b >= 0x80) {
+      c = 0xFFFD;  // 4-byte sequences and invalid bytes are never spaces
+      len = (b >= 0xF0 && b < 0xF8 && i + 3 < s.size()) ? 4 : 1;
+    }
+    if (is_space(c)) {
+      in_field = false;
+    } else if (!in_field) {
+      in_field = true;
+      n++;
+    }
+    i += len;
+  }
+  return n;
+}
 
 struct ScoredEndpoint {
   const Endpoint* Endpoint_ = nullptr;
@@ -100,6 +141,35 @@ struct QueueScorer : Scorer { QueueScorer() : Scorer("queue-scorer", EPPSCORE_SC
 struct LoraAffinityScorer : Scorer { LoraAffinityScorer() : Scorer("lora-affinity-scorer", EPPSCORE_SCORER_LORA) {} };
 struct PrefixCacheScorer : Scorer { PrefixCacheScorer() : Scorer("prefix-cache-scorer", EPPSCORE_SCORER_PREFIX) {} };
 struct RunningRequestsScorer : Scorer { RunningRequestsScorer() : Scorer("running-requests-size-scorer", EPPSCORE_SCORER_RUNNING) {} };
+// token-load-scorer (scorer/tokenload/token_load.go:36-67)
+struct TokenLoadScorer : Scorer {
+  int64_t QueueThresholdTokens;
+  explicit TokenLoadScorer(int64_t thr = 4194304) : Scorer("token-load-scorer", EPPSCORE_SCORER_TOKEN_LOAD), QueueThresholdTokens(thr > 0 ? thr : 4194304) {}
+};
+// latency-scorer (scorer/latency/plugin.go:59-90); fed by the PredictedLatencyProducer below
+struct LatencyScorer : Scorer {
+  double TTFTWeight = 0.8, TPOTWeight = 0.2;
+  bool StrategyMost = false;  // HeadroomSelectionStrategy "most"; default "least"
+  double CompositeKVWeight = 1, CompositeQueueWeight = 1, CompositePrefixWeight = 1;
+  LatencyScorer() : Scorer("latency-scorer", EPPSCORE_SCORER_LATENCY) {}
+};
+
+// predicted-latency-producer (requestcontrol/dataproducer/predictedlatency): its Config (plugin.go:118-136), the
+// Bayesian-ridge coefficients the Go client caches (latencypredictorasync/prediction.go:164-194) and the
+// per-endpoint running-request bookkeeping it reads while predicting (plugin.go:347-363).
+struct PredictedLatencyProducer {
+  double SLOBufferFactor = 1.0;
+  bool StreamingMode = false;
+  std::string EndpointRoleLabel;
+  bool HavePredictions = true;  // false = sidecar down / timed out: the scorer's composite fallback
+  double TTFTIntercept = 0, TPOTIntercept = 0;
+  std::map<std::string, double> TTFTCoeffs, TPOTCoeffs;  // keys as in the reference's MetricsResponse
+  struct EndpointState {
+    double MinTPOTSLO = 0;   // getEndpointMinTPOTSLO
+    int RunningRequests = 0; // getEndpointRunningRequestCount
+  };
+  std::map<std::string, EndpointState> State;  // keyed by NamespacedName.String()
+};
 
 struct WeightedScorer {
   std::shared_ptr<Scorer> Scorer_;
@@ -125,6 +195,8 @@ class SchedulerProfile {
   SchedulerProfile& WithFilters(std::vector<std::shared_ptr<Filter>> f) { filters_ = std::move(f); return *this; }
   SchedulerProfile& WithScorers(std::vector<WeightedScorer> s) { scorers_ = std::move(s); return *this; }
   SchedulerProfile& WithPicker(MaxScorePicker p) { picker_ = p; return *this; }
+  SchedulerProfile& WithPredictedLatencyProducer(std::shared_ptr<PredictedLatencyProducer> p) { producer_ = std::move(p); return *this; }
+  const std::shared_ptr<PredictedLatencyProducer>& producer() const { return producer_; }
   const std::vector<std::shared_ptr<Filter>>& filters() const { return filters_; }
   const std::vector<WeightedScorer>& scorers() const { return scorers_; }
   const MaxScorePicker& picker() const { return picker_; }
@@ -133,6 +205,7 @@ class SchedulerProfile {
   std::vector<std::shared_ptr<Filter>> filters_;
   std::vector<WeightedScorer> scorers_;
   MaxScorePicker picker_;
+  std::shared_ptr<PredictedLatencyProducer> producer_;
 };
 
 // approximateprefix config (types.go:77-141)
@@ -168,7 +241,10 @@ class Scheduler {
     for (size_t i = 0; i < sc.size(); i++) {
       c.scorer_kind[i] = sc[i].Scorer_->Kind;
       c.scorer_weight[i] = sc[i].Weight();
+      if (auto* tl = dynamic_cast<TokenLoadScorer*>(sc[i].Scorer_.get())) c.token_load_threshold = (double)tl->QueueThresholdTokens;
+      if (auto* ls = dynamic_cast<LatencyScorer*>(sc[i].Scorer_.get())) latency_scorer_ = ls;
     }
+    if (latency_scorer_ && !cfg.Profile.producer()) throw SchedulingError("latency-scorer needs a predicted-latency-producer");
     c.block_chars = cfg.Prefix.BlockSizeTokens * 4;  // averageCharactersPerToken (types.go:112)
     c.max_blocks = cfg.Prefix.MaxPrefixBlocksToMatch;
     c.lru_capacity_default = cfg.Prefix.LRUCapacityPerServer;
@@ -231,7 +307,25 @@ class Scheduler {
     if (cfg_.Prefix.MaxPrefixTokensToMatch > 0 && block_tokens > 0) max_blocks = cfg_.Prefix.MaxPrefixTokensToMatch / block_tokens;
     std::vector<uint8_t> bytes;
     std::vector<int64_t> off((size_t)R + 1, 0);
-    std::vector<int32_t> len((size_t)R), adapter((size_t)R);
+    std::vector<int32_t> len((size_t)R), adapter((size_t)R), in_tokens;
+    std::vector<double> ttft_slo, tpot_slo;
+    if (latency_scorer_) {  // predictedlatency/plugin.go:276-290, :315-343
+      in_tokens.resize((size_t)R);
+      ttft_slo.assign((size_t)R, 0.0);
+      tpot_slo.assign((size_t)R, 0.0);
+      auto header = [](const InferenceRequest& q, const char* key) {
+        auto it = q.Headers.find(key);
+        if (it == q.Headers.end()) return 0.0;
+        char* end = nullptr;
+        const double v = strtod(it->second.c_str(), &end);
+        return (end && *end == 0 && end != it->second.c_str()) ? v : 0.0;  // parse error ⇒ 0 (logged only)
+      };
+      for (int r = 0; r < R; r++) {
+        in_tokens[r] = CountFields(requests[r].Prompt);
+        ttft_slo[r] = header(requests[r], "x-slo-ttft-ms");
+        tpot_slo[r] = header(requests[r], "x-slo-tpot-ms");
+      }
+    }
     std::vector<uint64_t> seed((size_t)R);
     for (int r = 0; r < R; r++) {
       while (bytes.size() % 16) bytes.push_back(0);  // 16-byte aligned starts: the fast hash path
@@ -262,6 +356,11 @@ class Scheduler {
     b.max_blocks = max_blocks;
     b.adapter_id = adapter.data();
     b.cand_mask = have_filters ? mask.data() : nullptr;
+    if (latency_scorer_) {
+      b.input_tokens = in_tokens.data();
+      b.ttft_slo = ttft_slo.data();
+      b.tpot_slo = tpot_slo.data();
+    }
     b.pick = pick.data();
     b.pick_score = score.data();
     b.tie_count = ties.data();
@@ -315,7 +414,60 @@ class Scheduler {
     std::vector<double> kv((size_t)M);
     std::vector<int64_t> queue((size_t)M), running((size_t)M);
     std::vector<uint64_t> act((size_t)M * words, 0), wait((size_t)M * words, 0);
-    std::vector<int32_t> nm((size_t)M), mx((size_t)M);
+    std::vector<int32_t> nm((size_t)M), mx((size_t)M), dispatched((size_t)M, 0);
+    std::vector<int64_t> tokens((size_t)M, 0);
+    std::vector<double> min_tpot((size_t)M, 0.0);
+    std::vector<uint8_t> prefill((size_t)M, 0);
+    bool have_tokens = false;
+    const PredictedLatencyProducer* prod = cfg_.Profile.producer().get();
+    for (int m = 0; m < M; m++) {
+      const Endpoint& ep = eps[(size_t)m];
+      if (ep.InFlightTokens >= 0) {
+        tokens[m] = ep.InFlightTokens;
+        have_tokens = true;
+      }
+      if (prod) {
+        auto st = prod->State.find(ep.GetMetadata()->NamespacedName_.String());
+        if (st != prod->State.end()) {
+          min_tpot[m] = st->second.RunningRequests > 0 ? st->second.MinTPOTSLO : 0.0;  // plugin.go:349-354
+          dispatched[m] = st->second.RunningRequests;
+        }
+        if (!prod->EndpointRoleLabel.empty()) {  // hasPrefillRole, prediction.go:168-175
+          auto lb = ep.GetMetadata()->Labels.find(prod->EndpointRoleLabel);
+          prefill[m] = lb != ep.GetMetadata()->Labels.end() && lb->second == "prefill";
+        }
+      }
+    }
+    if (latency_scorer_ && prod) {
+      eppscore_latency_params lp;
+      eppscore_latency_params_default(&lp);
+      auto coef = [](const std::map<std::string, double>& c, const char* k) {
+        auto it = c.find(k);
+        return it == c.end() ? 0.0 : it->second;  // Go map lookup of a missing key yields 0
+      };
+      lp.has_predictions = prod->HavePredictions ? 1 : 0;
+      lp.ttft_intercept = prod->TTFTIntercept;
+      lp.ttft_kv = coef(prod->TTFTCoeffs, "kv_cache_percentage");
+      lp.ttft_input = coef(prod->TTFTCoeffs, "input_token_length");
+      lp.ttft_waiting = coef(prod->TTFTCoeffs, "num_request_waiting");
+      lp.ttft_running = coef(prod->TTFTCoeffs, "num_request_running");
+      lp.ttft_prefix = coef(prod->TTFTCoeffs, "prefix_cache_score");
+      lp.tpot_intercept = prod->TPOTIntercept;
+      lp.tpot_kv = coef(prod->TPOTCoeffs, "kv_cache_percentage");
+      lp.tpot_input = coef(prod->TPOTCoeffs, "input_token_length");
+      lp.tpot_waiting = coef(prod->TPOTCoeffs, "num_request_waiting");
+      lp.tpot_running = coef(prod->TPOTCoeffs, "num_request_running");
+      lp.tpot_generated = coef(prod->TPOTCoeffs, "num_tokens_generated");
+      lp.slo_buffer_factor = prod->SLOBufferFactor;
+      lp.streaming_mode = prod->StreamingMode ? 1 : 0;
+      lp.strategy_most = latency_scorer_->StrategyMost ? 1 : 0;
+      lp.ttft_weight = latency_scorer_->TTFTWeight;
+      lp.tpot_weight = latency_scorer_->TPOTWeight;
+      lp.composite_kv = latency_scorer_->CompositeKVWeight;
+      lp.composite_queue = latency_scorer_->CompositeQueueWeight;
+      lp.composite_prefix = latency_scorer_->CompositePrefixWeight;
+      if (eppscore_set_latency_params(eng_, &lp) != EPPSCORE_OK) throw SchedulingError(std::string("eppscore_set_latency_params: ") + eppscore_last_error(eng_));
+    }
     for (int m = 0; m < M; m++) {
       const Metrics* x = eps[(size_t)m].GetMetrics();
       kv[m] = x->KVCacheUsagePercent;
@@ -337,12 +489,19 @@ class Scheduler {
     s.lora_waiting = wait.data();
     s.lora_nmodels = nm.data();
     s.lora_max = mx.data();
+    s.inflight_tokens = have_tokens ? tokens.data() : nullptr;
+    if (prod) {
+      s.min_tpot_slo = min_tpot.data();
+      s.dispatched = dispatched.data();
+      s.prefill_role = prefill.data();
+    }
     s.epoch = ++epoch_;
     if (eppscore_set_snapshot(eng_, &s) != EPPSCORE_OK) throw SchedulingError(std::string("eppscore_set_snapshot: ") + eppscore_last_error(eng_));
   }
 
   SchedulerConfig cfg_;
   eppscore_engine* eng_ = nullptr;
+  const LatencyScorer* latency_scorer_ = nullptr;
   std::unordered_map<std::string, int> adapter_ids_;
   uint64_t epoch_ = 0;
   std::vector<uint64_t> last_hashes_;

@@ -5,6 +5,8 @@
 //   TestSchedulePlugins (filters)     pkg/epp/scheduling/scheduler_profile_test.go:33-183
 //   integration routing scenarios     test/integration/epp/common_tests.go:283-312, hermetic_test.go:120-272
 //   TestPrefixPluginCompletion        .../approximateprefix/plugin_test.go:161-227 (via PreRequest)
+//   TestTokenLoadScorer               pkg/epp/framework/plugins/scheduling/scorer/tokenload/token_load_test.go:32-61
+//   TestScore* (latency-scorer)       pkg/epp/framework/plugins/scheduling/scorer/latency/plugin_test.go:52-208
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -176,12 +178,100 @@ static void TestPrefixCompletionViaPreRequest() {
   CHECK(r3[0].result.ProfileResults.at("default").TargetEndpoints[0].Score == 0.0);
 }
 
+
+static void TestTokenLoadScorer() {
+  SchedulerConfig c;
+  c.Profile.WithScorers({NewWeightedScorer(std::make_shared<TokenLoadScorer>(1000), 1)}).WithPicker(MaxScorePicker{});
+  c.MaxEndpoints = 8;
+  Scheduler s(c);
+  std::vector<Endpoint> eps = {NewEndpoint("pod1", Metrics{}, "default"), NewEndpoint("pod2", Metrics{}, "default"),
+                               NewEndpoint("pod3", Metrics{}, "default")};
+  eps[1].InFlightTokens = 500;   // pod1: attribute absent => 0 tokens => 1.0
+  eps[2].InFlightTokens = 1000;
+  auto r = s.Schedule(InferenceRequest{"t", "m", "", ""}, eps);
+  const auto& te = r.ProfileResults.at("default").TargetEndpoints[0];
+  CHECK(te.Index == 0 && te.Score == 1.0 && te.TieCount == 1);
+  eps[0].InFlightTokens = 750;   // 0.25 < pod2's 0.5
+  r = s.Schedule(InferenceRequest{"t", "m", "", ""}, eps);
+  CHECK(r.ProfileResults.at("default").TargetEndpoints[0].Index == 1);
+  CHECK(std::fabs(r.ProfileResults.at("default").TargetEndpoints[0].Score - 0.5) < 1e-4);
+}
+
+// latency-scorer tests: the scorer consumes LatencyPredictionInfo{ttftHeadroom, tpotHeadroom, dispatched}. Here the
+// producer is configured so that TTFT = WaitingQueueSize, TPOT = RunningRequestsSize and both SLO headers are
+// 1000, i.e. headroom = 1000 - metric: each test's headroom values are encoded in the metrics.
+struct LatEp { double th, ph; int dispatched; };
+static int LatencyPick(const std::vector<LatEp>& info, double* score, int* ties) {
+  SchedulerConfig c;
+  auto prod = std::make_shared<PredictedLatencyProducer>();
+  prod->StreamingMode = true;
+  prod->TTFTCoeffs["num_request_waiting"] = 1.0;
+  prod->TPOTCoeffs["num_request_running"] = 1.0;
+  c.Profile.WithScorers({NewWeightedScorer(std::make_shared<LatencyScorer>(), 1)}).WithPicker(MaxScorePicker{}).WithPredictedLatencyProducer(prod);
+  c.MaxEndpoints = 8;
+  std::vector<Endpoint> eps;
+  for (size_t i = 0; i < info.size(); i++) {
+    Metrics m;
+    m.WaitingQueueSize = 1000 - (int)info[i].th;
+    m.RunningRequestsSize = 1000 - (int)info[i].ph;
+    eps.push_back(NewEndpoint("pod" + std::to_string(i), m, "default"));
+    prod->State["default/pod" + std::to_string(i)].RunningRequests = info[i].dispatched;
+  }
+  Scheduler s(c);
+  InferenceRequest q{"l", "m", "a prompt of five words", ""};
+  q.Headers["x-slo-ttft-ms"] = "1000";
+  q.Headers["x-slo-tpot-ms"] = "1000";
+  auto r = s.Schedule(q, eps);
+  const auto& te = r.ProfileResults.at("default").TargetEndpoints[0];
+  *score = te.Score;
+  *ties = te.TieCount;
+  return te.Index;
+}
+
+static void TestLatencyScorer() {
+  double sc;
+  int ties;
+  // TestScoreTierSplit (plugin_test.go:103-133): less headroom scores higher under "least"
+  CHECK(LatencyPick({{10, 2, 0}, {50, 10, 0}}, &sc, &ties) == 0 && sc == 1.0 && ties == 1);
+  // TestScoreNegativeOnly (:75-101): the smaller violation wins
+  CHECK(LatencyPick({{-10, -5, 0}, {-100, -30, 0}}, &sc, &ties) == 0 && sc > 0);
+  // TestScoreIdlePodPreference (:135-162): same deficit, only the idle pod is scored
+  CHECK(LatencyPick({{-50, -10, 5}, {-50, -10, 0}}, &sc, &ties) == 1 && std::fabs(sc - 0.51) < 1e-12 && ties == 1);
+  // TestScoreHierarchicalBuckets (:164-188): all negative and idle => one bucket; tpot-only deficit closest to SLO
+  CHECK(LatencyPick({{-50, -10, 0}, {-30, 5, 0}, {10, -8, 0}}, &sc, &ties) == 2 && std::fabs(sc - 0.89) < 1e-12);
+  // busy variants: the least severe non-empty bucket (negTPOTonly > negTTFTonly > bothNeg, :209-238) is the only one scored
+  CHECK(LatencyPick({{-50, -10, 3}, {-30, 5, 2}, {10, -8, 1}}, &sc, &ties) == 2);
+  CHECK(LatencyPick({{-50, -10, 3}, {-30, 5, 2}}, &sc, &ties) == 1);
+  // TestScoreCompositeFallback (:190-208): no predictions => kv/queue/prefix composite
+  {
+    SchedulerConfig c;
+    auto prod = std::make_shared<PredictedLatencyProducer>();
+    prod->HavePredictions = false;
+    c.Profile.WithScorers({NewWeightedScorer(std::make_shared<LatencyScorer>(), 1)}).WithPicker(MaxScorePicker{}).WithPredictedLatencyProducer(prod);
+    c.MaxEndpoints = 8;
+    Scheduler s(c);
+    Metrics a, b;
+    a.KVCacheUsagePercent = 0.2; a.WaitingQueueSize = 0; a.RunningRequestsSize = 3;
+    b.KVCacheUsagePercent = 0.8; b.WaitingQueueSize = 5; b.RunningRequestsSize = 10;
+    auto r = s.Schedule(InferenceRequest{"c", "m", "", ""}, {NewEndpoint("pod1", a), NewEndpoint("pod2", b)});
+    const auto& te = r.ProfileResults.at("default").TargetEndpoints[0];
+    CHECK(te.Index == 0 && std::fabs(te.Score - 0.6) < 1e-12);
+  }
+  // strings.Fields semantics of the input-token count (predictedlatency/plugin.go:286)
+  CHECK(CountFields("") == 0);
+  CHECK(CountFields("  a  b\tc\n") == 3);
+  CHECK(CountFields("one\xC2\xA0two\xE2\x80\x83three\xE3\x80\x80" "four") == 4);  // NBSP, EM SPACE, IDEOGRAPHIC SPACE
+  CHECK(CountFields("\xE2\x80\x8B") == 1);                                          // ZERO WIDTH SPACE is not White_Space
+}
+
 int main() {
   try {
     TestSchedule();
     TestFilterChain();
     TestIntegrationRouting();
     TestPrefixCompletionViaPreRequest();
+    TestTokenLoadScorer();
+    TestLatencyScorer();
   } catch (const std::exception& e) {
     std::printf("FAIL exception: %s\n", e.what());
     return 2;
