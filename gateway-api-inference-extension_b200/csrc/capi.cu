@@ -71,7 +71,7 @@ struct eppscore_engine {
   int32_t M = 0, A = 0, lora_words = 0;
   uint64_t epoch = 0;
   DevBuf raw_kv, raw_queue, raw_running, raw_act, raw_wait, raw_nmodels, raw_max, raw_col[4];
-  DevBuf raw_min_tpot, raw_dispatched, raw_prefill, raw_tokens, lat_ep, lat_flags;
+  DevBuf raw_min_tpot, raw_dispatched, raw_prefill, raw_tokens, lat_ep;
   eppscore_latency_params lat_params{};  // pending: applied by the next set_snapshot
   LatArgs lat_args{};                    // what the current snapshot was prepared with
   bool have_col[4] = {false, false, false, false};
@@ -515,7 +515,6 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
     CK(nullptr, ep->raw_dispatched.reserve(mp * 4));
     CK(nullptr, ep->raw_prefill.reserve(mp));
     CK(nullptr, ep->lat_ep.reserve(mp * 8 * kLatArrays));
-    CK(nullptr, ep->lat_flags.reserve(mp * 4));
   }
   for (int i = 0; i < kMaxSteps; i++) CK(nullptr, ep->term[i].reserve(mp * 8));
   CK(nullptr, ep->fold_unmasked.reserve(mp * 8));
@@ -566,7 +565,7 @@ void eppscore_destroy(eppscore_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep, &e->lat_flags,
+  DevBuf* bufs[] = {&e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep,
                     &e->s_intok, &e->s_tslo, &e->s_pslo, &e->s_pred, &e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
                     &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->prefix_lut2d, &e->st_idx, &e->st_val, &e->st_slot,
                     &e->probe_out, &e->s_prompts, &e->s_off, &e->s_len, &e->s_seed, &e->s_hashes, &e->s_nh, &e->s_adapter,
@@ -703,7 +702,7 @@ int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
     wpref = wpref / sumw;
     pa.lat_ckv = wkv;
     pa.lat_ep = e->lat_ep.as<double>();
-    pa.lat_flags = e->lat_flags.as<int32_t>();
+    pa.lat_has_predictions = lp.has_predictions;
     LatArgs& L = e->lat_args;
     L.enabled = 1;
     L.has_predictions = lp.has_predictions;
@@ -725,7 +724,6 @@ int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
     L.wq = wq;
     L.wpref = wpref;
     L.ep = pa.lat_ep;
-    L.flags = pa.lat_flags;
   }
   pa.lora_words = e->lora_words;
   pa.A = e->A;

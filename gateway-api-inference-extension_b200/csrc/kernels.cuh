@@ -37,11 +37,14 @@ enum StepKind : int32_t {
   STEP_LATENCY = 5   // + clamp(latency-scorer)*w: prediction + headroom + tier/bucket logic (scorer/latency/plugin.go:144-318)
 };
 
-// Latency fold-in (score_matrix.cu).  Per-endpoint arrays are prepared once per snapshot (prepare_kernel.cu):
-//   ep[0] tA = ttft_intercept + ttft_kv*kv      ep[1] tW = ttft_waiting*waiting   ep[2] tR = ttft_running*running
-//   ep[3] pA = tpot_intercept + tpot_kv*kv      ep[4] pW = tpot_waiting*waiting   ep[5] pR = tpot_running*running
-//   ep[6] lim = podMinTPOTSLO > 0 ? podMinTPOTSLO*buffer : +inf                   ep[7] cK = composite_kv*(1-kv)
-//   flags bit 0: dispatched == 0 (idle), bit 1: TPOT neutralised (!streaming || prefill role)
+// Latency fold-in (score_matrix.cu).  Per-endpoint values are prepared once per snapshot (prepare_kernel.cu) in
+// TILES of 32 endpoints x 8 slots: slot i of endpoint (t*32 + lane) is ep[(t*8 + i)*32 + lane], so a warp reads a
+// slot of 32 consecutive endpoints with one coalesced load and all slots of a pair sit at immediate offsets.
+//   with predictions:  0 tA = ttft_intercept + ttft_kv*kv   1 tW = ttft_waiting*waiting   2 tR = ttft_running*running
+//                      3 pA = tpot_intercept + tpot_kv*kv   4 pW = tpot_waiting*waiting   5 pR = tpot_running*running
+//                      6 lim = podMinTPOTSLO > 0 ? podMinTPOTSLO*buffer : +inf
+//                      7 flags (int64 bits): bit 0 dispatched == 0 (idle), bit 1 TPOT neutralised (!streaming || prefill)
+//   composite fallback: 0 cK = composite_kv*(1-kv)           1 WaitingQueueSize (int64 bits)
 constexpr int kLatArrays = 8;
 struct LatArgs {
   int32_t enabled;
@@ -52,8 +55,7 @@ struct LatArgs {
   double buffer;            // SLOBufferFactor
   double alpha, beta;       // normalizedWeights(ttftWeight, tpotWeight), plugin.go:373-379
   double wq, wpref;         // normalised composite weights (queue, prefix); the kv one is folded into ep[7]
-  const double* ep;         // [kLatArrays][Mpad]
-  const int32_t* flags;     // [Mpad]
+  const double* ep;         // [Mpad/32][kLatArrays][32] tiles
   const int32_t* input_tokens;  // [R] or null
   const double* ttft_slo;   // [R] or null
   const double* tpot_slo;   // [R] or null
@@ -189,8 +191,8 @@ struct PrepareArgs {
   double lat_coef[8];           // ttft {intercept, kv, waiting, running}, tpot {intercept, kv, waiting, running}
   double lat_buffer, lat_ckv;
   int32_t lat_streaming;
-  double* lat_ep;               // [kLatArrays][Mpad]
-  int32_t* lat_flags;           // [Mpad]
+  int32_t lat_has_predictions;
+  double* lat_ep;               // [Mpad/32][kLatArrays][32] tiles
   // outputs of the endpoint kernel
   double* term[kMaxSteps];      // per scorer (null where not an endpoint term)
   double* fold_unmasked;        // leading run folded (or null)

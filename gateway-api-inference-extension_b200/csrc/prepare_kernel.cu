@@ -93,20 +93,26 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const __grid_co
     // left to right, so "intercept + c_kv*kv" is a rounded partial sum and the products are rounded terms)
     if (a.lat_ep) {
       const double kv = m < M ? a.kv[m] : 0.0;
-      const double wt = (m < M && a.queue) ? __ll2double_rn(a.queue[m]) : 0.0;
+      const long long qi = (m < M && a.queue) ? a.queue[m] : 0;
+      const double wt = __ll2double_rn(qi);
       const double rn = (m < M && a.running) ? __ll2double_rn(a.running[m]) : 0.0;
       const double pod_min = (m < M && a.min_tpot) ? a.min_tpot[m] : 0.0;
-      a.lat_ep[0 * Mpad + m] = __dadd_rn(a.lat_coef[0], __dmul_rn(a.lat_coef[1], kv));
-      a.lat_ep[1 * Mpad + m] = __dmul_rn(a.lat_coef[2], wt);
-      a.lat_ep[2 * Mpad + m] = __dmul_rn(a.lat_coef[3], rn);
-      a.lat_ep[3 * Mpad + m] = __dadd_rn(a.lat_coef[4], __dmul_rn(a.lat_coef[5], kv));
-      a.lat_ep[4 * Mpad + m] = __dmul_rn(a.lat_coef[6], wt);
-      a.lat_ep[5 * Mpad + m] = __dmul_rn(a.lat_coef[7], rn);
-      a.lat_ep[6 * Mpad + m] = pod_min > 0.0 ? __dmul_rn(pod_min, a.lat_buffer) : __longlong_as_double(0x7ff0000000000000LL);
-      a.lat_ep[7 * Mpad + m] = __dmul_rn(a.lat_ckv, __dsub_rn(1.0, kv));         // plugin.go:351,355
-      const bool idle = !(m < M && a.dispatched) || a.dispatched[m] == 0;
-      const bool neutral = !a.lat_streaming || (m < M && a.prefill && a.prefill[m]);
-      a.lat_flags[m] = (idle ? 1 : 0) | (neutral ? 2 : 0);
+      double* tile = a.lat_ep + (size_t)(m >> 5) * 256 + (m & 31);  // slot i at tile[i*32] (kernels.cuh: LatArgs)
+      if (a.lat_has_predictions) {
+        tile[0 * 32] = __dadd_rn(a.lat_coef[0], __dmul_rn(a.lat_coef[1], kv));
+        tile[1 * 32] = __dmul_rn(a.lat_coef[2], wt);
+        tile[2 * 32] = __dmul_rn(a.lat_coef[3], rn);
+        tile[3 * 32] = __dadd_rn(a.lat_coef[4], __dmul_rn(a.lat_coef[5], kv));
+        tile[4 * 32] = __dmul_rn(a.lat_coef[6], wt);
+        tile[5 * 32] = __dmul_rn(a.lat_coef[7], rn);
+        tile[6 * 32] = pod_min > 0.0 ? __dmul_rn(pod_min, a.lat_buffer) : __longlong_as_double(0x7ff0000000000000LL);
+        const bool idle = !(m < M && a.dispatched) || a.dispatched[m] == 0;
+        const bool neutral = !a.lat_streaming || (m < M && a.prefill && a.prefill[m]);
+        tile[7 * 32] = __longlong_as_double((long long)((idle ? 1 : 0) | (neutral ? 2 : 0)));
+      } else {
+        tile[0 * 32] = __dmul_rn(a.lat_ckv, __dsub_rn(1.0, kv));                    // plugin.go:351,355
+        tile[1 * 32] = __longlong_as_double(qi);                                     // raw WaitingQueueSize
+      }
     }
   }
 }

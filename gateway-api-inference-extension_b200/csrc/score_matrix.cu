@@ -31,16 +31,17 @@ struct LatPair {
   double ttft, tpot, hT, hP;
   int rank;
 };
-__device__ __forceinline__ LatPair lat_pair(const LatArgs& L, int MPAD, int m, double pref_term, double x_in, double y_in,
-                                            double ttft_slo, double buf_tpot) {
+// tile layout of the per-endpoint arrays: slot i of endpoint (t*32 + lane) lives at ((t*8 + i)*32 + lane), so one
+// address per pair and seven coalesced 8-byte loads at immediate offsets (kernels.cuh: LatArgs)
+__device__ __forceinline__ LatPair lat_pair(const double* tp, double tpot_generated, double pref_term, double x_in,
+                                            double y_in, double ttft_slo, double buf_tpot) {
   LatPair o;
-  const double* ep = L.ep + m;
-  o.ttft = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__ldg(ep), x_in), __ldg(ep + MPAD)), __ldg(ep + 2 * MPAD)), pref_term);
-  o.tpot = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__ldg(ep + 3 * MPAD), y_in), __ldg(ep + 4 * MPAD)), __ldg(ep + 5 * MPAD)),
-                     L.tpot_generated);                      // NumTokensGenerated = 1 (prediction.go:69)
+  o.ttft = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__ldg(tp), x_in), __ldg(tp + 32)), __ldg(tp + 64)), pref_term);
+  o.tpot = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__ldg(tp + 96), y_in), __ldg(tp + 128)), __ldg(tp + 160)),
+                     tpot_generated);                        // NumTokensGenerated = 1 (prediction.go:69)
   o.hT = __dsub_rn(ttft_slo, o.ttft);
-  const int fl = __ldg(L.flags + m);
-  const double lim = __ldg(ep + 6 * MPAD);
+  const int fl = __ldg(reinterpret_cast<const int*>(tp + 224));
+  const double lim = __ldg(tp + 192);
   const double buffered = lim < buf_tpot ? lim : buf_tpot;   // min(bufferedTPOT, podMinTPOTSLO*factor)
   o.hP = (fl & 2) ? 0.0 : __dsub_rn(buffered, o.tpot);
   const bool tn = o.hT < 0.0, pn = o.hP < 0.0;
@@ -215,9 +216,10 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
     // ---------------- latency fold-in: per-request inputs and tier selection (plugin.go:174-243) ----------------
     double l_x = 0.0, l_y = 0.0, l_tslo = 0.0, l_buf = 0.0;
     double l_mnT = 0.0, l_rgT = 0.0, l_mnP = 0.0, l_rgP = 0.0, l_alpha = 0.0, l_beta = 0.0, l_qrange = 0.0;
+    double l_rT = 0.0, l_rP = 0.0;
     long long l_maxq = 0;
     int l_sel = 5;
-    bool l_tok = false, l_pok = false;
+    bool l_tok = false, l_pok = false, l_fast = false;
     const bool llut_ok = total <= kLutMax;
     if (LAT && lat_step >= 0) {
       const LatArgs& L = a.lat;
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
       }
       if (L.has_predictions) {
         // one pass: every lane tracks the best (lowest) tier it has seen and the |headroom| min/max inside it
+        // (branch-free: a non-candidate is tier 5, which never wins against a candidate)
         int rank_l = 5;
         double mnT = 1.7976931348623157e308, mxT = -1.7976931348623157e308, mnP = mnT, mxP = mxT;
 #pragma unroll
@@ -243,26 +246,23 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
           if (j >= J) break;
           const uint32_t anyj = any[j];
           const int cbase = (j * 32 + lane) << LOG_EPL;
+#pragma unroll 2
           for (int k = 0; k < EPL; k++) {
             const int t = j * EPL + k, m = t * 32 + lane;
             bool cand = m < M;
             if (MASKED) cand = cand && ((__ldg(mrow + t) >> lane) & 1u);
-            if (!cand) continue;
             int c = wide_cnt ? (int)cnt16[cbase + k] : (int)cnt8[cbase + k];
             c = (c == 0 && ((anyj >> k) & 1u)) ? (wide_cnt ? 65536 : 256) : c;
             const double pt = llut_ok ? lut_l[c] : __dmul_rn(pcoef, total ? __ddiv_rn((double)c, (double)total) : 0.0);
-            const LatPair lp = lat_pair(L, MPAD, m, pt, l_x, l_y, l_tslo, l_buf);
+            const LatPair lp = lat_pair(L.ep + (size_t)t * 256 + lane, L.tpot_generated, pt, l_x, l_y, l_tslo, l_buf);
+            const int rk = cand ? lp.rank : 5;
             const double aT = fabs(lp.hT), aP = fabs(lp.hP);
-            if (lp.rank < rank_l) {
-              rank_l = lp.rank;
-              mnT = mxT = aT;
-              mnP = mxP = aP;
-            } else if (lp.rank == rank_l) {
-              mnT = aT < mnT ? aT : mnT;
-              mxT = aT > mxT ? aT : mxT;
-              mnP = aP < mnP ? aP : mnP;
-              mxP = aP > mxP ? aP : mxP;
-            }
+            const bool better = rk < rank_l, same = rk == rank_l;
+            mnT = (better || (same && aT < mnT)) ? aT : mnT;
+            mxT = (better || (same && aT > mxT)) ? aT : mxT;
+            mnP = (better || (same && aP < mnP)) ? aP : mnP;
+            mxP = (better || (same && aP > mxP)) ? aP : mxP;
+            rank_l = better ? rk : rank_l;
           }
         }
         l_sel = __reduce_min_sync(0xffffffffu, rank_l);
@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
         const double eps = 1e-9;                                                // plugin.go:41
         l_tok = l_rgT > eps;
         l_pok = l_rgP > eps;
+        l_rT = l_tok ? __drcp_rn(l_rgT) : 0.0;                                  // fast path of the normalisation, see below
+        l_rP = l_pok ? __drcp_rn(l_rgP) : 0.0;
+        l_fast = l_alpha >= 0.0 && l_alpha <= 1.0 && l_beta >= 0.0 && l_beta <= 1.0;
         l_alpha = L.alpha;
         l_beta = L.beta;
         if (!l_tok && l_pok) {                                                  // plugin.go:275-279
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
           bool cand = m < M;
           if (MASKED) cand = cand && ((__ldg(mrow + t) >> lane) & 1u);
           if (cand) {
-            const long long q = __ldg(a.minmax_q[0] + m);
+            const long long q = __ldg(reinterpret_cast<const long long*>(L.ep + (size_t)t * 256 + 32 + lane));
             mq = q > mq ? q : mq;
           }
         }
@@ -313,6 +316,8 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
         }
         l_maxq = mq;
         l_qrange = __ll2double_rn(mq);
+        l_rT = mq > 0 ? __drcp_rn(l_qrange) : 0.0;
+        l_fast = L.wq >= 0.0 && L.wq <= 1.0;
       }
     }
 
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
       }
       const uint32_t anyj = any[j];
       const int cbase = (j * 32 + lane) << LOG_EPL;
-#pragma unroll 4
+#pragma unroll(LAT ? 2 : 4)
       for (int k = 0; k < EPL; k++) {
         const int t = j * EPL + k, m = t * 32 + lane;
         bool cand = m < M;
@@ -372,30 +377,47 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
               term = __dmul_rn(clamp01(sc), wq[s]);
             }
           } else if (LAT && kind == STEP_LATENCY) {
+            // The score is quantised (w/100 with w an integer), so the two normalising divides are only needed to
+            // decide on which side of an integer boundary v falls.  Fast path: multiply by the correctly rounded
+            // reciprocal of the range (|v' - v| < 2e-13 when alpha, beta are in [0,1]); if v' is farther than 1e-9
+            // from an integer the truncation is already decided, otherwise redo it exactly as plugin.go:283-306.
             const LatArgs& L = a.lat;
             const double pt = llut_ok ? lut_l[c] : __dmul_rn(L.has_predictions ? L.ttft_prefix : L.wpref,
                                                              total ? __ddiv_rn((double)c, (double)total) : 0.0);
+            const double* tp = L.ep + (size_t)t * 256 + lane;
             int w = 0;
             if (L.has_predictions) {
-              const LatPair lp = lat_pair(L, MPAD, m < M ? m : 0, pt, l_x, l_y, l_tslo, l_buf);
+              const LatPair lp = lat_pair(tp, L.tpot_generated, pt, l_x, l_y, l_tslo, l_buf);
               if (DIAG && L.pred_out && m < M) {
                 L.pred_out[((size_t)r * M + m) * 2] = lp.ttft;
                 L.pred_out[((size_t)r * M + m) * 2 + 1] = lp.tpot;
               }
-              if (lp.rank == l_sel) {                                          // scoreBucket, plugin.go:281-306
-                const double nT = l_tok ? __ddiv_rn(__dsub_rn(fabs(lp.hT), l_mnT), l_rgT) : 0.5;
-                const double nP = l_pok ? __ddiv_rn(__dsub_rn(fabs(lp.hP), l_mnP), l_rgP) : 0.5;
-                const double combined = __dadd_rn(__dmul_rn(l_alpha, nT), __dmul_rn(l_beta, nP));
-                const double v = (L.strategy_most && l_sel == 0) ? __dmul_rn(combined, 100.0)
-                                                                 : __dmul_rn(__dsub_rn(1.0, combined), 100.0);
-                w = __double2int_rz(v) + 1;                                    // float64(int(x) + minWeight + 1)
+              const bool most = L.strategy_most && l_sel == 0;
+              const double dT = __dsub_rn(fabs(lp.hT), l_mnT), dP = __dsub_rn(fabs(lp.hP), l_mnP);
+              const double nT = l_tok ? __dmul_rn(dT, l_rT) : 0.5, nP = l_pok ? __dmul_rn(dP, l_rP) : 0.5;
+              const double comb = __dadd_rn(__dmul_rn(l_alpha, nT), __dmul_rn(l_beta, nP));
+              const double v = most ? __dmul_rn(comb, 100.0) : __dmul_rn(__dsub_rn(1.0, comb), 100.0);
+              const int vn = __double2int_rn(v);
+              w = __double2int_rz(v) + 1;                                      // float64(int(x) + minWeight + 1)
+              if (lp.rank != l_sel) {
+                w = 0;                                                         // outside the scored tier: scores[ep] = 0
+              } else if (!l_fast || fabs(__dsub_rn(v, (double)vn)) < 1e-9) {   // scoreBucket, plugin.go:281-306, exactly
+                const double eT = l_tok ? __ddiv_rn(dT, l_rgT) : 0.5, eP = l_pok ? __ddiv_rn(dP, l_rgP) : 0.5;
+                const double ec = __dadd_rn(__dmul_rn(l_alpha, eT), __dmul_rn(l_beta, eP));
+                w = __double2int_rz(most ? __dmul_rn(ec, 100.0) : __dmul_rn(__dsub_rn(1.0, ec), 100.0)) + 1;
               }
             } else {                                                           // compositeScores, plugin.go:346-360
-              const int mm = m < M ? m : 0;
-              const long long q = __ldg(a.minmax_q[0] + mm);
-              const double rel = l_qrange > 0.0 ? __ddiv_rn(__ll2double_rn(l_maxq - q), l_qrange) : 1.0;
-              const double comp = __dadd_rn(__dadd_rn(__ldg(L.ep + 7 * MPAD + mm), __dmul_rn(L.wq, rel)), pt);
-              w = (int)__double2ll_rz(round(__dmul_rn(100.0, comp)));          // int(math.Round(0 + 100*composite))
+              const long long q = __ldg(reinterpret_cast<const long long*>(tp + 32));
+              const double dq = __ll2double_rn(l_maxq - q);
+              const double rel = l_maxq > 0 ? __dmul_rn(dq, l_rT) : 1.0;
+              const double ck = __ldg(tp);
+              const double v = __dmul_rn(100.0, __dadd_rn(__dadd_rn(ck, __dmul_rn(L.wq, rel)), pt));
+              const double fl = floor(v);
+              w = (int)__double2ll_rz(round(v));                               // int(math.Round(0 + 100*composite))
+              if (!l_fast || !(fabs(v) < 1e4) || fabs(__dsub_rn(__dsub_rn(v, fl), 0.5)) < 1e-9) {
+                const double er = l_maxq > 0 ? __ddiv_rn(dq, l_qrange) : 1.0;
+                w = (int)__double2ll_rz(round(__dmul_rn(100.0, __dadd_rn(__dadd_rn(ck, __dmul_rn(L.wq, er)), pt))));
+              }
               if (DIAG && L.pred_out && m < M) {
                 L.pred_out[((size_t)r * M + m) * 2] = nan64();
                 L.pred_out[((size_t)r * M + m) * 2 + 1] = nan64();
