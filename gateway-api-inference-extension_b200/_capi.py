@@ -11,6 +11,7 @@ MAX_ENDPOINT_COLS = 4
 SCORER = {"queue": 0, "kv": 1, "prefix": 2, "lora": 3, "running": 4, "latency": 5, "token_load": 6,
           "col0": 8, "col1": 9, "col2": 10, "col3": 11, "pair0": 16, "pair1": 17}
 TIE_LOWEST_INDEX, TIE_SEEDED_RANDOM = 0, 1
+PICK_MAX_SCORE, PICK_WEIGHTED_RANDOM, PICK_RANDOM = 0, 1, 2
 
 ERR_NAMES = {0: "OK", -1: "ERR_INVALID", -2: "ERR_CUDA", -3: "ERR_CAPACITY", -4: "ERR_NO_SNAPSHOT", -5: "ERR_NO_DEVICE"}
 
@@ -26,7 +27,7 @@ class Config(C.Structure):
                 ("scorer_weight", C.c_double * MAX_SCORERS), ("block_chars", C.c_int32), ("max_blocks", C.c_int32),
                 ("tie_mode", C.c_int32), ("tie_seed", C.c_uint64), ("max_endpoints", C.c_int32),
                 ("max_adapters", C.c_int32), ("prefix_capacity", C.c_int64), ("lru_capacity_default", C.c_int32),
-                ("token_load_threshold", C.c_double)]
+                ("token_load_threshold", C.c_double), ("pick_mode", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class LatencyParams(C.Structure):

@@ -187,7 +187,8 @@ void build_plan(eppscore_engine* e, bool masked, PlanSet* ps) {
       ok = false;
     }
   }
-  p.sparse_ok = (ok && n_prefix <= 1) ? 1 : 0;
+  p.pick_mode = c.pick_mode;
+  p.sparse_ok = (ok && n_prefix <= 1 && c.pick_mode == EPPSCORE_PICK_MAX_SCORE) ? 1 : 0;
 }
 
 int32_t flush_table(eppscore_engine* e) {
@@ -321,6 +322,8 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
   a.match_out = b.match_blocks;
   a.total_out = b.total_blocks;
   a.scores_out = b.scores_out;
+  if (dense && e->cfg.pick_mode != EPPSCORE_PICK_MAX_SCORE)
+    return fail(e, EPPSCORE_ERR_INVALID, "the stochastic pickers are not available on dense feature rows");
   if (cfg_has(e->cfg, EPPSCORE_SCORER_LATENCY)) {
     if (dense) return fail(e, EPPSCORE_ERR_INVALID, "the latency scorer is not available on dense feature rows");
     if (!e->lat_args.enabled) return fail(e, EPPSCORE_ERR_INVALID, "latency scorer configured but the snapshot was prepared without latency params");
@@ -462,6 +465,7 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
     for (int i = 0; i < cfg->n_scorers; i++) nlat += cfg->scorer_kind[i] == EPPSCORE_SCORER_LATENCY;
     if (nlat > 1) return fail(nullptr, EPPSCORE_ERR_INVALID, "at most one latency scorer per profile");
   }
+  if (cfg->pick_mode < 0 || cfg->pick_mode > EPPSCORE_PICK_RANDOM) return fail(nullptr, EPPSCORE_ERR_INVALID, "unknown pick_mode");
   if (cfg->max_endpoints < 1 || cfg->max_endpoints > 8192)
     return fail(nullptr, EPPSCORE_ERR_CAPACITY, "max_endpoints must be in [1, 8192]");
   if (cfg->max_blocks < 0 || cfg->max_blocks > EPPSCORE_MAX_BLOCKS) return fail(nullptr, EPPSCORE_ERR_CAPACITY, "max_blocks out of range");

@@ -106,6 +106,64 @@ __device__ __forceinline__ void best_group_reduce(Best& b, int tie_mode) {
   }
 }
 
+// ---- stochastic pickers (weightedrandom/picker.go:111-155, random/picker.go:85-101) ----
+// 53-bit uniform in (0,1] derived from the tie priority; -ln(u) from +,-,*,/ only, in a fixed order, so the
+// oracle (plain C) reproduces every bit: u = f*2^e, f in (sqrt(1/2), sqrt(2)], ln f = 2 atanh((f-1)/(f+1)).
+__device__ __forceinline__ double uniform01(uint32_t prio, int m) {
+  const uint32_t hi = lowbias32(prio ^ 0x85EBCA6BU);
+  const uint32_t lo = lowbias32(hi + 0xC2B2AE35U + (uint32_t)m);
+  const unsigned long long k = ((((unsigned long long)hi) << 32) | lo) >> 11;
+  return __dmul_rn(__ull2double_rn(k + 1ULL), 1.1102230246251565e-16);  // * 2^-53, exact
+}
+__device__ __forceinline__ double neg_log(double u) {
+  unsigned long long bits = (unsigned long long)__double_as_longlong(u);
+  int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  double f = __longlong_as_double((long long)((bits & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL));
+  if (f > 1.4142135623730951) {
+    f = __dmul_rn(f, 0.5);
+    e += 1;
+  }
+  const double z = __ddiv_rn(__dsub_rn(f, 1.0), __dadd_rn(f, 1.0));
+  const double z2 = __dmul_rn(z, z);
+  double p = 1.0 / 21.0;
+#pragma unroll
+  for (int k = 19; k >= 1; k -= 2) p = __dadd_rn(__dmul_rn(p, z2), 1.0 / (double)k);
+  const double lnf = __dmul_rn(__dmul_rn(2.0, z), p);
+  return -__dadd_rn(__dmul_rn((double)e, 0.6931471805599453), lnf);
+}
+// arg-max of a key with the pair's weighted score carried along; lowest index on (improbable) key ties
+struct RBest {
+  double key, score;
+  int32_t m, n;
+};
+__device__ __forceinline__ RBest rbest_none() {
+  RBest b;
+  b.key = 0.0;
+  b.score = 0.0;
+  b.m = -1;
+  b.n = 0;
+  return b;
+}
+__device__ __forceinline__ void rbest_update(RBest& b, double key, double score, int m) {
+  const bool t = b.m < 0 || key > b.key;
+  b.key = t ? key : b.key;
+  b.score = t ? score : b.score;
+  b.m = t ? m : b.m;
+  b.n++;
+}
+__device__ __forceinline__ void rbest_warp_reduce(RBest& b) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const double ok = shfl_xor_f64(b.key, o), os = shfl_xor_f64(b.score, o);
+    const int om = __shfl_xor_sync(0xffffffffu, b.m, o), on = __shfl_xor_sync(0xffffffffu, b.n, o);
+    const bool t = om >= 0 && (b.m < 0 || ok > b.key || (ok == b.key && om < b.m));
+    b.key = t ? ok : b.key;
+    b.score = t ? os : b.score;
+    b.m = t ? om : b.m;
+    b.n += on;
+  }
+}
+
 // Weighted score of one (request, endpoint) pair, steps in profile order from 0.0
 // (scheduler_profile.go:155-168). Runtime-generic: used on rare paths (exceptions, summaries).
 __device__ __forceinline__ double eval_steps(const Plan& plan, const double* const* term, int m, int c, int total, int cls) {

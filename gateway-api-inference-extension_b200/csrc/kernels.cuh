@@ -73,6 +73,7 @@ struct Plan {
   int32_t n_terms;       // number of term arrays the steps reference
   uint32_t seq;          // the step kinds packed 4 bits each (kind+1), 0 = end: selects a specialised kernel
   int32_t sparse_ok;     // unmasked plan only: steps are E/P/L with at most one prefix step of weight >= 0
+  int32_t pick_mode;     // 0 max-score, 1 weighted-random (A-Res), 2 random  (include/eppscore.h: eppscore_pick_mode)
 };
 
 // Geometry derived from config.max_endpoints (fixed per engine); M varies per snapshot.

@@ -323,6 +323,8 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
 
     const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
     Best best = best_none();
+    RBest rb_pos = rbest_none(), rb_all = rbest_none();  // stochastic pickers (runtime-generic variants only)
+    const int pick_mode = SEQ == 0 ? plan.pick_mode : 0;
 
     // ---------------- Score (scheduler_profile.go:151-174) + Pick (maxscore/picker.go:87-115) ----------------
     // per-step constants hoisted out of the pair loop (compile-time step index when SEQ != 0)
@@ -398,13 +400,14 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
               const double comb = __dadd_rn(__dmul_rn(l_alpha, nT), __dmul_rn(l_beta, nP));
               const double v = most ? __dmul_rn(comb, 100.0) : __dmul_rn(__dsub_rn(1.0, comb), 100.0);
               const int vn = __double2int_rn(v);
-              w = __double2int_rz(v) + 1;                                      // float64(int(x) + minWeight + 1)
-              if (lp.rank != l_sel) {
-                w = 0;                                                         // outside the scored tier: scores[ep] = 0
-              } else if (!l_fast || fabs(__dsub_rn(v, (double)vn)) < 1e-9) {   // scoreBucket, plugin.go:281-306, exactly
+              const bool in_tier = lp.rank == l_sel;
+              w = in_tier ? __double2int_rz(v) + 1 : 0;                        // float64(int(x) + minWeight + 1); 0 outside the tier
+              const bool redo = in_tier && (!l_fast || fabs(__dsub_rn(v, (double)vn)) < 1e-9);
+              if (__any_sync(0xffffffffu, redo)) {                             // warp-uniform: scoreBucket, plugin.go:281-306, exactly
                 const double eT = l_tok ? __ddiv_rn(dT, l_rgT) : 0.5, eP = l_pok ? __ddiv_rn(dP, l_rgP) : 0.5;
                 const double ec = __dadd_rn(__dmul_rn(l_alpha, eT), __dmul_rn(l_beta, eP));
-                w = __double2int_rz(most ? __dmul_rn(ec, 100.0) : __dmul_rn(__dsub_rn(1.0, ec), 100.0)) + 1;
+                const int we = __double2int_rz(most ? __dmul_rn(ec, 100.0) : __dmul_rn(__dsub_rn(1.0, ec), 100.0)) + 1;
+                w = redo ? we : w;
               }
             } else {                                                           // compositeScores, plugin.go:346-360
               const long long q = __ldg(reinterpret_cast<const long long*>(tp + 32));
@@ -414,9 +417,11 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
               const double v = __dmul_rn(100.0, __dadd_rn(__dadd_rn(ck, __dmul_rn(L.wq, rel)), pt));
               const double fl = floor(v);
               w = (int)__double2ll_rz(round(v));                               // int(math.Round(0 + 100*composite))
-              if (!l_fast || !(fabs(v) < 1e4) || fabs(__dsub_rn(__dsub_rn(v, fl), 0.5)) < 1e-9) {
+              const bool redo = !l_fast || !(fabs(v) < 1e4) || fabs(__dsub_rn(__dsub_rn(v, fl), 0.5)) < 1e-9;
+              if (__any_sync(0xffffffffu, redo)) {
                 const double er = l_maxq > 0 ? __ddiv_rn(dq, l_qrange) : 1.0;
-                w = (int)__double2ll_rz(round(__dmul_rn(100.0, __dadd_rn(__dadd_rn(ck, __dmul_rn(L.wq, er)), pt))));
+                const int we = (int)__double2ll_rz(round(__dmul_rn(100.0, __dadd_rn(__dadd_rn(ck, __dmul_rn(L.wq, er)), pt))));
+                w = redo ? we : w;
               }
               if (DIAG && L.pred_out && m < M) {
                 L.pred_out[((size_t)r * M + m) * 2] = nan64();
@@ -439,7 +444,15 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
           }
         }
         if (DIAG && a.scores_out && m < M) a.scores_out[(size_t)r * M + m] = cand ? acc : nan64();
-        if (cand) best_update(best, acc, m, tie_mode, areq, plan.seed_hi);
+        if (SEQ == 0 && pick_mode != 0) {
+          if (cand) {  // random: highest priority wins; weighted-random (A-Res): smallest -ln(U)/score among score > 0
+            const uint32_t pr = tie_prio(areq, m, plan.seed_hi);
+            rbest_update(rb_all, (double)pr, acc, m);
+            if (pick_mode == 1 && acc > 0.0) rbest_update(rb_pos, -__ddiv_rn(neg_log(uniform01(pr, m)), acc), acc, m);
+          }
+        } else if (cand) {
+          best_update(best, acc, m, tie_mode, areq, plan.seed_hi);
+        }
       }
       // re-zero exactly the counters this request touched
       uint32_t x = anyj;
@@ -451,6 +464,14 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
       }
     }
     best_group_reduce<32>(best, tie_mode);
+    if (SEQ == 0 && pick_mode != 0) {  // warp-uniform
+      rbest_warp_reduce(rb_pos);
+      rbest_warp_reduce(rb_all);
+      const RBest& w = rb_pos.m >= 0 ? rb_pos : rb_all;  // no positive score: the random picker (weightedrandom/picker.go:113-116)
+      best.m = w.m;
+      best.score = w.score;
+      best.cnt = w.n;
+    }
     if (lane == 0) {
       a.pick[r] = best.m;
       a.pick_score[r] = best.m >= 0 ? best.score : 0.0;
@@ -497,7 +518,7 @@ template <bool MASKED, bool DIAG>
 static int launch_matrix_seq(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   bool lat = false;
   for (int i = 0; i < a.plan.n_steps; i++) lat = lat || a.plan.kind[i] == STEP_LATENCY;
-  switch (a.plan.seq) {
+  switch (a.plan.pick_mode == 0 ? a.plan.seq : 0xffffffffu) {  // stochastic pickers: the runtime-generic variants
     case mseq(E): return MK(E);
     case mseq(E, P): return MK(E, P);
     case mseq(E, P, L): return MK(E, P, L);

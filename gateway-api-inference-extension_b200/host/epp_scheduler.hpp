@@ -188,7 +188,12 @@ struct Filter {
 
 struct MaxScorePicker {
   int MaxNumOfEndpoints = 1;  // picker.DefaultMaxNumOfEndpoints (picker/common.go:36); only 1 is supported on the GPU path
+  int Mode = EPPSCORE_PICK_MAX_SCORE;
 };
+// weighted-random-picker (A-Res, picker/weightedrandom/picker.go:111-155) and random-picker (picker/random/picker.go:85-101):
+// same descriptor with another pick mode; the engine's generator is counter-based (SchedulerConfig.TieSeed).
+struct WeightedRandomPicker : MaxScorePicker { WeightedRandomPicker() { Mode = EPPSCORE_PICK_WEIGHTED_RANDOM; } };
+struct RandomPicker : MaxScorePicker { RandomPicker() { Mode = EPPSCORE_PICK_RANDOM; } };
 
 class SchedulerProfile {
  public:
@@ -251,6 +256,7 @@ class Scheduler {
     c.max_endpoints = cfg.MaxEndpoints;
     c.max_adapters = cfg.MaxAdapters;
     c.prefix_capacity = cfg.PrefixCapacity;
+    c.pick_mode = cfg.Profile.picker().Mode;
     c.tie_mode = cfg.TieMode;
     c.tie_seed = cfg.TieSeed;
     if (eppscore_create(cfg.Device, &c, &eng_) != EPPSCORE_OK) throw SchedulingError(std::string("eppscore_create: ") + eppscore_last_error(nullptr));

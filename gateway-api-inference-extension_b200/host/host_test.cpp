@@ -6,6 +6,7 @@
 //   integration routing scenarios     test/integration/epp/common_tests.go:283-312, hermetic_test.go:120-272
 //   TestPrefixPluginCompletion        .../approximateprefix/plugin_test.go:161-227 (via PreRequest)
 //   TestTokenLoadScorer               pkg/epp/framework/plugins/scheduling/scorer/tokenload/token_load_test.go:32-61
+//   TestPickWeightedRandomPicker      pkg/epp/framework/plugins/scheduling/picker/weightedrandom/picker_test.go:30-140
 //   TestScore* (latency-scorer)       pkg/epp/framework/plugins/scheduling/scorer/latency/plugin_test.go:52-208
 #include <cmath>
 #include <cstdio>
@@ -264,6 +265,28 @@ static void TestLatencyScorer() {
   CHECK(CountFields("\xE2\x80\x8B") == 1);                                          // ZERO WIDTH SPACE is not White_Space
 }
 
+// custom per-endpoint score column: lets a test hand the picker exact scores (score = clamp(col) * weight)
+static void TestWeightedRandomPicker() {
+  // "Multi-tier weighted test": scores 100, 90, 50, 30, 20 -> P = score / 290, +-5 % over 10000 picks
+  const double scores[5] = {100, 90, 50, 30, 20};
+  SchedulerConfig c;
+  c.Profile.WithScorers({NewWeightedScorer(std::make_shared<KVCacheUtilizationScorer>(), 100)}).WithPicker(WeightedRandomPicker{});
+  c.MaxEndpoints = 8;
+  c.TieSeed = 2024;
+  Scheduler s(c);
+  std::vector<Endpoint> eps;
+  for (int i = 0; i < 5; i++) {
+    Metrics m;
+    m.KVCacheUsagePercent = 1.0 - scores[i] / 100.0;  // kv scorer: 1 - usage
+    eps.push_back(NewEndpoint("pod" + std::to_string(i + 1), m));
+  }
+  std::vector<InferenceRequest> reqs(10000, InferenceRequest{"w", "m", "", ""});
+  auto res = s.ScheduleBatch(reqs, eps);
+  int count[5] = {0, 0, 0, 0, 0};
+  for (auto& r : res) count[r.result.ProfileResults.at("default").TargetEndpoints[0].Index]++;
+  for (int i = 0; i < 5; i++) CHECK(std::fabs(count[i] / 10000.0 - scores[i] / 290.0) <= 0.05);
+}
+
 int main() {
   try {
     TestSchedule();
@@ -272,6 +295,7 @@ int main() {
     TestPrefixCompletionViaPreRequest();
     TestTokenLoadScorer();
     TestLatencyScorer();
+    TestWeightedRandomPicker();
   } catch (const std::exception& e) {
     std::printf("FAIL exception: %s\n", e.what());
     return 2;

@@ -78,6 +78,19 @@ typedef enum eppscore_tie_mode {
   EPPSCORE_TIE_SEEDED_RANDOM = 1
 } eppscore_tie_mode;
 
+/* Pickers (framework.Picker, interface/scheduling/plugins.go:74-78).  The reference's stochastic pickers draw from a
+ * process-wide PCG seeded with the wall clock (picker/common.go:40-55), so they have no bit-parity definition; the
+ * engine uses a counter-based generator keyed by (tie_seed, request_base + r, endpoint) — reproducible, identical on
+ * every shard — and is checked at the distribution level (the reference's own picker tests do the same, ±5 %). */
+typedef enum eppscore_pick_mode {
+  EPPSCORE_PICK_MAX_SCORE = 0,       /* max-score-picker: picker/maxscore/picker.go:87-115 */
+  /* weighted-random-picker (A-Res, picker/weightedrandom/picker.go:111-155): P(m) = score[m] / Σ score over the
+   * candidates with score > 0; key U^(1/score) maximal ⇔ -ln(U)/score minimal; no positive score ⇒ random picker.
+   * tie_count reports the size of the set the draw was over. */
+  EPPSCORE_PICK_WEIGHTED_RANDOM = 1,
+  EPPSCORE_PICK_RANDOM = 2           /* random-picker: picker/random/picker.go:85-101 — uniform over the candidates */
+} eppscore_pick_mode;
+
 /* Scheduler profile + engine sizing.  Replaces SchedulerProfile{scorers, picker}
  * (pkg/epp/scheduling/scheduler_profile.go:41-98) and the approximateprefix config
  * (approximateprefix/types.go:77-141). Zero-initialise, set struct_size = sizeof, fill. */
@@ -95,6 +108,8 @@ typedef struct eppscore_config {
   int64_t prefix_capacity; /* INITIAL capacity (distinct block hashes) of the device table; it doubles on demand. default 1<<18 */
   int32_t lru_capacity_default; /* defaultLRUCapacityPerServer = 31250 (types.go:109) */
   double token_load_threshold;  /* token-load-scorer queueThresholdTokens; <= 0 ⇒ 4194304 (token_load.go:33,57-61) */
+  int32_t pick_mode;            /* eppscore_pick_mode; default max-score */
+  int32_t reserved0;
 } eppscore_config;
 
 /* Latency fold-in parameters: the cached Bayesian-ridge coefficients (MetricsResponse.Coefficients,

@@ -863,6 +863,35 @@ uint32_t orc_tie_priority(uint64_t seed, int64_t request_index, int32_t endpoint
   return lowbias32(a + (uint32_t)endpoint * 0x9E3779B1U + (uint32_t)(seed >> 32));
 }
 
+/* 53-bit uniform in (0,1] from the tie priority (documented generator, see include/eppscore.h pick modes) */
+double orc_uniform01(uint64_t seed, int64_t request_index, int32_t endpoint) {
+  uint32_t prio = orc_tie_priority(seed, request_index, endpoint);
+  uint32_t hi = lowbias32(prio ^ 0x85EBCA6BU);
+  uint32_t lo = lowbias32(hi + 0xC2B2AE35U + (uint32_t)endpoint);
+  uint64_t k = ((((uint64_t)hi) << 32) | lo) >> 11;
+  return (double)(k + 1) * 0x1p-53;
+}
+/* -ln(u), u in (0,1]: u = f * 2^e with f in (sqrt(1/2), sqrt(2)], ln f = 2 atanh((f-1)/(f+1)) as an 11-term odd series */
+double orc_neg_log(double u) {
+  uint64_t bits;
+  memcpy(&bits, &u, 8);
+  int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  bits = (bits & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
+  double f;
+  memcpy(&f, &bits, 8);
+  if (f > 1.4142135623730951) {
+    f = f * 0.5;
+    e += 1;
+  }
+  double z = (f - 1.0) / (f + 1.0);
+  double z2 = z * z;
+  double p = 1.0 / 21.0;
+  for (int k = 19; k >= 1; k -= 2) p = p * z2 + 1.0 / (double)k;
+  double lnf = (2.0 * z) * p;
+  double lnu = (double)e * 0.6931471805599453 + lnf;
+  return -lnu;
+}
+
 static const double LORA_CLASS_SCORE[4] = {0.0, 0.6, 0.8, 1.0};
 
 int32_t orc_schedule_one(const orc_snapshot *s, const orc_profile *p, int64_t request_index,
@@ -944,6 +973,41 @@ int32_t orc_schedule_one_lat(const orc_snapshot *s, const orc_profile *p, int64_
       double t = orc_enforce_score_range(sc[m]) * weight; /* rounded product ... */
       w[m] = w[m] + t;                                    /* ... then rounded add (:168) */
     }
+  }
+  if (p->pick_mode != ORC_PICK_MAX_SCORE) {
+    /* weighted-random (A-Res, weightedrandom/picker.go:111-155): key = U^(1/score) maximal  <=>  -ln(U)/score minimal;
+     * endpoints with score <= 0 get key 0 (never chosen); no positive score at all => random picker.
+     * random picker (random/picker.go:85-101): shuffle and take the first = a uniform choice. */
+    int32_t n_pos = 0, pick_pos = -1, pick_all = -1;
+    double key_pos = 0;
+    uint32_t prio_all = 0;
+    for (int32_t m = 0; m < M; m++) {
+      if (!is_cand(mask, m)) continue;
+      uint32_t pr = orc_tie_priority(p->tie_seed, request_index, m);
+      if (pick_all < 0 || pr > prio_all) {
+        pick_all = m;
+        prio_all = pr;
+      }
+      if (p->pick_mode == ORC_PICK_WEIGHTED_RANDOM && w[m] > 0) {
+        double key = orc_neg_log(orc_uniform01(p->tie_seed, request_index, m)) / w[m];
+        if (pick_pos < 0 || key < key_pos) {
+          pick_pos = m;
+          key_pos = key;
+        }
+        n_pos++;
+      }
+    }
+    int32_t pk = pick_pos >= 0 ? pick_pos : pick_all;
+    *pick_out = pk;
+    *score_out = w[pk];
+    *tie_count_out = pick_pos >= 0 ? n_pos : ncand; /* size of the set the draw was over */
+    if (tie_set_out)
+      for (int32_t m = 0; m < M; m++)
+        if (is_cand(mask, m) && (pick_pos < 0 || w[m] > 0)) tie_set_out[m >> 5] |= 1u << (m & 31);
+    if (weighted_out)
+      for (int32_t m = 0; m < M; m++) weighted_out[m] = is_cand(mask, m) ? w[m] : NAN;
+    free(w);
+    return 0;
   }
   /* MaxScorePicker (maxscore/picker.go:87-115) as arg-max set */
   double best = 0;

@@ -45,6 +45,11 @@ enum {
 };
 
 enum { ORC_TIE_LOWEST_INDEX = 0, ORC_TIE_SEEDED_RANDOM = 1 };
+/* pickers: max-score (picker/maxscore/picker.go:87-115), weighted-random A-Res (picker/weightedrandom/picker.go:111-155),
+ * random (picker/random/picker.go:85-101).  The reference draws from a time-seeded process-wide PCG
+ * (picker/common.go:40-55), so the stochastic pickers have no bit-parity definition; engine and oracle share a
+ * documented counter-based generator instead and are checked at the distribution level. */
+enum { ORC_PICK_MAX_SCORE = 0, ORC_PICK_WEIGHTED_RANDOM = 1, ORC_PICK_RANDOM = 2 };
 
 /*
  * Latency-predictor fold-in: the Bayesian-ridge linear model the Go client evaluates from
@@ -72,6 +77,8 @@ typedef struct orc_profile {
   uint64_t tie_seed;
   const orc_latency_params *latency; /* required by ORC_SCORER_LATENCY */
   double token_load_threshold;       /* queueThresholdTokens (token_load.go:33,57-61); <= 0 => 4194304 */
+  int32_t pick_mode;                 /* ORC_PICK_* */
+  int32_t reserved;
 } orc_profile;
 
 /* One immutable metrics snapshot (interface/datalayer/metrics.go:26-42 fields the path reads). */
@@ -154,6 +161,10 @@ void orc_score_latency_info(const orc_latency_params *, const orc_snapshot *, co
 void orc_score_latency(const orc_latency_params *, const orc_snapshot *, const uint32_t *cand_mask,
                        const uint16_t *match, int32_t total, const orc_latency_request *, double *out,
                        double *pred_out);
+
+/* counter-based U in (0,1] and -ln(U) built from +,-,*,/ only (bit-reproducible on any IEEE machine) */
+double orc_uniform01(uint64_t seed, int64_t request_index, int32_t endpoint);
+double orc_neg_log(double u);
 
 /* counter-based tie priority shared (by specification) with the CUDA engine */
 uint32_t orc_tie_priority(uint64_t seed, int64_t request_index, int32_t endpoint);

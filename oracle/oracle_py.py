@@ -20,6 +20,7 @@ SCORER_LATENCY, SCORER_TOKEN_LOAD = 5, 6
 SCORER_ENDPOINT_COL0 = 8
 SCORER_PAIR_COL0 = 16
 TIE_LOWEST_INDEX, TIE_SEEDED_RANDOM = 0, 1
+PICK_MAX_SCORE, PICK_WEIGHTED_RANDOM, PICK_RANDOM = 0, 1, 2
 
 
 def build(force: bool = False) -> str:
@@ -69,7 +70,7 @@ class Profile(C.Structure):
     _fields_ = [("n_scorers", C.c_int32), ("scorer_kind", C.c_int32 * MAX_SCORERS),
                 ("scorer_weight", C.c_double * MAX_SCORERS), ("tie_mode", C.c_int32),
                 ("tie_seed", C.c_uint64), ("latency", C.POINTER(LatencyParams)),
-                ("token_load_threshold", C.c_double)]
+                ("token_load_threshold", C.c_double), ("pick_mode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Snapshot(C.Structure):
@@ -149,6 +150,10 @@ def lib():
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_score_latency.argtypes = [C.POINTER(LatencyParams), C.POINTER(Snapshot), C.c_void_p, C.c_void_p,
                                         C.c_int32, C.POINTER(LatencyRequest), C.c_void_p, C.c_void_p]
+        L.orc_uniform01.restype = C.c_double
+        L.orc_uniform01.argtypes = [C.c_uint64, C.c_int64, C.c_int32]
+        L.orc_neg_log.restype = C.c_double
+        L.orc_neg_log.argtypes = [C.c_double]
         L.orc_schedule_batch.restype = C.c_int32
         L.orc_schedule_batch.argtypes = [C.POINTER(Snapshot), C.POINTER(Profile), C.c_void_p, C.POINTER(Batch), C.c_int32]
         L.orc_commit_picks.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
@@ -188,13 +193,14 @@ def hash_prompt(prompt: bytes, seed: int, block_chars: int, max_blocks: int) -> 
 
 
 def make_profile(scorers, tie_mode=TIE_LOWEST_INDEX, tie_seed=0, latency: LatencyParams | None = None,
-                 token_load_threshold: float = 0.0) -> Profile:
+                 token_load_threshold: float = 0.0, pick_mode: int = 0) -> Profile:
     """scorers: list of (kind, weight) in profile order."""
     p = Profile()
     if latency is not None:
         p._latency_keep = latency  # keep the pointee alive with the struct
         p.latency = C.pointer(latency)
     p.token_load_threshold = token_load_threshold
+    p.pick_mode = pick_mode
     p.n_scorers = len(scorers)
     for i, (k, w) in enumerate(scorers):
         p.scorer_kind[i] = int(k)

@@ -30,7 +30,7 @@ def test_header_symbols_all_exported(pkg):
 
 def test_struct_sizes_match_header_layout(pkg):
     # natural C layout on x86-64 (computed by hand from include/eppscore.h)
-    assert C.sizeof(pkg.Config) == 4 + 4 + 32 + 64 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8
+    assert C.sizeof(pkg.Config) == 4 + 4 + 32 + 64 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4
     assert C.sizeof(pkg.LatencyParams) == 4 + 4 + 12 * 8 + 8 + 4 + 4 + 5 * 8
     assert C.sizeof(pkg.Snapshot) == 16 + 7 * 8 + 4 * 8 + 8 + 8 + 4 * 8
     assert C.sizeof(pkg.Batch) == 16 + 8 + 6 * 8 + 16 + 4 * 8 + 7 * 8 + 8 + 4 * 8
@@ -45,6 +45,7 @@ def test_default_config_is_reference_default(pkg):
     assert [cfg.scorer_weight[i] for i in range(3)] == [2.0, 2.0, 3.0]
     assert cfg.block_chars == 64 and cfg.max_blocks == 256 and cfg.lru_capacity_default == 31250
     assert cfg.token_load_threshold == 4194304.0  # token_load.go:33
+    assert cfg.pick_mode == pkg.PICK_MAX_SCORE    # max-score-picker (loader/defaults.go)
     lp = pkg.latency_params()
     # predictedlatency/plugin.go:128-136 and scorer/latency/plugin.go:83-90
     assert (lp.slo_buffer_factor, lp.streaming_mode, lp.has_predictions) == (1.0, 0, 1)

@@ -780,3 +780,67 @@ def test_token_load_scorer_parity(pkg, golden):
         want = o.schedule_batch(snap, prof, None, R, want_scores=True, **kw)
         assert_same(got, want, ("pick", "pick_score", "tie_count", "scores_out"))
         eng.close()
+
+
+# ------------------------------------------------------------------------------------------ stochastic pickers
+def test_stochastic_pickers_reference_distributions(pkg, golden):
+    """The reference's picker tests (weightedrandom/picker_test.go:30-140, random/picker_test.go:30-140) on the engine:
+    selection frequencies within the reference's own +-5 % of score/total (resp. uniform), zero scores never picked,
+    and bit-identical to the oracle, which runs the same counter-based generator."""
+    g = golden["stochastic_pickers"]
+    n, tol = g["iterations"], g["tolerance"]
+    for mode, cases in ((pkg.PICK_WEIGHTED_RANDOM, g["weighted"]), (pkg.PICK_RANDOM, g["random"])):
+        for c in cases:
+            sc = np.array(c["scores"], np.float64)
+            M = len(sc)
+            eng = make_engine(pkg, [("col0", 100.0)], M, pick_mode=mode, tie_seed=1234)
+            eng.set_snapshot(np.zeros(M), np.zeros(M, np.int64), endpoint_cols=[sc / 100.0])
+            got = eng.schedule(n)
+            snap = o.SnapshotData(np.zeros(M), np.zeros(M, np.int64), endpoint_cols=[sc / 100.0])
+            want = o.schedule_batch(snap, o.make_profile([(o.SCORER_ENDPOINT_COL0, 100.0)], tie_seed=1234, pick_mode=mode), None, n)
+            assert_same(got, want)
+            freq = np.bincount(got["pick"], minlength=M) / n
+            expect = sc / sc.sum() if mode == pkg.PICK_WEIGHTED_RANDOM else np.full(M, 1.0 / M)
+            assert np.abs(freq - expect).max() <= tol, (c["name"], freq)
+            if mode == pkg.PICK_WEIGHTED_RANDOM:
+                assert (freq[sc == 0] == 0).all()
+            eng.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_stochastic_pickers_parity_full_profile(pkg, mode):
+    """All four scorers + candidate masks under the stochastic pickers: pick, score of the pick and the size of the
+    draw set equal the oracle's; request_base shards agree (two half batches == one batch)."""
+    M, R = 600, 2048
+    scorers = [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)]
+    eng = make_engine(pkg, scorers, M, pick_mode=mode, tie_seed=77, prefix_capacity=1 << 16)
+    sd = synth_snapshot(M, seed=11)
+    eng.set_snapshot(**sd)
+    snap = o.SnapshotData(**sd)
+    prof = o.make_profile([(pkg.SCORER[k], w) for k, w in scorers], tie_seed=77, pick_mode=mode)
+    prompts, off, _ = synth_prompts(R, prompt_len=1024, groups=10, shared=512, seed=3)
+    seeds = np.full(R, eng.model_seed("m"), np.uint64)
+    idx = o.Index()
+    warm = o.schedule_batch(snap, profile_of(pkg, [("kv", 1)]), idx, R, prompt_bytes=prompts, prompt_off=off,
+                            model_seed=seeds, want_hashes=True, n_threads=8)
+    idx.commit(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    eng.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    rng = np.random.Generator(np.random.PCG64(5))
+    mask = rng.integers(0, 2 ** 32, (R, (M + 31) // 32), dtype=np.uint64).astype(np.uint32)
+    mask[0, :] = 0
+    kw = dict(prompt_bytes=prompts, prompt_off=off, model_seed=seeds, adapter_id=zipf_adapters(R, seed=3))
+    for extra in ({}, {"cand_mask": mask}):
+        got = eng.schedule(R, want_scores=True, **kw, **extra)
+        want = o.schedule_batch(snap, prof, idx, R, want_scores=True, want_tie_set=True, n_threads=8, **kw, **extra)
+        assert_same(got, want, ("pick", "pick_score", "tie_count", "scores_out"))
+        fast = eng.schedule(R, **kw, **extra)
+        assert_same(fast, want)
+    assert got["pick"][0] == -1
+    assert len(np.unique(got["pick"])) > 50   # spread over many endpoints, unlike the arg-max
+    h = R // 2
+    a = eng.schedule(h, prompt_bytes=prompts[: off[h]], prompt_off=off[: h + 1], model_seed=seeds[:h], adapter_id=kw["adapter_id"][:h])
+    b = eng.schedule(R - h, prompt_bytes=prompts[off[h]:], prompt_off=off[h:] - off[h], model_seed=seeds[h:],
+                     adapter_id=kw["adapter_id"][h:], request_base=h)
+    full = eng.schedule(R, **kw)
+    assert np.array_equal(np.concatenate([a["pick"], b["pick"]]), full["pick"])
+    eng.close()

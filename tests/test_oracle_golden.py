@@ -376,3 +376,47 @@ def test_latency_predict_and_pipeline():
         assert np.array_equal(got, want, equal_nan=True)
         cand = ~np.isnan(got)
         assert cand.sum() == sum(1 for m in range(M) if m % 3) and (got[cand] >= 0).all() and (got[cand] <= 1.01).all()
+
+
+# ---------------------------------------------------------------- stochastic pickers: distribution level
+def _scores_snapshot(scores):
+    # scores arrive through a custom per-endpoint column scorer with weight 100: score = clamp(col) * 100
+    M = len(scores)
+    return o.SnapshotData([0.0] * M, [0] * M, endpoint_cols=[np.array(scores, np.float64) / 100.0])
+
+
+def test_stochastic_pickers_distribution(golden):
+    g = golden["stochastic_pickers"]
+    n, tol = g["iterations"], g["tolerance"]
+    for c in g["weighted"]:
+        sc = np.array(c["scores"], np.float64)
+        prof = o.make_profile([(o.SCORER_ENDPOINT_COL0, 100.0)], tie_seed=1234, pick_mode=o.PICK_WEIGHTED_RANDOM)
+        res = o.schedule_batch(_scores_snapshot(sc), prof, None, n)
+        freq = np.bincount(res["pick"], minlength=len(sc)) / n
+        assert np.abs(freq - sc / sc.sum()).max() <= tol, (c["name"], freq)
+        assert (freq[sc == 0] == 0).all(), c["name"]                       # key 0: never selected (picker.go:127-131)
+        assert (res["tie_count"] == (sc > 0).sum()).all()
+        assert np.array_equal(res["pick_score"], sc[res["pick"]])
+    for c in g["random"]:
+        sc = np.array(c["scores"], np.float64)
+        prof = o.make_profile([(o.SCORER_ENDPOINT_COL0, 100.0)], tie_seed=99, pick_mode=o.PICK_RANDOM)
+        res = o.schedule_batch(_scores_snapshot(sc), prof, None, n)
+        freq = np.bincount(res["pick"], minlength=len(sc)) / n
+        assert np.abs(freq - 1.0 / len(sc)).max() <= tol, (c["name"], freq)
+    # all scores zero: the weighted-random picker delegates to the random picker (picker.go:113-116)
+    prof = o.make_profile([(o.SCORER_ENDPOINT_COL0, 100.0)], tie_seed=7, pick_mode=o.PICK_WEIGHTED_RANDOM)
+    res = o.schedule_batch(_scores_snapshot([0, 0, 0, 0]), prof, None, n)
+    freq = np.bincount(res["pick"], minlength=4) / n
+    assert np.abs(freq - 0.25).max() <= tol and (res["tie_count"] == 4).all()
+
+
+def test_stochastic_generator_properties():
+    L = o.lib()
+    import math
+    for u in (1.0, 0.5, 0.7, 1e-10, 2.0 ** -53, 0.9999999, 1.0 / 3.0, 0.70710678118654757, 0.7071067811865476):
+        assert abs(L.orc_neg_log(u) + math.log(u)) <= 4e-16 * max(1.0, abs(math.log(u))), u
+    us = np.array([L.orc_uniform01(42, r, r % 7) for r in range(50000)])
+    assert us.min() > 0.0 and us.max() <= 1.0
+    assert abs(us.mean() - 0.5) < 0.01 and abs(us.var() - 1.0 / 12.0) < 0.005
+    hist = np.histogram(us, bins=20, range=(0, 1))[0] / len(us)
+    assert np.abs(hist - 0.05).max() < 0.006
