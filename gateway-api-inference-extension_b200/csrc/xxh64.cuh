@@ -23,6 +23,38 @@ constexpr uint64_t XP3 = 0x165667B19E3779F9ULL;
 constexpr uint64_t XP4 = 0x85EBCA77C2B2AE63ULL;
 constexpr uint64_t XP5 = 0x27D4EB2F165667C5ULL;
 
+// Device forms: a 64-bit x*P + acc (low 64 bits) is exactly three 32-bit multiply-adds (IMAD.WIDE.U32 with the
+// 64-bit addend, then the two cross terms into the high word — the compiler's generic 64-bit multiply followed by
+// an add takes five), and a 64-bit rotate is two funnel shifts.  hash_bodies_kernel is bound by exactly
+// these integer instructions.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint64_t xmuladd(uint64_t x, uint64_t p, uint64_t acc) {
+  const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32), pl = (uint32_t)p, ph = (uint32_t)(p >> 32);
+  uint64_t w;  // IMAD.WIDE.U32 with the 64-bit addend
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(xl), "r"(pl), "l"(acc));
+  uint32_t hi = (uint32_t)(w >> 32);
+  hi = xh * pl + hi;                           // the cross terms only touch the high word
+  hi = xl * ph + hi;
+  return ((uint64_t)hi << 32) | (uint32_t)w;
+}
+__device__ __forceinline__ uint64_t xrotl(uint64_t x, int r) {  // r is a compile-time constant at every call site
+  uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+  if (r >= 32) {
+    const uint32_t t = lo;
+    lo = hi;
+    hi = t;
+    r -= 32;
+  }
+  if (r == 0) return ((uint64_t)hi << 32) | lo;
+  const uint32_t nh = __funnelshift_l(lo, hi, r), nl = __funnelshift_l(hi, lo, r);
+  return ((uint64_t)nh << 32) | nl;
+}
+__device__ __forceinline__ uint64_t xround(uint64_t acc, uint64_t in) {
+  return xmuladd(xrotl(xmuladd(in, XP2, acc), 31), XP1, 0);
+}
+__device__ __forceinline__ uint64_t xmerge(uint64_t h, uint64_t v) { return xmuladd(h ^ xround(0, v), XP1, XP4); }
+#else
+XXH_HD uint64_t xmuladd(uint64_t x, uint64_t p, uint64_t acc) { return x * p + acc; }
 XXH_HD uint64_t xrotl(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
 XXH_HD uint64_t xround(uint64_t acc, uint64_t in) {
   acc += in * XP2;
@@ -33,11 +65,12 @@ XXH_HD uint64_t xmerge(uint64_t h, uint64_t v) {
   h ^= xround(0, v);
   return h * XP1 + XP4;
 }
+#endif
 XXH_HD uint64_t xavalanche(uint64_t h) {
   h ^= h >> 33;
-  h *= XP2;
+  h = xmuladd(h, XP2, 0);
   h ^= h >> 29;
-  h *= XP3;
+  h = xmuladd(h, XP3, 0);
   h ^= h >> 32;
   return h;
 }
@@ -52,7 +85,7 @@ XXH_HD uint64_t xfinish_lanes(uint64_t v1, uint64_t v2, uint64_t v3, uint64_t v4
 // The serial part of one link when block_chars % 32 == 0: body = lanes-merged state + len.
 XXH_HD uint64_t xchain_aligned(uint64_t body, uint64_t prev) {
   uint64_t h = body ^ xround(0, prev);
-  h = xrotl(h, 27) * XP1 + XP4;
+  h = xmuladd(xrotl(h, 27), XP1, XP4);
   return xavalanche(h);
 }
 
