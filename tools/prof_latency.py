@@ -13,11 +13,12 @@ from tests.helpers import synth_snapshot  # noqa: E402
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-masked = len(sys.argv) > 4 and sys.argv[4] == "masked"
+masked = len(sys.argv) > 4 and "masked" in sys.argv[4]
+streaming = 0 if (len(sys.argv) > 4 and "nostream" in sys.argv[4]) else 1
 pkg = _pkg.load()
 coef = dict(ttft_intercept=12.5, ttft_kv=80.0, ttft_input=0.031, ttft_waiting=7.25, ttft_running=1.5, ttft_prefix=-40.0,
             tpot_intercept=9.0, tpot_kv=11.0, tpot_input=0.0007, tpot_waiting=0.9, tpot_running=0.35, tpot_generated=0.01,
-            streaming_mode=1)
+            streaming_mode=streaming)
 eng = pkg.Engine(pkg.default_config([("latency", 1.0)], max_endpoints=M, tie_mode=1, tie_seed=11))
 eng.set_latency_params(pkg.latency_params(**coef))
 rng = np.random.Generator(np.random.PCG64(77))
@@ -41,5 +42,5 @@ for i in range(iters + 1):
     eng.schedule(R, device=True, stream=stream.cuda_stream, out=out, **req)
 b.record(stream)
 torch.cuda.synchronize()
-print(f"R={R} M={M} masked={masked}: {a.elapsed_time(b) / iters * 1e3:.1f} us per launch, "
+print(f"R={R} M={M} masked={masked} streaming={streaming}: {a.elapsed_time(b) / iters * 1e3:.1f} us per launch, "
       f"{R / (a.elapsed_time(b) / iters * 1e-3) / 1e6:.1f} M picks/s; picked {(out['pick'] >= 0).sum().item()}")
