@@ -71,7 +71,7 @@ struct eppscore_engine {
   int32_t M = 0, A = 0, lora_words = 0;
   uint64_t epoch = 0;
   DevBuf raw_kv, raw_queue, raw_running, raw_act, raw_wait, raw_nmodels, raw_max, raw_col[4];
-  DevBuf raw_min_tpot, raw_dispatched, raw_prefill, raw_tokens, lat_ep;
+  DevBuf raw_min_tpot, raw_dispatched, raw_prefill, raw_tokens, lat_ep, qhdr[2], qbucket[2];
   eppscore_latency_params lat_params{};  // pending: applied by the next set_snapshot
   LatArgs lat_args{};                    // what the current snapshot was prepared with
   bool have_col[4] = {false, false, false, false};
@@ -305,6 +305,10 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
   for (int t = 0; t < ps.plan.n_terms; t++) a.term[t] = ps.term_ptr[t];
   a.minmax_q[0] = e->cur_queue;
   a.minmax_q[1] = e->cur_running;
+  for (int which = 0; which < 2; which++) {
+    a.qhdr[which] = e->qhdr[which].as<QBucketHdr>();
+    a.qbucket[which] = e->qbucket[which].as<uint32_t>();
+  }
   a.cls_lo = e->cls_lo.as<uint32_t>();
   a.cls_hi = e->cls_hi.as<uint32_t>();
   a.summ = ps.plan.sparse_ok ? e->summ.as<AdapterSummary>() : nullptr;
@@ -514,6 +518,12 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   CK(nullptr, ep->raw_max.reserve(mp * 4));
   for (int i = 0; i < 4; i++) CK(nullptr, ep->raw_col[i].reserve(mp * 8));
   CK(nullptr, ep->raw_tokens.reserve(mp * 8));
+  for (int which = 0; which < 2; which++)  // value buckets for the masked min/max of the queue / running scorers
+    if (cfg_has(ep->cfg, which == 0 ? EPPSCORE_SCORER_QUEUE : EPPSCORE_SCORER_RUNNING)) {
+      CK(nullptr, ep->qhdr[which].reserve(sizeof(QBucketHdr)));
+      CK(nullptr, ep->qbucket[which].reserve((size_t)kQBuckets * (mp / 32) * 4));
+      CK(nullptr, cudaMemsetAsync(ep->qhdr[which].p, 0, sizeof(QBucketHdr), ep->stream));
+    }
   if (cfg_has(ep->cfg, EPPSCORE_SCORER_LATENCY)) {
     CK(nullptr, ep->raw_min_tpot.reserve(mp * 8));
     CK(nullptr, ep->raw_dispatched.reserve(mp * 4));
@@ -569,7 +579,7 @@ void eppscore_destroy(eppscore_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep,
+  DevBuf* bufs[] = {&e->qhdr[0], &e->qhdr[1], &e->qbucket[0], &e->qbucket[1], &e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep,
                     &e->s_intok, &e->s_tslo, &e->s_pslo, &e->s_pred, &e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
                     &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->prefix_lut2d, &e->st_idx, &e->st_val, &e->st_slot,
                     &e->probe_out, &e->s_prompts, &e->s_off, &e->s_len, &e->s_seed, &e->s_hashes, &e->s_nh, &e->s_adapter,
@@ -676,6 +686,10 @@ int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
   pa.maxm = s->lora_max ? (on_device ? s->lora_max : e->raw_max.as<int32_t>()) : nullptr;
   for (int i = 0; i < 4; i++)
     pa.col[i] = s->endpoint_col[i] ? (on_device ? s->endpoint_col[i] : e->raw_col[i].as<double>()) : nullptr;
+  for (int which = 0; which < 2; which++) {
+    pa.qhdr[which] = e->qhdr[which].as<QBucketHdr>();
+    pa.qbucket[which] = e->qbucket[which].as<uint32_t>();
+  }
   pa.tokens = s->inflight_tokens ? (on_device ? s->inflight_tokens : e->raw_tokens.as<int64_t>()) : nullptr;
   pa.token_threshold = e->cfg.token_load_threshold;
   e->lat_args = LatArgs{};

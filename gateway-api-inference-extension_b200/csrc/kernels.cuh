@@ -115,6 +115,18 @@ struct __align__(16) AdapterSummary {
   int32_t gcnt;  // how many endpoints attain it
 };
 
+// Value buckets of WaitingQueueSize / RunningRequestsSize for the masked min/max (queue.go:79-91 over the FILTERED
+// endpoints): bucket v holds a natural-order bitset (same layout as a candidate-mask row) of the endpoints whose value
+// is base + v.  min/max over a request's candidates = first / last occupied bucket that intersects its mask row.
+// Built per snapshot when max - min <= 255 over all endpoints, otherwise valid = 0 and the kernel scans.
+struct QBucketHdr {
+  long long base;
+  int32_t valid;
+  int32_t pad;
+  uint32_t occ[8];  // bit v: bucket v is non-empty
+};
+constexpr int kQBuckets = 256;
+
 struct ScoreArgs {
   Geo geo;
   Plan plan;
@@ -123,6 +135,8 @@ struct ScoreArgs {
   // endpoint tile (natural order, Mpad entries each; padding scores are never candidates)
   const double* term[kMaxSteps];
   const int64_t* minmax_q[2];   // queue / running raw values for STEP_MINMAX (masked mode)
+  const QBucketHdr* qhdr[2];    // value buckets (null: not built)
+  const uint32_t* qbucket[2];   // [kQBuckets][Mpad/32]
   // LoRA class planes, permuted layout: [A+1][row_words] each; row A = "adapter not in dictionary"
   const uint32_t* cls_lo;
   const uint32_t* cls_hi;
@@ -192,6 +206,8 @@ struct PrepareArgs {
   double lat_coef[8];           // ttft {intercept, kv, waiting, running}, tpot {intercept, kv, waiting, running}
   double lat_buffer, lat_ckv;
   int32_t lat_streaming;
+  QBucketHdr* qhdr[2];          // value buckets for the masked min/max (null: scorer not in the profile)
+  uint32_t* qbucket[2];
   int32_t lat_has_predictions;
   double* lat_ep;               // [Mpad/32][kLatArrays][32] tiles
   // outputs of the endpoint kernel

@@ -48,6 +48,31 @@ __global__ void __launch_bounds__(1024) prepare_endpoints_kernel(const __grid_co
   }
   __syncthreads();
 
+  // value buckets for the masked min/max (kernels.cuh: QBucketHdr)
+  for (int which = 0; which < 2; which++) {
+    QBucketHdr* hdr = a.qhdr[which];
+    if (!hdr) continue;
+    const int64_t* q = which == 0 ? a.queue : a.running;
+    const long long mn = s_mm[which][0], mx = s_mm[which][1];
+    const bool ok = q && M > 0 && mx >= mn && (unsigned long long)(mx - mn) < (unsigned long long)kQBuckets;
+    const int MW = Mpad >> 5;
+    uint32_t* tbl = a.qbucket[which];
+    if (ok)
+      for (int i = tid; i < kQBuckets * MW; i += blockDim.x) tbl[i] = 0;
+    if (tid < 8) hdr->occ[tid] = 0;
+    if (tid == 0) {
+      hdr->base = mn;
+      hdr->valid = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (ok)
+      for (int m = tid; m < M; m += blockDim.x) {
+        const int v = (int)(q[m] - mn);
+        atomicOr(&tbl[v * MW + (m >> 5)], 1u << (m & 31));
+        atomicOr(&hdr->occ[v >> 5], 1u << (v & 31));
+      }
+  }
+
   // per-scorer terms: clamp(score) * weight — the rounded product of scheduler_profile.go:168.
   // Each thread keeps its endpoints' terms in registers to fold the leading runs without a re-read.
   for (int m = tid; m < Mpad; m += blockDim.x) {

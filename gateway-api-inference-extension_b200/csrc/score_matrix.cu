@@ -180,25 +180,76 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
     if (MASKED && (has_minmax[0] || has_minmax[1])) {
       mn[0] = mn[1] = 0x7fffffffffffffffLL;
       mx[0] = mx[1] = (long long)0x8000000000000000ULL;
-      for (int t = 0; t < J * EPL; t++) {
-        const int m = t * 32 + lane;
-        if (m < M && ((__ldg(mrow + t) >> lane) & 1u)) {
+      bool scanned[2] = {!has_minmax[0], !has_minmax[1]};
+      // fast path: first / last occupied value bucket that intersects the request's mask row
 #pragma unroll
-          for (int which = 0; which < 2; which++) {
-            const long long v = s_q[which * MPAD + m];
-            mn[which] = v < mn[which] ? v : mn[which];
-            mx[which] = v > mx[which] ? v : mx[which];
+      for (int which = 0; which < 2; which++) {
+        const QBucketHdr* hdr = a.qhdr[which];
+        if (!has_minmax[which] || !hdr || !__ldg(&hdr->valid)) continue;
+        const int MW = MPAD >> 5;
+        uint32_t mw[kMaxJ];  // this lane's words of the mask row (MW <= 256 words)
+#pragma unroll
+        for (int t = 0; t < kMaxJ; t++) {
+          const int w = t * 32 + lane;
+          mw[t] = (t * 32 < MW && w < a.mask_words) ? __ldg(mrow + w) : 0u;
+        }
+        const uint32_t* tbl = a.qbucket[which];
+        const long long base = __ldg(&hdr->base);
+        int vmin = -1, vmax = -1;
+        for (int wd = 0; wd < 8 && vmin < 0; wd++) {
+          uint32_t occ = __ldg(&hdr->occ[wd]);
+          while (occ && vmin < 0) {
+            const int v = wd * 32 + __ffs(occ) - 1;
+            occ &= occ - 1;
+            bool hit = false;
+#pragma unroll
+            for (int t = 0; t < kMaxJ; t++)
+              if (t * 32 < MW) hit = hit || (mw[t] & __ldg(tbl + (size_t)v * MW + t * 32 + lane)) != 0u;
+            if (__any_sync(0xffffffffu, hit)) vmin = v;
           }
         }
-      }
+        for (int wd = 7; wd >= 0 && vmin >= 0 && vmax < 0; wd--) {
+          uint32_t occ = __ldg(&hdr->occ[wd]);
+          while (occ && vmax < 0) {
+            const int b = 31 - __clz(occ);
+            const int v = wd * 32 + b;
+            occ &= ~(1u << b);
+            bool hit = false;
 #pragma unroll
-      for (int o = 16; o; o >>= 1)
-#pragma unroll
-        for (int which = 0; which < 2; which++) {
-          const long long omn = shfl_xor_i64(mn[which], o), omx = shfl_xor_i64(mx[which], o);
-          mn[which] = omn < mn[which] ? omn : mn[which];
-          mx[which] = omx > mx[which] ? omx : mx[which];
+            for (int t = 0; t < kMaxJ; t++)
+              if (t * 32 < MW) hit = hit || (mw[t] & __ldg(tbl + (size_t)v * MW + t * 32 + lane)) != 0u;
+            if (__any_sync(0xffffffffu, hit)) vmax = v;
+          }
         }
+        if (vmin >= 0) {
+          mn[which] = base + vmin;
+          mx[which] = base + vmax;
+        }
+        scanned[which] = true;  // (no candidate at all: the sentinels stay, exactly like the scan)
+      }
+      if (!scanned[0] || !scanned[1]) {
+        for (int t = 0; t < J * EPL; t++) {
+          const int m = t * 32 + lane;
+          if (m < M && ((__ldg(mrow + t) >> lane) & 1u)) {
+#pragma unroll
+            for (int which = 0; which < 2; which++) {
+              if (scanned[which]) continue;
+              const long long v = s_q[which * MPAD + m];
+              mn[which] = v < mn[which] ? v : mn[which];
+              mx[which] = v > mx[which] ? v : mx[which];
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+          for (int which = 0; which < 2; which++) {
+            if (scanned[which]) continue;
+            const long long omn = shfl_xor_i64(mn[which], o), omx = shfl_xor_i64(mx[which], o);
+            mn[which] = omn < mn[which] ? omn : mn[which];
+            mx[which] = omx > mx[which] ? omx : mx[which];
+          }
+      }
       if (q_step >= 0) {
         const int which = plan.arg[q_step];
         const long long range = mx[which] >= mn[which] ? mx[which] - mn[which] : 0;  // (no candidates: nothing to score)

@@ -844,3 +844,36 @@ def test_stochastic_pickers_parity_full_profile(pkg, mode):
     full = eng.schedule(R, **kw)
     assert np.array_equal(np.concatenate([a["pick"], b["pick"]]), full["pick"])
     eng.close()
+
+
+def test_masked_minmax_bucket_and_scan_paths(pkg):
+    """Masked queue / running scorers: the value-bucket fast path (range <= 255), the scanning fallback (wide range) and a
+    mix of both in one profile; sparse masks, single-candidate and empty rows."""
+    M, R = 777, 1024
+    scorers = [("queue", 2), ("running", 1.5), ("kv", 1)]
+    rng = np.random.Generator(np.random.PCG64(21))
+    for qmax, rmax in ((40, 12), (10 ** 6, 12), (40, 10 ** 9), (3, 1), (0, 0)):
+        sd = synth_snapshot(M, seed=9)
+        sd["queue"] = rng.integers(0, qmax + 1, M).astype(np.int64) - 5
+        sd["running"] = rng.integers(0, rmax + 1, M).astype(np.int64)
+        eng = make_engine(pkg, scorers, M, tie_mode=1, tie_seed=3)
+        eng.set_snapshot(**sd)
+        snap = o.SnapshotData(**sd)
+        prof = profile_of(pkg, scorers, tie_mode=1, tie_seed=3)
+        bits = rng.random((R, M)) < rng.choice([0.01, 0.1, 0.5, 1.0], (R, 1))
+        bits[0, :] = False
+        bits[1, :] = False
+        bits[1, 700] = True
+        mask = np.zeros((R, (M + 31) // 32), np.uint32)
+        for w in range(mask.shape[1]):
+            chunk = bits[:, w * 32:(w + 1) * 32]
+            mask[:, w] = (chunk * (1 << np.arange(chunk.shape[1], dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+        mask[:, -1] |= np.uint32((0xFFFFFFFF << (M % 32)) & 0xFFFFFFFF)  # garbage bits beyond M must be ignored
+        got = eng.schedule(R, cand_mask=mask, want_scores=True)
+        want = o.schedule_batch(snap, prof, None, R, cand_mask=mask, want_scores=True, n_threads=8)
+        # the oracle reads only bits < M; rows 0 and 1 are the empty / single-candidate rows
+        assert_same(got, want, ("pick", "pick_score", "tie_count", "scores_out"))
+        fast = eng.schedule(R, cand_mask=mask)
+        assert_same(fast, want)
+        assert got["pick"][0] == -1 and got["pick"][1] == 700
+        eng.close()
