@@ -93,7 +93,7 @@ struct eppscore_engine {
 
   // scratch for host-location batches and internal hashes
   DevBuf s_prompts, s_off, s_len, s_seed, s_hashes, s_nh, s_adapter, s_mask, s_dense, s_dtotal, s_pick, s_score,
-      s_tie, s_match, s_total, s_scores, s_intok, s_tslo, s_pslo, s_pred;
+      s_tie, s_match, s_total, s_scores, s_intok, s_tslo, s_pslo, s_pred, s_fields;
 };
 
 namespace {
@@ -333,6 +333,11 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
     if (!e->lat_args.enabled) return fail(e, EPPSCORE_ERR_INVALID, "latency scorer configured but the snapshot was prepared without latency params");
     a.lat = e->lat_args;
     a.lat.input_tokens = b.input_tokens;
+    if (!b.input_tokens && b.prompt_bytes && b.prompt_off) {  // count the fields of the prompt bytes on the device
+      CK(e, e->s_fields.reserve((size_t)b.R * 4));
+      e->launches += launch_count_fields(b.prompt_bytes, b.prompt_off, b.prompt_len, b.R, e->s_fields.as<int32_t>(), s, e->sm_count);
+      a.lat.input_tokens = e->s_fields.as<int32_t>();
+    }
     a.lat.ttft_slo = b.ttft_slo;
     a.lat.tpot_slo = b.tpot_slo;
     a.lat.pred_out = b.pred_out;
@@ -579,7 +584,7 @@ void eppscore_destroy(eppscore_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->qhdr[0], &e->qhdr[1], &e->qbucket[0], &e->qbucket[1], &e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep,
+  DevBuf* bufs[] = {&e->s_fields, &e->qhdr[0], &e->qhdr[1], &e->qbucket[0], &e->qbucket[1], &e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep,
                     &e->s_intok, &e->s_tslo, &e->s_pslo, &e->s_pred, &e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
                     &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->prefix_lut2d, &e->st_idx, &e->st_val, &e->st_slot,
                     &e->probe_out, &e->s_prompts, &e->s_off, &e->s_len, &e->s_seed, &e->s_hashes, &e->s_nh, &e->s_adapter,
@@ -957,6 +962,38 @@ uint64_t eppscore_model_seed(const void* model, size_t model_len, const void* sa
 }
 
 // ---------------- prefix index ----------------
+int32_t eppscore_count_fields(eppscore_engine* e, int32_t R, int32_t location, const uint8_t* prompt_bytes,
+                              const int64_t* prompt_off, const int32_t* prompt_len, int32_t* out, void* stream) {
+  if (!e) return EPPSCORE_ERR_INVALID;
+  if (R < 0 || (R > 0 && (!prompt_bytes || !prompt_off || !out))) return fail(e, EPPSCORE_ERR_INVALID, "count_fields: NULL argument");
+  if (R == 0) return EPPSCORE_OK;
+  CK(e, cudaSetDevice(e->device));
+  if (location == 1) {
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    e->launches += launch_count_fields(prompt_bytes, prompt_off, prompt_len, R, out, s, e->sm_count);
+    CK(e, cudaGetLastError());
+    return EPPSCORE_OK;
+  }
+  size_t total = (size_t)prompt_off[R];
+  if (prompt_len) {
+    total = 0;
+    for (int32_t r = 0; r < R; r++) total = std::max(total, (size_t)prompt_off[r] + (size_t)prompt_len[r]);
+  }
+  CK(e, e->s_prompts.reserve(total + 64));
+  if (total) CK(e, cudaMemcpyAsync(e->s_prompts.p, prompt_bytes, total, cudaMemcpyHostToDevice, e->stream));
+  const int64_t* d_off = nullptr;
+  const int32_t* d_len = nullptr;
+  int32_t rc;
+  if ((rc = h2d(e, e->s_off, prompt_off, (size_t)R + 1, &d_off)) != EPPSCORE_OK) return rc;
+  if ((rc = h2d(e, e->s_len, prompt_len, (size_t)R, &d_len)) != EPPSCORE_OK) return rc;
+  CK(e, e->s_fields.reserve((size_t)R * 4));
+  e->launches += launch_count_fields(e->s_prompts.as<uint8_t>(), d_off, d_len, R, e->s_fields.as<int32_t>(), e->stream, e->sm_count);
+  CK(e, cudaGetLastError());
+  CK(e, cudaMemcpyAsync(out, e->s_fields.p, (size_t)R * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaStreamSynchronize(e->stream));
+  return EPPSCORE_OK;
+}
+
 int32_t eppscore_commit_picks(eppscore_engine* e, int32_t R, const int32_t* pick, const uint64_t* hashes,
                               const uint16_t* n_hashes, int32_t hash_stride, const int32_t* lru_capacity) {
   if (!e) return EPPSCORE_ERR_INVALID;

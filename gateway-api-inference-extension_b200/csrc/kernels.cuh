@@ -228,6 +228,8 @@ struct PrepareArgs {
 // launchers. Each returns the number of kernels it launched (for gpu_launches).
 int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count);
 int launch_prepare_snapshot(const PrepareArgs& a, cudaStream_t s);
+int launch_count_fields(const uint8_t* bytes, const int64_t* off, const int32_t* len, int R, int32_t* out, cudaStream_t s,
+                        int sm_count);  // len(strings.Fields(prompt)) per request
 int launch_score_pick(const ScoreArgs& a, bool dense, cudaStream_t s, int sm_count);   // generic (any plan, masks, diagnostics)
 int launch_score_matrix(const ScoreArgs& a, cudaStream_t s, int sm_count);             // every pair scored (masks, diagnostics)
 int launch_score_dense_fast(const ScoreArgs& a, cudaStream_t s, int sm_count);         // 0 if no specialisation applies

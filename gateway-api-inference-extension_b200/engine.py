@@ -226,6 +226,15 @@ class Engine:
             a.ptr(model_seed, np.uint64), block_chars, max_blocks, hashes.ctypes.data, n.ctypes.data, None))
         return hashes[:R], n[:R]
 
+    def count_fields(self, prompt_bytes, prompt_off, prompt_len=None):
+        """len(strings.Fields(prompt)) per request, computed on the device (host arrays in and out)."""
+        R = len(prompt_off) - 1
+        a = _Args(False)
+        out = np.zeros(max(R, 1), np.int32)
+        self._check(self._lib.eppscore_count_fields(self._h, R, 0, a.ptr(prompt_bytes, np.uint8), a.ptr(prompt_off, np.int64),
+                                                    a.ptr(prompt_len, np.int32), out.ctypes.data, None))
+        return out[:R]
+
     @staticmethod
     def model_seed(model, salt=b"") -> int:
         if isinstance(model, str):

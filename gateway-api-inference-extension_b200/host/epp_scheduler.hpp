@@ -73,41 +73,36 @@ struct InferenceRequest {
   std::map<std::string, std::string> Headers;  // "x-slo-ttft-ms" / "x-slo-tpot-ms" feed the latency path
 };
 
-// len(strings.Fields(s)) (predictedlatency/plugin.go:286): runs of unicode.IsSpace separate fields.
-inline int CountFields(const std::string& s) {
-  auto is_space = [](uint32_t c) {
-    switch (c) {
-      case '\t': case '\n': case '\v': case '\f': case '\r': case ' ': case 0x85: case 0xA0: case 0x1680: case 0x2028:
-      case 0x2029: case 0x202F: case 0x205F: case 0x3000: return true;
-      default: return c >= 0x2000 && c <= 0x200A;
+// len(strings.Fields(s)) (predictedlatency/plugin.go:286): runs of unicode.IsSpace separate fields.  Go decodes
+// runes with utf8.DecodeRuneInString (any invalid or short sequence = U+FFFD, width 1); because a lead byte is never
+// a continuation byte, a byte belongs to a space rune exactly when it is an ASCII space or lies inside one of the
+// UTF-8 encodings of U+0085, U+00A0, U+1680, U+2000..U+200A, U+2028, U+2029, U+202F, U+205F, U+3000 — the same
+// byte-pattern rule the device kernel uses (csrc/fields_kernel.cu; fuzzed against the oracle's rune decoder).
+inline int CountFields(const std::string& str) {
+  const size_t n = str.size();
+  const unsigned char* s = reinterpret_cast<const unsigned char*>(str.data());
+  int count = 0;
+  bool prev_space = true;
+  size_t cover = 0;  // bytes [i, cover) still belong to a multi-byte space rune
+  for (size_t i = 0; i < n; i++) {
+    const unsigned b = s[i];
+    bool sp = (b >= 9 && b <= 13) || b == 32 || i < cover;
+    if (b == 0xC2 && i + 1 < n && (s[i + 1] == 0x85 || s[i + 1] == 0xA0)) {
+      sp = true;
+      cover = i + 2;
+    } else if (i + 2 < n) {
+      const unsigned b1 = s[i + 1], b2 = s[i + 2];
+      if ((b == 0xE1 && b1 == 0x9A && b2 == 0x80) ||
+          (b == 0xE2 && b1 == 0x80 && ((b2 >= 0x80 && b2 <= 0x8A) || b2 == 0xA8 || b2 == 0xA9 || b2 == 0xAF)) ||
+          (b == 0xE2 && b1 == 0x81 && b2 == 0x9F) || (b == 0xE3 && b1 == 0x80 && b2 == 0x80)) {
+        sp = true;
+        cover = i + 3;
+      }
     }
-  };
-  int n = 0;
-  bool in_field = false;
-  for (size_t i = 0; i < s.size();) {
-    const unsigned char b = (unsigned char)s[i];
-    uint32_t c = b;
-    size_t len = 1;
-    if (b >= 0xC2 && b < 0xE0 && i + 1 < s.size() && ((unsigned char)s[i + 1] & 0xC0) == 0x80) {
-      c = ((b & 0x1Fu) << 6) | ((unsigned char)s[i + 1] & 0x3Fu);
-      len = 2;
-    } else if (b >= 0xE0 && b < 0xF0 && i + 2 < s.size() && ((unsigned char)s[i + 1] & 0xC0) == 0x80 &&
-               ((unsigned char)s[i + 2] & 0xC0) == 0x80) {
-      c = ((b & 0x0Fu) << 12) | (((unsigned char)s[i + 1] & 0x3Fu) << 6) | ((unsigned char)s[i + 2] & 0x3Fu);
-      len = 3;
-    } else if (b >= 0x80) {
-      c = 0xFFFD;  // 4-byte sequences and invalid bytes are never spaces
-      len = (b >= 0xF0 && b < 0xF8 && i + 3 < s.size()) ? 4 : 1;
-    }
-    if (is_space(c)) {
-      in_field = false;
-    } else if (!in_field) {
-      in_field = true;
-      n++;
-    }
-    i += len;
+    if (!sp && prev_space) count++;
+    prev_space = sp;
   }
-  return n;
+  return count;
 }
 
 struct ScoredEndpoint {

@@ -191,7 +191,9 @@ typedef struct eppscore_batch {
                                   NaN for non-candidates — diagnostics / parity tests; 8*R*M bytes of HBM writes */
   void *stream;                /* cudaStream_t for location==1 (NULL = engine stream); the call is async on it */
   /* latency fold-in, per request (optional, NULL ⇒ 0) */
-  const int32_t *input_tokens; /* [R] len(strings.Fields(prompt)) (predictedlatency/training.go:51) */
+  const int32_t *input_tokens; /* [R] len(strings.Fields(prompt)) (predictedlatency/training.go:51); NULL with prompt_bytes given ⇒
+                                * counted on the device from those bytes (hosts whose PromptText() differs from the hashed
+                                * bytes, e.g. chat completions, pass it explicitly) */
   const double *ttft_slo;      /* [R] x-slo-ttft-ms header value or 0 (predictedlatency/plugin.go:330-343) */
   const double *tpot_slo;      /* [R] x-slo-tpot-ms header value or 0 */
   double *pred_out;            /* optional [R*M*2]: predicted {TTFT, TPOT} per (request, endpoint) — diagnostics */
@@ -237,6 +239,11 @@ int32_t eppscore_hash_prompts(struct eppscore_engine *e, int32_t R, int32_t loca
                               const int64_t *prompt_off, const int32_t *prompt_len /*optional*/,
                               const uint64_t *model_seed, int32_t block_chars, int32_t max_blocks,
                               uint64_t *hashes_out, uint16_t *n_hashes_out, void *stream);
+/* len(strings.Fields(prompt)) for R prompts — the latency path's input_token_length
+ * (predictedlatency/plugin.go:286, training.go:51); Go's rune decoding and unicode.IsSpace. out [R]. */
+int32_t eppscore_count_fields(struct eppscore_engine *e, int32_t R, int32_t location, const uint8_t *prompt_bytes,
+                              const int64_t *prompt_off, const int32_t *prompt_len /*optional*/, int32_t *out,
+                              void *stream);
 /* host helper: XXH64(model || salt), hashing.go:70-77 */
 uint64_t eppscore_model_seed(const void *model, size_t model_len, const void *salt, size_t salt_len);
 uint64_t eppscore_xxh64(const void *data, size_t len, uint64_t seed);

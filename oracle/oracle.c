@@ -600,6 +600,58 @@ void orc_score_token_load(const orc_snapshot *s, const uint32_t *mask, double th
   }
 }
 
+/* Go unicode/utf8 DecodeRune: returns the rune (0xFFFD for any invalid or short sequence, width 1) */
+static uint32_t go_decode_rune(const uint8_t *s, int64_t n, int *width) {
+  uint8_t b0 = s[0];
+  *width = 1;
+  if (b0 < 0x80) return b0;
+  int need;
+  uint8_t lo = 0x80, hi = 0xBF; /* accept range of the SECOND byte */
+  if (b0 >= 0xC2 && b0 <= 0xDF) {
+    need = 2;
+  } else if (b0 >= 0xE0 && b0 <= 0xEF) {
+    need = 3;
+    if (b0 == 0xE0) lo = 0xA0;
+    if (b0 == 0xED) hi = 0x9F;
+  } else if (b0 >= 0xF0 && b0 <= 0xF4) {
+    need = 4;
+    if (b0 == 0xF0) lo = 0x90;
+    if (b0 == 0xF4) hi = 0x8F;
+  } else {
+    return 0xFFFD;
+  }
+  if (n < need) return 0xFFFD;
+  if (s[1] < lo || s[1] > hi) return 0xFFFD;
+  for (int i = 2; i < need; i++)
+    if (s[i] < 0x80 || s[i] > 0xBF) return 0xFFFD;
+  *width = need;
+  if (need == 2) return ((uint32_t)(b0 & 0x1F) << 6) | (s[1] & 0x3F);
+  if (need == 3) return ((uint32_t)(b0 & 0x0F) << 12) | ((uint32_t)(s[1] & 0x3F) << 6) | (s[2] & 0x3F);
+  return ((uint32_t)(b0 & 0x07) << 18) | ((uint32_t)(s[1] & 0x3F) << 12) | ((uint32_t)(s[2] & 0x3F) << 6) | (s[3] & 0x3F);
+}
+/* unicode.IsSpace: Latin-1 set, else the White_Space property */
+static int go_is_space(uint32_t r) {
+  if (r <= 0xFF) return r == 0x09 || r == 0x0A || r == 0x0B || r == 0x0C || r == 0x0D || r == 0x20 || r == 0x85 || r == 0xA0;
+  return r == 0x1680 || (r >= 0x2000 && r <= 0x200A) || r == 0x2028 || r == 0x2029 || r == 0x202F || r == 0x205F ||
+         r == 0x3000;
+}
+int32_t orc_count_fields(const uint8_t *s, int64_t len) {
+  int32_t n = 0;
+  int in_field = 0;
+  for (int64_t i = 0; i < len;) {
+    int w;
+    uint32_t r = go_decode_rune(s + i, len - i, &w);
+    if (go_is_space(r)) {
+      in_field = 0;
+    } else if (!in_field) {
+      in_field = 1;
+      n++;
+    }
+    i += w;
+  }
+  return n;
+}
+
 /* =====================================================================================
  * Latency-predictor fold-in: predicted-latency producer + latency-scorer
  * ===================================================================================== */

@@ -138,6 +138,9 @@ double orc_enforce_score_range(double s); /* scheduler_profile.go:194-202 */
 
 void orc_score_token_load(const orc_snapshot *, const uint32_t *cand_mask, double threshold, double *out);
 
+/* len(strings.Fields(s)) (predictedlatency/plugin.go:286): Go's utf8.DecodeRuneInString + unicode.IsSpace restated */
+int32_t orc_count_fields(const uint8_t *s, int64_t len);
+
 /* per-request inputs of the latency path */
 typedef struct orc_latency_request {
   int64_t input_tokens; /* len(strings.Fields(prompt)), training.go:51 */

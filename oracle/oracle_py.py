@@ -150,6 +150,8 @@ def lib():
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_score_latency.argtypes = [C.POINTER(LatencyParams), C.POINTER(Snapshot), C.c_void_p, C.c_void_p,
                                         C.c_int32, C.POINTER(LatencyRequest), C.c_void_p, C.c_void_p]
+        L.orc_count_fields.restype = C.c_int32
+        L.orc_count_fields.argtypes = [C.c_char_p, C.c_int64]
         L.orc_uniform01.restype = C.c_double
         L.orc_uniform01.argtypes = [C.c_uint64, C.c_int64, C.c_int32]
         L.orc_neg_log.restype = C.c_double
@@ -318,6 +320,10 @@ class Index:
         gb = _arr(gpu_blocks, np.int32)
         stride = hashes.shape[1] if hashes.ndim == 2 else 0
         lib().orc_commit_picks(self._h, len(pick), _ptr(pick), _ptr(hashes), _ptr(n_hashes), stride, _ptr(gb))
+
+
+def count_fields(data: bytes) -> int:
+    return lib().orc_count_fields(data, len(data))
 
 
 def latency_predict(lp: LatencyParams, kv, input_tokens, waiting, running, prefix_score, generated=1):

@@ -877,3 +877,65 @@ def test_masked_minmax_bucket_and_scan_paths(pkg):
         assert_same(fast, want)
         assert got["pick"][0] == -1 and got["pick"][1] == 700
         eng.close()
+
+
+def _texty_prompts(R, seed, max_len=1400):
+    """Ragged prompts made of words, ASCII / Unicode spaces and some invalid UTF-8; returns bytes, offsets."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pieces = [b"the", b"quick", b"brown", b"fox", b"\xe7\x8c\xab", b"x", b"", b"\xf0\x9f\x98\x80", b"\xff", b"\xe2\x80", b"\xc2"]
+    spaces = [b" ", b" ", b" ", b"\t", b"\n", b"  ", b"\xc2\xa0", b"\xe2\x80\x83", b"\xe3\x80\x80", b"\xc2\x85", b"\xe2\x80\xa8",
+              b"\xe1\x9a\x80", b"\xe2\x81\x9f", b"\r\n"]
+    out, off = bytearray(), [0]
+    for r in range(R):
+        target = int(rng.integers(0, max_len))
+        s = bytearray()
+        while len(s) < target:
+            s += pieces[int(rng.integers(0, len(pieces)))]
+            s += spaces[int(rng.integers(0, len(spaces)))]
+        out += s[:target]
+        off.append(len(out))
+    return np.frombuffer(bytes(out) + b"\0" * 64, np.uint8), np.array(off, np.int64)
+
+
+def test_count_fields_parity(pkg):
+    """len(strings.Fields(prompt)) on the device vs Go's semantics restated in the oracle: ragged prompts, Unicode spaces,
+    invalid UTF-8, prompts crossing the 512-byte step, back-to-back (unaligned) and 16-byte aligned starts."""
+    eng = make_engine(pkg, [("kv", 1)], 8)
+    for seed in (1, 2):
+        data, off = _texty_prompts(600, seed)
+        R = len(off) - 1
+        want = np.array([o.count_fields(bytes(data[off[r]:off[r + 1]])) for r in range(R)], np.int32)
+        assert np.array_equal(eng.count_fields(data, off), want)
+        # 16-byte aligned starts with explicit lengths
+        buf, aoff, lens = bytearray(), [], []
+        for r in range(R):
+            buf.extend(b"\x20" * ((-len(buf)) % 16))
+            aoff.append(len(buf))
+            lens.append(int(off[r + 1] - off[r]))
+            buf.extend(bytes(data[off[r]:off[r + 1]]))
+        aoff.append(len(buf))
+        got = eng.count_fields(np.frombuffer(bytes(buf) + b"\0" * 64, np.uint8), np.array(aoff, np.int64), np.array(lens, np.int32))
+        assert np.array_equal(got, want)
+    assert want.max() > 100 and (want == 0).any()
+    eng.close()
+
+
+def test_latency_counts_prompt_fields_on_device(pkg):
+    """input_tokens omitted: the engine counts the fields of the prompt bytes itself (predictedlatency/plugin.go:286)."""
+    M, R = 200, 300
+    lkw = dict(LAT_COEF, streaming_mode=1)
+    eng = make_engine(pkg, [("latency", 1)], M, tie_mode=1, tie_seed=9)
+    eng.set_latency_params(pkg.latency_params(**lkw))
+    sd = synth_snapshot(M, seed=4)
+    eng.set_snapshot(**sd)
+    data, off = _texty_prompts(R, 5, max_len=3000)
+    seeds = np.full(R, eng.model_seed("m"), np.uint64)
+    slo = dict(ttft_slo=np.full(R, 180.0), tpot_slo=np.full(R, 28.0))
+    got = eng.schedule(R, prompt_bytes=data, prompt_off=off, model_seed=seeds, want_scores=True, **slo)
+    toks = np.array([o.count_fields(bytes(data[off[r]:off[r + 1]])) for r in range(R)], np.int32)
+    prof = o.make_profile([(o.SCORER_LATENCY, 1.0)], tie_mode=1, tie_seed=9, latency=o.make_latency_params(**lkw))
+    want = o.schedule_batch(o.SnapshotData(**sd), prof, o.Index(), R, prompt_bytes=data, prompt_off=off, model_seed=seeds,
+                            input_tokens=toks, want_scores=True, **slo)
+    assert_same(got, want, ("pick", "pick_score", "tie_count", "scores_out"))
+    assert toks.max() > 300
+    eng.close()

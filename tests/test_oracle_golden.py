@@ -420,3 +420,48 @@ def test_stochastic_generator_properties():
     assert abs(us.mean() - 0.5) < 0.01 and abs(us.var() - 1.0 / 12.0) < 0.005
     hist = np.histogram(us, bins=20, range=(0, 1))[0] / len(us)
     assert np.abs(hist - 0.05).max() < 0.006
+
+
+# ---------------------------------------------------------------- len(strings.Fields(prompt)), the latency path's token count
+FIELDS_CASES = [
+    (b"", 0), (b"   ", 0), (b"a", 1), (b"  a  b\tc\n", 3), (b"a\x0bb\x0cc\rd", 4),
+    (b"one\xc2\xa0two\xe2\x80\x83three\xe3\x80\x80four", 4),      # NBSP, EM SPACE, IDEOGRAPHIC SPACE
+    (b"x\xe1\x9a\x80y\xe2\x80\xa8z\xe2\x80\xafw\xe2\x81\x9f\xe2\x80\xa9q", 5),  # OGHAM, LINE SEP, NNBSP, MMSP, PARA SEP
+    (b"\xe2\x80\x8b", 1),                                        # ZERO WIDTH SPACE is not White_Space
+    (b"a\xc2\x85b", 2),                                          # NEL
+    (b"\xf0\xe2\x80\x80x", 2),                                   # invalid lead consumes ONE byte, then EN QUAD
+    (b"a\xe2\x80", 1), (b"\xc2\x85\xc2", 1), (b"\xe2\x80\x80", 0), (b"\x1c\x1d\x1e\x1f", 1),  # FS..US are not spaces in Go
+]
+
+
+def _fields_by_byte_patterns(s: bytes) -> int:
+    """The rule the device kernel and the C++ host mirror use: a byte is space iff ASCII space or inside one of the
+    UTF-8 encodings of the White_Space runes; no rune decoding."""
+    n = len(s)
+    sp = [False] * n
+    for i, b in enumerate(s):
+        if b in (9, 10, 11, 12, 13, 32):
+            sp[i] = True
+        if b == 0xC2 and i + 1 < n and s[i + 1] in (0x85, 0xA0):
+            sp[i] = sp[i + 1] = True
+        if i + 2 < n:
+            b1, b2 = s[i + 1], s[i + 2]
+            if ((b == 0xE1 and b1 == 0x9A and b2 == 0x80) or
+                    (b == 0xE2 and b1 == 0x80 and (0x80 <= b2 <= 0x8A or b2 in (0xA8, 0xA9, 0xAF))) or
+                    (b == 0xE2 and b1 == 0x81 and b2 == 0x9F) or (b == 0xE3 and b1 == 0x80 and b2 == 0x80)):
+                sp[i] = sp[i + 1] = sp[i + 2] = True
+    return sum(1 for i in range(n) if not sp[i] and (i == 0 or sp[i - 1]))
+
+
+def test_count_fields_go_semantics():
+    for s, want in FIELDS_CASES:
+        assert o.count_fields(s) == want, s
+        assert _fields_by_byte_patterns(s) == want, s
+    # the byte-pattern rule == Go's rune decoding, on adversarial byte soup
+    import random
+    rnd = random.Random(7)
+    alphabet = [0x20, 0x09, 0x41, 0x42, 0xC2, 0x85, 0xA0, 0xE1, 0x9A, 0x80, 0xE2, 0x81, 0x9F, 0xE3, 0x8A, 0xA8, 0xA9, 0xAF,
+                0xF0, 0xF4, 0xED, 0xE0, 0xC0, 0xFF, 0x0A, 0x8B, 0x90, 0xBF]
+    for _ in range(20000):
+        s = bytes(rnd.choice(alphabet) for _ in range(rnd.randint(0, 24)))
+        assert o.count_fields(s) == _fields_by_byte_patterns(s), s
