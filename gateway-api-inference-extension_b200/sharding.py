@@ -9,12 +9,16 @@ import numpy as np
 # field order and dtypes of the packed tile (== eppscore_snapshot's arrays)
 SNAPSHOT_FIELDS = (("kv_usage", np.float64), ("queue", np.int64), ("running", np.int64), ("lora_active", np.uint64),
                    ("lora_waiting", np.uint64), ("lora_nmodels", np.int32), ("lora_max", np.int32))
+# optional per-endpoint arrays (latency fold-in, token-load scorer); packed after the mandatory ones when present
+OPTIONAL_FIELDS = (("min_tpot_slo", np.float64), ("dispatched", np.int32), ("prefill_role", np.uint8),
+                   ("inflight_tokens", np.int64))
 
 
-def snapshot_layout(M: int, lora_words: int):
-    """[(name, byte offset, nbytes, dtype, shape)] — every field starts 16-byte aligned."""
+def snapshot_layout(M: int, lora_words: int, optional=()):
+    """[(name, byte offset, nbytes, dtype, shape)] — every field starts 16-byte aligned.
+    optional: names from OPTIONAL_FIELDS that the tile carries (every rank must pass the same tuple)."""
     out, off = [], 0
-    for name, dt in SNAPSHOT_FIELDS:
+    for name, dt in SNAPSHOT_FIELDS + tuple(f for f in OPTIONAL_FIELDS if f[0] in optional):
         shape = (M, lora_words) if name in ("lora_active", "lora_waiting") else (M,)
         nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
         out.append((name, off, nbytes, np.dtype(dt), shape))
@@ -25,7 +29,7 @@ def snapshot_layout(M: int, lora_words: int):
 def pack_snapshot(snap: dict):
     M = len(snap["kv_usage"])
     lw = int(np.asarray(snap["lora_active"]).size // M) if M else 1
-    layout, total = snapshot_layout(M, lw)
+    layout, total = snapshot_layout(M, lw, tuple(n for n, _ in OPTIONAL_FIELDS if snap.get(n) is not None))
     buf = np.zeros(total, np.uint8)
     for name, off, nbytes, dt, shape in layout:
         buf[off:off + nbytes] = np.ascontiguousarray(snap[name], dtype=dt).reshape(-1).view(np.uint8)

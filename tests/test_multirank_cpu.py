@@ -17,6 +17,56 @@ SCORERS = [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)]
 M, R_TOTAL = 160, 1001
 
 
+LAT = dict(ttft_intercept=12.5, ttft_kv=80.0, ttft_input=0.031, ttft_waiting=7.25, ttft_running=1.5, ttft_prefix=-40.0,
+           tpot_intercept=9.0, tpot_kv=11.0, tpot_input=0.0007, tpot_waiting=0.9, tpot_running=0.35, tpot_generated=0.01,
+           streaming_mode=1)
+OPT = ("min_tpot_slo", "dispatched", "prefill_role")
+
+
+def _worker_latency_weighted_random(rank, world, port, q):
+    """Latency-scorer profile + weighted-random picker: the per-endpoint producer state travels in the same tile, and the
+    counter-based generator keyed by request_base makes the union of the shards equal the unsharded batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sharding", os.path.join(_pkg.PKG_DIR, "sharding.py"))
+    sharding = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sharding)
+    layout, total = sharding.snapshot_layout(M, 1, OPT)
+    if rank == 0:
+        rng = np.random.Generator(np.random.PCG64(3))
+        snap = synth_snapshot(M, seed=4)
+        snap["min_tpot_slo"] = rng.choice([0.0, 22.0, 60.0], M)
+        snap["dispatched"] = rng.integers(0, 3, M).astype(np.int32)
+        snap["prefill_role"] = (rng.random(M) < 0.2).astype(np.uint8)
+        buf, layout0 = sharding.pack_snapshot(snap)
+        assert layout0 == layout
+        t = torch.from_numpy(buf)
+    else:
+        t = torch.zeros(total, dtype=torch.uint8)
+    dist.broadcast(t, src=0)
+    snap = sharding.unpack_snapshot(t.numpy(), layout)
+    rng = np.random.Generator(np.random.PCG64(8))  # the same global batch on every rank
+    req = dict(input_tokens=rng.integers(0, 4000, R_TOTAL).astype(np.int32), ttft_slo=rng.choice([0.0, 150.0, 400.0], R_TOTAL),
+               tpot_slo=rng.choice([0.0, 25.0, 60.0], R_TOTAL))
+    lo, hi = sharding.shard_range(R_TOTAL, rank, world)
+    osnap = o.SnapshotData(**snap)
+    prof = o.make_profile([(o.SCORER_LATENCY, 1.0)], tie_seed=5, pick_mode=o.PICK_WEIGHTED_RANDOM,
+                          latency=o.make_latency_params(**LAT))
+    res = o.schedule_batch(osnap, prof, None, hi - lo, request_base=lo, **{k: v[lo:hi] for k, v in req.items()})
+    width = (R_TOTAL + world - 1) // world + 1
+    mine = torch.full((width,), -7, dtype=torch.int32)
+    mine[: hi - lo] = torch.from_numpy(res["pick"])
+    allp = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allp, mine)
+    if rank == 0:
+        picks = np.concatenate([allp[r][: sharding.shard_range(R_TOTAL, r, world)[1] - sharding.shard_range(R_TOTAL, r, world)[0]].numpy()
+                                for r in range(world)])
+        whole = o.schedule_batch(osnap, prof, None, R_TOTAL, **req)
+        q.put((bool(np.array_equal(picks, whole["pick"])), int(len(np.unique(whole["pick"])))))
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -74,6 +124,20 @@ def test_two_rank_sharding_matches_single_batch():
         assert p.exitcode == 0
     same, max_ties = q.get(timeout=5)
     assert same and max_ties > 1
+
+
+def test_two_rank_latency_weighted_random_is_shard_invariant():
+    port = 31500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_latency_weighted_random, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    same, distinct = q.get(timeout=5)
+    assert same and distinct > 20   # a stochastic picker spreads the picks, identically with and without sharding
 
 
 def test_snapshot_pack_roundtrip_and_alignment():
