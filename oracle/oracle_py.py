@@ -23,9 +23,12 @@ TIE_LOWEST_INDEX, TIE_SEEDED_RANDOM = 0, 1
 PICK_MAX_SCORE, PICK_WEIGHTED_RANDOM, PICK_RANDOM = 0, 1, 2
 
 
+_GOSHAPE_PATH = os.path.join(_HERE, "_build", "libgoshape.so")
+
+
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "Makefile")]
-    stale = (not os.path.exists(_LIB_PATH)) or any(
+    src = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "Makefile", "goshape.cpp")]
+    stale = (not os.path.exists(_LIB_PATH)) or (not os.path.exists(_GOSHAPE_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -161,6 +164,22 @@ def lib():
         L.orc_commit_picks.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         _lib = L
     return _lib
+
+
+_goshape = None
+
+
+def goshape_lib():
+    """The "Go-shape" CPU baseline (oracle/goshape.cpp): maps, per-request clones, shuffle + stable sort."""
+    global _goshape
+    if _goshape is None:
+        lib()
+        G = C.CDLL(_GOSHAPE_PATH)
+        G.orc_goshape_schedule_batch.restype = C.c_int32
+        G.orc_goshape_schedule_batch.argtypes = [C.POINTER(Snapshot), C.POINTER(Profile), C.c_void_p, C.POINTER(Batch), C.c_int32,
+                                                 C.c_uint64]
+        _goshape = G
+    return _goshape
 
 
 def _ptr(a):
@@ -405,7 +424,8 @@ def schedule_batch(snap: SnapshotData, profile: Profile, index: Index | None, R:
                    prompt_off=None, model_seed=None, hashes_in=None, n_hashes_in=None, adapter_id=None,
                    cand_mask=None, dense_feat=None, dense_total=None, block_chars=64, max_blocks=256,
                    request_base=0, n_threads=1, want_match=False, want_hashes=False, want_tie_set=False,
-                   want_scores=False, input_tokens=None, ttft_slo=None, tpot_slo=None, want_pred=False):
+                   want_scores=False, input_tokens=None, ttft_slo=None, tpot_slo=None, want_pred=False, goshape=False,
+                   shuffle_seed=0):
     M = snap.M
     mw = (M + 31) // 32
     b = Batch()
@@ -448,6 +468,11 @@ def schedule_batch(snap: SnapshotData, profile: Profile, index: Index | None, R:
         out["pred_out"] = np.zeros((R, M, 2), np.float64)
     for k, v in out.items():
         setattr(b, k, _ptr(v))
+    if goshape:
+        rc = goshape_lib().orc_goshape_schedule_batch(C.byref(snap.struct), C.byref(profile),
+                                                      index._h if index is not None else None, C.byref(b), n_threads, shuffle_seed)
+        assert rc == 0, "goshape baseline covers the unfiltered prompt path only"
+        return out
     lib().orc_schedule_batch(C.byref(snap.struct), C.byref(profile), index._h if index is not None else None,
                              C.byref(b), n_threads)
     return out

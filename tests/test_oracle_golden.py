@@ -465,3 +465,37 @@ def test_count_fields_go_semantics():
     for _ in range(20000):
         s = bytes(rnd.choice(alphabet) for _ in range(rnd.randint(0, 24)))
         assert o.count_fields(s) == _fields_by_byte_patterns(s), s
+
+
+# ---------------------------------------------------------------- the "Go-shape" CPU baseline computes the same results
+def test_goshape_baseline_matches_oracle():
+    from tests.helpers import synth_prompts, synth_snapshot, zipf_adapters
+    M, R = 96, 300
+    sd = synth_snapshot(M, seed=2, tie_heavy=True)
+    snap = o.SnapshotData(**sd)
+    prof = o.make_profile(kinds([("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)]))
+    prompts, off, _ = synth_prompts(R, prompt_len=512, groups=7, shared=256, seed=2)
+    seeds = np.full(R, o.model_seed("m"), np.uint64)
+    ad = zipf_adapters(R, seed=2)
+    idx = o.Index()
+    warm = o.schedule_batch(snap, prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds, adapter_id=ad,
+                            want_hashes=True)
+    idx.commit(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    kw = dict(prompt_bytes=prompts, prompt_off=off, model_seed=seeds, adapter_id=ad)
+    want = o.schedule_batch(snap, prof, idx, R, want_tie_set=True, **kw)
+    for threads, seed in ((1, 0), (3, 99)):
+        got = o.schedule_batch(snap, prof, idx, R, goshape=True, n_threads=threads, shuffle_seed=seed, **kw)
+        assert np.array_equal(got["pick_score"].view(np.uint64), want["pick_score"].view(np.uint64))
+        assert np.array_equal(got["tie_count"], want["tie_count"])
+        ts = want["tie_set"]
+        assert ((ts[np.arange(R), got["pick"] >> 5] >> (got["pick"] & 31).astype(np.uint32)) & 1).all()
+    # a tie-heavy profile: the shuffle picks some member of the arg-max set, the set's size is the same
+    sd["kv_usage"] = np.round(sd["kv_usage"], 1)
+    snap2 = o.SnapshotData(**sd)
+    prof2 = o.make_profile(kinds([("kv", 1), ("lora", 1)]))
+    want2 = o.schedule_batch(snap2, prof2, None, R, adapter_id=ad, want_tie_set=True)
+    got2 = o.schedule_batch(snap2, prof2, None, R, adapter_id=ad, prompt_bytes=prompts, prompt_off=off, goshape=True, shuffle_seed=5)
+    assert np.array_equal(got2["tie_count"], want2["tie_count"]) and want2["tie_count"].max() > 1
+    ts2 = want2["tie_set"]
+    assert ((ts2[np.arange(R), got2["pick"] >> 5] >> (got2["pick"] & 31).astype(np.uint32)) & 1).all()
+    assert (got2["pick"] != want2["pick"]).any()  # the shuffle does not always land on the lowest index of a tie set
