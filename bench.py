@@ -575,9 +575,35 @@ def run_gpu(args):
                 o.schedule_batch(snap_l, prof_l, idx, Rl, hashes_in=hh[:Rl].cpu().numpy(), n_hashes_in=nn[:Rl].cpu().numpy(),
                                  max_blocks=MAX_BLOCKS, n_threads=os.cpu_count() or 1, **{k: v[:Rl] for k, v in lat_req.items()})
                 extra["latency_fold_in"]["cpu_port_picks_per_s"] = Rl / (time.perf_counter() - t0)
+            # len(strings.Fields(prompt)) on the device: the prompt stream once more (HBM-bound)
+            cnt = torch.empty(R, dtype=torch.int32, device=dev)
+
+            def fields_only(i):
+                d = dsets[i % NSETS]
+                rc = L.eppscore_count_fields(eng_l._h, R, 1, d["prompts"].data_ptr(), d["off"].data_ptr(), None, cnt.data_ptr(), sptr)
+                assert rc == 0
+
+            t_f = time_kernel(fields_only, iters=20)
+            plen_f = float(sets[0]["off"][R])
+            extra["count_fields"] = {"kernel": "count_fields_kernel", "us": t_f * 1e6, "algorithmic_bytes": plen_f + 12.0 * R,
+                                     "gbs": (plen_f + 12.0 * R) / t_f / 1e9, "frac_of_peak": (plen_f + 12.0 * R) / t_f / 1e9 / peak}
             eng_l.close()
         except Exception as ex:  # noqa: BLE001
             extra["latency_fold_in"] = {"error": repr(ex)}
+
+        # ---- stochastic pickers (weighted-random A-Res over the four-scorer profile): every pair scored + one draw per pair ----
+        try:
+            eng_w = pkg.Engine(pkg.default_config(SCORERS, max_endpoints=M, max_adapters=A, block_chars=BLOCK_CHARS, max_blocks=MAX_BLOCKS,
+                                                  prefix_capacity=1 << 19, pick_mode=pkg.PICK_WEIGHTED_RANDOM, tie_seed=3), device=local)
+            apply_snapshot(eng_w)
+            if rank == 0:
+                eng_w.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+            t_w = time_kernel(lambda i: pick_only(i, eng_w), iters=10)
+            extra["weighted_random_picker"] = {"kernel": "score_matrix_kernel<runtime sequence; A-Res>", "us": t_w * 1e6, "picks_per_s": R / t_w,
+                                               "pairs_per_s": R * M / t_w}
+            eng_w.close()
+        except Exception as ex:  # noqa: BLE001
+            extra["weighted_random_picker"] = {"error": repr(ex)}
 
         # ---- dense-row mode (R x M float4 feature rows streamed from HBM): reported beside the headline ----
         try:
@@ -621,6 +647,38 @@ def run_gpu(args):
                                      "sample": f"{Rc} requests of the same workload x {n_mt} runs (median), {cores} threads; "
                                                f"single-thread: {4096 / t_1:.0f} picks/s",
                                      "single_thread_value": 4096 / t_1}
+            # the "Go-shape" restatement (SURVEY §8d form (i)): per-request clones of the candidates, one hash map per
+            # scorer, accumulate map, shuffle + stable sort — same results (tests/test_oracle_golden.py), the reference's
+            # cost profile.  Labelled Go-shape, not Go: the Go toolchain is not in this image.
+            try:
+                w0 = sets[0]
+                seeds_c = np.full(Rc, seed, np.uint64)
+
+                def goshape(Rg, threads):
+                    t0 = time.perf_counter()
+                    o.schedule_batch(osnap, prof, idx, Rg, prompt_bytes=w0["prompts"][: w0["off"][Rg]], prompt_off=w0["off"][: Rg + 1],
+                                     model_seed=seeds_c[:Rg], adapter_id=w0["adapters"][:Rg], block_chars=BLOCK_CHARS,
+                                     max_blocks=MAX_BLOCKS, n_threads=threads, goshape=True, shuffle_seed=1)
+                    return time.perf_counter() - t0
+
+                t_g1 = goshape(256, 1)
+                Rg = min(Rc, max(cores * 32, 1024))
+                t_gm = goshape(Rg, cores)
+                # config A of BASELINE.json: 1 request x 4 pods, queue-depth scorer only, per call
+                snapA = synth_snapshot(4, A=A, seed=11)
+                oA = o.SnapshotData(**snapA)
+                profA = o.make_profile([(0, 1.0)])
+                nA = 200000
+                t0 = time.perf_counter()
+                o.schedule_batch(oA, profA, None, nA, n_threads=1, goshape=True)
+                t_A = time.perf_counter() - t0
+                extra["cpu_baseline_goshape"] = {"value": Rg / t_gm, "unit": "picks/s", "cores": cores, "kind": "port (Go-shape restatement)",
+                                                 "sample": f"{Rg} requests of the same workload, {cores} threads; single-thread: {256 / t_g1:.0f} picks/s",
+                                                 "single_thread_value": 256 / t_g1,
+                                                 "config_A_ns_per_call": 1e9 * t_A / nA,
+                                                 "config_A": "1 request x 4 pods, queue-depth scorer only, single thread, 200000 calls"}
+            except Exception as ex:  # noqa: BLE001
+                extra["cpu_baseline_goshape"] = {"error": repr(ex)}
 
     if rank == 0:
         cfg = config_dict(world)
