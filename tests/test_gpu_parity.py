@@ -887,7 +887,7 @@ def _texty_prompts(R, seed, max_len=1400):
               b"\xe1\x9a\x80", b"\xe2\x81\x9f", b"\r\n"]
     out, off = bytearray(), [0]
     for r in range(R):
-        target = int(rng.integers(0, max_len))
+        target = 0 if r == 0 else int(rng.integers(0, max_len))
         s = bytearray()
         while len(s) < target:
             s += pieces[int(rng.integers(0, len(pieces)))]
