@@ -944,6 +944,101 @@ double orc_neg_log(double u) {
   return -lnu;
 }
 
+/* =====================================================================================
+ * Device-side filters of the latency profile
+ * ===================================================================================== */
+static double filt_prefix_score(const uint16_t *match, int32_t total, int32_t m) { /* prefixcacheaffinity/plugin.go:160-171 */
+  if (match && total > 0) {
+    double sc = (double)match[m] / (double)total;
+    if (!isnan(sc)) return sc;
+  }
+  return 0;
+}
+
+void orc_apply_filters(const orc_snapshot *s, const orc_profile *p, int64_t request_index, const uint32_t *mask_in,
+                       const uint16_t *match, int32_t total, const orc_latency_request *lat, uint32_t *mask_out) {
+  const int32_t M = s->M, mw = (M + 31) / 32;
+  orc_latency_request zero = {0, 0.0, 0.0};
+  if (!lat) lat = &zero;
+  /* the current candidate list, in endpoint order (filters preserve order) */
+  int32_t *cur = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M > 0 ? M : 1) * 3);
+  int32_t *a = cur + (M > 0 ? M : 1), *b = a + (M > 0 ? M : 1);
+  int32_t n = 0;
+  for (int32_t m = 0; m < M; m++)
+    if (is_cand(mask_in, m)) cur[n++] = m;
+  /* LatencyPredictionInfo per endpoint, as PrepareRequestData leaves it (all endpoints, before the filters) */
+  const int have_pred = p->latency && p->latency->has_predictions;
+  double *ttft = (double *)malloc(sizeof(double) * (size_t)(M > 0 ? M : 1) * 3);
+  double *th = ttft + (M > 0 ? M : 1), *ph = th + (M > 0 ? M : 1);
+  if (have_pred)
+    for (int32_t m = 0; m < M; m++) {
+      double prefix = 0.0, tp;
+      if (match) {
+        prefix = (double)match[m] / (double)total;
+        if (isnan(prefix)) prefix = 0.0;
+      }
+      orc_latency_predict(p->latency, s->kv_usage[m], lat->input_tokens, s->queue[m], s->running ? s->running[m] : 0, 1, prefix,
+                          &ttft[m], &tp);
+      int neutralize = !p->latency->streaming_mode || (s->prefill_role && s->prefill_role[m]);
+      double hr[2];
+      orc_latency_validate(p->latency, ttft[m], tp, lat->ttft_slo, lat->tpot_slo, s->min_tpot_slo ? s->min_tpot_slo[m] : 0.0,
+                           neutralize, NULL, hr);
+      th[m] = hr[1];
+      ph[m] = hr[0];
+    }
+  for (int32_t f = 0; f < p->n_filters && n > 0; f++) { /* scheduler_profile.go:135-145: stop on an empty result */
+    const double *par = p->filter_param[f];
+    const double u = orc_uniform01(p->tie_seed, request_index, -(f + 1));
+    if (p->filter_kind[f] == ORC_FILTER_PREFIX_AFFINITY) { /* prefixcacheaffinity/plugin.go:105-151 */
+      if (n <= 1 || par[0] <= 0) continue;
+      if (u < par[1]) continue; /* exploration: keep all */
+      int32_t na = 0, nb = 0;   /* a = sticky, b = nonSticky */
+      for (int32_t i = 0; i < n; i++) {
+        if (filt_prefix_score(match, total, cur[i]) >= par[0])
+          a[na++] = cur[i];
+        else
+          b[nb++] = cur[i];
+      }
+      if (na == 0) continue;
+      if (par[2] > 0 && nb > 0) {
+        double best_a = DBL_MAX, best_b = DBL_MAX; /* bestTTFT :173-184 */
+        if (have_pred) {
+          for (int32_t i = 0; i < na; i++)
+            if (ttft[a[i]] < best_a) best_a = ttft[a[i]];
+          for (int32_t i = 0; i < nb; i++)
+            if (ttft[b[i]] < best_b) best_b = ttft[b[i]];
+        }
+        if (best_a - best_b > par[2]) continue; /* TTFT load gate broken: keep all */
+      }
+      memcpy(cur, a, sizeof(int32_t) * (size_t)na);
+      n = na;
+    } else if (p->filter_kind[f] == ORC_FILTER_SLO_HEADROOM_TIER) { /* sloheadroomtier/plugin.go:82-137 */
+      if (n <= 1) continue;
+      if (!have_pred) continue; /* no predictions: keep all */
+      int32_t na = 0, nb = 0;   /* a = positive, b = negative */
+      for (int32_t i = 0; i < n; i++) {
+        if (th[cur[i]] >= 0 && ph[cur[i]] >= 0)
+          a[na++] = cur[i];
+        else
+          b[nb++] = cur[i];
+      }
+      if (na > 0 && nb > 0) {
+        if (u < par[0]) {
+          memcpy(cur, b, sizeof(int32_t) * (size_t)nb);
+          n = nb;
+        } else {
+          memcpy(cur, a, sizeof(int32_t) * (size_t)na);
+          n = na;
+        }
+      } /* only one tier present: that tier == everything */
+    }
+  }
+  memset(mask_out, 0, sizeof(uint32_t) * (size_t)(mw > 0 ? mw : 1));
+  for (int32_t i = 0; i < n; i++) mask_out[cur[i] >> 5] |= 1u << (cur[i] & 31);
+  free(cur);
+  free(ttft);
+}
+
 static const double LORA_CLASS_SCORE[4] = {0.0, 0.6, 0.8, 1.0};
 
 int32_t orc_schedule_one(const orc_snapshot *s, const orc_profile *p, int64_t request_index,
@@ -1118,11 +1213,12 @@ static void *batch_worker(void *arg) {
   const orc_batch *b = j->b;
   const int32_t M = j->s->M;
   const int32_t mw = (M + 31) / 32;
-  const int need_prefix = profile_has(j->p, ORC_SCORER_PREFIX) || profile_has(j->p, ORC_SCORER_LATENCY) || b->match_blocks || b->total_blocks || b->hashes_out;
+  const int need_prefix = profile_has(j->p, ORC_SCORER_PREFIX) || profile_has(j->p, ORC_SCORER_LATENCY) || j->p->n_filters > 0 || b->match_blocks || b->total_blocks || b->hashes_out;
   int32_t hcap = b->max_blocks > 0 ? b->max_blocks : 1;
   if (b->hashes_in && b->hash_stride > hcap) hcap = b->hash_stride;
   uint64_t *hashes = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)hcap);
   uint16_t *match = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)M);
+  uint32_t *fmask = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(mw > 0 ? mw : 1));
   for (int32_t r = j->r0; r < j->r1; r++) {
     int32_t nh = 0;
     const uint16_t *match_p = NULL;
@@ -1154,6 +1250,19 @@ static void *batch_worker(void *arg) {
             pair ? (uint16_t)pair[(size_t)m * 4] : (match_p ? match_p[m] : 0);
     }
     const uint32_t *mask = b->cand_mask ? b->cand_mask + (size_t)r * mw : NULL;
+    orc_latency_request lr0 = {b->input_tokens ? b->input_tokens[r] : 0, b->ttft_slo ? b->ttft_slo[r] : 0.0,
+                               b->tpot_slo ? b->tpot_slo[r] : 0.0};
+    if (j->p->n_filters > 0) {
+      orc_apply_filters(j->s, j->p, b->request_base + r, mask, match_p, total, &lr0, fmask);
+      mask = fmask;
+    }
+    if (b->filter_mask_out) {
+      for (int32_t w = 0; w < mw; w++) {
+        uint32_t v = mask ? mask[w] : 0xffffffffu;
+        if (!mask && w == mw - 1 && (M & 31)) v = (1u << (M & 31)) - 1u;
+        b->filter_mask_out[(size_t)r * mw + w] = v;
+      }
+    }
     orc_latency_request lr = {b->input_tokens ? b->input_tokens[r] : 0, b->ttft_slo ? b->ttft_slo[r] : 0.0,
                               b->tpot_slo ? b->tpot_slo[r] : 0.0};
     orc_schedule_one_lat(j->s, j->p, b->request_base + r, b->adapter_id ? b->adapter_id[r] : -1, mask, match_p, total,
@@ -1164,6 +1273,7 @@ static void *batch_worker(void *arg) {
   }
   free(hashes);
   free(match);
+  free(fmask);
   return NULL;
 }
 

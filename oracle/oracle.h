@@ -69,6 +69,14 @@ typedef struct orc_latency_params {
   double composite_kv, composite_queue, composite_prefix; /* defaults 1,1,1 */
 } orc_latency_params;
 
+/* device-side Filter plugins of the latency profile (config/charts/epplib/templates/_config.yaml:47-75):
+ *   prefix-cache-affinity-filter  filter/prefixcacheaffinity/plugin.go:105-151  params {affinityThreshold, explorationProbability, maxTTFTPenaltyMs}
+ *   slo-headroom-tier-filter      filter/sloheadroomtier/plugin.go:82-137       params {epsilonExploreNeg}
+ * Their rand.Float64() draws come from the same counter-based generator as the pickers: draw of filter f for request r =
+ * orc_uniform01(tie_seed, r, -(f+1)). */
+enum { ORC_FILTER_PREFIX_AFFINITY = 1, ORC_FILTER_SLO_HEADROOM_TIER = 2 };
+#define ORC_MAX_FILTERS 4
+
 typedef struct orc_profile {
   int32_t n_scorers;
   int32_t scorer_kind[ORC_MAX_SCORERS];
@@ -78,7 +86,9 @@ typedef struct orc_profile {
   const orc_latency_params *latency; /* required by ORC_SCORER_LATENCY */
   double token_load_threshold;       /* queueThresholdTokens (token_load.go:33,57-61); <= 0 => 4194304 */
   int32_t pick_mode;                 /* ORC_PICK_* */
-  int32_t reserved;
+  int32_t n_filters;                 /* run in order before the scorers, on top of the caller's candidate mask */
+  int32_t filter_kind[ORC_MAX_FILTERS];
+  double filter_param[ORC_MAX_FILTERS][3];
 } orc_profile;
 
 /* One immutable metrics snapshot (interface/datalayer/metrics.go:26-42 fields the path reads). */
@@ -165,6 +175,11 @@ void orc_score_latency(const orc_latency_params *, const orc_snapshot *, const u
                        const uint16_t *match, int32_t total, const orc_latency_request *, double *out,
                        double *pred_out);
 
+/* runFilterPlugins (scheduler_profile.go:130-149) for the device-side filters: mask_in NULL = all M;
+ * mask_out receives ceil(M/32) words.  Predictions are made like PrepareRequestData (all endpoints). */
+void orc_apply_filters(const orc_snapshot *, const orc_profile *, int64_t request_index, const uint32_t *mask_in,
+                       const uint16_t *match, int32_t total, const orc_latency_request *lat, uint32_t *mask_out);
+
 /* counter-based U in (0,1] and -ln(U) built from +,-,*,/ only (bit-reproducible on any IEEE machine) */
 double orc_uniform01(uint64_t seed, int64_t request_index, int32_t endpoint);
 double orc_neg_log(double u);
@@ -221,6 +236,7 @@ typedef struct orc_batch {
   const double *ttft_slo;        /* R */
   const double *tpot_slo;        /* R */
   double *pred_out;              /* R x M x 2 {ttft, tpot} */
+  uint32_t *filter_mask_out;     /* optional R x ceil(M/32): the candidate set after the filter chain */
 } orc_batch;
 
 /* Whole hot path for a batch (hash → match → score → pick), requests partitioned over n_threads

@@ -21,6 +21,7 @@ SCORER_ENDPOINT_COL0 = 8
 SCORER_PAIR_COL0 = 16
 TIE_LOWEST_INDEX, TIE_SEEDED_RANDOM = 0, 1
 PICK_MAX_SCORE, PICK_WEIGHTED_RANDOM, PICK_RANDOM = 0, 1, 2
+FILTER_PREFIX_AFFINITY, FILTER_SLO_HEADROOM_TIER = 1, 2
 
 
 _GOSHAPE_PATH = os.path.join(_HERE, "_build", "libgoshape.so")
@@ -73,7 +74,8 @@ class Profile(C.Structure):
     _fields_ = [("n_scorers", C.c_int32), ("scorer_kind", C.c_int32 * MAX_SCORERS),
                 ("scorer_weight", C.c_double * MAX_SCORERS), ("tie_mode", C.c_int32),
                 ("tie_seed", C.c_uint64), ("latency", C.POINTER(LatencyParams)),
-                ("token_load_threshold", C.c_double), ("pick_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("token_load_threshold", C.c_double), ("pick_mode", C.c_int32), ("n_filters", C.c_int32),
+                ("filter_kind", C.c_int32 * 4), ("filter_param", (C.c_double * 3) * 4)]
 
 
 class Snapshot(C.Structure):
@@ -93,7 +95,7 @@ class Batch(C.Structure):
                 ("pick_score", C.c_void_p), ("tie_count", C.c_void_p), ("tie_set", C.c_void_p),
                 ("match_blocks", C.c_void_p), ("total_blocks", C.c_void_p), ("hashes_out", C.c_void_p),
                 ("weighted_out", C.c_void_p), ("input_tokens", C.c_void_p), ("ttft_slo", C.c_void_p),
-                ("tpot_slo", C.c_void_p), ("pred_out", C.c_void_p)]
+                ("tpot_slo", C.c_void_p), ("pred_out", C.c_void_p), ("filter_mask_out", C.c_void_p)]
 
 
 _lib = None
@@ -214,7 +216,7 @@ def hash_prompt(prompt: bytes, seed: int, block_chars: int, max_blocks: int) -> 
 
 
 def make_profile(scorers, tie_mode=TIE_LOWEST_INDEX, tie_seed=0, latency: LatencyParams | None = None,
-                 token_load_threshold: float = 0.0, pick_mode: int = 0) -> Profile:
+                 token_load_threshold: float = 0.0, pick_mode: int = 0, filters=()) -> Profile:
     """scorers: list of (kind, weight) in profile order."""
     p = Profile()
     if latency is not None:
@@ -222,6 +224,11 @@ def make_profile(scorers, tie_mode=TIE_LOWEST_INDEX, tie_seed=0, latency: Latenc
         p.latency = C.pointer(latency)
     p.token_load_threshold = token_load_threshold
     p.pick_mode = pick_mode
+    p.n_filters = len(filters)  # [(kind, (param0, param1, param2))]
+    for i, (k, par) in enumerate(filters):
+        p.filter_kind[i] = int(k)
+        for j2, v in enumerate(par):
+            p.filter_param[i][j2] = float(v)
     p.n_scorers = len(scorers)
     for i, (k, w) in enumerate(scorers):
         p.scorer_kind[i] = int(k)
@@ -425,7 +432,7 @@ def schedule_batch(snap: SnapshotData, profile: Profile, index: Index | None, R:
                    cand_mask=None, dense_feat=None, dense_total=None, block_chars=64, max_blocks=256,
                    request_base=0, n_threads=1, want_match=False, want_hashes=False, want_tie_set=False,
                    want_scores=False, input_tokens=None, ttft_slo=None, tpot_slo=None, want_pred=False, goshape=False,
-                   shuffle_seed=0):
+                   shuffle_seed=0, want_filter_mask=False):
     M = snap.M
     mw = (M + 31) // 32
     b = Batch()
@@ -466,6 +473,8 @@ def schedule_batch(snap: SnapshotData, profile: Profile, index: Index | None, R:
         out["weighted_out"] = np.zeros((R, M), np.float64)
     if want_pred:
         out["pred_out"] = np.zeros((R, M, 2), np.float64)
+    if want_filter_mask:
+        out["filter_mask_out"] = np.zeros((R, max(mw, 1)), np.uint32)
     for k, v in out.items():
         setattr(b, k, _ptr(v))
     if goshape:

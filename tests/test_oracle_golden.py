@@ -499,3 +499,57 @@ def test_goshape_baseline_matches_oracle():
     ts2 = want2["tie_set"]
     assert ((ts2[np.arange(R), got2["pick"] >> 5] >> (got2["pick"] & 31).astype(np.uint32)) & 1).all()
     assert (got2["pick"] != want2["pick"]).any()  # the shuffle does not always land on the lowest index of a tie set
+
+
+# ---------------------------------------------------------------- device-side filters of the latency profile
+def filter_case_inputs(kind, c):
+    """Encodes a reference filter test as engine/oracle inputs.  Headrooms / TTFTs ride on the identity model
+    TTFT = WaitingQueueSize, TPOT = RunningRequestsSize with both SLOs = 1000; prefix matches of 100 blocks come from an
+    index in which endpoint m holds the first `match` block hashes of the request."""
+    eps = c["endpoints"]
+    M = len(eps)
+    hashes = (np.arange(100, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+    if kind == "tier":
+        has_pred = all(e[2] for e in eps)
+        queue = [1000 - int(e[0]) for e in eps]
+        running = [1000 - int(e[1]) for e in eps]
+        adds = []
+        filters = [(o.FILTER_SLO_HEADROOM_TIER, (c["epsilon"],))]
+    else:
+        has_pred = True
+        queue = [int(e[1]) for e in eps]
+        running = [0] * M
+        adds = [(m, int(e[0])) for m, e in enumerate(eps) if e[0] > 0]
+        filters = [(o.FILTER_PREFIX_AFFINITY, tuple(c["params"]))]
+    lat = dict(ttft_waiting=1.0, tpot_running=1.0, streaming_mode=1, has_predictions=1 if has_pred else 0)
+    return dict(M=M, queue=queue, running=running, adds=adds, filters=filters, lat=lat, hashes=hashes)
+
+
+def test_filters_reference_cases(golden):
+    for kind, key in (("tier", "slo_headroom_tier"), ("affinity", "prefix_cache_affinity")):
+        for c in golden["filters"][key]["cases"]:
+            inp = filter_case_inputs(kind, c)
+            M = inp["M"]
+            snap = o.SnapshotData(np.zeros(M), inp["queue"], inp["running"])
+            idx = o.Index()
+            for m, n in inp["adds"]:
+                idx.add(inp["hashes"][:n], m)
+            prof = o.make_profile([(o.SCORER_LATENCY, 1.0)], latency=o.make_latency_params(**inp["lat"]), filters=inp["filters"], tie_seed=3)
+            res = o.schedule_batch(snap, prof, idx, 1, hashes_in=inp["hashes"][None, :], n_hashes_in=np.array([100], np.uint16),
+                                   ttft_slo=[1000.0], tpot_slo=[1000.0], want_filter_mask=True, want_match=True)
+            kept = [m for m in range(M) if (res["filter_mask_out"][0][m >> 5] >> (m & 31)) & 1]
+            assert kept == c["want"], (c["name"], kept)
+            assert res["pick"][0] in kept
+
+
+def test_filter_draws_are_bernoulli():
+    # both tiers present, epsilon 0.3: the negative tier is selected ~30 % of the time
+    lp = o.make_latency_params(ttft_waiting=1.0, tpot_running=1.0, streaming_mode=1)
+    snap = o.SnapshotData(np.zeros(3), [900, 800, 1100], [950, 920, 1050])
+    prof = o.make_profile([(o.SCORER_LATENCY, 1.0)], latency=lp, filters=[(o.FILTER_SLO_HEADROOM_TIER, (0.3,))], tie_seed=11)
+    R = 20000
+    res = o.schedule_batch(snap, prof, None, R, ttft_slo=np.full(R, 1000.0), tpot_slo=np.full(R, 1000.0), want_filter_mask=True)
+    neg = (res["filter_mask_out"][:, 0] == 0b100)
+    pos = (res["filter_mask_out"][:, 0] == 0b011)
+    assert (neg | pos).all() and abs(neg.mean() - 0.3) < 0.02
+    assert (res["pick"][neg] == 2).all() and (res["pick"][pos] != 2).all()
