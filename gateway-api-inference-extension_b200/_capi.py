@@ -12,6 +12,7 @@ SCORER = {"queue": 0, "kv": 1, "prefix": 2, "lora": 3, "running": 4, "latency": 
           "col0": 8, "col1": 9, "col2": 10, "col3": 11, "pair0": 16, "pair1": 17}
 TIE_LOWEST_INDEX, TIE_SEEDED_RANDOM = 0, 1
 PICK_MAX_SCORE, PICK_WEIGHTED_RANDOM, PICK_RANDOM = 0, 1, 2
+FILTER_PREFIX_AFFINITY, FILTER_SLO_HEADROOM_TIER = 1, 2
 
 ERR_NAMES = {0: "OK", -1: "ERR_INVALID", -2: "ERR_CUDA", -3: "ERR_CAPACITY", -4: "ERR_NO_SNAPSHOT", -5: "ERR_NO_DEVICE"}
 
@@ -27,7 +28,8 @@ class Config(C.Structure):
                 ("scorer_weight", C.c_double * MAX_SCORERS), ("block_chars", C.c_int32), ("max_blocks", C.c_int32),
                 ("tie_mode", C.c_int32), ("tie_seed", C.c_uint64), ("max_endpoints", C.c_int32),
                 ("max_adapters", C.c_int32), ("prefix_capacity", C.c_int64), ("lru_capacity_default", C.c_int32),
-                ("token_load_threshold", C.c_double), ("pick_mode", C.c_int32), ("reserved0", C.c_int32)]
+                ("token_load_threshold", C.c_double), ("pick_mode", C.c_int32), ("n_filters", C.c_int32),
+                ("filter_kind", C.c_int32 * 4), ("filter_param", (C.c_double * 3) * 4)]
 
 
 class LatencyParams(C.Structure):
@@ -60,7 +62,8 @@ class Batch(C.Structure):
                 ("pick", C.c_void_p), ("pick_score", C.c_void_p), ("tie_count", C.c_void_p),
                 ("match_blocks", C.c_void_p), ("total_blocks", C.c_void_p), ("hashes_out", C.c_void_p),
                 ("scores_out", C.c_void_p), ("stream", C.c_void_p), ("input_tokens", C.c_void_p),
-                ("ttft_slo", C.c_void_p), ("tpot_slo", C.c_void_p), ("pred_out", C.c_void_p)]
+                ("ttft_slo", C.c_void_p), ("tpot_slo", C.c_void_p), ("pred_out", C.c_void_p),
+                ("filter_mask_out", C.c_void_p)]
 
 
 class Stats(C.Structure):

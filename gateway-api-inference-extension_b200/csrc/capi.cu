@@ -93,7 +93,7 @@ struct eppscore_engine {
 
   // scratch for host-location batches and internal hashes
   DevBuf s_prompts, s_off, s_len, s_seed, s_hashes, s_nh, s_adapter, s_mask, s_dense, s_dtotal, s_pick, s_score,
-      s_tie, s_match, s_total, s_scores, s_intok, s_tslo, s_pslo, s_pred, s_fields;
+      s_tie, s_match, s_total, s_scores, s_intok, s_tslo, s_pslo, s_pred, s_fields, s_fmask;
 };
 
 namespace {
@@ -266,6 +266,7 @@ struct DevBatch {  // all device pointers
   const double* ttft_slo;
   const double* tpot_slo;
   double* pred_out;
+  uint32_t* filter_mask_out;
   int32_t* pick;
   double* pick_score;
   int32_t* tie_count;
@@ -341,6 +342,12 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
     a.lat.ttft_slo = b.ttft_slo;
     a.lat.tpot_slo = b.tpot_slo;
     a.lat.pred_out = b.pred_out;
+    a.n_filters = e->cfg.n_filters;
+    for (int f = 0; f < e->cfg.n_filters; f++) {
+      a.filter_kind[f] = e->cfg.filter_kind[f];
+      for (int q = 0; q < 3; q++) a.filter_param[f][q] = e->cfg.filter_param[f][q];
+    }
+    a.filter_mask_out = b.filter_mask_out;
   }
 
   if (!dense) {
@@ -475,6 +482,23 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
     if (nlat > 1) return fail(nullptr, EPPSCORE_ERR_INVALID, "at most one latency scorer per profile");
   }
   if (cfg->pick_mode < 0 || cfg->pick_mode > EPPSCORE_PICK_RANDOM) return fail(nullptr, EPPSCORE_ERR_INVALID, "unknown pick_mode");
+  if (cfg->n_filters < 0 || cfg->n_filters > EPPSCORE_MAX_FILTERS) return fail(nullptr, EPPSCORE_ERR_INVALID, "n_filters out of range");
+  if (cfg->n_filters > 0) {
+    if (!cfg_has(*cfg, EPPSCORE_SCORER_LATENCY)) return fail(nullptr, EPPSCORE_ERR_INVALID, "device-side filters need the latency scorer in the profile");
+    if (cfg_has(*cfg, EPPSCORE_SCORER_QUEUE) || cfg_has(*cfg, EPPSCORE_SCORER_RUNNING))
+      return fail(nullptr, EPPSCORE_ERR_INVALID, "device-side filters cannot be combined with the queue / running scorers");
+    for (int f = 0; f < cfg->n_filters; f++) {
+      const int k = cfg->filter_kind[f];
+      const double* par = cfg->filter_param[f];
+      if (k == EPPSCORE_FILTER_PREFIX_AFFINITY) {  // prefixcacheaffinity/plugin.go:80-91
+        if (par[0] > 1.0 || par[1] < 0 || par[1] > 1.0 || par[2] < 0) return fail(nullptr, EPPSCORE_ERR_INVALID, "prefix-cache-affinity-filter: invalid parameters");
+      } else if (k == EPPSCORE_FILTER_SLO_HEADROOM_TIER) {  // sloheadroomtier/plugin.go:66-68
+        if (par[0] < 0 || par[0] > 1.0) return fail(nullptr, EPPSCORE_ERR_INVALID, "slo-headroom-tier-filter: epsilonExploreNeg must be in [0, 1]");
+      } else {
+        return fail(nullptr, EPPSCORE_ERR_INVALID, "unknown filter kind");
+      }
+    }
+  }
   if (cfg->max_endpoints < 1 || cfg->max_endpoints > 8192)
     return fail(nullptr, EPPSCORE_ERR_CAPACITY, "max_endpoints must be in [1, 8192]");
   if (cfg->max_blocks < 0 || cfg->max_blocks > EPPSCORE_MAX_BLOCKS) return fail(nullptr, EPPSCORE_ERR_CAPACITY, "max_blocks out of range");
@@ -584,7 +608,7 @@ void eppscore_destroy(eppscore_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->s_fields, &e->qhdr[0], &e->qhdr[1], &e->qbucket[0], &e->qbucket[1], &e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep,
+  DevBuf* bufs[] = {&e->s_fmask, &e->s_fields, &e->qhdr[0], &e->qhdr[1], &e->qbucket[0], &e->qbucket[1], &e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep,
                     &e->s_intok, &e->s_tslo, &e->s_pslo, &e->s_pred, &e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
                     &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->prefix_lut2d, &e->st_idx, &e->st_val, &e->st_slot,
                     &e->probe_out, &e->s_prompts, &e->s_off, &e->s_len, &e->s_seed, &e->s_hashes, &e->s_nh, &e->s_adapter,
@@ -812,6 +836,7 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
     d.ttft_slo = b->ttft_slo;
     d.tpot_slo = b->tpot_slo;
     d.pred_out = b->pred_out;
+    d.filter_mask_out = b->filter_mask_out;
     d.pick = b->pick;
     d.pick_score = b->pick_score;
     d.tie_count = b->tie_count;
@@ -877,6 +902,10 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
     CK(e, e->s_pred.reserve(R * M * 16));
     d.pred_out = e->s_pred.as<double>();
   }
+  if (b->filter_mask_out) {
+    CK(e, e->s_fmask.reserve(R * mw * 4));
+    d.filter_mask_out = e->s_fmask.as<uint32_t>();
+  }
   uint64_t* hashes_dev = nullptr;
   if (b->hashes_out && !b->hashes_in) {
     // reuse the internal hash scratch as the device-side hashes_out
@@ -893,6 +922,7 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
   if (b->total_blocks) CK(e, cudaMemcpyAsync(b->total_blocks, d.total_blocks, R * 2, cudaMemcpyDeviceToHost, e->stream));
   if (b->scores_out) CK(e, cudaMemcpyAsync(b->scores_out, d.scores_out, R * M * 8, cudaMemcpyDeviceToHost, e->stream));
   if (b->pred_out) CK(e, cudaMemcpyAsync(b->pred_out, d.pred_out, R * M * 16, cudaMemcpyDeviceToHost, e->stream));
+  if (b->filter_mask_out) CK(e, cudaMemcpyAsync(b->filter_mask_out, d.filter_mask_out, R * mw * 4, cudaMemcpyDeviceToHost, e->stream));
   if (hashes_dev) CK(e, cudaMemcpyAsync(b->hashes_out, hashes_dev, R * (size_t)mb * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
   return EPPSCORE_OK;

@@ -165,6 +165,12 @@ struct ScoreArgs {
   uint16_t* total_out;          // [R] or null
   double* scores_out;           // [R][M] or null (diagnostics)
   LatArgs lat;
+  // device-side filters of the latency profile (run before the scorers, on top of cand_mask): kind 1 prefix-cache-affinity
+  // {threshold, explorationProbability, maxTTFTPenaltyMs}, kind 2 slo-headroom-tier {epsilonExploreNeg}
+  int32_t n_filters;
+  int32_t filter_kind[4];
+  double filter_param[4][3];
+  uint32_t* filter_mask_out;    // [R][mask_words] or null: the candidate set after the filter chain
 };
 
 struct HashArgs {

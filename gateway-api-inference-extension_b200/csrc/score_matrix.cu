@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
     int l_sel = 5;
     bool l_tok = false, l_pok = false, l_fast = false;
     const bool llut_ok = total <= kLutMax;
+    uint32_t cb[kMaxJ];
+    const uint32_t areq_f = tie_areq(a.request_base + r, plan.seed_lo);
     if (LAT && lat_step >= 0) {
       const LatArgs& L = a.lat;
       const double in_tok = (double)(L.input_tokens ? L.input_tokens[r] : 0);  // len(strings.Fields(prompt)), training.go:51
@@ -287,6 +289,113 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
         lutl_total = total;
         __syncwarp();
       }
+      // this lane's candidates as bits (bit k of cb[j] = endpoint (j*EPL+k)*32+lane): the caller's mask, then narrowed by
+      // the device-side filters
+#pragma unroll
+      for (int j = 0; j < kMaxJ; j++) {
+        cb[j] = 0;
+        if (j >= J) continue;
+        for (int k = 0; k < EPL; k++) {
+          const int t = j * EPL + k, m = t * 32 + lane;
+          bool cand = m < M;
+          if (MASKED) cand = cand && ((__ldg(mrow + t) >> lane) & 1u);
+          cb[j] |= (cand ? 1u : 0u) << k;
+        }
+      }
+      if (a.n_filters > 0) {
+        int ncand = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxJ; j++) ncand += __popc(cb[j]);
+        ncand = __reduce_add_sync(0xffffffffu, ncand);
+        for (int f = 0; f < a.n_filters && ncand > 1; f++) {  // (every filter returns its input when len(endpoints) <= 1)
+          const double u = uniform01(tie_prio(areq_f, -(f + 1), plan.seed_hi), -(f + 1));  // the filter's rand.Float64()
+          const int fkind = a.filter_kind[f];
+          const double p0 = a.filter_param[f][0], p1 = a.filter_param[f][1], p2 = a.filter_param[f][2];
+          uint32_t sb[kMaxJ];
+          int nA = 0;                                         // |sticky| resp. |positive|
+          double minA = 1.7976931348623157e308, minB = minA;  // bestTTFT of the two sides
+          if (fkind == 1) {                                   // prefix-cache-affinity-filter, prefixcacheaffinity/plugin.go:105-151
+            if (p0 <= 0.0 || u < p1 || total == 0) continue;  // disabled / exploration / no prefix info: keep all
+            // smallest match count whose score match/total reaches the threshold (monotone in the count)
+            int cmin = 0x7fffffff;
+            for (int c0 = 0; c0 <= total && cmin == 0x7fffffff; c0 += 32) {
+              const int c = c0 + lane;
+              const bool ok = c <= total && __ddiv_rn((double)c, (double)total) >= p0;
+              const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+              if (bal) cmin = c0 + __ffs(bal) - 1;
+            }
+#pragma unroll
+            for (int j = 0; j < kMaxJ; j++) {
+              sb[j] = 0;
+              if (j >= J) continue;
+              const uint32_t anyj = any[j];
+              const int cbase = (j * 32 + lane) << LOG_EPL;
+              for (int k = 0; k < EPL; k++) {
+                int c = wide_cnt ? (int)cnt16[cbase + k] : (int)cnt8[cbase + k];
+                c = (c == 0 && ((anyj >> k) & 1u)) ? (wide_cnt ? 65536 : 256) : c;
+                const bool cand = (cb[j] >> k) & 1u, sticky = cand && c >= cmin;
+                sb[j] |= (sticky ? 1u : 0u) << k;
+                if (L.has_predictions && p2 > 0.0) {
+                  const double pt = llut_ok ? lut_l[c] : __dmul_rn(pcoef, __ddiv_rn((double)c, (double)total));
+                  const LatPair lp = lat_pair(L.ep + (size_t)(j * EPL + k) * 256 + lane, L.tpot_generated, pt, l_x, l_y, l_tslo, l_buf);
+                  if (sticky) minA = lp.ttft < minA ? lp.ttft : minA;
+                  if (cand && !sticky) minB = lp.ttft < minB ? lp.ttft : minB;
+                }
+              }
+              nA += __popc(sb[j]);
+            }
+            nA = __reduce_add_sync(0xffffffffu, nA);
+            if (nA == 0) continue;                            // no sticky endpoints: keep all
+            if (p2 > 0.0 && nA < ncand) {                     // TTFT load gate (:133-142)
+#pragma unroll
+              for (int o = 16; o; o >>= 1) {
+                const double oa = shfl_xor_f64(minA, o), ob = shfl_xor_f64(minB, o);
+                minA = oa < minA ? oa : minA;
+                minB = ob < minB ? ob : minB;
+              }
+              if (__dsub_rn(minA, minB) > p2) continue;       // stickiness would cost too much TTFT: keep all
+            }
+#pragma unroll
+            for (int j = 0; j < kMaxJ; j++) cb[j] = sb[j];
+            ncand = nA;
+          } else if (fkind == 2) {                            // slo-headroom-tier-filter, sloheadroomtier/plugin.go:82-137
+            if (!L.has_predictions) continue;                 // no predictions: keep all
+#pragma unroll
+            for (int j = 0; j < kMaxJ; j++) {
+              sb[j] = 0;
+              if (j >= J) continue;
+              const uint32_t anyj = any[j];
+              const int cbase = (j * 32 + lane) << LOG_EPL;
+              for (int k = 0; k < EPL; k++) {
+                int c = wide_cnt ? (int)cnt16[cbase + k] : (int)cnt8[cbase + k];
+                c = (c == 0 && ((anyj >> k) & 1u)) ? (wide_cnt ? 65536 : 256) : c;
+                const double pt = llut_ok ? lut_l[c] : __dmul_rn(pcoef, total ? __ddiv_rn((double)c, (double)total) : 0.0);
+                const LatPair lp = lat_pair(L.ep + (size_t)(j * EPL + k) * 256 + lane, L.tpot_generated, pt, l_x, l_y, l_tslo, l_buf);
+                sb[j] |= ((((cb[j] >> k) & 1u) && lp.rank == 0) ? 1u : 0u) << k;  // positive: both headrooms >= 0
+              }
+              nA += __popc(sb[j]);
+            }
+            nA = __reduce_add_sync(0xffffffffu, nA);
+            if (nA > 0 && nA < ncand) {                       // both tiers present: explore the negative one with probability eps
+              const bool neg = u < p0;
+#pragma unroll
+              for (int j = 0; j < kMaxJ; j++) cb[j] = neg ? (cb[j] & ~sb[j]) : sb[j];
+              ncand = neg ? ncand - nA : nA;
+            }
+          }
+        }
+      }
+      if (a.filter_mask_out) {  // natural-order mask words (bit = lane) of the surviving candidates
+#pragma unroll
+        for (int j = 0; j < kMaxJ; j++) {
+          if (j >= J) continue;
+          for (int k = 0; k < EPL; k++) {
+            const uint32_t word = __ballot_sync(0xffffffffu, (cb[j] >> k) & 1u);
+            const int t = j * EPL + k;
+            if (lane == 0 && t < a.mask_words) a.filter_mask_out[(size_t)r * a.mask_words + t] = word;
+          }
+        }
+      }
       if (L.has_predictions) {
         // one pass: every lane tracks the best (lowest) tier it has seen and the |headroom| min/max inside it
         // (branch-free: a non-candidate is tier 5, which never wins against a candidate)
@@ -299,9 +408,8 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
           const int cbase = (j * 32 + lane) << LOG_EPL;
 #pragma unroll 2
           for (int k = 0; k < EPL; k++) {
-            const int t = j * EPL + k, m = t * 32 + lane;
-            bool cand = m < M;
-            if (MASKED) cand = cand && ((__ldg(mrow + t) >> lane) & 1u);
+            const int t = j * EPL + k;
+            const bool cand = (cb[j] >> k) & 1u;
             int c = wide_cnt ? (int)cnt16[cbase + k] : (int)cnt8[cbase + k];
             c = (c == 0 && ((anyj >> k) & 1u)) ? (wide_cnt ? 65536 : 256) : c;
             const double pt = llut_ok ? lut_l[c] : __dmul_rn(pcoef, total ? __ddiv_rn((double)c, (double)total) : 0.0);
@@ -351,13 +459,15 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
       } else {
         // composite fallback: maxQ over the candidates, starting from 0 (plugin.go:338-344)
         long long mq = 0;
-        for (int t = 0; t < J * EPL; t++) {
-          const int m = t * 32 + lane;
-          bool cand = m < M;
-          if (MASKED) cand = cand && ((__ldg(mrow + t) >> lane) & 1u);
-          if (cand) {
-            const long long q = __ldg(reinterpret_cast<const long long*>(L.ep + (size_t)t * 256 + 32 + lane));
-            mq = q > mq ? q : mq;
+#pragma unroll
+        for (int j = 0; j < kMaxJ; j++) {
+          if (j >= J) continue;
+          for (int k = 0; k < EPL; k++) {
+            const int t = j * EPL + k;
+            if ((cb[j] >> k) & 1u) {
+              const long long q = __ldg(reinterpret_cast<const long long*>(L.ep + (size_t)t * 256 + 32 + lane));
+              mq = q > mq ? q : mq;
+            }
           }
         }
 #pragma unroll
@@ -401,7 +511,8 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
       for (int k = 0; k < EPL; k++) {
         const int t = j * EPL + k, m = t * 32 + lane;
         bool cand = m < M;
-        if (MASKED) cand = cand && ((__ldg(mrow + t) >> lane) & 1u);
+        if (LAT && lat_step >= 0) cand = (cb[j] >> k) & 1u;
+        else if (MASKED) cand = cand && ((__ldg(mrow + t) >> lane) & 1u);
         // match count: untouched slots hold 0; a touched slot holds the count modulo 2^bits (never 0 modulo)
         int c = wide_cnt ? (int)cnt16[cbase + k] : (int)cnt8[cbase + k];
         c = (c == 0 && ((anyj >> k) & 1u)) ? (wide_cnt ? 65536 : 256) : c;

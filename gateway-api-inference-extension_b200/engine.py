@@ -10,7 +10,7 @@ from . import _capi as capi
 from ._capi import Batch, Config, EppscoreError, LatencyParams, SCORER, Snapshot, Stats
 
 
-def default_config(scorers=None, **kw) -> Config:
+def default_config(scorers=None, filters=(), **kw) -> Config:
     """scorers: list of (kind name | int, weight) in profile order; default = reference default config
     (queue 2, kv 2, prefix 3; pkg/epp/config/loader/defaults.go:46-103)."""
     cfg = Config()
@@ -22,6 +22,11 @@ def default_config(scorers=None, **kw) -> Config:
         for i, (k, w) in enumerate(scorers):
             cfg.scorer_kind[i] = SCORER[k] if isinstance(k, str) else int(k)
             cfg.scorer_weight[i] = float(w)
+    cfg.n_filters = len(filters)  # [(kind, (params...))] device-side filters, in order
+    for i, (k, par) in enumerate(filters):
+        cfg.filter_kind[i] = int(k)
+        for j, v in enumerate(par):
+            cfg.filter_param[i][j] = float(v)
     for k, v in kw.items():
         if not hasattr(cfg, k):
             raise TypeError(f"unknown config field {k}")
@@ -153,7 +158,7 @@ class Engine:
     def schedule(self, R, *, prompt_bytes=None, prompt_off=None, prompt_len=None, model_seed=None, hashes_in=None,
                  n_hashes_in=None, hash_stride=0, adapter_id=None, cand_mask=None, dense_feat=None, dense_total=None,
                  block_chars=0, max_blocks=0, request_base=0, want_match=False, want_total=True, want_hashes=False,
-                 want_scores=False, input_tokens=None, ttft_slo=None, tpot_slo=None, want_pred=False,
+                 want_scores=False, input_tokens=None, ttft_slo=None, tpot_slo=None, want_pred=False, want_filter_mask=False,
                  device=False, stream=None, out=None):
         """Host mode (device=False): numpy in, returns dict of numpy outputs (copies inside the call).
         Device mode: CUDA tensors / raw pointers in; `out` must hold preallocated CUDA tensors
@@ -195,6 +200,7 @@ class Engine:
             b.hashes_out = a.ptr(out.get("hashes_out"), None)
             b.scores_out = a.ptr(out.get("scores_out"), None)
             b.pred_out = a.ptr(out.get("pred_out"), None)
+            b.filter_mask_out = a.ptr(out.get("filter_mask_out"), None)
             self._check(self._lib.eppscore_schedule_batch(self._h, C.byref(b)))
             return out
         M = self.M
@@ -210,6 +216,8 @@ class Engine:
             res["scores_out"] = np.zeros((R, M), np.float64)
         if want_pred:
             res["pred_out"] = np.zeros((R, M, 2), np.float64)
+        if want_filter_mask:
+            res["filter_mask_out"] = np.zeros((R, max((M + 31) // 32, 1)), np.uint32)
         for k, v in res.items():
             setattr(b, k, v.ctypes.data)
         self._check(self._lib.eppscore_schedule_batch(self._h, C.byref(b)))

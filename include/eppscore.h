@@ -91,6 +91,19 @@ typedef enum eppscore_pick_mode {
   EPPSCORE_PICK_RANDOM = 2           /* random-picker: picker/random/picker.go:85-101 — uniform over the candidates */
 } eppscore_pick_mode;
 
+/* Filter plugins evaluated on the device, in order, before the scorers and on top of batch.cand_mask (host-side Filters
+ * of any other kind keep reaching the engine as that mask).  Both need the latency scorer in the profile (they read the same
+ * per-pair predictions) and cannot be combined with the queue / running scorers.  Their rand.Float64() draws come from the
+ * counter-based generator of eppscore_pick_mode: draw of filter f for request r is keyed by (tie_seed, request_base + r, -(f+1)). */
+typedef enum eppscore_filter_kind {
+  /* prefix-cache-affinity-filter (filter/prefixcacheaffinity/plugin.go:105-151): params {affinityThreshold,
+   * explorationProbability, maxTTFTPenaltyMs}; reference defaults 0.80, 0.01, 5000 */
+  EPPSCORE_FILTER_PREFIX_AFFINITY = 1,
+  /* slo-headroom-tier-filter (filter/sloheadroomtier/plugin.go:82-137): params {epsilonExploreNeg}; default 0.01 */
+  EPPSCORE_FILTER_SLO_HEADROOM_TIER = 2
+} eppscore_filter_kind;
+#define EPPSCORE_MAX_FILTERS 4
+
 /* Scheduler profile + engine sizing.  Replaces SchedulerProfile{scorers, picker}
  * (pkg/epp/scheduling/scheduler_profile.go:41-98) and the approximateprefix config
  * (approximateprefix/types.go:77-141). Zero-initialise, set struct_size = sizeof, fill. */
@@ -109,7 +122,9 @@ typedef struct eppscore_config {
   int32_t lru_capacity_default; /* defaultLRUCapacityPerServer = 31250 (types.go:109) */
   double token_load_threshold;  /* token-load-scorer queueThresholdTokens; <= 0 ⇒ 4194304 (token_load.go:33,57-61) */
   int32_t pick_mode;            /* eppscore_pick_mode; default max-score */
-  int32_t reserved0;
+  int32_t n_filters;            /* device-side filters, see eppscore_filter_kind */
+  int32_t filter_kind[EPPSCORE_MAX_FILTERS];
+  double filter_param[EPPSCORE_MAX_FILTERS][3];
 } eppscore_config;
 
 /* Latency fold-in parameters: the cached Bayesian-ridge coefficients (MetricsResponse.Coefficients,
@@ -197,6 +212,7 @@ typedef struct eppscore_batch {
   const double *ttft_slo;      /* [R] x-slo-ttft-ms header value or 0 (predictedlatency/plugin.go:330-343) */
   const double *tpot_slo;      /* [R] x-slo-tpot-ms header value or 0 */
   double *pred_out;            /* optional [R*M*2]: predicted {TTFT, TPOT} per (request, endpoint) — diagnostics */
+  uint32_t *filter_mask_out;   /* optional [R*ceil(M/32)]: the candidate set left by the device-side filters — diagnostics */
 } eppscore_batch;
 
 typedef struct eppscore_stats {

@@ -30,10 +30,10 @@ def test_header_symbols_all_exported(pkg):
 
 def test_struct_sizes_match_header_layout(pkg):
     # natural C layout on x86-64 (computed by hand from include/eppscore.h)
-    assert C.sizeof(pkg.Config) == 4 + 4 + 32 + 64 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4
+    assert C.sizeof(pkg.Config) == 4 + 4 + 32 + 64 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 8 + 4 + 4 + 16 + 96
     assert C.sizeof(pkg.LatencyParams) == 4 + 4 + 12 * 8 + 8 + 4 + 4 + 5 * 8
     assert C.sizeof(pkg.Snapshot) == 16 + 7 * 8 + 4 * 8 + 8 + 8 + 4 * 8
-    assert C.sizeof(pkg.Batch) == 16 + 8 + 6 * 8 + 16 + 4 * 8 + 7 * 8 + 8 + 4 * 8
+    assert C.sizeof(pkg.Batch) == 16 + 8 + 6 * 8 + 16 + 4 * 8 + 7 * 8 + 8 + 5 * 8
     assert C.sizeof(pkg.Stats) == 8 + 8 + 8 + 5 * 8
 
 

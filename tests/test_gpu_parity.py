@@ -939,3 +939,91 @@ def test_latency_counts_prompt_fields_on_device(pkg):
     assert_same(got, want, ("pick", "pick_score", "tie_count", "scores_out"))
     assert toks.max() > 300
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------ device-side filters
+def test_filters_reference_cases_on_device(pkg, golden):
+    """The reference's filter tests (sloheadroomtier/plugin_test.go:43-115, prefixcacheaffinity/plugin_test.go:48-105) through
+    the engine: the surviving candidate set is exactly the one the Go tests expect."""
+    from tests.test_oracle_golden import filter_case_inputs
+    for kind, key in (("tier", "slo_headroom_tier"), ("affinity", "prefix_cache_affinity")):
+        for c in golden["filters"][key]["cases"]:
+            inp = filter_case_inputs(kind, c)
+            M = inp["M"]
+            filters = [(k, par) for k, par in inp["filters"]]
+            eng = pkg.Engine(pkg.default_config([("latency", 1.0)], filters=filters, max_endpoints=M, max_blocks=128, tie_seed=3,
+                                                prefix_capacity=1 << 12))
+            eng.set_latency_params(pkg.latency_params(**inp["lat"]))
+            eng.set_snapshot(np.zeros(M), np.array(inp["queue"], np.int64), np.array(inp["running"], np.int64))
+            for m, n in inp["adds"]:
+                eng.prefix_add(inp["hashes"][:n], m)
+            res = eng.schedule(1, hashes_in=inp["hashes"][None, :].copy(), n_hashes_in=np.array([100], np.uint16),
+                               ttft_slo=np.array([1000.0]), tpot_slo=np.array([1000.0]), want_filter_mask=True)
+            kept = [m for m in range(M) if (res["filter_mask_out"][0][m >> 5] >> (m & 31)) & 1]
+            assert kept == c["want"], (c["name"], kept)
+            assert res["pick"][0] in kept
+            eng.close()
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_latency_chart_profile_parity(pkg, masked):
+    """The latency profile of the reference chart (config/charts/epplib/templates/_config.yaml:66-75) entirely on the device:
+    strict affinity filter -> slo-headroom-tier filter -> loose affinity filter -> latency scorer -> weighted-random picker.
+    Exploration probabilities are raised so that every branch is taken; filter results, picks, scores: bit-equal to the oracle."""
+    M, R = 300, 1024
+    lkw = dict(LAT_COEF, streaming_mode=1)
+    filt = [(pkg.FILTER_PREFIX_AFFINITY, (0.95, 0.2, 40.0)), (pkg.FILTER_SLO_HEADROOM_TIER, (0.3,)),
+            (pkg.FILTER_PREFIX_AFFINITY, (0.50, 0.1, 5000.0))]
+    scorers = [("latency", 1.0)]
+    eng = pkg.Engine(pkg.default_config(scorers, filters=filt, max_endpoints=M, max_blocks=16, pick_mode=pkg.PICK_WEIGHTED_RANDOM, tie_seed=21,
+                                        prefix_capacity=1 << 15))
+    eng.set_latency_params(pkg.latency_params(**lkw))
+    rng = np.random.Generator(np.random.PCG64(31))
+    sd = synth_snapshot(M, seed=6)
+    sd["min_tpot_slo"] = rng.choice([0.0, 22.0, 60.0], M)
+    sd["dispatched"] = rng.integers(0, 3, M).astype(np.int32)
+    sd["prefill_role"] = (rng.random(M) < 0.1).astype(np.uint8)
+    eng.set_snapshot(**sd)
+    snap = o.SnapshotData(**sd)
+    prof = o.make_profile([(o.SCORER_LATENCY, 1.0)], latency=o.make_latency_params(**lkw), pick_mode=o.PICK_WEIGHTED_RANDOM, tie_seed=21,
+                          filters=[(k, par) for k, par in filt])
+    prompts, off, _ = synth_prompts(R, prompt_len=1024, groups=6, shared=1024 - 64, seed=8)  # 15 of 16 blocks shared: scores up to 1.0
+    seeds = np.full(R, eng.model_seed("m"), np.uint64)
+    idx = o.Index()
+    # warm-up: every request lands on a uniformly random endpoint, so each shared prefix is cached on many endpoints;
+    # half of the warm-up prompts are truncated to 8 blocks so that partial matches (score 0.5) exist as well
+    warm_prof = o.make_profile([(o.SCORER_KV_CACHE, 1.0)], pick_mode=o.PICK_RANDOM, tie_seed=2)
+    warm = o.schedule_batch(snap, warm_prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds, max_blocks=16,
+                            want_hashes=True, n_threads=8)
+    nblk = np.where(np.arange(R) % 2 == 0, warm["total_blocks"], np.minimum(warm["total_blocks"], 8)).astype(np.uint16)
+    idx.commit(warm["pick"], warm["hashes_out"], nblk)
+    eng.commit_picks(warm["pick"], warm["hashes_out"], nblk)
+    kw = dict(prompt_bytes=prompts, prompt_off=off, model_seed=seeds, input_tokens=rng.integers(0, 3000, R).astype(np.int32),
+              ttft_slo=rng.choice([0.0, 120.0, 180.0, 400.0], R), tpot_slo=rng.choice([0.0, 22.0, 30.0], R))
+    if masked:
+        mask = rng.integers(0, 2 ** 32, (R, (M + 31) // 32), dtype=np.uint64).astype(np.uint32)
+        mask[0, :] = 0
+        mask[1, :] = 0
+        mask[1, 3] = 1 << 7
+        kw["cand_mask"] = mask
+    got = eng.schedule(R, want_scores=True, want_filter_mask=True, want_match=True, **kw)
+    want = o.schedule_batch(snap, prof, idx, R, max_blocks=16, want_scores=True, want_filter_mask=True, want_match=True, n_threads=8, **kw)
+    lastw = np.uint32((1 << (M % 32)) - 1) if M % 32 else np.uint32(0xFFFFFFFF)
+    gm, wm = got["filter_mask_out"].copy(), want["filter_mask_out"].copy()
+    gm[:, -1] &= lastw
+    wm[:, -1] &= lastw
+    assert np.array_equal(got["match_blocks"], want["match_blocks"])
+    assert np.array_equal(gm, wm)
+    assert_same(got, want, ("pick", "pick_score", "tie_count"))
+    # the weighted scores of the surviving candidates (the oracle reports NaN outside the filtered set, the engine outside the input mask)
+    keep = np.zeros((R, M), bool)
+    for w in range(gm.shape[1]):
+        bits = (gm[:, w:w + 1] >> np.arange(32, dtype=np.uint32)) & 1
+        keep[:, w * 32:(w + 1) * 32] = bits[:, : min(32, M - w * 32)].astype(bool)
+    assert np.array_equal(got["scores_out"][keep].view(np.uint64), want["weighted_out"][keep].view(np.uint64))
+    sizes = keep.sum(axis=1)
+    full = (~np.isnan(want["weighted_out"]) | keep).sum(axis=1)
+    assert (sizes[2:] >= 1).all() and (sizes < (M if not masked else M)).any()   # the filters did narrow some requests
+    fast = eng.schedule(R, **kw)
+    assert_same(fast, want, ("pick", "pick_score", "tie_count"))
+    eng.close()
