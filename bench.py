@@ -575,6 +575,33 @@ def run_gpu(args):
                 o.schedule_batch(snap_l, prof_l, idx, Rl, hashes_in=hh[:Rl].cpu().numpy(), n_hashes_in=nn[:Rl].cpu().numpy(),
                                  max_blocks=MAX_BLOCKS, n_threads=os.cpu_count() or 1, **{k: v[:Rl] for k, v in lat_req.items()})
                 extra["latency_fold_in"]["cpu_port_picks_per_s"] = Rl / (time.perf_counter() - t0)
+            # the reference chart's whole latency profile on the device: strict affinity filter -> slo-headroom-tier filter ->
+            # loose affinity filter -> latency scorer -> weighted-random picker (config/charts/epplib/templates/_config.yaml:66-75)
+            try:
+                chart_filters = [(pkg.FILTER_PREFIX_AFFINITY, (0.99, 0.01, 5000.0)), (pkg.FILTER_SLO_HEADROOM_TIER, (0.01,)),
+                                 (pkg.FILTER_PREFIX_AFFINITY, (0.80, 0.01, 5000.0))]
+                eng_c = pkg.Engine(pkg.default_config([("latency", 1.0)], filters=chart_filters, max_endpoints=M, max_adapters=A,
+                                                      block_chars=BLOCK_CHARS, max_blocks=MAX_BLOCKS, prefix_capacity=1 << 19,
+                                                      pick_mode=pkg.PICK_WEIGHTED_RANDOM, tie_seed=11), device=local)
+                eng_c.set_latency_params(pkg.latency_params(**lat_coef))
+                eng_c.set_snapshot(views["kv_usage"], views["queue"], views["running"], device=True, stream=sptr, M=M, lora_words=0,
+                                   **lat_ep_dev)
+                if rank == 0:
+                    eng_c.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+
+                def chart_only(i):
+                    hh, nn = hsets_dev[i % NSETS]
+                    eng_c.schedule(R, hashes_in=hh, n_hashes_in=nn, hash_stride=MAX_BLOCKS, request_base=rank * R, device=True,
+                                   stream=sptr, out=out, **lat_req_dev)
+
+                t_c = time_kernel(chart_only, iters=6)
+                extra["latency_chart_profile"] = {"kernel": "score_matrix_kernel<runtime sequence; LAT; 3 filters; A-Res>",
+                                                  "profile": "affinity 0.99 -> slo-headroom-tier -> affinity 0.80 -> latency-scorer -> weighted-random-picker",
+                                                  "us": t_c * 1e6, "picks_per_s": R / t_c, "pairs_per_s": R * M / t_c}
+                eng_c.close()
+            except Exception as ex:  # noqa: BLE001
+                extra["latency_chart_profile"] = {"error": repr(ex)}
+
             # len(strings.Fields(prompt)) on the device: the prompt stream once more (HBM-bound)
             cnt = torch.empty(R, dtype=torch.int32, device=dev)
 

@@ -181,6 +181,23 @@ struct Filter {
                                    const std::vector<int>& candidates) = 0;
 };
 
+// Filters the engine evaluates on the device (include/eppscore.h: eppscore_filter_kind).  They are descriptors like the
+// scorers; any other Filter subclass runs on the host and reaches the engine as the candidate mask.  Device filters
+// run AFTER the host filters, in the order given to WithDeviceFilters.
+struct DeviceFilter {
+  int32_t Kind;
+  double Param[3];
+};
+// prefix-cache-affinity-filter (filter/prefixcacheaffinity/plugin.go:52-62): defaults 0.80 / 0.01 / 5000
+inline DeviceFilter PrefixCacheAffinityFilter(double affinityThreshold = 0.80, double explorationProbability = 0.01,
+                                              double maxTTFTPenaltyMs = 5000) {
+  return DeviceFilter{EPPSCORE_FILTER_PREFIX_AFFINITY, {affinityThreshold, explorationProbability, maxTTFTPenaltyMs}};
+}
+// slo-headroom-tier-filter (filter/sloheadroomtier/plugin.go:50-52): default epsilonExploreNeg 0.01
+inline DeviceFilter SLOHeadroomTierFilter(double epsilonExploreNeg = 0.01) {
+  return DeviceFilter{EPPSCORE_FILTER_SLO_HEADROOM_TIER, {epsilonExploreNeg, 0, 0}};
+}
+
 struct MaxScorePicker {
   int MaxNumOfEndpoints = 1;  // picker.DefaultMaxNumOfEndpoints (picker/common.go:36); only 1 is supported on the GPU path
   int Mode = EPPSCORE_PICK_MAX_SCORE;
@@ -195,6 +212,8 @@ class SchedulerProfile {
   SchedulerProfile& WithFilters(std::vector<std::shared_ptr<Filter>> f) { filters_ = std::move(f); return *this; }
   SchedulerProfile& WithScorers(std::vector<WeightedScorer> s) { scorers_ = std::move(s); return *this; }
   SchedulerProfile& WithPicker(MaxScorePicker p) { picker_ = p; return *this; }
+  SchedulerProfile& WithDeviceFilters(std::vector<DeviceFilter> f) { device_filters_ = std::move(f); return *this; }
+  const std::vector<DeviceFilter>& device_filters() const { return device_filters_; }
   SchedulerProfile& WithPredictedLatencyProducer(std::shared_ptr<PredictedLatencyProducer> p) { producer_ = std::move(p); return *this; }
   const std::shared_ptr<PredictedLatencyProducer>& producer() const { return producer_; }
   const std::vector<std::shared_ptr<Filter>>& filters() const { return filters_; }
@@ -206,6 +225,7 @@ class SchedulerProfile {
   std::vector<WeightedScorer> scorers_;
   MaxScorePicker picker_;
   std::shared_ptr<PredictedLatencyProducer> producer_;
+  std::vector<DeviceFilter> device_filters_;
 };
 
 // approximateprefix config (types.go:77-141)
@@ -252,6 +272,12 @@ class Scheduler {
     c.max_adapters = cfg.MaxAdapters;
     c.prefix_capacity = cfg.PrefixCapacity;
     c.pick_mode = cfg.Profile.picker().Mode;
+    if (cfg.Profile.device_filters().size() > EPPSCORE_MAX_FILTERS) throw SchedulingError("too many device filters");
+    c.n_filters = (int32_t)cfg.Profile.device_filters().size();
+    for (size_t i = 0; i < cfg.Profile.device_filters().size(); i++) {
+      c.filter_kind[i] = cfg.Profile.device_filters()[i].Kind;
+      for (int q = 0; q < 3; q++) c.filter_param[i][q] = cfg.Profile.device_filters()[i].Param[q];
+    }
     c.tie_mode = cfg.TieMode;
     c.tie_seed = cfg.TieSeed;
     if (eppscore_create(cfg.Device, &c, &eng_) != EPPSCORE_OK) throw SchedulingError(std::string("eppscore_create: ") + eppscore_last_error(nullptr));

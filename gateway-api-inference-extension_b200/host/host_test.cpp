@@ -229,6 +229,32 @@ static int LatencyPick(const std::vector<LatEp>& info, double* score, int* ties)
   return te.Index;
 }
 
+// slo-headroom-tier-filter through the host mirror (sloheadroomtier/plugin_test.go:80-101): with both tiers present the
+// positive tier is selected (epsilon 0) resp. the negative one (epsilon 1)
+static int TierFilterPick(double epsilon) {
+  SchedulerConfig c;
+  auto prod = std::make_shared<PredictedLatencyProducer>();
+  prod->StreamingMode = true;
+  prod->TTFTCoeffs["num_request_waiting"] = 1.0;
+  prod->TPOTCoeffs["num_request_running"] = 1.0;
+  c.Profile.WithScorers({NewWeightedScorer(std::make_shared<LatencyScorer>(), 1)}).WithPicker(MaxScorePicker{})
+      .WithPredictedLatencyProducer(prod).WithDeviceFilters({SLOHeadroomTierFilter(epsilon)});
+  c.MaxEndpoints = 8;
+  const double th[3] = {100, 200, -100}, ph[3] = {50, 80, -50};
+  std::vector<Endpoint> eps;
+  for (int i = 0; i < 3; i++) {
+    Metrics m;
+    m.WaitingQueueSize = 1000 - (int)th[i];
+    m.RunningRequestsSize = 1000 - (int)ph[i];
+    eps.push_back(NewEndpoint("pod" + std::to_string(i), m, "default"));
+  }
+  Scheduler s(c);
+  InferenceRequest q{"f", "m", "", ""};
+  q.Headers["x-slo-ttft-ms"] = "1000";
+  q.Headers["x-slo-tpot-ms"] = "1000";
+  return s.Schedule(q, eps).ProfileResults.at("default").TargetEndpoints[0].Index;
+}
+
 static void TestLatencyScorer() {
   double sc;
   int ties;
@@ -243,6 +269,8 @@ static void TestLatencyScorer() {
   // busy variants: the least severe non-empty bucket (negTPOTonly > negTTFTonly > bothNeg, :209-238) is the only one scored
   CHECK(LatencyPick({{-50, -10, 3}, {-30, 5, 2}, {10, -8, 1}}, &sc, &ties) == 2);
   CHECK(LatencyPick({{-50, -10, 3}, {-30, 5, 2}}, &sc, &ties) == 1);
+  CHECK(TierFilterPick(0.0) != 2);  // positive tier kept: the overloaded pod is filtered out
+  CHECK(TierFilterPick(1.0) == 2);  // epsilon-explore: only the negative tier is left
   // TestScoreCompositeFallback (:190-208): no predictions => kv/queue/prefix composite
   {
     SchedulerConfig c;
