@@ -52,14 +52,21 @@ __global__ void __launch_bounds__(kFieldWarps * 32) count_fields_kernel(const ui
       }
       const uint32_t w[5] = {before | (mine[0] << 16), (mine[0] >> 16) | (mine[1] << 16), (mine[1] >> 16) | (mine[2] << 16),
                              (mine[2] >> 16) | (mine[3] << 16), (mine[3] >> 16) | (after << 16)};
-      uint32_t sp = 0;  // bit i: window byte i is a space byte
-      const bool any_high = ((w[0] | w[1] | w[2] | w[3] | w[4]) & 0x80808080u) != 0;
+      // ASCII spaces (\t \n \v \f \r and ' '), four bytes per word: for the low 7 bits v of a byte, bit 7 of v+0x77 is set iff
+      // v >= 9, of v+0x72 iff v >= 14, of ~((v^0x20)+0x7f) iff v == 0x20; bytes >= 0x80 are masked out; the four flag
+      // bits are gathered with one multiply
+      uint32_t my_sp = 0;
 #pragma unroll
-      for (int i = 2; i < 18; i++) {
-        const uint32_t b = byte_at(w, i);
-        if ((b - 9u) < 5u || b == 32u) sp |= 1u << i;
+      for (int q = 0; q < 4; q++) {
+        const uint32_t x = mine[q], v = x & 0x7f7f7f7fu;
+        const uint32_t in_9_13 = (v + 0x77777777u) & ~(v + 0x72727272u);
+        const uint32_t is_20 = ~((v ^ 0x20202020u) + 0x7f7f7f7fu);
+        const uint32_t m = (in_9_13 | is_20) & ~x & 0x80808080u;
+        my_sp |= ((((m >> 7) * 0x00204081u) >> 21) & 0xfu) << (4 * q);
       }
-      if (any_high) {
+      // multi-byte space runes: only when the 20-byte window holds a byte >= 0x80 at all
+      if (((w[0] | w[1] | w[2] | w[3] | w[4]) & 0x80808080u) != 0) {
+        uint32_t sp = 0;  // bit i: window byte i lies inside a space rune
         for (int i = 0; i < 18; i++) {
           const uint32_t b0 = byte_at(w, i), b1 = byte_at(w, i + 1), b2 = byte_at(w, i + 2);
           if (b0 == 0xC2u && (b1 == 0x85u || b1 == 0xA0u)) sp |= 3u << i;
@@ -68,9 +75,9 @@ __global__ void __launch_bounds__(kFieldWarps * 32) count_fields_kernel(const ui
                           (b0 == 0xE2u && b1 == 0x81u && b2 == 0x9Fu) || (b0 == 0xE3u && b1 == 0x80u && b2 == 0x80u);
           if (m3) sp |= 7u << i;
         }
+        my_sp |= (sp >> 2) & 0xffffu;
       }
       // (bytes past the end of the prompt read as 0: never a space, never part of a pattern — and masked out below)
-      const uint32_t my_sp = (sp >> 2) & 0xffffu;
       uint32_t prev = __shfl_up_sync(0xffffffffu, my_sp >> 15, 1);  // is the previous lane's last byte a space?
       if (lane == 0) prev = carry_space;
       const int64_t left = n - o;
