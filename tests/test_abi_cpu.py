@@ -81,3 +81,20 @@ def test_invalid_config_rejected(pkg):
     cfg.scorer_kind[0] = 99
     assert pkg.lib().eppscore_create(0, C.byref(cfg), C.byref(h)) == -1
     assert b"scorer" in pkg.lib().eppscore_last_error(None)
+    # profile validation happens before any device is touched, so it is checkable on a CPU-only box
+    L = pkg.lib()
+
+    def rejected(cfg, needle):
+        assert L.eppscore_create(0, C.byref(cfg), C.byref(h)) == -1
+        assert needle in L.eppscore_last_error(None), L.eppscore_last_error(None)
+
+    rejected(pkg.default_config([("latency", 1.0), ("latency", 2.0)]), b"at most one latency scorer")
+    rejected(pkg.default_config([("kv", 1.0)], pick_mode=7), b"pick_mode")
+    rejected(pkg.default_config([("kv", 1.0)], filters=[(pkg.FILTER_SLO_HEADROOM_TIER, (0.01,))]), b"need the latency scorer")
+    rejected(pkg.default_config([("latency", 1.0), ("queue", 1.0)], filters=[(pkg.FILTER_SLO_HEADROOM_TIER, (0.01,))]), b"queue / running")
+    rejected(pkg.default_config([("latency", 1.0)], filters=[(pkg.FILTER_SLO_HEADROOM_TIER, (1.5,))]), b"epsilonExploreNeg")   # sloheadroomtier/plugin.go:66-68
+    rejected(pkg.default_config([("latency", 1.0)], filters=[(pkg.FILTER_PREFIX_AFFINITY, (1.2, 0.0, 0.0))]), b"prefix-cache-affinity")  # prefixcacheaffinity/plugin.go:80-91
+    rejected(pkg.default_config([("latency", 1.0)], filters=[(9, (0.0,))]), b"unknown filter kind")
+    cfg = pkg.default_config([("latency", 1.0)])
+    cfg.n_filters = 9
+    rejected(cfg, b"n_filters")
