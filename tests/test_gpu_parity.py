@@ -632,6 +632,47 @@ def test_full_size_headline_parity(pkg):
     eng.close()
 
 
+FULL_CONFIGS = [
+    # BASELINE.json configs[1..4] at their full per-GPU sizes: name, M, R, scorers, prompts?, adapters?, request_base
+    ("B_64K_x_256_kv_queue", 256, 65536, [("kv", 1), ("queue", 1)], False, False, 0),
+    ("C_64K_x_512_prefix_2KB", 512, 65536, [("queue", 2), ("kv", 2), ("prefix", 3)], True, False, 0),
+    ("D_256K_x_1024_lora_kv", 1024, 262144, [("lora", 1), ("kv", 1)], False, True, 0),
+    ("E_shard_128K_x_4096_all_four", 4096, 131072, [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)], True, True, 3 * 131072),
+]
+
+
+@pytest.mark.parametrize("name,M,R,scorers,use_prompts,use_adapters,base", FULL_CONFIGS, ids=[c[0] for c in FULL_CONFIGS])
+def test_full_size_baseline_configs(pkg, name, M, R, scorers, use_prompts, use_adapters, base):
+    """Every request of the full-size configuration against the oracle (picks, float64 scores, tie counts, block totals);
+    E is one GPU's shard of the 1M x 4096 configuration (request_base = its offset in the global batch)."""
+    eng = make_engine(pkg, scorers, M, prefix_capacity=1 << 18, tie_mode=1, tie_seed=8)
+    sd = synth_snapshot(M, seed=12)
+    eng.set_snapshot(**sd)
+    snap, prof = o.SnapshotData(**sd), profile_of(pkg, scorers, tie_mode=1, tie_seed=8)
+    kw, idx = {}, None
+    if use_prompts:
+        idx = o.Index()
+        seed = eng.model_seed("full")
+        nwarm = 4 * M
+        wp, woff, _ = synth_prompts(nwarm, seed=12, prefix_seed=5)
+        wkw = dict(adapter_id=zipf_adapters(nwarm, seed=13)) if use_adapters else {}
+        warm = o.schedule_batch(snap, prof, idx, nwarm, prompt_bytes=wp, prompt_off=woff, model_seed=np.full(nwarm, seed, np.uint64),
+                                want_hashes=True, n_threads=32, **wkw)
+        idx.commit(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+        eng.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+        prompts, off, _ = synth_prompts(R, seed=14, prefix_seed=5)
+        kw.update(prompt_bytes=prompts, prompt_off=off, model_seed=np.full(R, seed, np.uint64))
+    if use_adapters:
+        kw["adapter_id"] = zipf_adapters(R, seed=15)
+    got = eng.schedule(R, request_base=base, **kw)
+    want = o.schedule_batch(snap, prof, idx, R, request_base=base, n_threads=32, **kw)
+    assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks"))
+    assert (got["pick"] >= 0).all()
+    if use_prompts:
+        assert (got["total_blocks"] == 32).all()
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------ latency fold-in (SURVEY §8 f1), token load (f2)
 LAT_COEF = dict(ttft_intercept=12.5, ttft_kv=80.0, ttft_input=0.031, ttft_waiting=7.25, ttft_running=1.5,
                 ttft_prefix=-40.0, tpot_intercept=9.0, tpot_kv=11.0, tpot_input=0.0007, tpot_waiting=0.9,
