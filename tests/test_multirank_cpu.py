@@ -52,7 +52,8 @@ def _worker_latency_weighted_random(rank, world, port, q):
     lo, hi = sharding.shard_range(R_TOTAL, rank, world)
     osnap = o.SnapshotData(**snap)
     prof = o.make_profile([(o.SCORER_LATENCY, 1.0)], tie_seed=5, pick_mode=o.PICK_WEIGHTED_RANDOM,
-                          latency=o.make_latency_params(**LAT))
+                          latency=o.make_latency_params(**LAT),
+                          filters=[(o.FILTER_SLO_HEADROOM_TIER, (0.3,))])  # the filter's draw is keyed by the global request index too
     res = o.schedule_batch(osnap, prof, None, hi - lo, request_base=lo, **{k: v[lo:hi] for k, v in req.items()})
     width = (R_TOTAL + world - 1) // world + 1
     mine = torch.full((width,), -7, dtype=torch.int32)
