@@ -154,6 +154,13 @@ def test_single_scorer_tables(pkg, golden):
         got = eng.schedule(1, want_scores=True)["scores_out"][0]
         assert np.allclose(got, c["want"], atol=golden["queue_scorer"]["tolerance"], rtol=0)
         eng.close()
+    for c in golden["running_scorer"]["cases"]:
+        n = len(c["running"])
+        eng = make_engine(pkg, [("running", 1.0)], n)
+        eng.set_snapshot(np.zeros(n), np.zeros(n, np.int64), np.array(c["running"], np.int64))
+        got = eng.schedule(1, want_scores=True)["scores_out"][0]
+        assert np.allclose(got, c["want"], atol=golden["running_scorer"]["tolerance"], rtol=0)
+        eng.close()
     for c in golden["lora_scorer"]["cases"]:
         if not c["endpoints"]:
             continue

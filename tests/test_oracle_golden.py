@@ -77,6 +77,14 @@ def test_queue_scorer(golden):
     assert got[0] == 0.0 and got[1] == 1.0 and np.isnan(got[2])
 
 
+def test_running_requests_scorer(golden):
+    g = golden["running_scorer"]
+    for c in g["cases"]:
+        n = len(c["running"])
+        snap = o.SnapshotData(kv_usage=np.zeros(n), queue=np.zeros(n, np.int64), running=c["running"])
+        assert np.allclose(o.score_single("running", snap), c["want"], atol=g["tolerance"], rtol=0)
+
+
 def test_lora_scorer(golden):
     g = golden["lora_scorer"]
     for c in g["cases"]:
