@@ -561,3 +561,32 @@ def test_filter_draws_are_bernoulli():
     pos = (res["filter_mask_out"][:, 0] == 0b011)
     assert (neg | pos).all() and abs(neg.mean() - 0.3) < 0.02
     assert (res["pick"][neg] == 2).all() and (res["pick"][pos] != 2).all()
+
+
+# ---------------------------------------------------------------- the latency kernel's reciprocal fast path
+def test_latency_fast_path_never_changes_the_quantised_weight():
+    """score_matrix.cu normalises with d * rcp(range) instead of d / range and redoes a pair exactly only when
+    v = (1 - combined) * 100 (or combined * 100) lies within 1e-9 of an integer.  Claim: outside that band the truncated
+    weight int(v) is identical.  Checked here in IEEE float64 (numpy: every operation individually rounded, like the _rn
+    intrinsics) on adversarial inputs — ranges over 15 decades, weights on and off the simplex, headrooms at the extremes."""
+    rng = np.random.Generator(np.random.PCG64(2024))
+    n = 2_000_000
+    worst = 0.0
+    for most in (False, True):
+        rg_t = 10.0 ** rng.uniform(-8.9, 6, n)
+        rg_p = 10.0 ** rng.uniform(-8.9, 6, n)
+        # numerators d = |h| - min in [0, range], with mass at the ends and on k/100 grid points
+        frac_t = np.where(rng.random(n) < 0.3, rng.integers(0, 101, n) / 100.0, rng.random(n))
+        frac_p = np.where(rng.random(n) < 0.3, rng.integers(0, 101, n) / 100.0, rng.random(n))
+        d_t, d_p = np.minimum(frac_t * rg_t, rg_t), np.minimum(frac_p * rg_p, rg_p)
+        alpha = np.where(rng.random(n) < 0.5, 0.8, rng.random(n))
+        beta = np.where(rng.random(n) < 0.5, 1.0 - alpha, rng.random(n))
+        exact_c = alpha * (d_t / rg_t) + beta * (d_p / rg_p)
+        fast_c = alpha * (d_t * (1.0 / rg_t)) + beta * (d_p * (1.0 / rg_p))
+        v_exact = exact_c * 100.0 if most else (1.0 - exact_c) * 100.0
+        v_fast = fast_c * 100.0 if most else (1.0 - fast_c) * 100.0
+        worst = max(worst, float(np.abs(v_exact - v_fast).max()))
+        decided = np.abs(v_fast - np.rint(v_fast)) >= 1e-9          # the kernel keeps the fast result only here
+        assert np.array_equal(np.trunc(v_fast[decided]), np.trunc(v_exact[decided]))
+        assert decided.mean() > 0.5                                  # and the exact redo stays the rare path
+    assert worst < 2e-13, worst
