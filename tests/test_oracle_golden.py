@@ -590,3 +590,24 @@ def test_latency_fast_path_never_changes_the_quantised_weight():
         assert np.array_equal(np.trunc(v_fast[decided]), np.trunc(v_exact[decided]))
         assert decided.mean() > 0.5                                  # and the exact redo stays the rare path
     assert worst < 2e-13, worst
+
+
+def test_composite_fast_path_never_changes_the_rounded_weight():
+    """Same argument for the composite fallback (plugin.go:346-360): relQueue via d * rcp(maxQ) instead of d / maxQ, exact
+    redo only when 100 * composite is within 1e-9 of a half-integer (math.Round's decision points) or beyond 1e4."""
+    rng = np.random.Generator(np.random.PCG64(7))
+    n = 2_000_000
+    maxq = rng.integers(1, 100000, n).astype(np.float64)
+    dq = np.floor(rng.random(n) * (maxq + 1)).clip(0, maxq)
+    w = rng.random((3, n))
+    w /= w.sum(axis=0)                      # the normalised weights (each in [0,1])
+    kv_free = np.where(rng.random(n) < 0.2, rng.integers(0, 101, n) / 100.0, rng.random(n))
+    prefix = rng.integers(0, 33, n) / 32.0
+    ck, pt = w[0] * kv_free, w[2] * prefix
+    v_exact = 100.0 * ((ck + w[1] * (dq / maxq)) + pt)
+    v_fast = 100.0 * ((ck + w[1] * (dq * (1.0 / maxq))) + pt)
+    assert np.abs(v_exact - v_fast).max() < 1e-12
+    decided = np.abs((v_fast - np.floor(v_fast)) - 0.5) >= 1e-9
+    half_away = lambda x: np.floor(x + 0.5)  # == math.Round for x >= 0
+    assert np.array_equal(half_away(v_fast[decided]), half_away(v_exact[decided]))
+    assert decided.mean() > 0.99
