@@ -611,3 +611,45 @@ def test_composite_fast_path_never_changes_the_rounded_weight():
     half_away = lambda x: np.floor(x + 0.5)  # == math.Round for x >= 0
     assert np.array_equal(half_away(v_fast[decided]), half_away(v_exact[decided]))
     assert decided.mean() > 0.99
+
+
+# ---------------------------------------------------------------- the identity behind the sparse pick kernel (pick_sparse.cu)
+def test_sparse_pick_identity_holds_on_the_oracle():
+    """pick_sparse.cu never scores the endpoints without a prefix match: it combines the per-adapter summary of the
+    zero-match score map G[a][m] with the few "exception" endpoints.  The claim (top of pick_sparse.cu), checked here purely
+    on the CPU oracle's float64 score maps for tie-heavy snapshots:
+        max_m S = max(gmax, T),  T = max over exceptions of S
+        T > gmax : arg-max set = exceptions attaining T
+        T < gmax : arg-max set = precomputed set (no exception belongs to it)
+        T == gmax: (precomputed set minus its exception members) + exceptions attaining gmax"""
+    from tests.helpers import synth_snapshot, zipf_adapters
+    rng = np.random.Generator(np.random.PCG64(99))
+    M, R = 160, 600
+    for scorers in ([("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)], [("kv", 1), ("prefix", 0.5)], [("lora", 1), ("prefix", 2), ("kv", 1)]):
+        sd = synth_snapshot(M, seed=int(rng.integers(0, 1000)), tie_heavy=True)
+        sd["kv_usage"] = np.round(sd["kv_usage"], 1)
+        snap = o.SnapshotData(**sd)
+        prof = o.make_profile(kinds(scorers))
+        ad = zipf_adapters(R, seed=1)
+        total = 8
+        for r in range(R):
+            match = np.zeros(M, np.uint16)
+            nexc = int(rng.integers(0, 12))
+            exc = rng.choice(M, nexc, replace=False)
+            match[exc] = rng.integers(1, total + 1, nexc)
+            full = o.schedule_one(snap, prof, adapter_id=int(ad[r]), match=match, total=total)
+            zero = o.schedule_one(snap, prof, adapter_id=int(ad[r]), match=np.zeros(M, np.uint16), total=total)
+            S, G = full["weighted"], zero["weighted"]
+            assert (S[exc] >= G[exc]).all()                    # monotonicity: a match can only raise a score (weight >= 0)
+            gmax, gset = G.max(), set(np.nonzero(G == G.max())[0])
+            T = S[exc].max() if nexc else -np.inf
+            assert full["score"] == max(gmax, T)
+            eset = set(int(e) for e in exc)
+            if T > gmax:
+                want = {int(e) for e in exc if S[e] == T}
+            elif T < gmax:
+                assert not (gset & eset) or all(S[e] < gmax or G[e] < gmax for e in gset & eset)
+                want = {m for m in gset if m not in eset} | {int(e) for e in exc if S[e] == gmax}
+            else:
+                want = {m for m in gset if m not in eset} | {int(e) for e in exc if S[e] == gmax}
+            assert set(full["tie_set"]) == want, (r, scorers)
