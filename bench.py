@@ -246,7 +246,9 @@ def run_gpu(args):
     o = osnap = prof = idx = seed = warm = None
     if rank == 0:
         o, osnap, prof, idx, seed, warm = oracle_setup(snap)
+        t_commit = time.perf_counter()
         eng.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+        t_commit = time.perf_counter() - t_commit  # PreRequest for 4*M requests: host LRUs + interned rows (one core)
     info = eng.prefix_image_info()
     meta = torch.tensor(info["meta"], dtype=torch.int64, device=dev)
     seed_t = torch.from_numpy(np.array([seed if rank == 0 else 0], np.uint64).view(np.int64)).to(dev)
@@ -411,6 +413,9 @@ def run_gpu(args):
 
     extra = {}
     if rank == 0:
+        extra["commit_picks"] = {"requests": 4 * M, "hashes_per_request": 32, "host_seconds": t_commit,
+                                 "picks_per_s": 4 * M / t_commit if t_commit > 0 else None,
+                                 "note": "eppscore_commit_picks (PreRequest): host-side, off the scoring path like the reference's goroutine"}
         peak, peak_src = peaks()
         traffic = {}
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")

@@ -182,6 +182,14 @@ class PrefixIndex {
     // row 0 is the permanent empty set: every new hash starts there (and returns there when emptied)
     rows_.assign((size_t)geo_.row_words, 0u);
     row_ref_.assign(1, 1u);
+    row_hash_.assign(1, 0ULL);  // row 0 = the empty set
+    zob_.resize((size_t)geo.Mpad);
+    for (size_t i = 0; i < zob_.size(); i++) {  // splitmix64: one fixed random word per endpoint bit
+      uint64_t z = 0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1);
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+      zob_[i] = z ^ (z >> 31);
+    }
     n_rows_ = 1;
     word_dirty_flag_.assign((rows_.size() + 7) / 8, 0);
   }
@@ -314,14 +322,15 @@ class PrefixIndex {
   // ---- row interning: hashes whose endpoint SETS are identical share one bitset row, so the pick kernel can
   // run-length merge a request's consecutive matched blocks by row id and read each distinct set once.
   // (Consecutive blocks of a prompt are normally cached on exactly the same endpoints.)
-  static uint64_t content_hash(const uint32_t* w, int nwords) { return xxh64_host(w, (size_t)nwords * 4, 0x5eed); }
+  // The content hash of a set is the XOR of one fixed random word per member (Zobrist): adding or removing an endpoint
+  // updates it in O(1), and every row remembers the hash of its content.  Equal hashes are confirmed with a memcmp.
   bool same_content(uint32_t row, const uint32_t* w) const {
     return std::memcmp(&rows_[(size_t)row * geo_.row_words], w, (size_t)geo_.row_words * 4) == 0;
   }
   void release_row(uint32_t row) {
     if (row == 0) return;
     if (--row_ref_[row] == 0) {
-      const uint64_t ch = content_hash(&rows_[(size_t)row * geo_.row_words], geo_.row_words);
+      const uint64_t ch = row_hash_[row];
       uint32_t r;
       if (intern_.get(ch, &r) && r == row) intern_.erase(ch);
       free_rows_.push_back(row);
@@ -336,7 +345,7 @@ class PrefixIndex {
       release_row(old);
       return true;
     }
-    const uint64_t ch = content_hash(content, RW);
+    const uint64_t ch = row_hash_[old] ^ zob_[pos];  // the set changed by exactly the endpoint at bit `pos`
     uint32_t r;
     if (intern_.get(ch, &r) && same_content(r, content)) {  // an identical set already has a row: share it
       row_ref_[r]++;
@@ -346,9 +355,10 @@ class PrefixIndex {
     }
     const bool clash = intern_.get(ch, &r);  // (64-bit content-hash collision: keep this row un-interned)
     if (old != 0 && row_ref_[old] == 1) {    // sole owner: mutate in place, only one word changes
-      const uint64_t och = content_hash(&rows_[(size_t)old * RW], RW);
+      const uint64_t och = row_hash_[old];
       uint32_t t;
       if (intern_.get(och, &t) && t == old) intern_.erase(och);
+      row_hash_[old] = ch;
       const uint64_t wi = (uint64_t)old * RW + (pos >> 5);
       rows_[wi] = content[pos >> 5];
       touch_word(wi);
@@ -364,9 +374,11 @@ class PrefixIndex {
       nr = (uint32_t)n_rows_++;
       rows_.resize((size_t)n_rows_ * RW, 0u);
       row_ref_.resize((size_t)n_rows_, 0u);
+      row_hash_.resize((size_t)n_rows_, 0ULL);
       word_dirty_flag_.resize((rows_.size() + 7) / 8, 0);
     }
     row_ref_[nr] = 1;
+    row_hash_[nr] = ch;
     for (int w = 0; w < RW; w++) {
       const uint64_t wi = (uint64_t)nr * RW + w;
       if (rows_[wi] != content[w]) {
@@ -434,6 +446,8 @@ class PrefixIndex {
   std::vector<Slot> slots_;
   std::vector<uint32_t> rows_;
   std::vector<uint32_t> row_ref_;    // slots pointing at each row
+  std::vector<uint64_t> row_hash_;   // Zobrist hash of each row's content
+  std::vector<uint64_t> zob_;        // per endpoint bit position
   std::vector<uint32_t> free_rows_;
   FlatMap64 intern_{1024};           // content hash -> row id
   std::vector<std::unique_ptr<LruSet>> lru_;
