@@ -74,6 +74,12 @@ class FlatMap64 {
     }
   }
 
+  void prefetch(uint64_t k) const {
+    const size_t h = home(k);
+    __builtin_prefetch(&keys_[h]);
+    __builtin_prefetch(&used_[h]);
+  }
+
  private:
   static uint64_t scramble(uint64_t x) {
     x *= 0x9E3779B97F4A7C15ULL;
@@ -133,6 +139,7 @@ class LruSet {
     len_--;
     return true;
   }
+  void prefetch(uint64_t k) const { map_.prefetch(k); }
   template <typename F>
   void for_each_oldest_first(F&& f) const {  // lru.Keys(): oldest -> newest
     for (int32_t n = back_; n >= 0; n = prev_[n]) f(key_[n]);
@@ -214,6 +221,12 @@ class PrefixIndex {
   bool add(const uint64_t* hashes, int32_t n, int32_t endpoint, int32_t lru_capacity) {
     if (endpoint < 0 || endpoint >= geo_.Mpad) return false;
     LruSet* l = lru_for(endpoint, lru_capacity);
+    // both phases are chains of dependent cache misses into big tables (the LRU's map, the key slots): touch the home
+    // lines of all n hashes first so that the misses overlap
+    for (int32_t i = 0; i < n; i++) {
+      l->prefetch(hashes[i]);
+      __builtin_prefetch(&slots_[hashes[i] & slot_mask_]);
+    }
     for (int32_t i = 0; i < n; i++) {
       uint64_t ev;
       if (l->add(hashes[i], &ev)) clear_bit(ev, endpoint);  // makeEvictionFn, indexer.go:105-115
