@@ -190,7 +190,7 @@ class PrefixIndex {
     rows_.assign((size_t)geo_.row_words, 0u);
     row_ref_.assign(1, 1u);
     row_hash_.assign(1, 0ULL);  // row 0 = the empty set
-    zob_.resize((size_t)geo.Mpad);
+    zob_.resize((size_t)geo.row_words * 32);  // indexed by permuted bit position (perm_bitpos), which spans row_words*32
     for (size_t i = 0; i < zob_.size(); i++) {  // splitmix64: one fixed random word per endpoint bit
       uint64_t z = 0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1);
       z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;

@@ -21,7 +21,7 @@ def pit():
     deps = [SRC, os.path.join(ROOT, "gateway-api-inference-extension_b200", "csrc", "prefix_index.hpp"),
             os.path.join(ROOT, "gateway-api-inference-extension_b200", "csrc", "kernels.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include", SRC, "-o", OUT])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-D_GLIBCXX_ASSERTIONS", "-I/usr/local/cuda/include", SRC, "-o", OUT])  # bounds-checked std::vector
     L = C.CDLL(OUT)
     L.pit_new.restype = C.c_void_p
     L.pit_new.argtypes = [C.c_int, C.c_longlong, C.c_int]
