@@ -46,7 +46,7 @@ def _get(L, h, key):
     return set(int(x) for x in buf[:n])
 
 
-@pytest.mark.parametrize("M,lru,seed", [(40, 12, 0), (300, 50, 1), (1024, 9, 2), (5000, 30, 3)])
+@pytest.mark.parametrize("M,lru,seed", [(40, 12, 0), (300, 50, 1), (1024, 9, 2), (5000, 30, 3), (257, 20, 4), (513, 40, 5), (8192, 6, 6)])
 def test_random_ops_match_oracle(pit, M, lru, seed):
     L = pit
     rng = np.random.Generator(np.random.PCG64(seed))
