@@ -653,3 +653,52 @@ def test_sparse_pick_identity_holds_on_the_oracle():
             else:
                 want = {m for m in gset if m not in eset} | {int(e) for e in exc if S[e] == gmax}
             assert set(full["tie_set"]) == want, (r, scorers)
+
+
+# ---------------------------------------------------------------- a second, independent restatement (NumPy) pins the C oracle
+def test_numpy_restatement_agrees_with_c_oracle():
+    """The Go reference cannot run here, so the C oracle is additionally cross-checked against an independent NumPy
+    restatement of the same reference lines (queue.go:78-108, kvcache_utilization.go:76-82, lora_affinity.go:76-102,
+    prefix/plugin.go:95-117, scheduler_profile.go:151-202, maxscore/picker.go:87-115) on random snapshots and masks."""
+    from tests.helpers import synth_snapshot, zipf_adapters
+    rng = np.random.Generator(np.random.PCG64(314))
+    for trial in range(6):
+        M = int(rng.integers(3, 200))
+        sd = synth_snapshot(M, seed=trial, tie_heavy=trial % 2 == 0)
+        snap = o.SnapshotData(**sd)
+        order = [("queue", 2.0), ("kv", 2.0), ("prefix", 3.0), ("lora", 1.0), ("running", 0.5)]
+        rng.shuffle(order)
+        weights = [(k, float(w) * float(rng.choice([1.0, -0.5, 1.5]))) for k, w in order]
+        prof = o.make_profile(kinds(weights))
+        for r in range(40):
+            cand = rng.random(M) < rng.choice([0.2, 0.7, 1.0])
+            if not cand.any():
+                cand[int(rng.integers(0, M))] = True
+            total = int(rng.integers(0, 9))
+            match = rng.integers(0, total + 1, M).astype(np.uint16)
+            ad = int(zipf_adapters(1, seed=r)[0])
+            got = o.schedule_one(snap, prof, adapter_id=ad, mask=mask_from_list(M, list(np.nonzero(cand)[0])), match=match, total=total)
+            acc = np.zeros(M)
+            for k, w in weights:
+                if k in ("queue", "running"):
+                    q = np.asarray(sd["queue" if k == "queue" else "running"], np.int64)[cand]
+                    sc = np.ones(M)
+                    if q.max() != q.min():
+                        full = np.asarray(sd["queue" if k == "queue" else "running"], np.int64)
+                        sc = (q.max() - full).astype(np.float64) / np.float64(q.max() - q.min())
+                elif k == "kv":
+                    sc = 1.0 - np.asarray(sd["kv_usage"])
+                elif k == "prefix":
+                    sc = match.astype(np.float64) / np.float64(total) if total else np.zeros(M)
+                else:
+                    act = wai = np.zeros(M, np.uint64)  # a target model outside the adapter dictionary is on no endpoint
+                    if ad >= 0:
+                        w_, b_ = ad >> 6, np.uint64(ad & 63)
+                        act = (sd["lora_active"][:, w_] >> b_) & np.uint64(1)
+                        wai = (sd["lora_waiting"][:, w_] >> b_) & np.uint64(1)
+                    sc = np.where(act == 1, 1.0, np.where(sd["lora_nmodels"] < sd["lora_max"], 0.8, np.where(wai == 1, 0.6, 0.0)))
+                acc = acc + np.clip(sc, 0.0, 1.0) * np.float64(w)
+            best = acc[cand].max()
+            ties = [int(m) for m in np.nonzero(cand & (acc == best))[0]]
+            assert got["score"] == best and got["tie_set"] == ties and got["pick"] == ties[0], (trial, r)
+            assert np.array_equal(got["weighted"][cand].view(np.uint64), acc[cand].view(np.uint64))
