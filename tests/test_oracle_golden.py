@@ -702,3 +702,65 @@ def test_numpy_restatement_agrees_with_c_oracle():
             ties = [int(m) for m in np.nonzero(cand & (acc == best))[0]]
             assert got["score"] == best and got["tie_set"] == ties and got["pick"] == ties[0], (trial, r)
             assert np.array_equal(got["weighted"][cand].view(np.uint64), acc[cand].view(np.uint64))
+
+
+def _latency_scorer_py(th, ph, disp, cand, ttft_w=0.8, tpot_w=0.2, most=False):
+    """scorer/latency/plugin.go:144-318 restated with Python lists (independent of oracle.c)."""
+    import math
+    M = len(th)
+    scores = [0.0 if cand[m] else float("nan") for m in range(M)]
+    data = [m for m in range(M) if cand[m]]
+
+    def bucket(ms, force_least):
+        s = ttft_w + tpot_w
+        a, b = (1.0, 0.0) if s <= 0 else (ttft_w / s, tpot_w / s)
+        at, ap = [abs(th[m]) for m in ms], [abs(ph[m]) for m in ms]
+        rt, rp = max(at) - min(at), max(ap) - min(ap)
+        if rt <= 1e-9 and rp > 1e-9:
+            a, b = 0.0, 1.0
+        elif rp <= 1e-9 and rt > 1e-9:
+            a, b = 1.0, 0.0
+        for m, x, y in zip(ms, at, ap):
+            nt = (x - min(at)) / rt if rt > 1e-9 else 0.5
+            np_ = (y - min(ap)) / rp if rp > 1e-9 else 0.5
+            c = a * nt + b * np_
+            w = int(c * 100.0) + 1 if (most and not force_least) else int((1.0 - c) * 100.0) + 1
+            scores[m] = float(w) / 100.0
+
+    positive = [m for m in data if not (th[m] < 0 or ph[m] < 0)]
+    negative = [m for m in data if th[m] < 0 or ph[m] < 0]
+    if positive:
+        bucket(positive, False)
+        return scores
+    idle = [m for m in negative if disp[m] == 0]
+    if idle:
+        bucket(idle, True)
+        return scores
+    for sel in (lambda m: not th[m] < 0 and ph[m] < 0, lambda m: th[m] < 0 and not ph[m] < 0, lambda m: th[m] < 0 and ph[m] < 0):
+        b_ = [m for m in negative if sel(m)]
+        if b_:
+            bucket(b_, True)
+            return scores
+    return scores
+
+
+def test_python_restatement_of_latency_scorer_agrees_with_c_oracle():
+    rng = np.random.Generator(np.random.PCG64(2718))
+    for trial in range(400):
+        M = int(rng.integers(1, 40))
+        scale = rng.choice([1.0, 50.0, 1e-10])            # incl. ranges below the scorer's eps
+        th = np.round(rng.normal(rng.choice([-30, 0, 40]), 25, M), int(rng.integers(0, 3))) * scale
+        ph = np.round(rng.normal(rng.choice([-5, 0, 8]), 6, M), int(rng.integers(0, 3))) * scale
+        if trial % 7 == 0:
+            ph[:] = 0.0                                   # neutralised TPOT (non-streaming)
+        disp = rng.integers(0, 3, M).astype(np.int32) if trial % 3 else np.ones(M, np.int32)
+        cand = rng.random(M) < rng.choice([0.3, 1.0])
+        if not cand.any():
+            cand[0] = True
+        most = bool(trial % 2)
+        lp = o.make_latency_params(strategy_most=1 if most else 0, ttft_weight=float(rng.choice([0.8, 0.0, 1.0])),
+                                   tpot_weight=float(rng.choice([0.2, 0.0, 3.0])))
+        snap = o.SnapshotData(np.zeros(M), np.zeros(M, np.int64))
+        got = o.score_latency_info(lp, snap, np.ones(M, np.uint8), th, ph, disp, mask=mask_from_list(M, list(np.nonzero(cand)[0])))
+        want = _latency_scorer_py(list(th), list(ph), list(disp), list(cand), lp.ttft_weight, lp.tpot_weight, most)
+        assert np.array_equal(np.array(want), got, equal_nan=True), (trial, want, got)
