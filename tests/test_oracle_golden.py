@@ -764,3 +764,67 @@ def test_python_restatement_of_latency_scorer_agrees_with_c_oracle():
         got = o.score_latency_info(lp, snap, np.ones(M, np.uint8), th, ph, disp, mask=mask_from_list(M, list(np.nonzero(cand)[0])))
         want = _latency_scorer_py(list(th), list(ph), list(disp), list(cand), lp.ttft_weight, lp.tpot_weight, most)
         assert np.array_equal(np.array(want), got, equal_nan=True), (trial, want, got)
+
+
+def test_python_restatement_of_filters_agrees_with_c_oracle():
+    """prefixcacheaffinity/plugin.go:105-151 and sloheadroomtier/plugin.go:82-137 restated with Python lists, chained in random
+    orders with random parameters; the draws come from the shared counter-based generator (orc_uniform01)."""
+    L = o.lib()
+    rng = np.random.Generator(np.random.PCG64(1618))
+    lp = o.make_latency_params(ttft_waiting=1.0, tpot_running=1.0, streaming_mode=1)   # TTFT = waiting, TPOT = running
+    for trial in range(300):
+        M = int(rng.integers(1, 30))
+        total = int(rng.integers(0, 11))
+        match = rng.integers(0, total + 1, M).astype(np.uint16)
+        queue = rng.integers(0, 400, M).astype(np.int64)
+        running = rng.integers(0, 60, M).astype(np.int64)
+        ttft_slo, tpot_slo = float(rng.choice([0.0, 150.0, 500.0])), float(rng.choice([0.0, 30.0, 100.0]))
+        cand = rng.random(M) < rng.choice([0.4, 1.0])
+        filters = []
+        for _ in range(int(rng.integers(1, 4))):
+            if rng.random() < 0.5:
+                filters.append((o.FILTER_PREFIX_AFFINITY, (float(rng.choice([0.0, 0.3, 0.8, 1.0])), float(rng.choice([0.0, 0.3, 1.0])),
+                                                           float(rng.choice([0.0, 20.0, 5000.0])))))
+            else:
+                filters.append((o.FILTER_SLO_HEADROOM_TIER, (float(rng.choice([0.0, 0.3, 1.0])),)))
+        seed, req = int(rng.integers(0, 2 ** 40)), int(rng.integers(0, 10 ** 6))
+        # ---- Python restatement ----
+        cur = [m for m in range(M) if cand[m]]
+        score = lambda m: (match[m] / total) if total > 0 else 0.0
+        th = {m: ttft_slo - float(queue[m]) for m in range(M)}
+        ph = {m: tpot_slo - float(running[m]) for m in range(M)}
+        for f, (kind, par) in enumerate(filters):
+            if not cur:
+                break
+            u = L.orc_uniform01(seed, req, -(f + 1))
+            if kind == o.FILTER_PREFIX_AFFINITY:
+                thr, pexp, maxpen = par
+                if len(cur) <= 1 or thr <= 0 or u < pexp:
+                    continue
+                sticky = [m for m in cur if score(m) >= thr]
+                non = [m for m in cur if score(m) < thr]
+                if not sticky:
+                    continue
+                if maxpen > 0 and non and min(float(queue[m]) for m in sticky) - min(float(queue[m]) for m in non) > maxpen:
+                    continue
+                cur = sticky
+            else:
+                if len(cur) <= 1:
+                    continue
+                pos = [m for m in cur if th[m] >= 0 and ph[m] >= 0]
+                neg = [m for m in cur if not (th[m] >= 0 and ph[m] >= 0)]
+                if pos and neg:
+                    cur = neg if u < par[0] else pos
+        # ---- C oracle ----
+        snap = o.SnapshotData(np.zeros(M), queue, running)
+        prof = o.make_profile([(o.SCORER_LATENCY, 1.0)], latency=lp, filters=filters, tie_seed=seed)
+        out = np.zeros(max((M + 31) // 32, 1), np.uint32)
+        lr = o.LatencyRequest(0, ttft_slo, tpot_slo)
+        import ctypes as C
+        L.orc_apply_filters.argtypes = [C.POINTER(o.Snapshot), C.POINTER(o.Profile), C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.POINTER(o.LatencyRequest), C.c_void_p]
+        mask = mask_from_list(M, [m for m in range(M) if cand[m]])
+        L.orc_apply_filters(C.byref(snap.struct), C.byref(prof), req, mask.ctypes.data, match.ctypes.data, total, C.byref(lr),
+                            out.ctypes.data)
+        kept = [m for m in range(M) if (out[m >> 5] >> (m & 31)) & 1]
+        assert kept == cur, (trial, filters, kept, cur)
