@@ -1199,7 +1199,9 @@ typedef struct {
   const orc_profile *p;
   const orc_index *idx;
   const orc_batch *b;
-  int32_t r0, r1;
+  int32_t r0, r1;          /* static range (single-thread call) */
+  int32_t *next;           /* shared cursor: workers claim chunks of `chunk` requests (goroutine-style balancing) */
+  int32_t chunk;
 } job_t;
 
 static int profile_has(const orc_profile *p, int kind) {
@@ -1219,7 +1221,14 @@ static void *batch_worker(void *arg) {
   uint64_t *hashes = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)hcap);
   uint16_t *match = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)M);
   uint32_t *fmask = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(mw > 0 ? mw : 1));
-  for (int32_t r = j->r0; r < j->r1; r++) {
+  for (;;) {
+  int32_t c0 = j->r0, c1 = j->r1;
+  if (j->next) { /* dynamic chunks */
+    c0 = __atomic_fetch_add(j->next, j->chunk, __ATOMIC_RELAXED);
+    if (c0 >= b->R) break;
+    c1 = c0 + j->chunk < b->R ? c0 + j->chunk : b->R;
+  }
+  for (int32_t r = c0; r < c1; r++) {
     int32_t nh = 0;
     const uint16_t *match_p = NULL;
     int32_t total = 0;
@@ -1271,9 +1280,44 @@ static void *batch_worker(void *arg) {
                          b->weighted_out ? b->weighted_out + (size_t)r * M : NULL,
                          b->pred_out ? b->pred_out + (size_t)r * M * 2 : NULL);
   }
+  if (!j->next) break;
+  }
   free(hashes);
   free(match);
   free(fmask);
+  return NULL;
+}
+
+/* Persistent worker pool: created once (grown on demand), parked on a condition variable between batches, so a timed
+ * batch pays no pthread_create/join — the shape of a Go runtime whose goroutines are scheduled onto existing Ms. */
+static struct {
+  pthread_mutex_t mu;
+  pthread_cond_t go, done;
+  pthread_t *th;
+  int32_t n_threads;   /* workers created */
+  int32_t want;        /* workers that take part in the current batch */
+  int32_t running;     /* participants that have not finished yet */
+  uint64_t gen;        /* batch generation */
+  job_t job;
+  pthread_mutex_t call_mu; /* one batch at a time */
+  int init;
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0, 0,
+            {0}, PTHREAD_MUTEX_INITIALIZER, 0};
+
+static void *pool_worker(void *arg) {
+  const int32_t id = (int32_t)(intptr_t)arg;
+  uint64_t seen = 0;
+  pthread_mutex_lock(&g_pool.mu);
+  for (;;) {
+    while (g_pool.gen == seen) pthread_cond_wait(&g_pool.go, &g_pool.mu);
+    seen = g_pool.gen;
+    if (id >= g_pool.want) continue;
+    job_t j = g_pool.job;
+    pthread_mutex_unlock(&g_pool.mu);
+    batch_worker(&j);
+    pthread_mutex_lock(&g_pool.mu);
+    if (--g_pool.running == 0) pthread_cond_signal(&g_pool.done);
+  }
   return NULL;
 }
 
@@ -1281,24 +1325,39 @@ int32_t orc_schedule_batch(const orc_snapshot *s, const orc_profile *p, const or
                            const orc_batch *b, int32_t n_threads) {
   if (n_threads < 1) n_threads = 1;
   if (n_threads > b->R) n_threads = b->R > 0 ? b->R : 1;
-  job_t *jobs = (job_t *)calloc((size_t)n_threads, sizeof(job_t));
-  pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
-  for (int32_t t = 0; t < n_threads; t++) {
-    jobs[t].s = s;
-    jobs[t].p = p;
-    jobs[t].idx = idx;
-    jobs[t].b = b;
-    jobs[t].r0 = (int32_t)((int64_t)b->R * t / n_threads);
-    jobs[t].r1 = (int32_t)((int64_t)b->R * (t + 1) / n_threads);
-  }
+  job_t job;
+  memset(&job, 0, sizeof(job));
+  job.s = s;
+  job.p = p;
+  job.idx = idx;
+  job.b = b;
+  job.r0 = 0;
+  job.r1 = b->R;
   if (n_threads == 1) {
-    batch_worker(&jobs[0]);
-  } else {
-    for (int32_t t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
-    for (int32_t t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+    batch_worker(&job);
+    return 0;
   }
-  free(jobs);
-  free(th);
+  int32_t cursor = 0;
+  job.next = &cursor;
+  job.chunk = b->R / (n_threads * 8);
+  if (job.chunk < 1) job.chunk = 1;
+  if (job.chunk > 256) job.chunk = 256;
+  pthread_mutex_lock(&g_pool.call_mu);
+  pthread_mutex_lock(&g_pool.mu);
+  if (g_pool.n_threads < n_threads) { /* grow the pool; workers never exit */
+    g_pool.th = (pthread_t *)realloc(g_pool.th, sizeof(pthread_t) * (size_t)n_threads);
+    for (int32_t t = g_pool.n_threads; t < n_threads; t++)
+      pthread_create(&g_pool.th[t], NULL, pool_worker, (void *)(intptr_t)t);
+    g_pool.n_threads = n_threads;
+  }
+  g_pool.job = job;
+  g_pool.want = n_threads;
+  g_pool.running = n_threads;
+  g_pool.gen++;
+  pthread_cond_broadcast(&g_pool.go);
+  while (g_pool.running > 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+  pthread_mutex_unlock(&g_pool.mu);
+  pthread_mutex_unlock(&g_pool.call_mu);
   return 0;
 }
 
