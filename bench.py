@@ -253,35 +253,29 @@ def run_gpu(args):
 
     apply_snapshot(eng)
 
-    # ---- prefix table: rank 0 replays 4*M earlier requests (oracle-routed) through commit_picks, then the device
-    #      image (key slots + bitset rows) is replicated with NCCL broadcasts ----
+    # ---- prefix index: 4*M earlier requests are routed by the oracle on rank 0; the resulting COMMIT STREAM (picks + block
+    #      hashes, 1 MiB) is broadcast with NCCL and every rank replays it through eppscore_commit_picks_device — the index is a
+    #      deterministic function of the ordered commits, so all replicas are identical ----
     o = osnap = prof = idx = seed = warm = None
+    W = 4 * M
     if rank == 0:
         o, osnap, prof, idx, seed, warm = oracle_setup(snap)
-        t_commit = time.perf_counter()
-        eng.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
-        t_commit = time.perf_counter() - t_commit  # PreRequest for 4*M requests: host LRUs + interned rows (one core)
-    info = eng.prefix_image_info()
-    meta = torch.tensor(info["meta"], dtype=torch.int64, device=dev)
+        w_pick = torch.from_numpy(warm["pick"]).to(dev)
+        w_hash = torch.from_numpy(np.ascontiguousarray(warm["hashes_out"]).view(np.int64)).to(dev)
+        w_nh = torch.from_numpy(warm["total_blocks"].astype(np.int16)).to(dev)
+    else:
+        w_pick = torch.empty(W, dtype=torch.int32, device=dev)
+        w_hash = torch.empty((W, MAX_BLOCKS), dtype=torch.int64, device=dev)
+        w_nh = torch.empty(W, dtype=torch.int16, device=dev)
     seed_t = torch.from_numpy(np.array([seed if rank == 0 else 0], np.uint64).view(np.int64)).to(dev)
     if world > 1:
-        dist.broadcast(meta, src=0)
-        dist.broadcast(seed_t, src=0)
-        m = [int(x) for x in meta.cpu()]
-
-        def as_tensor(ptr, nbytes):
-            class _W:  # expose a raw device pointer to torch via the CUDA array interface
-                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-            return torch.as_tensor(_W(), device=dev)
-
-        ts = as_tensor(info["slots_ptr"], m[0] * 16)
-        dist.broadcast(ts, src=0)
-        if m[2] > 0:
-            tr = as_tensor(info["rows_ptr"], m[2] * m[1] * 4)
-            dist.broadcast(tr, src=0)
-        torch.cuda.synchronize()
-        if rank != 0:
-            eng.prefix_image_adopt(m)
+        for t in (w_pick, w_hash, w_nh, seed_t):
+            dist.broadcast(t, src=0)
+    torch.cuda.synchronize()
+    t_commit = time.perf_counter()
+    eng.commit_picks_device(w_pick, w_hash, w_nh, touch_bound=W * (PROMPT_LEN // BLOCK_CHARS), stream=sptr)
+    torch.cuda.synchronize()
+    t_commit = time.perf_counter() - t_commit  # includes the one-time allocation of the per-endpoint LRU regions
     seed = int(seed_t.cpu().numpy().view(np.uint64)[0])
 
     # ---- device-resident inputs ----
@@ -427,7 +421,7 @@ def run_gpu(args):
     if rank == 0:
         extra["commit_picks"] = {"requests": 4 * M, "hashes_per_request": 32, "host_seconds": t_commit,
                                  "picks_per_s": 4 * M / t_commit if t_commit > 0 else None,
-                                 "note": "eppscore_commit_picks (PreRequest): host-side, off the scoring path like the reference's goroutine"}
+                                 "note": "warm-up replay through eppscore_commit_picks_device, incl. the one-time allocation of the LRU regions"}
         peak, peak_src = peaks()
         traffic = {}
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -513,7 +507,7 @@ def run_gpu(args):
             eng_g = make_engine()
             eng_g.set_debug(1, 1)               # diagnostics knob: always the fully general kernels
             apply_snapshot(eng_g)
-            eng_g.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+            eng_g.commit_picks_device(w_pick, w_hash, w_nh, touch_bound=W * 32, stream=sptr)
             t_gen = time_kernel(lambda i: pick_only(i, eng_g), iters=10)
             extra["generic_full_matrix"] = {"kernel": "score_matrix_kernel<E,P,L>", "us": t_gen * 1e6, "picks_per_s": R / t_gen,
                                             "pairs_per_s": R * M / t_gen}
@@ -554,8 +548,7 @@ def run_gpu(args):
             lat_ep_dev = {k: torch.from_numpy(v).to(dev) for k, v in lat_ep.items()}
             eng_l.set_snapshot(views["kv_usage"], views["queue"], views["running"], device=True, stream=sptr, M=M, lora_words=0,
                                **lat_ep_dev)
-            if rank == 0:
-                eng_l.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+            eng_l.commit_picks_device(w_pick, w_hash, w_nh, touch_bound=W * 32, stream=sptr)
             lat_req = dict(input_tokens=lrng.integers(16, 6000, R).astype(np.int32),
                            ttft_slo=lrng.choice([0.0, 90.0, 140.0, 200.0, 400.0, 1e6], R),
                            tpot_slo=lrng.choice([0.0, 18.0, 24.0, 30.0, 80.0], R))
@@ -603,8 +596,7 @@ def run_gpu(args):
                 eng_c.set_latency_params(pkg.latency_params(**lat_coef))
                 eng_c.set_snapshot(views["kv_usage"], views["queue"], views["running"], device=True, stream=sptr, M=M, lora_words=0,
                                    **lat_ep_dev)
-                if rank == 0:
-                    eng_c.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+                eng_c.commit_picks_device(w_pick, w_hash, w_nh, touch_bound=W * 32, stream=sptr)
 
                 def chart_only(i):
                     hh, nn = hsets_dev[i % NSETS]
@@ -640,8 +632,7 @@ def run_gpu(args):
             eng_w = pkg.Engine(pkg.default_config(SCORERS, max_endpoints=M, max_adapters=A, block_chars=BLOCK_CHARS, max_blocks=MAX_BLOCKS,
                                                   prefix_capacity=1 << 19, pick_mode=pkg.PICK_WEIGHTED_RANDOM, tie_seed=3), device=local)
             apply_snapshot(eng_w)
-            if rank == 0:
-                eng_w.commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+            eng_w.commit_picks_device(w_pick, w_hash, w_nh, touch_bound=W * 32, stream=sptr)
             t_w = time_kernel(lambda i: pick_only(i, eng_w), iters=10)
             extra["weighted_random_picker"] = {"kernel": "score_matrix_kernel<runtime sequence; A-Res>", "us": t_w * 1e6, "picks_per_s": R / t_w,
                                                "pairs_per_s": R * M / t_w}

@@ -28,7 +28,7 @@ class Config(C.Structure):
                 ("scorer_weight", C.c_double * MAX_SCORERS), ("block_chars", C.c_int32), ("max_blocks", C.c_int32),
                 ("tie_mode", C.c_int32), ("tie_seed", C.c_uint64), ("max_endpoints", C.c_int32),
                 ("max_adapters", C.c_int32), ("prefix_capacity", C.c_int64), ("lru_capacity_default", C.c_int32),
-                ("token_load_threshold", C.c_double), ("pick_mode", C.c_int32), ("n_filters", C.c_int32),
+                ("lru_capacity_max", C.c_int32), ("token_load_threshold", C.c_double), ("pick_mode", C.c_int32), ("n_filters", C.c_int32),
                 ("filter_kind", C.c_int32 * 4), ("filter_param", (C.c_double * 3) * 4)]
 
 
@@ -69,7 +69,9 @@ class Batch(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("M", C.c_int32), ("epoch", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("prefix_hashes", C.c_int64), ("prefix_live_hashes", C.c_int64), ("prefix_capacity", C.c_int64),
-                ("prefix_table_bytes", C.c_int64), ("lru_entries", C.c_int64)]
+                ("prefix_table_bytes", C.c_int64), ("lru_entries", C.c_int64), ("lru_bytes", C.c_int64),
+                ("prefix_overflow_rows", C.c_int64), ("prefix_rebuilds", C.c_int64), ("index_error", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 # every symbol include/eppscore.h declares: (name, restype, argtypes)
@@ -97,9 +99,7 @@ ABI_SYMBOLS = [
     ("eppscore_prefix_get", C.c_int32, [_P, C.c_uint64, _P, C.c_int32]),
     ("eppscore_prefix_lru_len", C.c_int32, [_P, C.c_int32]),
     ("eppscore_prefix_lru_keys", C.c_int32, [_P, C.c_int32, _P, C.c_int32]),
-    ("eppscore_prefix_image_info", C.c_int32, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(_P),
-                                               C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-    ("eppscore_prefix_image_adopt", C.c_int32, [_P, C.POINTER(C.c_int64)]),
+    ("eppscore_commit_picks_device", C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_int32, _P, C.c_int64, _P]),
     ("eppscore_host_alloc", _P, [C.c_size_t]),
     ("eppscore_host_free", None, [_P]),
 ]

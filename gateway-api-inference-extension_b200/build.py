@@ -13,8 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeppscore.so")
 SOURCES = ["capi.cu", "hash_kernel.cu", "prepare_kernel.cu", "score_generic.cu", "score_matrix.cu", "score_dense.cu", "pick_sparse.cu",
-           "table_kernels.cu", "fields_kernel.cu"]
-HEADERS = ["kernels.cuh", "device_common.cuh", "xxh64.cuh", "prefix_index.hpp",
+           "prefix_index.cu", "fields_kernel.cu"]
+HEADERS = ["kernels.cuh", "device_common.cuh", "xxh64.cuh", "prefix_index.hpp", "prefix_table.cuh",
            os.path.join("..", "..", "include", "eppscore.h")]
 
 NVCC_FLAGS = [

@@ -58,13 +58,13 @@ struct eppscore_engine {
   Geo geo{};
   int32_t A_cap = 64;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_snapshot = nullptr, ev_table = nullptr;
+  cudaEvent_t ev_snapshot = nullptr, ev_table = nullptr, ev_caller = nullptr;
   cudaStream_t snapshot_stream = nullptr;        // stream the last snapshot preparation ran on
   unsigned long long snapshot_capture_id = 0;    // != 0: ev_snapshot was recorded inside that CUDA-graph capture
   std::string err;
   uint64_t launches = 0;
   bool force_generic = false;  // EPPSCORE_FORCE_GENERIC=1 / eppscore_set_debug(1): skip the specialised kernels
-  int32_t hash_stage_mask = 3;  // eppscore_set_debug(2): profiling only
+  int32_t hash_stage_mask = 7;  // eppscore_set_debug(2): profiling only (bit 2: the fused kernel)
 
   // snapshot
   bool have_snapshot = false;
@@ -82,19 +82,27 @@ struct eppscore_engine {
   bool have_lut2d = false;
   PlanSet plan_unmasked{}, plan_masked{};
 
-  // prefix table
-  std::unique_ptr<PrefixIndex> index;
-  Slot* d_slots = nullptr;
-  uint32_t* d_rows = nullptr;
-  bool table_adopted = false;
-  int64_t dev_capacity = 0;  // capacity (hashes) the device slot/row buffers were allocated for
-  DevBuf st_idx, st_val, st_slot;
-  DevBuf probe_out;
+  // prefix index: hashToPods + the per-endpoint LRUs, both device-resident (prefix_index.hpp); mutated on `stream`
+  std::unique_ptr<DeviceIndex> index;
+  cudaEvent_t ev_sched = nullptr;   // last device-location schedule on a caller stream (index mutations wait for it)
+  bool sched_pending = false;
+  DevBuf c_pick, c_hash, c_nh, c_ep, c_op;  // staging for the host-array forms of commit_picks / prefix_add / prefix_apply
 
-  // scratch for host-location batches and internal hashes
-  DevBuf s_prompts, s_off, s_len, s_seed, s_hashes, s_nh, s_adapter, s_mask, s_dense, s_dtotal, s_pick, s_score,
-      s_tie, s_match, s_total, s_scores, s_intok, s_tslo, s_pslo, s_pred, s_fields, s_fmask;
+  // scratch for host-location batches and internal hashes: two sets, so the chunks of a host batch can alternate
+  // between two streams (H2D of chunk i+1 under the kernels and the D2H of chunk i)
+  struct Scratch {
+    DevBuf s_prompts, s_off, s_len, s_seed, s_hashes, s_nh, s_adapter, s_mask, s_dense, s_dtotal, s_pick, s_score,
+        s_tie, s_match, s_total, s_scores, s_intok, s_tslo, s_pslo, s_pred, s_fields, s_fmask;
+    void release() {
+      DevBuf* all[] = {&s_prompts, &s_off, &s_len, &s_seed, &s_hashes, &s_nh, &s_adapter, &s_mask, &s_dense, &s_dtotal, &s_pick,
+                       &s_score, &s_tie, &s_match, &s_total, &s_scores, &s_intok, &s_tslo, &s_pslo, &s_pred, &s_fields, &s_fmask};
+      for (DevBuf* b : all) b->release();
+    }
+  } sc[2];
+  cudaStream_t stream2 = nullptr;   // second copy/compute stream of the chunked host path
+  int32_t host_chunk = 8192;        // requests per chunk of a host-location batch (eppscore_set_debug key 3)
 };
+using Scratch = eppscore_engine::Scratch;
 
 namespace {
 
@@ -191,58 +199,16 @@ void build_plan(eppscore_engine* e, bool masked, PlanSet* ps) {
   p.sparse_ok = (ok && n_prefix <= 1 && c.pick_mode == EPPSCORE_PICK_MAX_SCORE) ? 1 : 0;
 }
 
-int32_t flush_table(eppscore_engine* e) {
-  PrefixIndex* ix = e->index.get();
-  if (!ix || e->table_adopted) return EPPSCORE_OK;
-  if (!ix->full_upload_needed() && ix->dirty_slots().empty() && ix->dirty_words().empty()) return EPPSCORE_OK;
-  if (ix->capacity_rows() != e->dev_capacity) {  // the host index grew: reallocate the device table, then upload it all
-    CK(e, cudaStreamSynchronize(e->stream));
-    if (e->d_slots) cudaFree(e->d_slots);
-    if (e->d_rows) cudaFree(e->d_rows);
-    e->d_slots = nullptr;
-    e->d_rows = nullptr;
-    const size_t rb = ((size_t)ix->capacity_rows() + 1) * e->geo.row_words * 4;
-    CK(e, cudaMalloc(&e->d_slots, ix->slots().size() * sizeof(Slot)));
-    CK(e, cudaMalloc(&e->d_rows, rb));
-    CK(e, cudaMemsetAsync(e->d_rows, 0, rb, e->stream));
-    e->dev_capacity = ix->capacity_rows();
-    ix->mark_full_upload();
+// Index mutations run on the engine stream.  They must not overtake scoring kernels that other streams launched
+// earlier against the same table, and later scoring on other streams waits for ev_table.
+int32_t index_begin(eppscore_engine* e) {
+  if (e->sched_pending) {
+    CK(e, cudaStreamWaitEvent(e->stream, e->ev_sched, 0));
+    e->sched_pending = false;
   }
-  const size_t nrow_words = ix->rows().size();
-  const size_t nds = ix->dirty_slots().size(), ndw = ix->dirty_words().size();
-  const bool full = ix->full_upload_needed() || (nds + ndw) * 8 > ix->slots().size() + nrow_words;
-  if (full) {
-    CK(e, cudaMemcpyAsync(e->d_slots, ix->slots().data(), ix->slots().size() * sizeof(Slot), cudaMemcpyHostToDevice,
-                          e->stream));
-    if (nrow_words)
-      CK(e, cudaMemcpyAsync(e->d_rows, ix->rows().data(), nrow_words * 4, cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaStreamSynchronize(e->stream));
-  } else {
-    if (ndw) {
-      std::vector<uint32_t> vals(ndw);
-      for (size_t i = 0; i < ndw; i++) vals[i] = ix->rows()[ix->dirty_words()[i]];
-      CK(e, e->st_idx.reserve(ndw * 4));
-      CK(e, e->st_val.reserve(ndw * 4));
-      CK(e, cudaMemcpyAsync(e->st_idx.p, ix->dirty_words().data(), ndw * 4, cudaMemcpyHostToDevice, e->stream));
-      CK(e, cudaMemcpyAsync(e->st_val.p, vals.data(), ndw * 4, cudaMemcpyHostToDevice, e->stream));
-      e->launches += launch_scatter_u32(e->d_rows, e->st_idx.as<uint32_t>(), e->st_val.as<uint32_t>(), (int64_t)ndw,
-                                        e->stream);
-      CK(e, cudaStreamSynchronize(e->stream));  // staging vectors are pageable and reused
-    }
-    if (nds) {
-      std::vector<Slot> vals(nds);
-      for (size_t i = 0; i < nds; i++) vals[i] = ix->slots()[ix->dirty_slots()[i]];
-      CK(e, e->st_idx.reserve(nds * 4));
-      CK(e, e->st_slot.reserve(nds * sizeof(Slot)));
-      CK(e, cudaMemcpyAsync(e->st_idx.p, ix->dirty_slots().data(), nds * 4, cudaMemcpyHostToDevice, e->stream));
-      CK(e, cudaMemcpyAsync(e->st_slot.p, vals.data(), nds * sizeof(Slot), cudaMemcpyHostToDevice, e->stream));
-      e->launches += launch_scatter_slots(e->d_slots, e->st_idx.as<uint32_t>(), e->st_slot.as<Slot>(), (int64_t)nds,
-                                          e->stream);
-      CK(e, cudaStreamSynchronize(e->stream));
-    }
-  }
-  CK(e, cudaGetLastError());
-  ix->clear_dirty();
+  return EPPSCORE_OK;
+}
+int32_t index_end(eppscore_engine* e) {
   CK(e, cudaEventRecord(e->ev_table, e->stream));
   return EPPSCORE_OK;
 }
@@ -277,7 +243,7 @@ struct DevBatch {  // all device pointers
 };
 
 // The hot path on device-resident buffers: [hash kernel] + score/pick kernel, asynchronous on `s`.
-int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
+int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s, Scratch& sc) {
   if (!e->have_snapshot) return fail(e, EPPSCORE_ERR_NO_SNAPSHOT, "schedule_batch before set_snapshot");
   if (b.R <= 0) return EPPSCORE_OK;
   if (!b.pick || !b.pick_score || !b.tie_count) return fail(e, EPPSCORE_ERR_INVALID, "pick/pick_score/tie_count required");
@@ -335,9 +301,9 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
     a.lat = e->lat_args;
     a.lat.input_tokens = b.input_tokens;
     if (!b.input_tokens && b.prompt_bytes && b.prompt_off) {  // count the fields of the prompt bytes on the device
-      CK(e, e->s_fields.reserve((size_t)b.R * 4));
-      e->launches += launch_count_fields(b.prompt_bytes, b.prompt_off, b.prompt_len, b.R, e->s_fields.as<int32_t>(), s, e->sm_count);
-      a.lat.input_tokens = e->s_fields.as<int32_t>();
+      CK(e, sc.s_fields.reserve((size_t)b.R * 4));
+      e->launches += launch_count_fields(b.prompt_bytes, b.prompt_off, b.prompt_len, b.R, sc.s_fields.as<int32_t>(), s, e->sm_count);
+      a.lat.input_tokens = sc.s_fields.as<int32_t>();
     }
     a.lat.ttft_slo = b.ttft_slo;
     a.lat.tpot_slo = b.tpot_slo;
@@ -366,10 +332,10 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
         if (!b.prompt_off) return fail(e, EPPSCORE_ERR_INVALID, "prompt_off required with prompt_bytes");
         uint64_t* hashes = b.hashes_out;
         if (!hashes) {
-          CK(e, e->s_hashes.reserve((size_t)b.R * mb * 8));
-          hashes = e->s_hashes.as<uint64_t>();
+          CK(e, sc.s_hashes.reserve((size_t)b.R * mb * 8));
+          hashes = sc.s_hashes.as<uint64_t>();
         }
-        CK(e, e->s_nh.reserve((size_t)b.R * 2));
+        CK(e, sc.s_nh.reserve((size_t)b.R * 2));
         HashArgs h{};
         h.R = b.R;
         h.bytes = b.prompt_bytes;
@@ -380,18 +346,14 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
         h.max_blocks = mb;
         h.hashes = hashes;
         h.stride = mb;
-        h.n_hashes = e->s_nh.as<uint16_t>();
+        h.n_hashes = sc.s_nh.as<uint16_t>();
         h.stage_mask = e->hash_stage_mask;
         e->launches += launch_hash_prompts(h, s, e->sm_count);
         a.hashes = hashes;
         a.n_hashes = h.n_hashes;
         a.hash_stride = mb;
       }
-      if (e->index && (e->index->n_rows() > 0 || e->table_adopted)) {
-        a.slots = e->d_slots;
-        a.slot_mask = e->index->slot_mask();
-        a.rows = e->d_rows;
-      }
+      a.table = e->index->view();
     }
   }
   if (wait_snapshot) CK(e, cudaStreamWaitEvent(s, e->ev_snapshot, 0));
@@ -401,15 +363,19 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s) {
   if (launched == 0) launched = launch_score_pick(a, dense, s, e->sm_count);
   e->launches += launched;
   CK(e, cudaGetLastError());
+  if (!capturing && s != e->stream && a.table) {  // a later index mutation (engine stream) must wait for this batch
+    CK(e, cudaEventRecord(e->ev_sched, s));
+    e->sched_pending = true;
+  }
   return EPPSCORE_OK;
 }
 
 template <typename T>
-int32_t h2d(eppscore_engine* e, DevBuf& buf, const T* src, size_t count, const T** out) {
+int32_t h2d(eppscore_engine* e, DevBuf& buf, const T* src, size_t count, const T** out, cudaStream_t st = nullptr) {
   *out = nullptr;
   if (!src || count == 0) return EPPSCORE_OK;
   CK(e, buf.reserve(count * sizeof(T)));
-  CK(e, cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, st ? st : e->stream));
   *out = buf.as<T>();
   return EPPSCORE_OK;
 }
@@ -520,8 +486,7 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
   eppscore_latency_params_default(&e->lat_params);
   e->geo = make_geo(e->cfg.max_endpoints);
   e->A_cap = (e->cfg.max_adapters + 63) / 64 * 64;
-  if (((uint64_t)e->cfg.prefix_capacity + 1) * (uint64_t)e->geo.row_words >= (1ULL << 32))
-    return fail(nullptr, EPPSCORE_ERR_CAPACITY, "prefix_capacity * row_words must be < 2^32");
+  if (e->cfg.lru_capacity_max < 0) return fail(nullptr, EPPSCORE_ERR_INVALID, "lru_capacity_max < 0");
   eppscore_engine* ep = e.get();
   CK(nullptr, cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -587,19 +552,15 @@ int32_t eppscore_create(int32_t device, const eppscore_config* cfg, eppscore_eng
     ep->have_lut2d = true;
     break;
   }
-  // prefix table
-  ep->index = std::make_unique<PrefixIndex>(ep->geo, ep->cfg.prefix_capacity, ep->cfg.lru_capacity_default);
-  const size_t nslots = ep->index->slots().size();
-  CK(nullptr, cudaMalloc(&ep->d_slots, nslots * sizeof(Slot)));
-  CK(nullptr, cudaMalloc(&ep->d_rows, ((size_t)ep->cfg.prefix_capacity + 1) * ep->geo.row_words * 4));
-  CK(nullptr, cudaMemsetAsync(ep->d_slots, 0xFF, nslots * sizeof(Slot), ep->stream));
-  CK(nullptr, cudaMemsetAsync(ep->d_rows, 0, ((size_t)ep->cfg.prefix_capacity + 1) * ep->geo.row_words * 4, ep->stream));
-  ep->dev_capacity = ep->index->capacity_rows();
-  CK(nullptr, ep->probe_out.reserve((size_t)(2 + ep->geo.row_words) * 4));
+  // prefix index (device-resident: slot table + per-endpoint LRUs; the LRU regions are allocated by the first Add)
+  CK(nullptr, cudaEventCreateWithFlags(&ep->ev_sched, cudaEventDisableTiming));
+  CK(nullptr, cudaEventCreateWithFlags(&ep->ev_caller, cudaEventDisableTiming));
+  ep->index = std::make_unique<DeviceIndex>(ep->geo.Mpad, ep->geo.Mpad / 32, ep->cfg.prefix_capacity, ep->cfg.lru_capacity_default,
+                                            ep->cfg.lru_capacity_max);
+  CK(nullptr, ep->index->init(ep->stream));
   CK(nullptr, cudaEventRecord(ep->ev_table, ep->stream));
   CK(nullptr, cudaEventRecord(ep->ev_snapshot, ep->stream));
   CK(nullptr, cudaStreamSynchronize(ep->stream));
-  ep->index->clear_dirty();
   *out = e.release();
   return EPPSCORE_OK;
 }
@@ -608,16 +569,22 @@ void eppscore_destroy(eppscore_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  DevBuf* bufs[] = {&e->s_fmask, &e->s_fields, &e->qhdr[0], &e->qhdr[1], &e->qbucket[0], &e->qbucket[1], &e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep,
-                    &e->s_intok, &e->s_tslo, &e->s_pslo, &e->s_pred, &e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
-                    &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->prefix_lut2d, &e->st_idx, &e->st_val, &e->st_slot,
-                    &e->probe_out, &e->s_prompts, &e->s_off, &e->s_len, &e->s_seed, &e->s_hashes, &e->s_nh, &e->s_adapter,
-                    &e->s_mask, &e->s_dense, &e->s_dtotal, &e->s_pick, &e->s_score, &e->s_tie, &e->s_match, &e->s_total, &e->s_scores};
+  DevBuf* bufs[] = {&e->qhdr[0], &e->qhdr[1], &e->qbucket[0], &e->qbucket[1], &e->raw_min_tpot, &e->raw_dispatched, &e->raw_prefill, &e->raw_tokens, &e->lat_ep,
+                    &e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
+                    &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->prefix_lut2d, &e->c_pick, &e->c_hash, &e->c_nh,
+                    &e->c_ep, &e->c_op};
+  e->sc[0].release();
+  e->sc[1].release();
+  if (e->stream2) {
+    cudaStreamSynchronize(e->stream2);
+    cudaStreamDestroy(e->stream2);
+  }
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; i++) e->raw_col[i].release();
   for (int i = 0; i < kMaxSteps; i++) e->term[i].release();
-  if (e->d_slots) cudaFree(e->d_slots);
-  if (e->d_rows) cudaFree(e->d_rows);
+  e->index.reset();
+  if (e->ev_sched) cudaEventDestroy(e->ev_sched);
+  if (e->ev_caller) cudaEventDestroy(e->ev_caller);
   if (e->ev_snapshot) cudaEventDestroy(e->ev_snapshot);
   if (e->ev_table) cudaEventDestroy(e->ev_table);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -626,19 +593,26 @@ void eppscore_destroy(eppscore_engine* e) {
 
 const char* eppscore_last_error(const eppscore_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
-int32_t eppscore_get_stats(const eppscore_engine* e, eppscore_stats* out) {
+int32_t eppscore_get_stats(const eppscore_engine* ce, eppscore_stats* out) {
+  eppscore_engine* e = const_cast<eppscore_engine*>(ce);
   if (!e || !out) return EPPSCORE_ERR_INVALID;
   memset(out, 0, sizeof(*out));
   out->struct_size = sizeof(*out);
   out->M = e->M;
   out->epoch = e->epoch;
-  out->kernel_launches = e->launches;
-  out->prefix_hashes = e->index->n_keys();
-  out->prefix_live_hashes = e->index->n_live();
-  out->prefix_capacity = e->index->capacity_rows();
-  out->prefix_table_bytes = (int64_t)(e->index->slots().size() * sizeof(Slot)) +
-                            (int64_t)e->index->n_rows() * e->geo.row_words * 4;
-  out->lru_entries = e->index->lru_entries();
+  CK(e, cudaSetDevice(e->device));
+  IndexStats st{};
+  CK(e, e->index->stats(&st, e->stream));
+  out->kernel_launches = e->launches + e->index->launches();
+  out->prefix_hashes = st.used;
+  out->prefix_live_hashes = st.live;
+  out->prefix_capacity = st.capacity;
+  out->prefix_table_bytes = st.table_bytes;
+  out->lru_entries = st.lru_entries;
+  out->lru_bytes = st.lru_bytes;
+  out->prefix_overflow_rows = st.ovf_rows;
+  out->prefix_rebuilds = st.rebuilds;
+  out->index_error = st.error;
   return EPPSCORE_OK;
 }
 
@@ -649,7 +623,11 @@ int32_t eppscore_set_debug(eppscore_engine* e, int32_t key, int64_t value) {
     return EPPSCORE_OK;
   }
   if (key == 2) {
-    e->hash_stage_mask = (int32_t)(value & 3);
+    e->hash_stage_mask = (int32_t)(value & 7);
+    return EPPSCORE_OK;
+  }
+  if (key == 3) {
+    e->host_chunk = (int32_t)value;
     return EPPSCORE_OK;
   }
   return fail(e, EPPSCORE_ERR_INVALID, "unknown debug key");
@@ -813,8 +791,7 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
   if (b->R < 0) return fail(e, EPPSCORE_ERR_INVALID, "R < 0");
   if (b->R == 0) return EPPSCORE_OK;
   CK(e, cudaSetDevice(e->device));
-  int32_t rc = flush_table(e);
-  if (rc != EPPSCORE_OK) return rc;
+  int32_t rc = EPPSCORE_OK;
   DevBatch d{};
   d.R = b->R;
   d.request_base = b->request_base;
@@ -844,87 +821,122 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
     d.total_blocks = b->total_blocks;
     d.hashes_out = b->hashes_out;
     d.scores_out = b->scores_out;
-    return schedule_device(e, d, b->stream ? (cudaStream_t)b->stream : e->stream);
+    return schedule_device(e, d, b->stream ? (cudaStream_t)b->stream : e->stream, e->sc[0]);
   }
   // ---- host buffers: H2D, kernels, D2H, all inside this call ----
+  // The batch is cut into chunks that alternate between two streams (each with its own scratch set): the H2D copy of
+  // chunk i+1 runs under the kernels and the D2H copy of chunk i, so the call costs about max(copy, compute) instead of
+  // their sum.  Requests are independent given (snapshot, table), so any cut gives identical results (request_base keeps
+  // the tie priorities of the whole batch).
   if (!e->have_snapshot) return fail(e, EPPSCORE_ERR_NO_SNAPSHOT, "schedule_batch before set_snapshot");
-  const size_t R = (size_t)b->R, M = (size_t)e->M;
+  if (b->prompt_bytes && !b->prompt_off) return fail(e, EPPSCORE_ERR_INVALID, "prompt_off required with prompt_bytes");
+  if (b->hashes_out && (b->hashes_in || !b->prompt_bytes))
+    return fail(e, EPPSCORE_ERR_INVALID, "hashes_out needs prompt_bytes (hashes supplied as hashes_in are already the caller's)");
+  const size_t M = (size_t)e->M;
   const size_t mw = (M + 31) / 32;
   const int32_t mb = b->max_blocks > 0 ? b->max_blocks : e->cfg.max_blocks;
-  if (b->prompt_bytes) {
-    if (!b->prompt_off) return fail(e, EPPSCORE_ERR_INVALID, "prompt_off required with prompt_bytes");
-    size_t total = (size_t)b->prompt_off[R];
-    if (b->prompt_len) {
-      total = 0;
-      for (size_t r = 0; r < R; r++) total = std::max(total, (size_t)b->prompt_off[r] + (size_t)b->prompt_len[r]);
+  const bool diag = b->match_blocks || b->scores_out || b->pred_out || b->dense_feat;  // R x M arrays: one chunk at a time is plenty
+  int32_t chunk = e->host_chunk > 0 ? e->host_chunk : b->R;
+  if (diag || b->R < 2 * chunk) chunk = b->R;
+  const int nstreams = chunk < b->R ? 2 : 1;
+  if (nstreams == 2 && !e->stream2) CK(e, cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  int ci = 0;
+  for (int32_t r0 = 0; r0 < b->R; r0 += chunk, ci++) {
+    const int32_t r1 = std::min(b->R, r0 + chunk);
+    const size_t R = (size_t)(r1 - r0);
+    Scratch& sc = e->sc[ci & 1];
+    cudaStream_t st = (ci & 1) ? e->stream2 : e->stream;
+    DevBatch d{};
+    d.R = (int32_t)R;
+    d.request_base = b->request_base + r0;
+    d.hash_stride = b->hash_stride;
+    d.block_chars = b->block_chars;
+    d.max_blocks = b->max_blocks;
+    if (b->prompt_bytes) {
+      // byte range of the chunk; the device copy starts at a 16-byte aligned source offset so every prompt keeps its
+      // alignment (the fast hash path needs 16-byte aligned starts), and the kernel keeps using the caller's offsets
+      size_t lo = (size_t)b->prompt_off[r0], hi = (size_t)b->prompt_off[r1];
+      if (b->prompt_len) {
+        lo = SIZE_MAX;
+        hi = 0;
+        for (int32_t r = r0; r < r1; r++) {
+          lo = std::min(lo, (size_t)b->prompt_off[r]);
+          hi = std::max(hi, (size_t)b->prompt_off[r] + (size_t)b->prompt_len[r]);
+        }
+        if (lo > hi) lo = hi = 0;
+      }
+      const size_t start = lo & ~(size_t)15;
+      // pad the device copy so 16-byte vector loads of the last block never leave the allocation
+      CK(e, sc.s_prompts.reserve(hi - start + 64));
+      if (hi > start) CK(e, cudaMemcpyAsync(sc.s_prompts.p, b->prompt_bytes + start, hi - start, cudaMemcpyHostToDevice, st));
+      d.prompt_bytes = sc.s_prompts.as<uint8_t>() - start;
+      if ((rc = h2d(e, sc.s_off, b->prompt_off + r0, R + 1, &d.prompt_off, st)) != EPPSCORE_OK) return rc;
     }
-    // pad the device copy so 16-byte vector loads of the last block never leave the allocation
-    CK(e, e->s_prompts.reserve(total + 64));
-    if (total) CK(e, cudaMemcpyAsync(e->s_prompts.p, b->prompt_bytes, total, cudaMemcpyHostToDevice, e->stream));
-    d.prompt_bytes = e->s_prompts.as<uint8_t>();
-  }
-#define H2D(buf, field, count) \
-  if ((rc = h2d(e, buf, b->field, (count), &d.field)) != EPPSCORE_OK) return rc;
-  H2D(e->s_off, prompt_off, R + 1)
-  H2D(e->s_len, prompt_len, R)
-  H2D(e->s_seed, model_seed, R)
-  if (b->hashes_in) {
-    if ((rc = h2d(e, e->s_hashes, b->hashes_in, R * (size_t)b->hash_stride, &d.hashes_in)) != EPPSCORE_OK) return rc;
-    H2D(e->s_nh, n_hashes_in, R)
-  }
-  H2D(e->s_adapter, adapter_id, R)
-  H2D(e->s_mask, cand_mask, R * mw)
-  H2D(e->s_dense, dense_feat, R * M * 4)
-  H2D(e->s_dtotal, dense_total, R)
-  H2D(e->s_intok, input_tokens, R)
-  H2D(e->s_tslo, ttft_slo, R)
-  H2D(e->s_pslo, tpot_slo, R)
+#define H2D(buf, field, per) \
+  if ((rc = h2d(e, sc.buf, b->field ? b->field + (size_t)r0 * (per) : b->field, R * (per), &d.field, st)) != EPPSCORE_OK) return rc;
+    H2D(s_len, prompt_len, 1)
+    H2D(s_seed, model_seed, 1)
+    if (b->hashes_in) {
+      H2D(s_hashes, hashes_in, (size_t)b->hash_stride)
+      H2D(s_nh, n_hashes_in, 1)
+    }
+    H2D(s_adapter, adapter_id, 1)
+    H2D(s_mask, cand_mask, mw)
+    H2D(s_dense, dense_feat, M * 4)
+    H2D(s_dtotal, dense_total, 1)
+    H2D(s_intok, input_tokens, 1)
+    H2D(s_tslo, ttft_slo, 1)
+    H2D(s_pslo, tpot_slo, 1)
 #undef H2D
-  CK(e, e->s_pick.reserve(R * 4));
-  CK(e, e->s_score.reserve(R * 8));
-  CK(e, e->s_tie.reserve(R * 4));
-  d.pick = e->s_pick.as<int32_t>();
-  d.pick_score = e->s_score.as<double>();
-  d.tie_count = e->s_tie.as<int32_t>();
-  if (b->match_blocks) {
-    CK(e, e->s_match.reserve(R * M * 2));
-    d.match_blocks = e->s_match.as<uint16_t>();
+    CK(e, sc.s_pick.reserve(R * 4));
+    CK(e, sc.s_score.reserve(R * 8));
+    CK(e, sc.s_tie.reserve(R * 4));
+    d.pick = sc.s_pick.as<int32_t>();
+    d.pick_score = sc.s_score.as<double>();
+    d.tie_count = sc.s_tie.as<int32_t>();
+    if (b->match_blocks) {
+      CK(e, sc.s_match.reserve(R * M * 2));
+      d.match_blocks = sc.s_match.as<uint16_t>();
+    }
+    if (b->total_blocks) {
+      CK(e, sc.s_total.reserve(R * 2));
+      d.total_blocks = sc.s_total.as<uint16_t>();
+    }
+    if (b->scores_out) {
+      CK(e, sc.s_scores.reserve(R * M * 8));
+      d.scores_out = sc.s_scores.as<double>();
+    }
+    if (b->pred_out) {
+      CK(e, sc.s_pred.reserve(R * M * 16));
+      d.pred_out = sc.s_pred.as<double>();
+    }
+    if (b->filter_mask_out) {
+      CK(e, sc.s_fmask.reserve(R * mw * 4));
+      d.filter_mask_out = sc.s_fmask.as<uint32_t>();
+    }
+    uint64_t* hashes_dev = nullptr;
+    if (b->hashes_out) {
+      // reuse the internal hash scratch as the device-side hashes_out; entries past n_hashes[r] are zero
+      CK(e, sc.s_hashes.reserve(R * (size_t)mb * 8));
+      CK(e, cudaMemsetAsync(sc.s_hashes.p, 0, R * (size_t)mb * 8, st));
+      hashes_dev = sc.s_hashes.as<uint64_t>();
+      d.hashes_out = hashes_dev;
+    }
+    rc = schedule_device(e, d, st, sc);
+    if (rc != EPPSCORE_OK) return rc;
+    if (b->pick) CK(e, cudaMemcpyAsync(b->pick + r0, d.pick, R * 4, cudaMemcpyDeviceToHost, st));
+    if (b->pick_score) CK(e, cudaMemcpyAsync(b->pick_score + r0, d.pick_score, R * 8, cudaMemcpyDeviceToHost, st));
+    if (b->tie_count) CK(e, cudaMemcpyAsync(b->tie_count + r0, d.tie_count, R * 4, cudaMemcpyDeviceToHost, st));
+    if (b->match_blocks) CK(e, cudaMemcpyAsync(b->match_blocks + (size_t)r0 * M, d.match_blocks, R * M * 2, cudaMemcpyDeviceToHost, st));
+    if (b->total_blocks) CK(e, cudaMemcpyAsync(b->total_blocks + r0, d.total_blocks, R * 2, cudaMemcpyDeviceToHost, st));
+    if (b->scores_out) CK(e, cudaMemcpyAsync(b->scores_out + (size_t)r0 * M, d.scores_out, R * M * 8, cudaMemcpyDeviceToHost, st));
+    if (b->pred_out) CK(e, cudaMemcpyAsync(b->pred_out + (size_t)r0 * M * 2, d.pred_out, R * M * 16, cudaMemcpyDeviceToHost, st));
+    if (b->filter_mask_out) CK(e, cudaMemcpyAsync(b->filter_mask_out + (size_t)r0 * mw, d.filter_mask_out, R * mw * 4, cudaMemcpyDeviceToHost, st));
+    if (hashes_dev) CK(e, cudaMemcpyAsync(b->hashes_out + (size_t)r0 * mb, hashes_dev, R * (size_t)mb * 8, cudaMemcpyDeviceToHost, st));
   }
-  if (b->total_blocks) {
-    CK(e, e->s_total.reserve(R * 2));
-    d.total_blocks = e->s_total.as<uint16_t>();
-  }
-  if (b->scores_out) {
-    CK(e, e->s_scores.reserve(R * M * 8));
-    d.scores_out = e->s_scores.as<double>();
-  }
-  if (b->pred_out) {
-    CK(e, e->s_pred.reserve(R * M * 16));
-    d.pred_out = e->s_pred.as<double>();
-  }
-  if (b->filter_mask_out) {
-    CK(e, e->s_fmask.reserve(R * mw * 4));
-    d.filter_mask_out = e->s_fmask.as<uint32_t>();
-  }
-  uint64_t* hashes_dev = nullptr;
-  if (b->hashes_out && !b->hashes_in) {
-    // reuse the internal hash scratch as the device-side hashes_out
-    CK(e, e->s_hashes.reserve(R * (size_t)mb * 8));
-    hashes_dev = e->s_hashes.as<uint64_t>();
-    d.hashes_out = hashes_dev;
-  }
-  rc = schedule_device(e, d, e->stream);
-  if (rc != EPPSCORE_OK) return rc;
-  if (b->pick) CK(e, cudaMemcpyAsync(b->pick, d.pick, R * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (b->pick_score) CK(e, cudaMemcpyAsync(b->pick_score, d.pick_score, R * 8, cudaMemcpyDeviceToHost, e->stream));
-  if (b->tie_count) CK(e, cudaMemcpyAsync(b->tie_count, d.tie_count, R * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (b->match_blocks) CK(e, cudaMemcpyAsync(b->match_blocks, d.match_blocks, R * M * 2, cudaMemcpyDeviceToHost, e->stream));
-  if (b->total_blocks) CK(e, cudaMemcpyAsync(b->total_blocks, d.total_blocks, R * 2, cudaMemcpyDeviceToHost, e->stream));
-  if (b->scores_out) CK(e, cudaMemcpyAsync(b->scores_out, d.scores_out, R * M * 8, cudaMemcpyDeviceToHost, e->stream));
-  if (b->pred_out) CK(e, cudaMemcpyAsync(b->pred_out, d.pred_out, R * M * 16, cudaMemcpyDeviceToHost, e->stream));
-  if (b->filter_mask_out) CK(e, cudaMemcpyAsync(b->filter_mask_out, d.filter_mask_out, R * mw * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (hashes_dev) CK(e, cudaMemcpyAsync(b->hashes_out, hashes_dev, R * (size_t)mb * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
+  if (nstreams == 2) CK(e, cudaStreamSynchronize(e->stream2));
+  e->sched_pending = false;  // everything launched above has completed
   return EPPSCORE_OK;
 }
 
@@ -962,17 +974,17 @@ int32_t eppscore_hash_prompts(eppscore_engine* e, int32_t R, int32_t location, c
     total = 0;
     for (int32_t r = 0; r < R; r++) total = std::max(total, (size_t)prompt_off[r] + (size_t)prompt_len[r]);
   }
-  CK(e, e->s_prompts.reserve(total + 64));
-  if (total) CK(e, cudaMemcpyAsync(e->s_prompts.p, prompt_bytes, total, cudaMemcpyHostToDevice, e->stream));
-  h.bytes = e->s_prompts.as<uint8_t>();
-  if ((rc = h2d(e, e->s_off, prompt_off, (size_t)R + 1, &h.off)) != EPPSCORE_OK) return rc;
-  if ((rc = h2d(e, e->s_len, prompt_len, (size_t)R, &h.len)) != EPPSCORE_OK) return rc;
-  if ((rc = h2d(e, e->s_seed, model_seed, (size_t)R, &h.seed)) != EPPSCORE_OK) return rc;
-  CK(e, e->s_hashes.reserve((size_t)R * mb * 8));
-  CK(e, e->s_nh.reserve((size_t)R * 2));
-  CK(e, cudaMemsetAsync(e->s_hashes.p, 0, (size_t)R * mb * 8, e->stream));
-  h.hashes = e->s_hashes.as<uint64_t>();
-  h.n_hashes = e->s_nh.as<uint16_t>();
+  CK(e, e->sc[0].s_prompts.reserve(total + 64));
+  if (total) CK(e, cudaMemcpyAsync(e->sc[0].s_prompts.p, prompt_bytes, total, cudaMemcpyHostToDevice, e->stream));
+  h.bytes = e->sc[0].s_prompts.as<uint8_t>();
+  if ((rc = h2d(e, e->sc[0].s_off, prompt_off, (size_t)R + 1, &h.off)) != EPPSCORE_OK) return rc;
+  if ((rc = h2d(e, e->sc[0].s_len, prompt_len, (size_t)R, &h.len)) != EPPSCORE_OK) return rc;
+  if ((rc = h2d(e, e->sc[0].s_seed, model_seed, (size_t)R, &h.seed)) != EPPSCORE_OK) return rc;
+  CK(e, e->sc[0].s_hashes.reserve((size_t)R * mb * 8));
+  CK(e, e->sc[0].s_nh.reserve((size_t)R * 2));
+  CK(e, cudaMemsetAsync(e->sc[0].s_hashes.p, 0, (size_t)R * mb * 8, e->stream));
+  h.hashes = e->sc[0].s_hashes.as<uint64_t>();
+  h.n_hashes = e->sc[0].s_nh.as<uint16_t>();
   e->launches += launch_hash_prompts(h, e->stream, e->sm_count);
   CK(e, cudaGetLastError());
   CK(e, cudaMemcpyAsync(hashes_out, h.hashes, (size_t)R * mb * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -1009,138 +1021,179 @@ int32_t eppscore_count_fields(eppscore_engine* e, int32_t R, int32_t location, c
     total = 0;
     for (int32_t r = 0; r < R; r++) total = std::max(total, (size_t)prompt_off[r] + (size_t)prompt_len[r]);
   }
-  CK(e, e->s_prompts.reserve(total + 64));
-  if (total) CK(e, cudaMemcpyAsync(e->s_prompts.p, prompt_bytes, total, cudaMemcpyHostToDevice, e->stream));
+  CK(e, e->sc[0].s_prompts.reserve(total + 64));
+  if (total) CK(e, cudaMemcpyAsync(e->sc[0].s_prompts.p, prompt_bytes, total, cudaMemcpyHostToDevice, e->stream));
   const int64_t* d_off = nullptr;
   const int32_t* d_len = nullptr;
   int32_t rc;
-  if ((rc = h2d(e, e->s_off, prompt_off, (size_t)R + 1, &d_off)) != EPPSCORE_OK) return rc;
-  if ((rc = h2d(e, e->s_len, prompt_len, (size_t)R, &d_len)) != EPPSCORE_OK) return rc;
-  CK(e, e->s_fields.reserve((size_t)R * 4));
-  e->launches += launch_count_fields(e->s_prompts.as<uint8_t>(), d_off, d_len, R, e->s_fields.as<int32_t>(), e->stream, e->sm_count);
+  if ((rc = h2d(e, e->sc[0].s_off, prompt_off, (size_t)R + 1, &d_off)) != EPPSCORE_OK) return rc;
+  if ((rc = h2d(e, e->sc[0].s_len, prompt_len, (size_t)R, &d_len)) != EPPSCORE_OK) return rc;
+  CK(e, e->sc[0].s_fields.reserve((size_t)R * 4));
+  e->launches += launch_count_fields(e->sc[0].s_prompts.as<uint8_t>(), d_off, d_len, R, e->sc[0].s_fields.as<int32_t>(), e->stream, e->sm_count);
   CK(e, cudaGetLastError());
-  CK(e, cudaMemcpyAsync(out, e->s_fields.p, (size_t)R * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(e, cudaMemcpyAsync(out, e->sc[0].s_fields.p, (size_t)R * 4, cudaMemcpyDeviceToHost, e->stream));
   CK(e, cudaStreamSynchronize(e->stream));
   return EPPSCORE_OK;
+}
+
+// lru_capacity (host, [M] or NULL) -> a padded host vector the index can copy; validates the values
+static int32_t pad_caps(eppscore_engine* e, const int32_t* lru_capacity, std::vector<int32_t>* out) {
+  out->clear();
+  if (!lru_capacity) return EPPSCORE_OK;
+  out->assign((size_t)e->geo.Mpad, 0);
+  const int32_t n = e->M > 0 ? e->M : e->geo.Mpad;
+  for (int32_t i = 0; i < n; i++) (*out)[i] = lru_capacity[i] > 0 ? lru_capacity[i] : 0;
+  return EPPSCORE_OK;
+}
+static int32_t index_status(eppscore_engine* e, cudaError_t c, const char* what) {
+  if (c == cudaSuccess) return EPPSCORE_OK;
+  if (c == cudaErrorInvalidValue)
+    return fail(e, EPPSCORE_ERR_CAPACITY, std::string(what) + ": an LRU capacity above the engine's lru_capacity_max (the per-endpoint regions were sized at the first Add)");
+  return cuda_fail(e, c, what);
 }
 
 int32_t eppscore_commit_picks(eppscore_engine* e, int32_t R, const int32_t* pick, const uint64_t* hashes,
                               const uint16_t* n_hashes, int32_t hash_stride, const int32_t* lru_capacity) {
   if (!e) return EPPSCORE_ERR_INVALID;
   if (R < 0 || (R > 0 && (!pick || !hashes || !n_hashes))) return fail(e, EPPSCORE_ERR_INVALID, "NULL argument");
-  if (e->table_adopted) return fail(e, EPPSCORE_ERR_INVALID, "engine holds an adopted (read-only) table image");
+  if (R == 0) return EPPSCORE_OK;
+  if (hash_stride <= 0) return fail(e, EPPSCORE_ERR_INVALID, "hash_stride must be > 0");
+  CK(e, cudaSetDevice(e->device));
+  int32_t lo = e->geo.Mpad, hi = -1;
+  int64_t touches = 0;
   for (int32_t r = 0; r < R; r++) {
     const int32_t ep = pick[r];
     if (ep < 0) continue;  // no target endpoint: nothing to record (plugin.go:173-175)
     if (ep >= e->geo.Mpad) return fail(e, EPPSCORE_ERR_INVALID, "pick out of range");
-    const int32_t cap = lru_capacity ? lru_capacity[ep] : 0;  // makeserver, plugin.go:207-216
-    if (!e->index->add(hashes + (size_t)r * hash_stride, n_hashes[r], ep, cap))
-      return fail(e, EPPSCORE_ERR_CAPACITY, "prefix table cannot grow further (row index space exhausted)");
+    if (n_hashes[r] > hash_stride) return fail(e, EPPSCORE_ERR_INVALID, "n_hashes exceeds hash_stride");
+    lo = std::min(lo, ep);
+    hi = std::max(hi, ep);
+    touches += n_hashes[r];
   }
+  if (hi < 0) return EPPSCORE_OK;  // (a pick with zero hashes still creates the endpoint's LRU, indexer.go:57-68)
+  std::vector<int32_t> caps;
+  int32_t rc = pad_caps(e, lru_capacity, &caps);
+  if (rc != EPPSCORE_OK) return rc;
+  if ((rc = index_begin(e)) != EPPSCORE_OK) return rc;
+  CK(e, e->c_pick.reserve((size_t)R * 4));
+  CK(e, e->c_hash.reserve((size_t)R * hash_stride * 8));
+  CK(e, e->c_nh.reserve((size_t)R * 2));
+  CK(e, cudaMemcpyAsync(e->c_pick.p, pick, (size_t)R * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(e->c_hash.p, hashes, (size_t)R * hash_stride * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(e->c_nh.p, n_hashes, (size_t)R * 2, cudaMemcpyHostToDevice, e->stream));
+  rc = index_status(e, e->index->commit(R, e->c_pick.as<int32_t>(), e->c_hash.as<uint64_t>(), e->c_nh.as<uint16_t>(), hash_stride,
+                                        caps.empty() ? nullptr : caps.data(), 0, lo, hi - lo + 1, std::max<int64_t>(touches, 1), e->stream),
+                    "commit_picks");
+  if (rc != EPPSCORE_OK) return rc;
+  CK(e, cudaStreamSynchronize(e->stream));  // the caller's host arrays (pageable) may be reused
+  return index_end(e);
+}
+
+int32_t eppscore_commit_picks_device(eppscore_engine* e, int32_t R, const int32_t* pick, const uint64_t* hashes,
+                                     const uint16_t* n_hashes, int32_t hash_stride, const int32_t* lru_capacity,
+                                     int64_t touch_bound, void* stream) {
+  if (!e) return EPPSCORE_ERR_INVALID;
+  if (R < 0 || (R > 0 && (!pick || !hashes || !n_hashes))) return fail(e, EPPSCORE_ERR_INVALID, "NULL argument");
+  if (R == 0) return EPPSCORE_OK;
+  if (hash_stride <= 0) return fail(e, EPPSCORE_ERR_INVALID, "hash_stride must be > 0");
+  CK(e, cudaSetDevice(e->device));
+  std::vector<int32_t> caps;
+  int32_t rc = pad_caps(e, lru_capacity, &caps);
+  if (rc != EPPSCORE_OK) return rc;
+  cudaStream_t cs = stream ? (cudaStream_t)stream : e->stream;
+  if (cs != e->stream) {  // the arrays are produced on the caller's stream
+    CK(e, cudaEventRecord(e->ev_caller, cs));
+    CK(e, cudaStreamWaitEvent(e->stream, e->ev_caller, 0));
+  }
+  if ((rc = index_begin(e)) != EPPSCORE_OK) return rc;
+  const int32_t n_eps = e->M > 0 ? e->M : e->geo.Mpad;
+  rc = index_status(e, e->index->commit(R, pick, hashes, n_hashes, hash_stride, caps.empty() ? nullptr : caps.data(), 0, 0, n_eps,
+                                        touch_bound, e->stream),
+                    "commit_picks_device");
+  if (rc != EPPSCORE_OK) return rc;
+  if ((rc = index_end(e)) != EPPSCORE_OK) return rc;
+  if (cs != e->stream) CK(e, cudaStreamWaitEvent(cs, e->ev_table, 0));  // stream-ordered for the caller
   return EPPSCORE_OK;
 }
 
 int32_t eppscore_prefix_add(eppscore_engine* e, const uint64_t* hashes, int32_t n, int32_t endpoint, int32_t lru_capacity) {
   if (!e) return EPPSCORE_ERR_INVALID;
   if (n < 0 || (n > 0 && !hashes)) return fail(e, EPPSCORE_ERR_INVALID, "NULL argument");
+  if (n > EPPSCORE_MAX_BLOCKS) return fail(e, EPPSCORE_ERR_CAPACITY, "more than 65535 hashes in one Add");
   if (endpoint < 0 || endpoint >= e->geo.Mpad) return fail(e, EPPSCORE_ERR_INVALID, "endpoint out of range");
-  if (e->table_adopted) return fail(e, EPPSCORE_ERR_INVALID, "engine holds an adopted (read-only) table image");
-  if (!e->index->add(hashes, n, endpoint, lru_capacity)) return fail(e, EPPSCORE_ERR_CAPACITY, "prefix table full");
-  return EPPSCORE_OK;
+  CK(e, cudaSetDevice(e->device));
+  int32_t rc = index_begin(e);
+  if (rc != EPPSCORE_OK) return rc;
+  const int32_t stride = n > 0 ? n : 1;
+  const uint16_t nh = (uint16_t)n;
+  CK(e, e->c_pick.reserve(4));
+  CK(e, e->c_hash.reserve((size_t)stride * 8));
+  CK(e, e->c_nh.reserve(2));
+  CK(e, cudaMemcpyAsync(e->c_pick.p, &endpoint, 4, cudaMemcpyHostToDevice, e->stream));
+  if (n) CK(e, cudaMemcpyAsync(e->c_hash.p, hashes, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(e->c_nh.p, &nh, 2, cudaMemcpyHostToDevice, e->stream));
+  rc = index_status(e, e->index->commit(1, e->c_pick.as<int32_t>(), e->c_hash.as<uint64_t>(), e->c_nh.as<uint16_t>(), stride, nullptr,
+                                        lru_capacity, endpoint, 1, std::max(n, 1), e->stream),
+                    "prefix_add");
+  if (rc != EPPSCORE_OK) return rc;
+  CK(e, cudaStreamSynchronize(e->stream));
+  return index_end(e);
 }
 
 int32_t eppscore_prefix_apply(eppscore_engine* e, int64_t n, const uint64_t* hash, const int32_t* endpoint, const uint8_t* op) {
   if (!e) return EPPSCORE_ERR_INVALID;
   if (n < 0 || (n > 0 && (!hash || !endpoint || !op))) return fail(e, EPPSCORE_ERR_INVALID, "NULL argument");
-  if (e->table_adopted) return fail(e, EPPSCORE_ERR_INVALID, "engine holds an adopted (read-only) table image");
+  if (n == 0) return EPPSCORE_OK;
   for (int64_t i = 0; i < n; i++)
-    if (!e->index->apply(hash[i], endpoint[i], op[i])) return fail(e, EPPSCORE_ERR_CAPACITY, "prefix table full or endpoint out of range");
-  return EPPSCORE_OK;
+    if (endpoint[i] < 0 || endpoint[i] >= e->geo.Mpad) return fail(e, EPPSCORE_ERR_CAPACITY, "prefix_apply: endpoint out of range");
+  CK(e, cudaSetDevice(e->device));
+  int32_t rc = index_begin(e);
+  if (rc != EPPSCORE_OK) return rc;
+  CK(e, e->c_hash.reserve((size_t)n * 8));
+  CK(e, e->c_ep.reserve((size_t)n * 4));
+  CK(e, e->c_op.reserve((size_t)n));
+  CK(e, cudaMemcpyAsync(e->c_hash.p, hash, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(e->c_ep.p, endpoint, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(e, cudaMemcpyAsync(e->c_op.p, op, (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  rc = index_status(e, e->index->apply(n, e->c_hash.as<uint64_t>(), e->c_ep.as<int32_t>(), e->c_op.as<uint8_t>(), e->stream), "prefix_apply");
+  if (rc != EPPSCORE_OK) return rc;
+  CK(e, cudaStreamSynchronize(e->stream));
+  return index_end(e);
 }
 
 int32_t eppscore_prefix_remove_endpoint(eppscore_engine* e, int32_t endpoint) {
   if (!e) return EPPSCORE_ERR_INVALID;
-  e->index->remove_endpoint(endpoint);
-  return EPPSCORE_OK;
+  CK(e, cudaSetDevice(e->device));
+  int32_t rc = index_begin(e);
+  if (rc != EPPSCORE_OK) return rc;
+  rc = index_status(e, e->index->remove_endpoint(endpoint, e->stream), "prefix_remove_endpoint");
+  if (rc != EPPSCORE_OK) return rc;
+  return index_end(e);
 }
 
-int32_t eppscore_prefix_lru_len(const eppscore_engine* e, int32_t endpoint) { return e ? e->index->lru_len(endpoint) : -1; }
-int32_t eppscore_prefix_lru_keys(const eppscore_engine* e, int32_t endpoint, uint64_t* out, int32_t cap) {
-  return e ? e->index->lru_keys(endpoint, out, cap) : -1;
+int32_t eppscore_prefix_lru_len(const eppscore_engine* ce, int32_t endpoint) {
+  eppscore_engine* e = const_cast<eppscore_engine*>(ce);
+  if (!e) return -1;
+  if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+  int32_t len = -1;
+  if (e->index->lru_keys(endpoint, nullptr, 0, &len, e->stream) != cudaSuccess) return -1;
+  return len;
 }
-
-}  // extern "C"
-
-// single-thread probe of the DEVICE table (so eppscore_prefix_get checks what the kernels see)
-__global__ void probe_one_kernel(const Slot* slots, uint64_t mask, const uint32_t* rows, int rw, uint64_t h, uint32_t* out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  uint32_t cnt = 0, row = kEmptyRow;
-  for (uint64_t i = h & mask;; i = (i + 1) & mask) {
-    const Slot s = slots[i];
-    if (s.row == kEmptyRow) break;
-    if (s.key == h) {
-      cnt = s.cnt;
-      row = s.row;
-      break;
-    }
-  }
-  out[0] = cnt;
-  out[1] = row;
-  for (int w = 0; w < rw; w++) out[2 + w] = (row != kEmptyRow) ? rows[(size_t)row * rw + w] : 0u;
+int32_t eppscore_prefix_lru_keys(const eppscore_engine* ce, int32_t endpoint, uint64_t* out, int32_t cap) {
+  eppscore_engine* e = const_cast<eppscore_engine*>(ce);
+  if (!e) return -1;
+  if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+  int32_t len = -1;
+  if (e->index->lru_keys(endpoint, out, cap, &len, e->stream) != cudaSuccess) return -1;
+  return len;
 }
-
-extern "C" {
 
 int32_t eppscore_prefix_get(eppscore_engine* e, uint64_t hash, uint32_t* bitset_out, int32_t words) {
   if (!e) return EPPSCORE_ERR_INVALID;
   CK(e, cudaSetDevice(e->device));
-  int32_t rc = flush_table(e);
-  if (rc != EPPSCORE_OK) return rc;
-  const int rw = e->geo.row_words;
-  probe_one_kernel<<<1, 32, 0, e->stream>>>(e->d_slots, e->index->slot_mask(), e->d_rows, rw, hash, e->probe_out.as<uint32_t>());
-  e->launches++;
-  std::vector<uint32_t> host((size_t)rw + 2);
-  CK(e, cudaMemcpyAsync(host.data(), e->probe_out.p, host.size() * 4, cudaMemcpyDeviceToHost, e->stream));
-  CK(e, cudaStreamSynchronize(e->stream));
-  if (bitset_out) {
-    for (int32_t w = 0; w < words; w++) bitset_out[w] = 0;
-    for (int32_t m = 0; m < e->geo.Mpad && (m >> 5) < words; m++) {
-      const uint32_t pos = perm_bitpos((uint32_t)m, e->geo.log_epl);
-      if ((host[2 + (pos >> 5)] >> (pos & 31)) & 1u) bitset_out[m >> 5] |= 1u << (m & 31);
-    }
-  }
-  return (int32_t)host[0];
-}
-
-int32_t eppscore_prefix_image_info(eppscore_engine* e, void** slots_dev, int64_t* slots_bytes, void** rows_dev,
-                                   int64_t* rows_bytes, int64_t* meta) {
-  if (!e) return EPPSCORE_ERR_INVALID;
-  CK(e, cudaSetDevice(e->device));
-  int32_t rc = flush_table(e);
-  if (rc != EPPSCORE_OK) return rc;
-  if (slots_dev) *slots_dev = e->d_slots;
-  if (slots_bytes) *slots_bytes = (int64_t)(e->index->slots().size() * sizeof(Slot));
-  if (rows_dev) *rows_dev = e->d_rows;
-  if (rows_bytes) *rows_bytes = e->index->n_rows() * (int64_t)e->geo.row_words * 4;
-  if (meta) {
-    meta[0] = (int64_t)e->index->slots().size();
-    meta[1] = e->geo.row_words;
-    meta[2] = e->index->n_rows();
-    meta[3] = e->index->n_live();
-  }
-  return EPPSCORE_OK;
-}
-
-int32_t eppscore_prefix_image_adopt(eppscore_engine* e, const int64_t* meta) {
-  if (!e || !meta) return EPPSCORE_ERR_INVALID;
-  if (meta[0] != (int64_t)e->index->slots().size() || meta[1] != e->geo.row_words)
-    return fail(e, EPPSCORE_ERR_INVALID, "image geometry differs (engines must share max_endpoints and prefix_capacity)");
-  if (meta[2] > e->index->capacity_rows() + 1) return fail(e, EPPSCORE_ERR_CAPACITY, "image has more rows than prefix_capacity");
-  e->index->adopt_counts(meta[2], meta[3]);
-  e->index->clear_dirty();
-  e->table_adopted = true;
-  CK(e, cudaEventRecord(e->ev_table, e->stream));
-  return EPPSCORE_OK;
+  int32_t count = 0;
+  CK(e, e->index->get(hash, bitset_out, bitset_out ? words : 0, &count, e->stream));
+  return count;
 }
 
 void* eppscore_host_alloc(size_t bytes) {

@@ -174,10 +174,151 @@ __global__ void __launch_bounds__(kHashWarps * 32) hash_chain_kernel(HashArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// hash_fused_kernel: both stages in ONE kernel, warp-specialised.  A CTA owns tiles of 32 requests; seven BODY warps
+// stream the prompts (lane = block, the stripe states go to a shared-memory buffer [request][block]), the CHAIN warp
+// (lane = request) turns a buffer of body states into chained hashes in place, and the body warps write a finished
+// buffer out (coalesced, 256 bytes per request row) when they get it back.  Two buffers ping-pong through named barriers
+// (FULL: bodies -> chain, EMPTY: chain -> bodies), so the serial chain of chunk q overlaps the HBM stream of chunk q+1:
+// the 8-byte body states never travel through HBM and the second launch is gone (r1: 28.9 us + 12.4 us as two kernels).
+// ---------------------------------------------------------------------------------------------
+constexpr int kFusedWarps = 8;                   // 7 body warps + 1 chain warp
+constexpr int kFusedBody = kFusedWarps - 1;
+constexpr int kFusedTile = 32;                   // requests per tile (one chain lane each)
+
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int BC>
+__global__ void __launch_bounds__(kFusedWarps * 32, 3) hash_fused_kernel(HashArgs a) {
+  __shared__ uint64_t buf[2][kFusedTile][33];
+  __shared__ int s_nfull[2][kFusedTile];
+  __shared__ int s_base[2], s_c0[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bc = BC ? BC : a.block_chars;
+  const int ntiles = (a.R + kFusedTile - 1) / kFusedTile;
+  constexpr int FULL0 = 1, EMPTY0 = 3, NT = kFusedWarps * 32;
+  int q = 0;  // chunk counter of this CTA: identical in every warp (same tile / chunk loop bounds)
+
+  if (warp < kFusedBody) {
+    // ---------------- body warps ----------------
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int base = tile * kFusedTile;
+      // descriptors of this tile's requests: lane = request (every body warp computes the same 32 descriptors)
+      ReqDesc d;
+      d.p = nullptr;
+      d.seed = 0;
+      d.nfull = 0;
+      d.rem = 0;
+      d.fast = false;
+      if (base + lane < a.R) d = load_desc(a, base + lane, bc);
+      int maxfull = d.nfull;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) maxfull = max(maxfull, __shfl_xor_sync(0xffffffffu, maxfull, o));
+      int nchunks = (maxfull + 31) >> 5;
+      if (nchunks < 1) nchunks = 1;  // the chain warp still runs once per tile (partial blocks, n_hashes)
+      for (int ch = 0; ch < nchunks; ch++, q++) {
+        const int b = q & 1, c0 = ch * 32;
+        if (q >= 2) {
+          nbar_sync(EMPTY0 + b, NT);  // the chain warp is done with the chunk that used this buffer
+          // write that chunk's hashes out: 32 consecutive blocks of a request per warp store
+          const int ob = s_base[b], oc = s_c0[b];
+          for (int rq = warp; rq < kFusedTile; rq += kFusedBody) {
+            const int blk = oc + lane;
+            if (ob + rq < a.R && blk < s_nfull[b][rq]) a.hashes[(size_t)(ob + rq) * a.stride + blk] = buf[b][rq][lane];
+          }
+          nbar_sync(7, kFusedBody * 32);  // every body warp has read the old descriptors before they are replaced
+        }
+        if (warp == 0) {
+          s_nfull[b][lane] = d.nfull;  // (rows of the generic path are filled by the chain lane and flushed like the others)
+          if (lane == 0) {
+            s_base[b] = base;
+            s_c0[b] = c0;
+          }
+        }
+        // body states of blocks [c0, c0+32) of this warp's requests
+        for (int rq = warp; rq < kFusedTile; rq += kFusedBody) {
+          const int nf = __shfl_sync(0xffffffffu, d.nfull, rq);
+          const int fs = __shfl_sync(0xffffffffu, d.fast ? 1 : 0, rq);
+          const unsigned long long pp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(d.p), rq);
+          const int blk = c0 + lane;
+          if (fs && blk < nf)
+            buf[b][rq][lane] = block_body_state<BC>(reinterpret_cast<const uint8_t*>((uintptr_t)pp) + (size_t)blk * bc, bc);
+        }
+        __threadfence_block();
+        nbar_arrive(FULL0 + b, NT);
+      }
+    }
+    // drain: the last (up to two) chunks still sit in the buffers
+    for (int k = (q >= 2 ? q - 2 : 0); k < q; k++) {
+      const int b = k & 1;
+      nbar_sync(EMPTY0 + b, NT);
+      const int ob = s_base[b], oc = s_c0[b];
+      for (int rq = warp; rq < kFusedTile; rq += kFusedBody) {
+        const int blk = oc + lane;
+        if (ob + rq < a.R && blk < s_nfull[b][rq]) a.hashes[(size_t)(ob + rq) * a.stride + blk] = buf[b][rq][lane];
+      }
+    }
+  } else {
+    // ---------------- chain warp: lane = request ----------------
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int base = tile * kFusedTile;
+      const int r = base + lane;
+      ReqDesc d;
+      d.p = nullptr;
+      d.seed = 0;
+      d.nfull = 0;
+      d.rem = 0;
+      d.fast = false;
+      if (r < a.R) d = load_desc(a, r, bc);
+      int maxfull = d.nfull;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) maxfull = max(maxfull, __shfl_xor_sync(0xffffffffu, maxfull, o));
+      int nchunks = (maxfull + 31) >> 5;
+      if (nchunks < 1) nchunks = 1;
+      uint64_t prev = d.seed;
+      for (int ch = 0; ch < nchunks; ch++, q++) {
+        const int b = q & 1, c0 = ch * 32;
+        nbar_sync(FULL0 + b, NT);
+        const int nb = min(32, d.nfull - c0);
+        for (int i = 0; i < nb; i++) {
+          if (d.fast)
+            prev = xchain_aligned(buf[b][lane][i], prev);
+          else
+            prev = xxh64_link<false>(d.p + (size_t)(c0 + i) * bc, (uint32_t)bc, prev);  // hashing.go:80-87
+          buf[b][lane][i] = prev;
+        }
+        if (ch == nchunks - 1 && r < a.R) {
+          if (d.rem > 0) {                                   // trailing partial block, hashing.go:89-95
+            const uint8_t* t = d.p + (size_t)d.nfull * bc;
+            const uint64_t h = ((reinterpret_cast<uintptr_t>(t) & 7) == 0) ? xxh64_link<true>(t, (uint32_t)d.rem, prev)
+                                                                            : xxh64_link<false>(t, (uint32_t)d.rem, prev);
+            a.hashes[(size_t)r * a.stride + d.nfull] = h;
+          }
+          a.n_hashes[r] = (uint16_t)(d.nfull + (d.rem > 0 ? 1 : 0));
+        }
+        __threadfence_block();
+        nbar_arrive(EMPTY0 + b, NT);
+      }
+    }
+  }
+}
+
 int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
+  const int stages0 = a.stage_mask ? a.stage_mask : 7;
+  if ((stages0 & 4) && a.block_chars > 0 && (a.block_chars & 31) == 0) {  // default: the fused kernel
+    const int ntiles = (a.R + kFusedTile - 1) / kFusedTile;
+    int blocks = sm_count * 3;
+    if (blocks > ntiles) blocks = ntiles;
+    if (a.block_chars == 64)
+      hash_fused_kernel<64><<<blocks, kFusedWarps * 32, 0, s>>>(a);
+    else
+      hash_fused_kernel<0><<<blocks, kFusedWarps * 32, 0, s>>>(a);
+    return 1;
+  }
   int launched = 0;
-  const int stages = a.stage_mask ? a.stage_mask : 3;
+  const int stages = (stages0 & 3) ? (stages0 & 3) : 3;
   if ((stages & 1) && a.block_chars > 0 && (a.block_chars & 31) == 0) {
     long long blocks = ((long long)a.R + kBodyWarps - 1) / kBodyWarps;
     const long long cap = (long long)sm_count * 64;      // grid-stride beyond a few waves

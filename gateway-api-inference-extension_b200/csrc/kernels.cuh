@@ -10,23 +10,19 @@
 //     (EPL = endpoints per lane per pass = 8/16/32 chosen from max_endpoints, j = pass).  Natural-order
 //     arrays (terms, candidate masks, dense rows, match output) are then read/written with consecutive
 //     lanes touching consecutive endpoints — coalesced and bank-conflict free;
-//   * prefix table: open-addressing key slots {hash, row, count} + bitset rows of J*32 words.
+//   * prefix table: device-resident index (prefix_table.cuh): 32-byte open-addressing slots that carry sets of up to
+//     8 endpoints inline, natural-order bitset rows for larger sets, per-endpoint log-structured LRUs.
 #pragma once
 #include <cuda_runtime.h>
 
 #include <cstdint>
 
+#include "prefix_table.cuh"
+
 namespace eppscore {
 
 constexpr int kMaxSteps = 8;
 constexpr int kLutMax = 256;  // per-warp prefix LUT covers total <= 256 (defaultMaxPrefixBlocks)
-constexpr uint32_t kEmptyRow = 0xFFFFFFFFu;
-
-struct __align__(16) Slot {
-  uint64_t key;
-  uint32_t row;  // kEmptyRow = never used
-  uint32_t cnt;  // |endpoint set|; 0 = emptied (a miss, like a deleted hashToPods key)
-};
 
 enum StepKind : int32_t {
   STEP_EP_TERM = 0,  // + term[arg][m]                  (request-independent scorer, precomputed)
@@ -151,9 +147,7 @@ struct ScoreArgs {
   const uint64_t* hashes;       // [R][hash_stride] or null
   const uint16_t* n_hashes;     // [R]
   int32_t hash_stride;
-  const Slot* slots;
-  uint64_t slot_mask;           // capacity-1
-  const uint32_t* rows;
+  const TableView* table;       // device pointer to the prefix index's view (null: no table) — stable across rebuilds
   // dense rows
   const float4* dense;          // [R][M]
   const uint16_t* dense_total;  // [R]
@@ -184,7 +178,7 @@ struct HashArgs {
   uint64_t* hashes;         // [R][stride]
   int32_t stride;
   uint16_t* n_hashes;       // [R]
-  int32_t stage_mask;       // diagnostics: bit 0 body kernel, bit 1 chain kernel (0 => both)
+  int32_t stage_mask;       // diagnostics: bit 2 fused kernel (default); else bit 0 body kernel, bit 1 chain kernel
 };
 
 struct PrepareArgs {
@@ -240,7 +234,5 @@ int launch_score_pick(const ScoreArgs& a, bool dense, cudaStream_t s, int sm_cou
 int launch_score_matrix(const ScoreArgs& a, cudaStream_t s, int sm_count);             // every pair scored (masks, diagnostics)
 int launch_score_dense_fast(const ScoreArgs& a, cudaStream_t s, int sm_count);         // 0 if no specialisation applies
 int launch_pick_sparse(const ScoreArgs& a, cudaStream_t s, int sm_count);              // 0 if not applicable
-int launch_scatter_u32(uint32_t* dst, const uint32_t* idx, const uint32_t* val, int64_t n, cudaStream_t s);
-int launch_scatter_slots(Slot* dst, const uint32_t* idx, const Slot* val, int64_t n, cudaStream_t s);
 
 }  // namespace eppscore

@@ -15,9 +15,11 @@
 // So a request costs O(matched blocks + exceptions) instead of O(M) — bit-identical picks, scores and
 // tie counts (tests compare against the oracle and against the generic kernel).
 //
-// Work split: a group of G = row_words/4 lanes serves one request (each lane owns 16 bytes of every
-// bitset row), so a warp serves 32/G requests at once; per-request match counters live in shared memory.
+// Work split: a group of G = row_words/4 lanes serves one request, so a warp serves 32/G requests at once; per-request
+// match counters (natural endpoint order) and the bitmap of endpoints that have one live in shared memory.  The table is
+// the device-resident index of prefix_table.cuh: a hit brings its endpoint set along in the 32-byte slot.
 #include "device_common.cuh"
+#include "prefix_table.cuh"
 
 namespace eppscore {
 
@@ -52,22 +54,28 @@ __device__ __forceinline__ double eval_exception(const ScoreArgs& a, int m, int 
 template <int J, typename CNT, uint32_t SEQ>
 __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const __grid_constant__ ScoreArgs a) {
   const int LOG_EPL = a.geo.log_epl;
-  constexpr int RW = J * 32;                       // words per bitset row
+  constexpr int RW = J * 32;                       // words per PERMUTED bit row (LoRA class planes, tie masks)
   constexpr int G = (RW / 4 < 32) ? RW / 4 : 32;   // lanes per request
-  constexpr int QW = RW / (4 * G);                 // 16-byte quads per lane per row
+  constexpr int PW = RW / G;                       // permuted words per lane
   constexpr int RPW = 32 / G;                      // requests per warp
-  constexpr int NPOS = RW * 32;                    // counter slots per request (indexed by permuted bit position)
+  const int MPAD = a.geo.Mpad;
+  const int NW = MPAD >> 5;                        // words of a NATURAL-order bitmap (overflow rows, touched bitmap)
+  const int WPL = NW / G;                          // ... per lane (>= 1 for every geometry of make_geo)
+  // per request in shared memory: match counters (natural endpoint order) + the bitmap of endpoints with a match
+  const int REQ_BYTES = MPAD * (int)sizeof(CNT) + NW * 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Plan& plan = a.plan;
   const int M = a.geo.M;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gi = lane / G, gl = lane % G;
-  CNT* cnt = reinterpret_cast<CNT*>(smem_raw) + (size_t)(warp * RPW + gi) * NPOS;
+  unsigned char* mine = smem_raw + (size_t)(warp * RPW + gi) * REQ_BYTES;
+  CNT* cnt = reinterpret_cast<CNT*>(mine);
+  uint32_t* touched = reinterpret_cast<uint32_t*>(mine + MPAD * sizeof(CNT));
 
-  // zero all counters once; afterwards each request re-zeroes exactly the slots it touched
+  // zero everything once; afterwards each request re-zeroes exactly what it touched
   {
     uint32_t* z = reinterpret_cast<uint32_t*>(smem_raw);
-    const int nwords = (int)((size_t)kSparseWarps * RPW * NPOS * sizeof(CNT) / 4);
+    const int nwords = kSparseWarps * RPW * REQ_BYTES / 4;
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) z[i] = 0;
   }
   __syncthreads();
@@ -76,7 +84,15 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
   for (int s = 0; s < plan.n_steps; s++)
     if (plan.kind[s] == STEP_PREFIX) prefix_step = s;
   const int tie_mode = plan.tie_mode;
-  const bool have_table = a.slots != nullptr && a.hashes != nullptr && prefix_step >= 0;
+  const bool have_table = a.table != nullptr && a.hashes != nullptr && prefix_step >= 0;
+  const TSlot* slots = nullptr;
+  uint64_t slot_mask = 0;
+  const uint32_t* ovf_rows = nullptr;
+  if (have_table) {
+    slots = a.table->slots;
+    slot_mask = a.table->mask;
+    ovf_rows = a.table->ovf_rows;
+  }
 
   const int wstride = gridDim.x * kSparseWarps * RPW;
   for (int rbase = (blockIdx.x * kSparseWarps + warp) * RPW; rbase < a.R; rbase += wstride) {
@@ -85,46 +101,42 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
     const int n = (valid && a.hashes) ? (int)a.n_hashes[r] : 0;
     int ad = (valid && a.adapter_id) ? a.adapter_id[r] : -1;
     if (ad < 0 || ad >= a.A) ad = a.A;
-    const AdapterSummary sm = a.summ[ad];  // issued early: only consumed after the probe / row phase
-    uint32_t any[QW][4];
-#pragma unroll
-    for (int q = 0; q < QW; q++) any[q][0] = any[q][1] = any[q][2] = any[q][3] = 0;
+    const AdapterSummary sm = a.summ[ad];  // issued early: only consumed after the probe phase
 
     // ---------------- matchLongestPrefix: probe U*G hashes per round, stop at the first global miss ----------------
-    // Hashes whose endpoint sets are identical share ONE interned row (prefix_index.hpp), and consecutive blocks
-    // of a prompt are normally cached on the same endpoints: the hits are run-length merged by row id and each
-    // distinct set is read once, its members' counters bumped by the run length.
+    // A hit returns the endpoint set with the slot itself (up to 8 members inline).  Consecutive blocks of a prompt are
+    // normally cached on the same endpoints: hits whose slots carry identical inline sets are run-length merged, lane k of
+    // the request's group bumps member k's counter by the run length.
     if (have_table) {
       constexpr int U = 4;            // hashes probed per lane per round (independent loads in flight)
       bool stop = n == 0;
       int c0 = 0;
       while (__any_sync(0xffffffffu, !stop)) {
         uint64_t h[U], idx[U];
-        uint4 sv[U];
-        uint32_t row[U];
-        bool act[U];
+        uint4 lo[U];   // {key.lo, key.hi, cnt, ovf}; the members (second half of the slot, same sector) are loaded per run
+        bool act[U], hit[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
           const int i = c0 + u * G + gl;
           act[u] = !stop && i < n;
           h[u] = act[u] ? a.hashes[(size_t)r * a.hash_stride + i] : 0ULL;
-          idx[u] = h[u] & a.slot_mask;
+          idx[u] = h[u] & slot_mask;
         }
 #pragma unroll
         for (int u = 0; u < U; u++)
-          if (act[u]) sv[u] = ldg16(&a.slots[idx[u]]);
+          if (act[u]) lo[u] = ldg16(&slots[idx[u]]);
 #pragma unroll
         for (int u = 0; u < U; u++) {                           // indexer.Get, indexer.go:86-102
-          row[u] = kEmptyRow;
+          hit[u] = false;
           if (act[u]) {
             for (;;) {
-              if (sv[u].z == kEmptyRow) break;                  // never-used slot: hash unknown
-              if ((((uint64_t)sv[u].y << 32) | sv[u].x) == h[u]) {
-                if (sv[u].w != 0) row[u] = sv[u].z;             // emptied set == deleted key
+              if (lo[u].z == kCntFree) break;                   // never-used slot: hash unknown
+              if ((((uint64_t)lo[u].y << 32) | lo[u].x) == h[u]) {
+                hit[u] = lo[u].z != 0;                          // emptied set == deleted key
                 break;
               }
-              idx[u] = (idx[u] + 1) & a.slot_mask;
-              sv[u] = ldg16(&a.slots[idx[u]]);
+              idx[u] = (idx[u] + 1) & slot_mask;
+              lo[u] = ldg16(&slots[idx[u]]);
             }
           }
         }
@@ -132,7 +144,7 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
         bool open = !stop;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          const uint32_t miss = __ballot_sync(0xffffffffu, row[u] == kEmptyRow);
+          const uint32_t miss = __ballot_sync(0xffffffffu, !hit[u]);
           const uint32_t gmiss = (G == 32) ? miss : ((miss >> (gi * G)) & ((1u << G) - 1u));
           if (open) {
             const int nh_u = gmiss ? (__ffs(gmiss) - 1) : G;
@@ -144,8 +156,24 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
         for (int u = 0; u < U; u++) {
           int nh_u = nh_total - u * G;
           nh_u = nh_u < 0 ? 0 : (nh_u > G ? G : nh_u);
-          const uint32_t prev_rr = __shfl_up_sync(0xffffffffu, row[u], 1, G);
-          const bool boundary = gl < nh_u && (gl == 0 || row[u] != prev_rr);
+          if (__all_sync(0xffffffffu, nh_u == 0)) continue;
+          // the members: second 16 bytes of the slot (the sector is already in L1)
+          uint4 hi = make_uint4(0, 0, 0, 0);
+          if (gl < nh_u && lo[u].w == kNoRow) hi = ldg16(reinterpret_cast<const uint4*>(&slots[idx[u]]) + 1);
+          // run boundaries: a hit starts a new run unless its inline set equals the previous hit's, member for member
+          const uint32_t pc = __shfl_up_sync(0xffffffffu, lo[u].z, 1, G), po = __shfl_up_sync(0xffffffffu, lo[u].w, 1, G);
+          const uint32_t p0 = __shfl_up_sync(0xffffffffu, hi.x, 1, G), p1 = __shfl_up_sync(0xffffffffu, hi.y, 1, G);
+          const uint32_t p2 = __shfl_up_sync(0xffffffffu, hi.z, 1, G), p3 = __shfl_up_sync(0xffffffffu, hi.w, 1, G);
+          const uint32_t c = lo[u].z;
+          bool same = gl > 0 && lo[u].w == kNoRow && po == kNoRow && pc == c;
+          if (same) {  // compare the first c members (the tail of ep[] is unspecified)
+            const uint32_t m1 = c >= 2 ? 0xFFFFFFFFu : 0x0000FFFFu;
+            same = ((p0 ^ hi.x) & m1) == 0;
+            if (c > 2) same = same && ((p1 ^ hi.y) & (c >= 4 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+            if (c > 4) same = same && ((p2 ^ hi.z) & (c >= 6 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+            if (c > 6) same = same && ((p3 ^ hi.w) & (c >= 8 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+          }
+          const bool boundary = gl < nh_u && !same;
           const uint32_t ball = __ballot_sync(0xffffffffu, boundary);
           uint32_t bm = (G == 32) ? ball : ((ball >> (gi * G)) & ((1u << G) - 1u));
           while (__any_sync(0xffffffffu, bm != 0)) {
@@ -155,27 +183,33 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
               bm &= bm - 1;
               len = (bm ? (__ffs(bm) - 1) : nh_u) - s0;
             }
-            const uint32_t rr = __shfl_sync(0xffffffffu, row[u], gi * G + s0);
+            const int src = gi * G + s0;
+            const uint32_t rc = __shfl_sync(0xffffffffu, lo[u].z, src), ro = __shfl_sync(0xffffffffu, lo[u].w, src);
+            const uint32_t e0 = __shfl_sync(0xffffffffu, hi.x, src), e1 = __shfl_sync(0xffffffffu, hi.y, src);
+            const uint32_t e2 = __shfl_sync(0xffffffffu, hi.z, src), e3 = __shfl_sync(0xffffffffu, hi.w, src);
             if (len > 0) {
-#pragma unroll
-              for (int q = 0; q < QW; q++) {
-                const int w0 = (q * G + gl) * 4;
-                const uint4 w = ldg16(a.rows + (size_t)rr * RW + w0);
-                if (w.x | w.y | w.z | w.w) {                     // res[server] += len for every server in the set
-                  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                  for (int t = 0; t < 4; t++) {
-                    uint32_t x = ww[t];
-                    any[q][t] |= x;
-                    while (x) {
-                      const int k = __ffs(x) - 1;
-                      x &= x - 1;
-                      cnt[(w0 + t) * 32 + k] += (CNT)len;
-                    }
+              if (ro == kNoRow) {                                 // inline set: lane k owns member k
+                if (gl < (int)rc && gl < kInlineEps) {
+                  const uint32_t wsel = (gl >> 1) == 0 ? e0 : ((gl >> 1) == 1 ? e1 : ((gl >> 1) == 2 ? e2 : e3));
+                  const int m = (int)((gl & 1) ? (wsel >> 16) : (wsel & 0xFFFFu));
+                  const CNT old = cnt[m];                         // res[server] += len
+                  cnt[m] = (CNT)(old + (CNT)len);
+                  if (old == 0) atomicOr(&touched[m >> 5], 1u << (m & 31));
+                }
+              } else {                                            // a set of more than 8: one bitset row, natural order
+                for (int q = 0; q < WPL; q++) {
+                  const int w = gl * WPL + q;
+                  uint32_t x = __ldg(ovf_rows + (size_t)ro * NW + w);
+                  touched[w] |= x;                                // this lane owns word w of the bitmap in this step
+                  while (x) {
+                    const int k = __ffs(x) - 1;
+                    x &= x - 1;
+                    cnt[w * 32 + k] += (CNT)len;
                   }
                 }
               }
             }
+            __syncwarp();  // members of the next run may alias this run's counters
           }
         }
         c0 += U * G;
@@ -187,30 +221,25 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
     const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
     Best best = best_none();
     int xg = 0;
-#pragma unroll
-    for (int q = 0; q < QW; q++) {
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        uint32_t x = any[q][t];
-        if (x) {
-          const int wi = (q * G + gl) * 4 + t;
+    for (int q = 0; q < WPL; q++) {
+      const int w = gl * WPL + q;
+      uint32_t x = touched[w];
+      while (x) {                                                 // ascending k == ascending m for this lane
+        const int k = __ffs(x) - 1;
+        x &= x - 1;
+        const int m = w * 32 + k;
+        int c = (int)cnt[m];   // stored modulo 2^bits(CNT); a touched slot holds c >= 1, so 0 means 2^bits
+        if (c == 0) c = 1 << (8 * (int)sizeof(CNT));
+        cnt[m] = 0;
+        if (m < M) {
+          const uint32_t pos = perm_bitpos((uint32_t)m, LOG_EPL);
+          const int wi = (int)(pos >> 5), kb = (int)(pos & 31);
           const uint32_t clo = __ldg(a.cls_lo + (size_t)ad * RW + wi), chi = __ldg(a.cls_hi + (size_t)ad * RW + wi);
-          const uint32_t tmw = __ldg(a.tiemask + (size_t)ad * RW + wi);  // bit k: G[ad][m] == gmax
-          const int j = wi >> 5, ln = wi & 31;
-          while (x) {                                             // ascending k == ascending m for this lane
-            const int k = __ffs(x) - 1;
-            x &= x - 1;
-            int c = (int)cnt[wi * 32 + k];   // stored modulo 2^bits(CNT); touched slots hold c >= 1, so 0 means 2^bits
-            if (c == 0) c = 1 << (8 * (int)sizeof(CNT));
-            cnt[wi * 32 + k] = 0;
-            const int m = (((j << LOG_EPL) + k) << 5) + ln;
-            if (m < M) {
-              const int cls = (int)((clo >> k) & 1u) | ((int)((chi >> k) & 1u) << 1);
-              const double s_true = eval_exception<SEQ>(a, m, c, n, cls);
-              best_update(best, s_true, m, tie_mode, areq, plan.seed_hi);
-              xg += (int)((tmw >> k) & 1u);
-            }
-          }
+          const uint32_t tmw = __ldg(a.tiemask + (size_t)ad * RW + wi);  // bit kb: G[ad][m] == gmax
+          const int cls = (int)((clo >> kb) & 1u) | ((int)((chi >> kb) & 1u) << 1);
+          const double s_true = eval_exception<SEQ>(a, m, c, n, cls);
+          best_update(best, s_true, m, tie_mode, areq, plan.seed_hi);
+          xg += (int)((tmw >> kb) & 1u);
         }
       }
     }
@@ -243,18 +272,15 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
       if (need && exc_ties && gl == 0) b2 = best;  // already reduced over the group
       if (need) {
 #pragma unroll
-        for (int q = 0; q < QW; q++) {
-#pragma unroll
-          for (int t = 0; t < 4; t++) {
-            const int wi = (q * G + gl) * 4 + t;
-            uint32_t x = __ldg(a.tiemask + (size_t)ad * RW + wi) & ~any[q][t];
-            const int j = wi >> 5, ln = wi & 31;
-            while (x) {
-              const int k = __ffs(x) - 1;
-              x &= x - 1;
-              const int m = (((j << LOG_EPL) + k) << 5) + ln;
-              if (m < M) best_update(b2, sm.gmax, m, tie_mode, areq, plan.seed_hi);
-            }
+        for (int q = 0; q < PW; q++) {
+          const int wi = gl * PW + q;              // a word of the PERMUTED tie mask
+          uint32_t x = __ldg(a.tiemask + (size_t)ad * RW + wi);
+          const int j = wi >> 5, ln = wi & 31;
+          while (x) {
+            const int k = __ffs(x) - 1;
+            x &= x - 1;
+            const int m = (((j << LOG_EPL) + k) << 5) + ln;
+            if (m < M && !((touched[m >> 5] >> (m & 31)) & 1u)) best_update(b2, sm.gmax, m, tie_mode, areq, plan.seed_hi);
           }
         }
       }
@@ -262,6 +288,8 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
       best_group_reduce<G>(b2, tie_mode);
       if (need) pick = b2.m;
     }
+    __syncwarp();
+    for (int q = 0; q < WPL; q++) touched[gl * WPL + q] = 0;
     // the warp-level shuffles above need every lane; only now drop the padding groups
     if (valid && gl == 0) {
       a.pick[r] = pick;
@@ -279,7 +307,7 @@ static int launch_sparse_inst(const ScoreArgs& a, cudaStream_t s, int sm_count) 
   constexpr int G = (RW / 4 < 32) ? RW / 4 : 32;
   constexpr int RPW = 32 / G;
   auto kernel = pick_sparse_kernel<J, CNT, SEQ>;
-  const size_t smem = (size_t)kSparseWarps * RPW * RW * 32 * sizeof(CNT);
+  const size_t smem = (size_t)kSparseWarps * RPW * ((size_t)a.geo.Mpad * sizeof(CNT) + (size_t)(a.geo.Mpad >> 5) * 4);
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSparseWarps * 32, smem);
@@ -319,6 +347,7 @@ static int launch_sparse_geo(const ScoreArgs& a, cudaStream_t s, int sm_count) {
 int launch_pick_sparse(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
   if (!a.plan.sparse_ok || !a.summ || !a.tiemask || a.cand_mask || a.dense || a.match_out || a.scores_out) return 0;
+  if (a.geo.Mpad > 65535 + 1) return 0;  // inline members are uint16
   switch (a.geo.J) {
     case 1: return launch_sparse_geo<1>(a, s, sm_count);
     case 2: return launch_sparse_geo<2>(a, s, sm_count);

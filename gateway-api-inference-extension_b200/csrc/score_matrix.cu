@@ -15,6 +15,7 @@
 //                                                             candidates in one pass, then the normalised score
 // The scorer sequence is a template parameter (SEQ packs kind+1 per step, 4 bits each; 0 = runtime loop).
 #include "device_common.cuh"
+#include "prefix_table.cuh"
 
 namespace eppscore {
 
@@ -69,8 +70,9 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
   double* lut_q = lut_p + (kLutMax + 1);
   double* lut_l = lut_q + (LAT ? (kLutMax + 1) : 0);  // coef * (c/total) of the prediction / composite
   unsigned char* s_cnt_all = reinterpret_cast<unsigned char*>(s_lut + (size_t)kMatrixWarps * NLUT * (kLutMax + 1));
-  const int cnt_bytes = MPAD * (wide_cnt ? 2 : 1);
+  const int cnt_bytes = MPAD * (wide_cnt ? 2 : 1) + RW * 4;  // match counters + the permuted bitmap of touched endpoints
   unsigned char* cnt_raw = s_cnt_all + (size_t)warp * cnt_bytes;
+  uint32_t* tperm = reinterpret_cast<uint32_t*>(cnt_raw + MPAD * (wide_cnt ? 2 : 1));
   uint8_t* cnt8 = cnt_raw;
   uint16_t* cnt16 = reinterpret_cast<uint16_t*>(cnt_raw);
 
@@ -116,49 +118,90 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
     if (want_prefix && a.hashes) {
       const int n = a.n_hashes[r];
       total = n;
-      bool stop = n == 0 || a.slots == nullptr;
+      bool stop = n == 0 || a.table == nullptr;
+      const TSlot* slots = stop ? nullptr : a.table->slots;
+      const uint64_t slot_mask = stop ? 0 : a.table->mask;
+      const uint32_t* ovf_rows = stop ? nullptr : a.table->ovf_rows;
+      const int NW = MPAD >> 5;                               // words of a natural-order overflow row
+      bool touched_any = false;
       for (int c0 = 0; !stop; c0 += 32) {
         const int i = c0 + lane;
-        uint32_t row = kEmptyRow;
+        uint4 lo = make_uint4(0, 0, 0, kNoRow), hi = make_uint4(0, 0, 0, 0);
+        bool hit = false;
         if (i < n) {
           const uint64_t h = a.hashes[(size_t)r * a.hash_stride + i];
-          uint64_t idx = h & a.slot_mask;
+          uint64_t idx = h & slot_mask;
           for (;;) {                                        // indexer.Get, indexer.go:86-102
-            const uint4 sv = ldg16(&a.slots[idx]);
-            if (sv.z == kEmptyRow) break;                   // never-used slot: hash unknown
-            if ((((uint64_t)sv.y << 32) | sv.x) == h) {
-              if (sv.w != 0) row = sv.z;                    // emptied set == deleted key
+            lo = ldg16(&slots[idx]);
+            if (lo.z == kCntFree) break;                    // never-used slot: hash unknown
+            if ((((uint64_t)lo.y << 32) | lo.x) == h) {
+              hit = lo.z != 0;                              // emptied set == deleted key
+              if (hit) hi = ldg16(reinterpret_cast<const uint4*>(&slots[idx]) + 1);
               break;
             }
-            idx = (idx + 1) & a.slot_mask;
+            idx = (idx + 1) & slot_mask;
           }
         }
-        const uint32_t miss = __ballot_sync(0xffffffffu, row == kEmptyRow);
+        const uint32_t miss = __ballot_sync(0xffffffffu, !hit);
         const int nh = miss ? (__ffs(miss) - 1) : 32;       // blocks matched before the first global miss
-        // identical sets are interned to one row id: read each run of equal ids once
-        const uint32_t prev_rr = __shfl_up_sync(0xffffffffu, row, 1);
-        uint32_t bm = __ballot_sync(0xffffffffu, lane < nh && (lane == 0 || row != prev_rr));
+        // consecutive blocks are normally cached on the same endpoints: hits with identical inline sets form one run
+        const uint32_t pc = __shfl_up_sync(0xffffffffu, lo.z, 1), po = __shfl_up_sync(0xffffffffu, lo.w, 1);
+        const uint32_t p0 = __shfl_up_sync(0xffffffffu, hi.x, 1), p1 = __shfl_up_sync(0xffffffffu, hi.y, 1);
+        const uint32_t p2 = __shfl_up_sync(0xffffffffu, hi.z, 1), p3 = __shfl_up_sync(0xffffffffu, hi.w, 1);
+        const uint32_t c = lo.z;
+        bool same = lane > 0 && lo.w == kNoRow && po == kNoRow && pc == c;
+        if (same) {
+          same = ((p0 ^ hi.x) & (c >= 2 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+          if (c > 2) same = same && ((p1 ^ hi.y) & (c >= 4 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+          if (c > 4) same = same && ((p2 ^ hi.z) & (c >= 6 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+          if (c > 6) same = same && ((p3 ^ hi.w) & (c >= 8 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+        }
+        uint32_t bm = __ballot_sync(0xffffffffu, lane < nh && !same);
         while (bm) {
           const int s0 = __ffs(bm) - 1;
           bm &= bm - 1;
           const int len = (bm ? (__ffs(bm) - 1) : nh) - s0;
-          const uint32_t rr = __shfl_sync(0xffffffffu, row, s0);
-#pragma unroll
-          for (int j = 0; j < kMaxJ; j++) {
-            if (j < J) {
-              uint32_t x = __ldg(a.rows + (size_t)rr * RW + j * 32 + lane);  // res[server] += len for the set's members
-              any[j] |= x;
-              const int base = (j * 32 + lane) << LOG_EPL;  // compact counter index: EPL slots per lane-word
+          const uint32_t rc = __shfl_sync(0xffffffffu, lo.z, s0), ro = __shfl_sync(0xffffffffu, lo.w, s0);
+          const uint32_t e0 = __shfl_sync(0xffffffffu, hi.x, s0), e1 = __shfl_sync(0xffffffffu, hi.y, s0);
+          const uint32_t e2 = __shfl_sync(0xffffffffu, hi.z, s0), e3 = __shfl_sync(0xffffffffu, hi.w, s0);
+          touched_any = true;
+          if (ro == kNoRow) {                               // inline set: lane k bumps member k (res[server] += len)
+            if (lane < (int)rc && lane < kInlineEps) {
+              const uint32_t wsel = (lane >> 1) == 0 ? e0 : ((lane >> 1) == 1 ? e1 : ((lane >> 1) == 2 ? e2 : e3));
+              const uint32_t m = (lane & 1) ? (wsel >> 16) : (wsel & 0xFFFFu);
+              const uint32_t pos = perm_bitpos(m, LOG_EPL);
+              const int ci = (int)((pos >> 5) << LOG_EPL) + (int)(pos & 31);  // compact counter index of endpoint m
+              if (wide_cnt) cnt16[ci] += (uint16_t)len;
+              else cnt8[ci] += (uint8_t)len;
+              atomicOr(&tperm[pos >> 5], 1u << (pos & 31));
+            }
+          } else {                                          // more than 8 members: a natural-order bitset row
+            for (int w = lane; w < NW; w += 32) {
+              uint32_t x = __ldg(ovf_rows + (size_t)ro * NW + w);
               while (x) {
                 const int k = __ffs(x) - 1;
                 x &= x - 1;
-                if (wide_cnt) cnt16[base + k] += (uint16_t)len;
-                else cnt8[base + k] += (uint8_t)len;
+                const uint32_t pos = perm_bitpos((uint32_t)(w * 32 + k), LOG_EPL);
+                const int ci = (int)((pos >> 5) << LOG_EPL) + (int)(pos & 31);
+                if (wide_cnt) cnt16[ci] += (uint16_t)len;
+                else cnt8[ci] += (uint8_t)len;
+                atomicOr(&tperm[pos >> 5], 1u << (pos & 31));
               }
             }
           }
+          __syncwarp();                                     // the next run may bump the same counters
         }
         if (nh < 32 || c0 + 32 >= n) stop = true;
+      }
+      if (touched_any) {                                    // each lane collects (and clears) the bits of its own endpoints
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kMaxJ; j++)
+          if (j < J) {
+            any[j] = tperm[j * 32 + lane];
+            tperm[j * 32 + lane] = 0;
+          }
+        __syncwarp();
       }
     }
     if (prefix_step >= 0 && total != lut_total && total <= kLutMax) {
@@ -650,7 +693,7 @@ static int launch_matrix(K kernel, const ScoreArgs& a, bool masked, bool lat, cu
   const bool wide = a.hash_stride > 256;
   const size_t smem = (size_t)a.plan.n_terms * MPAD * 8 + (masked ? 2 * (size_t)MPAD * 8 : 0) + kMaxSteps * 4 * 8 +
                       (lat ? kLatW * 8 : 0) + (size_t)kMatrixWarps * (lat ? 3 : 2) * (kLutMax + 1) * 8 +
-                      (size_t)kMatrixWarps * MPAD * (wide ? 2 : 1);
+                      (size_t)kMatrixWarps * ((size_t)MPAD * (wide ? 2 : 1) + (size_t)a.geo.row_words * 4);
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kMatrixWarps * 32, smem);

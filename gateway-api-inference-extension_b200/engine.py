@@ -259,6 +259,16 @@ class Engine:
         self._check(self._lib.eppscore_commit_picks(self._h, len(pick), a.ptr(pick, np.int32), a.ptr(hashes, np.uint64),
                                                     a.ptr(n_hashes, np.uint16), stride, a.ptr(lru_capacity, np.int32)))
 
+    def commit_picks_device(self, pick, hashes, n_hashes, lru_capacity=None, touch_bound=0, stream=None):
+        """PreRequest with DEVICE arrays (CUDA tensors / raw pointers), asynchronous and ordered on `stream`:
+        pick int32[R], hashes uint64[R, stride], n_hashes uint16[R]; lru_capacity is a HOST array."""
+        a = _Args(True)
+        ah = _Args(False)
+        R = int(pick.shape[0])
+        stride = int(hashes.shape[1])
+        self._check(self._lib.eppscore_commit_picks_device(self._h, R, a.ptr(pick, None), a.ptr(hashes, None), a.ptr(n_hashes, None),
+                                                           stride, ah.ptr(lru_capacity, np.int32), int(touch_bound), stream))
+
     def prefix_add(self, hashes, endpoint, lru_capacity=0):
         a = _Args(False)
         h = np.ascontiguousarray(hashes, np.uint64)
@@ -292,14 +302,3 @@ class Engine:
         out = np.zeros(max(n, 1), np.uint64)
         self._lib.eppscore_prefix_lru_keys(self._h, endpoint, out.ctypes.data, len(out))
         return [int(x) for x in out[:n]]
-
-    def prefix_image_info(self):
-        sd, rd = C.c_void_p(), C.c_void_p()
-        sb, rb = C.c_int64(), C.c_int64()
-        meta = (C.c_int64 * 4)()
-        self._check(self._lib.eppscore_prefix_image_info(self._h, C.byref(sd), C.byref(sb), C.byref(rd), C.byref(rb), meta))
-        return dict(slots_ptr=sd.value, slots_bytes=sb.value, rows_ptr=rd.value, rows_bytes=rb.value, meta=list(meta))
-
-    def prefix_image_adopt(self, meta):
-        m = (C.c_int64 * 4)(*meta)
-        self._check(self._lib.eppscore_prefix_image_adopt(self._h, m))

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define EPPSCORE_ABI_VERSION 2
+#define EPPSCORE_ABI_VERSION 3
 #define EPPSCORE_MAX_SCORERS 8
 #define EPPSCORE_MAX_ENDPOINT_COLS 4
 #define EPPSCORE_MAX_BLOCKS 65535 /* match/total are uint16 (attribute/prefix/data_types.go:27-34 are Go ints) */
@@ -118,8 +118,12 @@ typedef struct eppscore_config {
   uint64_t tie_seed;
   int32_t max_endpoints;   /* capacity for M (rounded up internally); default 1024 */
   int32_t max_adapters;    /* capacity for the LoRA adapter dictionary A; default 64 */
-  int64_t prefix_capacity; /* INITIAL capacity (distinct block hashes) of the device table; it doubles on demand. default 1<<18 */
+  int64_t prefix_capacity; /* INITIAL capacity (distinct block hashes) of the device table; it is rebuilt (emptied keys
+                              dropped) or doubled on demand. default 1<<18 */
   int32_t lru_capacity_default; /* defaultLRUCapacityPerServer = 31250 (types.go:109) */
+  int32_t lru_capacity_max;     /* largest per-endpoint LRU size (CacheNumBlocks, plugin.go:207-216) the engine must support;
+                                   0 ⇒ max(lru_capacity_default, the capacities named by the first Add).  It fixes the size of the
+                                   per-endpoint device regions; a later Add that names a larger size fails with ERR_CAPACITY. */
   double token_load_threshold;  /* token-load-scorer queueThresholdTokens; <= 0 ⇒ 4194304 (token_load.go:33,57-61) */
   int32_t pick_mode;            /* eppscore_pick_mode; default max-score */
   int32_t n_filters;            /* device-side filters, see eppscore_filter_kind */
@@ -220,11 +224,16 @@ typedef struct eppscore_stats {
   int32_t M;
   uint64_t epoch;
   uint64_t kernel_launches;     /* CUDA kernels launched by this engine since creation */
-  int64_t prefix_hashes;        /* distinct block hashes resident (len(hashToPods) incl. emptied rows) */
+  int64_t prefix_hashes;        /* table slots in use, emptied keys included (they are dropped at the next rebuild) */
   int64_t prefix_live_hashes;   /* hashes with a non-empty endpoint set == len(hashToPods) of the reference */
-  int64_t prefix_capacity;
-  int64_t prefix_table_bytes;   /* device bytes: key slots + endpoint bitset rows */
+  int64_t prefix_capacity;      /* hashes the table holds at load 0.5 before it is rebuilt / doubled */
+  int64_t prefix_table_bytes;   /* device bytes: 32-byte slots + overflow bitset rows */
   int64_t lru_entries;          /* Σ per-endpoint LRU lengths (prefix_indexer_size metric, metrics.go:349) */
+  int64_t lru_bytes;            /* device bytes of the per-endpoint LRU regions (maps + logs) */
+  int64_t prefix_overflow_rows; /* sets of more than 8 endpoints (bitset rows in use) */
+  int64_t prefix_rebuilds;      /* table rebuilds so far */
+  uint32_t index_error;         /* sticky device-side error flags of the index (0 = healthy) */
+  uint32_t reserved;
 } eppscore_stats;
 
 /* ---- lifecycle ---- */
@@ -236,7 +245,8 @@ const char *eppscore_last_error(const struct eppscore_engine *e); /* e may be NU
 int32_t eppscore_get_stats(const struct eppscore_engine *e, eppscore_stats *out);
 /* Diagnostics knobs (profiling / A-B runs only; never needed for correct operation):
  *   key 1: 1 = always use the fully general kernels (same as env EPPSCORE_FORCE_GENERIC=1), 0 = normal dispatch;
- *   key 2: hash stage mask — bit 0 run the body kernel, bit 1 run the chain kernel (default 3 = both). */
+ *   key 2: hash stage mask — bit 2 (default 7): the fused body+chain kernel; with bit 2 clear the two-kernel form:
+ *          bit 0 run the body kernel, bit 1 run the chain kernel. */
 int32_t eppscore_set_debug(struct eppscore_engine *e, int32_t key, int64_t value);
 
 /* ---- snapshot (replaces the per-request deep clone, director.go:342-349) ---- */
@@ -265,28 +275,33 @@ uint64_t eppscore_model_seed(const void *model, size_t model_len, const void *sa
 uint64_t eppscore_xxh64(const void *data, size_t len, uint64_t seed);
 
 /* ---- prefix index (approximateprefix/indexer.go) ----
- * The engine keeps the per-endpoint LRUs on the host (exact hashicorp/golang-lru semantics) and the
- * hash → endpoint-set map on the device as an open-addressing key table + bitset rows. */
-/* PreRequest for the batch (plugin.go:169-197): for r in order: indexer.Add(hashes[r], pick[r]).
- * lru_capacity: optional [M] CacheNumBlocks per endpoint (autotune, plugin.go:207-216); NULL/<=0 ⇒ default. */
+ * Both halves of the reference's indexer are DEVICE-RESIDENT and maintained by kernels: hashToPods as an open-addressing
+ * table of 32-byte slots (sets of up to 8 endpoints inline, bitset rows beyond), podToLRU as one log-structured exact LRU
+ * per endpoint (hashicorp/golang-lru semantics).  The host keeps no copy. */
+/* PreRequest for the batch (plugin.go:169-197): for r in order: indexer.Add(hashes[r], pick[r]) — one kernel, one CTA per
+ * endpoint (Adds for different endpoints commute), calls replayed in request order within an endpoint.
+ * lru_capacity: optional HOST [M] CacheNumBlocks per endpoint (autotune, plugin.go:207-216); NULL/<=0 ⇒ default. */
 int32_t eppscore_commit_picks(struct eppscore_engine *e, int32_t R, const int32_t *pick, const uint64_t *hashes,
                               const uint16_t *n_hashes, int32_t hash_stride, const int32_t *lru_capacity);
+/* The same with DEVICE arrays (e.g. the pick / hashes_out buffers of a device-location eppscore_schedule_batch): nothing
+ * crosses PCIe, the call is asynchronous and ordered on `stream` (NULL = engine stream).  touch_bound: an upper bound on
+ * Σ n_hashes (room is guaranteed up front); <= 0 ⇒ the engine sums n_hashes itself (one small synchronous read-back). */
+int32_t eppscore_commit_picks_device(struct eppscore_engine *e, int32_t R, const int32_t *pick, const uint64_t *hashes,
+                                     const uint16_t *n_hashes, int32_t hash_stride, const int32_t *lru_capacity,
+                                     int64_t touch_bound, void *stream);
 /* indexer.Add for one server (tests, the "prefill" profile's pick plugin.go:180-184). */
 int32_t eppscore_prefix_add(struct eppscore_engine *e, const uint64_t *hashes, int32_t n, int32_t endpoint,
                             int32_t lru_capacity);
-/* Raw deltas for hosts that keep their own LRU: op 0 = insert (hash,endpoint), 1 = evict. */
+/* Raw deltas for hosts that keep their own LRU: op 0 = insert (hash,endpoint), 1 = evict; applied in order. */
 int32_t eppscore_prefix_apply(struct eppscore_engine *e, int64_t n, const uint64_t *hash, const int32_t *endpoint,
                               const uint8_t *op);
 int32_t eppscore_prefix_remove_endpoint(struct eppscore_engine *e, int32_t endpoint); /* indexer.RemovePod :167-182 */
-/* indexer.Get (reads the DEVICE table): bitset_out[ceil(M/32)] words; returns set size or <0. */
+/* indexer.Get (reads the DEVICE table): bitset_out[ceil(M/32)] words, natural order; returns set size or <0. */
 int32_t eppscore_prefix_get(struct eppscore_engine *e, uint64_t hash, uint32_t *bitset_out, int32_t words);
 int32_t eppscore_prefix_lru_len(const struct eppscore_engine *e, int32_t endpoint); /* -1: endpoint has no LRU */
-int32_t eppscore_prefix_lru_keys(const struct eppscore_engine *e, int32_t endpoint, uint64_t *out, int32_t cap);
-/* Replication across GPUs: export the device table image of one engine / adopt it on another
- * (the image buffers are what a rank broadcasts with NCCL). */
-int32_t eppscore_prefix_image_info(struct eppscore_engine *e, void **slots_dev, int64_t *slots_bytes, void **rows_dev,
-                                   int64_t *rows_bytes, int64_t *meta /*[4]: cap, row_words, n_rows, n_keys*/);
-int32_t eppscore_prefix_image_adopt(struct eppscore_engine *e, const int64_t *meta);
+int32_t eppscore_prefix_lru_keys(const struct eppscore_engine *e, int32_t endpoint, uint64_t *out, int32_t cap); /* oldest first */
+/* Replication across GPUs: the index is a deterministic function of the ordered commit stream, so every rank applies the
+ * same eppscore_commit_picks[_device] calls (the shards' picks all-gathered in global request order) — SURVEY §8e. */
 
 /* pinned host memory for callers that want the fast copy path (cudaHostAlloc / cudaFreeHost) */
 void *eppscore_host_alloc(size_t bytes);

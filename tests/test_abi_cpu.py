@@ -25,7 +25,7 @@ def test_header_symbols_all_exported(pkg):
     L = pkg.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.eppscore_abi_version() == 2
+    assert L.eppscore_abi_version() == 3
 
 
 def test_struct_sizes_match_header_layout(pkg):
@@ -34,7 +34,7 @@ def test_struct_sizes_match_header_layout(pkg):
     assert C.sizeof(pkg.LatencyParams) == 4 + 4 + 12 * 8 + 8 + 4 + 4 + 5 * 8
     assert C.sizeof(pkg.Snapshot) == 16 + 7 * 8 + 4 * 8 + 8 + 8 + 4 * 8
     assert C.sizeof(pkg.Batch) == 16 + 8 + 6 * 8 + 16 + 4 * 8 + 7 * 8 + 8 + 5 * 8
-    assert C.sizeof(pkg.Stats) == 8 + 8 + 8 + 5 * 8
+    assert C.sizeof(pkg.Stats) == 8 + 8 + 8 + 8 * 8 + 8
 
 
 def test_default_config_is_reference_default(pkg):

@@ -1075,3 +1075,157 @@ def test_latency_chart_profile_parity(pkg, masked):
     fast = eng.schedule(R, **kw)
     assert_same(fast, want, ("pick", "pick_score", "tie_count"))
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------ device-resident prefix index
+def _lru_equal(eng, idx, eps):
+    for m in eps:
+        assert eng.prefix_lru_keys(m) == idx.lru_keys(m), m
+
+
+def test_device_commit_closed_loop_matches_oracle(pkg):
+    """schedule -> commit -> schedule entirely on the device (eppscore_commit_picks_device on the pick / hashes_out buffers of
+    a device-location batch, nothing crosses PCIe) against the oracle's scheduler + indexer: picks, scores, tie counts,
+    match counts every round; LRU contents (oldest -> newest) and len(hashToPods) at the end.  LRU capacity 600 with
+    ~430 new blocks per endpoint per round: evictions reach back over earlier rounds, logs compact, the table is rebuilt."""
+    import torch
+    M, R, rounds = 96, 6000, 5
+    scorers = [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)]
+    eng = make_engine(pkg, scorers, M, lru_capacity_default=600, max_blocks=16, prefix_capacity=1 << 10)
+    sd = synth_snapshot(M, seed=31)
+    eng.set_snapshot(**sd)
+    snap, prof, idx = o.SnapshotData(**sd), profile_of(pkg, scorers), o.Index(600)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(device=dev)
+    out = dict(pick=torch.empty(R, dtype=torch.int32, device=dev), pick_score=torch.empty(R, dtype=torch.float64, device=dev),
+               tie_count=torch.empty(R, dtype=torch.int32, device=dev), total_blocks=torch.empty(R, dtype=torch.uint16, device=dev),
+               hashes_out=torch.zeros((R, 16), dtype=torch.uint64, device=dev))
+    for rnd in range(rounds):
+        prompts, off, _ = synth_prompts(R, prompt_len=640, groups=40, shared=320, seed=40 + rnd, prefix_seed=3)
+        seeds = np.full(R, eng.model_seed("loop"), np.uint64)
+        ad = zipf_adapters(R, seed=rnd)
+        with torch.cuda.stream(st):
+            dp, do = torch.from_numpy(prompts).to(dev), torch.from_numpy(off).to(dev)
+            ds, da = torch.from_numpy(seeds.view(np.int64)).to(dev), torch.from_numpy(ad).to(dev)
+            eng.schedule(R, prompt_bytes=dp, prompt_off=do, model_seed=ds, adapter_id=da, request_base=rnd * R, device=True,
+                         stream=st.cuda_stream, out=out)
+            eng.commit_picks_device(out["pick"], out["hashes_out"], out["total_blocks"], touch_bound=R * 10, stream=st.cuda_stream)
+        want = o.schedule_batch(snap, prof, idx, R, prompt_bytes=prompts, prompt_off=off, model_seed=seeds, adapter_id=ad,
+                                max_blocks=16, want_hashes=True, request_base=rnd * R, n_threads=8)
+        st.synchronize()
+        got = {k: v.cpu().numpy() for k, v in out.items()}
+        assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks"))
+        idx.commit(want["pick"], want["hashes_out"], want["total_blocks"])
+        if rnd > 0:
+            assert int((want["pick_score"] > 4.0).sum()) > 0  # prefix matches really contribute
+    _lru_equal(eng, idx, range(M))
+    s = eng.stats()
+    assert s.prefix_live_hashes == idx.num_hashes() and s.index_error == 0
+    assert s.lru_entries == sum(max(idx.lru_len(m), 0) for m in range(M))
+    assert s.prefix_rebuilds >= 1 and s.prefix_hashes <= s.prefix_capacity
+    # the table answers Get like the oracle for a sample of committed hashes
+    for h in want["hashes_out"][::97, :4].reshape(-1):
+        assert eng.prefix_get(int(h)) == idx.get(int(h))
+    eng.close()
+
+
+def test_replicas_replay_the_commit_stream(pkg):
+    """Replication across GPUs is replay: two engines fed the same ordered commits hold the same index — checked at
+    the headline shape (64K requests x 1024 endpoints, 2 KB prompts): engine B never sees engine A's table, only the commit stream
+    (with the second batch split differently), and must return the oracle's picks, scores, tie counts and match counts."""
+    M, R = 1024, 65536
+    scorers = [("queue", 2), ("kv", 2), ("prefix", 3), ("lora", 1)]
+    sd = synth_snapshot(M, seed=2)
+    snap, prof, idx = o.SnapshotData(**sd), profile_of(pkg, scorers), o.Index()
+    engs = [make_engine(pkg, scorers, M, prefix_capacity=1 << 12) for _ in range(2)]
+    for e in engs:
+        e.set_snapshot(**sd)
+    seed = engs[0].model_seed("replica")
+    wp, woff, _ = synth_prompts(4 * M, groups=150, seed=9, prefix_seed=1)
+    warm = o.schedule_batch(snap, prof, idx, 4 * M, prompt_bytes=wp, prompt_off=woff, model_seed=np.full(4 * M, seed, np.uint64),
+                            want_hashes=True, n_threads=8)
+    idx.commit(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    engs[0].commit_picks(warm["pick"], warm["hashes_out"], warm["total_blocks"])
+    half = 2 * M
+    engs[1].commit_picks(warm["pick"][:half], warm["hashes_out"][:half], warm["total_blocks"][:half])   # same stream,
+    engs[1].commit_picks(warm["pick"][half:], warm["hashes_out"][half:], warm["total_blocks"][half:])   # cut elsewhere
+    prompts, off, _ = synth_prompts(R, groups=150, seed=10, prefix_seed=1)
+    kw = dict(prompt_bytes=prompts, prompt_off=off, model_seed=np.full(R, seed, np.uint64), adapter_id=zipf_adapters(R, seed=4))
+    want = o.schedule_batch(snap, prof, idx, R, n_threads=8, want_hashes=True, **kw)
+    for e in engs:
+        got = e.schedule(R, want_hashes=True, **kw)
+        assert_same(got, want, ("pick", "pick_score", "tie_count", "total_blocks"))
+        e.commit_picks(got["pick"], got["hashes_out"], got["total_blocks"])
+    idx.commit(want["pick"], want["hashes_out"], want["total_blocks"])
+    n = 4096
+    kw2 = {k: (v[: off[n]] if k == "prompt_bytes" else v[: n + 1] if k == "prompt_off" else v[:n]) for k, v in kw.items()}
+    want2 = o.schedule_batch(snap, prof, idx, n, want_match=True, n_threads=8, **kw2)
+    for e in engs:
+        got2 = e.schedule(n, want_match=True, **kw2)
+        assert_same(got2, want2, ("pick", "pick_score", "tie_count", "match_blocks"))
+        assert e.stats().prefix_live_hashes == idx.num_hashes()
+        e.close()
+    assert int(want2["match_blocks"].max()) >= 16
+
+
+def test_sets_beyond_eight_endpoints_and_universal_prefix(pkg):
+    """Blocks cached on more than 8 endpoints live in bitset rows; a system prompt cached on EVERY endpoint makes every endpoint
+    an exception of the sparse pick.  One batch builds those sets concurrently (every endpoint's CTA adds itself to the same
+    16 slots); the sparse and the full-matrix kernels must both agree with the oracle afterwards."""
+    M, R = 200, 3000
+    scorers = [("queue", 2), ("kv", 2), ("prefix", 3)]
+    eng = make_engine(pkg, scorers, M, tie_mode=1, tie_seed=5)
+    sd = synth_snapshot(M, seed=8, tie_heavy=True)
+    eng.set_snapshot(**sd)
+    snap, prof, idx = o.SnapshotData(**sd), profile_of(pkg, scorers, tie_mode=1, tie_seed=5), o.Index()
+    prompts, off, _ = synth_prompts(R, prompt_len=1536, groups=3, shared=1024, seed=12)  # 3 system prompts, 16 + 8 blocks
+    seeds = np.full(R, eng.model_seed("sys"), np.uint64)
+    hashes, nh = eng.hash_prompts(prompts, off, seeds)
+    pick = (np.arange(R) % M).astype(np.int32)            # round-robin: every endpoint caches all three system prompts
+    eng.commit_picks(pick, hashes, nh)
+    idx.commit(pick, hashes, nh)
+    st0 = eng.stats()
+    distinct = len({int(h) for r in range(R) for h in hashes[r, : nh[r]]})
+    bad = [(g, b, sorted(idx.get(int(hashes[g, b])) - eng.prefix_get(int(hashes[g, b]))))
+           for g in range(12) for b in range(16) if eng.prefix_get(int(hashes[g, b])) != idx.get(int(hashes[g, b]))]
+    assert not bad and st0.prefix_hashes == distinct == st0.prefix_live_hashes and st0.index_error == 0, \
+        (bad[:6], st0.prefix_hashes, st0.prefix_live_hashes, distinct, st0.index_error)
+    assert len(idx.get(int(hashes[0, 0]))) >= M - 8       # (nearly) every endpoint holds the first system prompt
+    assert eng.stats().prefix_overflow_rows == 3 * 16 and eng.stats().index_error == 0
+    kw = dict(prompt_bytes=prompts, prompt_off=off, model_seed=seeds)
+    want = o.schedule_batch(snap, prof, idx, R, want_match=True, n_threads=8, **kw)
+    got = eng.schedule(R, **kw)                                        # sparse kernel
+    assert_same(got, want, ("pick", "pick_score", "tie_count"))
+    full = eng.schedule(R, want_match=True, **kw)                      # full-matrix kernel
+    assert_same(full, want, ("pick", "pick_score", "tie_count", "match_blocks"))
+    assert int((want["match_blocks"] >= 16).sum(axis=1).min()) >= M - 8  # (nearly) every endpoint is an exception of every request
+    for m in range(0, M, 2):
+        eng.prefix_remove_endpoint(m)
+        idx.remove_pod(m)
+    want = o.schedule_batch(snap, prof, idx, R, want_match=True, n_threads=8, **kw)
+    got = eng.schedule(R, want_match=True, **kw)
+    assert_same(got, want, ("pick", "pick_score", "tie_count", "match_blocks"))
+    assert_same(eng.schedule(R, **kw), want, ("pick", "pick_score", "tie_count"))
+    eng.close()
+
+
+def test_index_churn_stays_bounded_on_device(pkg):
+    """emptied keys are reclaimed.  4 endpoints x LRU 100, 64 fresh hashes per Add, 1200 Adds: 76 800 hashes
+    pass through, 400 stay — the table must be rebuilt in place, never grown, and stay exact."""
+    eng = make_engine(pkg, [("prefix", 1.0)], 4, lru_capacity_default=100, prefix_capacity=512)
+    idx = o.Index(100)
+    rng = np.random.Generator(np.random.PCG64(9))
+    R = 48
+    for it in range(25):
+        hashes = rng.integers(1, 2 ** 63, size=(R, 64), dtype=np.uint64)
+        pick = (np.arange(R) % 4).astype(np.int32)
+        nh = np.full(R, 64, np.uint16)
+        eng.commit_picks(pick, hashes, nh)
+        idx.commit(pick, hashes, nh)
+    s = eng.stats()
+    assert s.prefix_live_hashes == idx.num_hashes() == 400 and s.index_error == 0
+    assert s.prefix_rebuilds >= 3 and s.prefix_capacity <= 8192
+    _lru_equal(eng, idx, range(4))
+    for h in hashes[-1, ::9]:
+        assert eng.prefix_get(int(h)) == idx.get(int(h))
+    eng.close()
