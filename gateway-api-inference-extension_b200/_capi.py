@@ -90,6 +90,7 @@ ABI_SYMBOLS = [
     ("eppscore_schedule_batch", C.c_int32, [_P, C.POINTER(Batch)]),
     ("eppscore_hash_prompts", C.c_int32, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     ("eppscore_count_fields", C.c_int32, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    ("eppscore_hash_prompts_host", C.c_int32, [C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32]),
     ("eppscore_model_seed", C.c_uint64, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     ("eppscore_xxh64", C.c_uint64, [C.c_char_p, C.c_size_t, C.c_uint64]),
     ("eppscore_commit_picks", C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_int32, _P]),

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeppscore.so")
 SOURCES = ["capi.cu", "hash_kernel.cu", "prepare_kernel.cu", "score_generic.cu", "score_matrix.cu", "score_dense.cu", "pick_sparse.cu",
-           "prefix_index.cu", "fields_kernel.cu"]
+           "prefix_index.cu", "fields_kernel.cu", "host_path.cu"]
 HEADERS = ["kernels.cuh", "device_common.cuh", "xxh64.cuh", "prefix_index.hpp", "prefix_table.cuh",
            os.path.join("..", "..", "include", "eppscore.h")]
 

@@ -64,7 +64,7 @@ struct eppscore_engine {
   std::string err;
   uint64_t launches = 0;
   bool force_generic = false;  // EPPSCORE_FORCE_GENERIC=1 / eppscore_set_debug(1): skip the specialised kernels
-  int32_t hash_stage_mask = 7;  // eppscore_set_debug(2): profiling only (bit 2: the fused kernel)
+  int32_t hash_stage_mask = 3;  // eppscore_set_debug(2): profiling only (see include/eppscore.h)
 
   // snapshot
   bool have_snapshot = false;
@@ -99,6 +99,10 @@ struct eppscore_engine {
       for (DevBuf* b : all) b->release();
     }
   } sc[2];
+  // pinned staging for the small per-request results of a host batch: a D2H copy into the caller's (usually pageable)
+  // arrays would block the host after every chunk and serialise the pipeline
+  void* h_res = nullptr;
+  size_t h_res_bytes = 0;
   cudaStream_t stream2 = nullptr;   // second copy/compute stream of the chunked host path
   int32_t host_chunk = 8192;        // requests per chunk of a host-location batch (eppscore_set_debug key 3)
 };
@@ -575,6 +579,7 @@ void eppscore_destroy(eppscore_engine* e) {
                     &e->c_ep, &e->c_op};
   e->sc[0].release();
   e->sc[1].release();
+  if (e->h_res) cudaFreeHost(e->h_res);
   if (e->stream2) {
     cudaStreamSynchronize(e->stream2);
     cudaStreamDestroy(e->stream2);
@@ -623,7 +628,7 @@ int32_t eppscore_set_debug(eppscore_engine* e, int32_t key, int64_t value) {
     return EPPSCORE_OK;
   }
   if (key == 2) {
-    e->hash_stage_mask = (int32_t)(value & 7);
+    e->hash_stage_mask = (int32_t)(value & 31);
     return EPPSCORE_OK;
   }
   if (key == 3) {
@@ -840,6 +845,21 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
   if (diag || b->R < 2 * chunk) chunk = b->R;
   const int nstreams = chunk < b->R ? 2 : 1;
   if (nstreams == 2 && !e->stream2) CK(e, cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  // pinned staging: pick i32 | score f64 | tie i32 | total u16, each [R]
+  const size_t RR = (size_t)b->R;
+  const size_t o_score = (RR * 4 + 7) & ~(size_t)7, o_tie = o_score + RR * 8, o_total = o_tie + RR * 4, res_bytes = o_total + RR * 2;
+  if (e->h_res_bytes < res_bytes) {
+    if (e->h_res) cudaFreeHost(e->h_res);
+    e->h_res = nullptr;
+    e->h_res_bytes = 0;
+    CK(e, cudaHostAlloc(&e->h_res, res_bytes + res_bytes / 4, cudaHostAllocDefault));
+    e->h_res_bytes = res_bytes + res_bytes / 4;
+  }
+  unsigned char* hres = static_cast<unsigned char*>(e->h_res);
+  int32_t* hp_pick = reinterpret_cast<int32_t*>(hres);
+  double* hp_score = reinterpret_cast<double*>(hres + o_score);
+  int32_t* hp_tie = reinterpret_cast<int32_t*>(hres + o_tie);
+  uint16_t* hp_total = reinterpret_cast<uint16_t*>(hres + o_total);
   int ci = 0;
   for (int32_t r0 = 0; r0 < b->R; r0 += chunk, ci++) {
     const int32_t r1 = std::min(b->R, r0 + chunk);
@@ -924,11 +944,11 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
     }
     rc = schedule_device(e, d, st, sc);
     if (rc != EPPSCORE_OK) return rc;
-    if (b->pick) CK(e, cudaMemcpyAsync(b->pick + r0, d.pick, R * 4, cudaMemcpyDeviceToHost, st));
-    if (b->pick_score) CK(e, cudaMemcpyAsync(b->pick_score + r0, d.pick_score, R * 8, cudaMemcpyDeviceToHost, st));
-    if (b->tie_count) CK(e, cudaMemcpyAsync(b->tie_count + r0, d.tie_count, R * 4, cudaMemcpyDeviceToHost, st));
+    if (b->pick) CK(e, cudaMemcpyAsync(hp_pick + r0, d.pick, R * 4, cudaMemcpyDeviceToHost, st));
+    if (b->pick_score) CK(e, cudaMemcpyAsync(hp_score + r0, d.pick_score, R * 8, cudaMemcpyDeviceToHost, st));
+    if (b->tie_count) CK(e, cudaMemcpyAsync(hp_tie + r0, d.tie_count, R * 4, cudaMemcpyDeviceToHost, st));
     if (b->match_blocks) CK(e, cudaMemcpyAsync(b->match_blocks + (size_t)r0 * M, d.match_blocks, R * M * 2, cudaMemcpyDeviceToHost, st));
-    if (b->total_blocks) CK(e, cudaMemcpyAsync(b->total_blocks + r0, d.total_blocks, R * 2, cudaMemcpyDeviceToHost, st));
+    if (b->total_blocks) CK(e, cudaMemcpyAsync(hp_total + r0, d.total_blocks, R * 2, cudaMemcpyDeviceToHost, st));
     if (b->scores_out) CK(e, cudaMemcpyAsync(b->scores_out + (size_t)r0 * M, d.scores_out, R * M * 8, cudaMemcpyDeviceToHost, st));
     if (b->pred_out) CK(e, cudaMemcpyAsync(b->pred_out + (size_t)r0 * M * 2, d.pred_out, R * M * 16, cudaMemcpyDeviceToHost, st));
     if (b->filter_mask_out) CK(e, cudaMemcpyAsync(b->filter_mask_out + (size_t)r0 * mw, d.filter_mask_out, R * mw * 4, cudaMemcpyDeviceToHost, st));
@@ -936,6 +956,10 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
   }
   CK(e, cudaStreamSynchronize(e->stream));
   if (nstreams == 2) CK(e, cudaStreamSynchronize(e->stream2));
+  if (b->pick) memcpy(b->pick, hp_pick, RR * 4);
+  if (b->pick_score) memcpy(b->pick_score, hp_score, RR * 8);
+  if (b->tie_count) memcpy(b->tie_count, hp_tie, RR * 4);
+  if (b->total_blocks) memcpy(b->total_blocks, hp_total, RR * 2);
   e->sched_pending = false;  // everything launched above has completed
   return EPPSCORE_OK;
 }

@@ -174,6 +174,72 @@ __global__ void __launch_bounds__(kHashWarps * 32) hash_chain_kernel(HashArgs a)
   }
 }
 
+// out-of-line slow paths (generic block sizes / unaligned prompts / the trailing partial block): keeping them out of the
+// hot loops holds the fused kernel's register count down
+// XXH64(data[0..n) || LE64(prev)) written for FEW REGISTERS (byte reads, no unrolling): the slow paths are rare, and a
+// callee's register count is the kernel's register count.
+static __device__ __noinline__ uint64_t link_slow(const uint8_t* d, uint32_t n, uint64_t prev) {
+  const uint32_t len = n + 8;
+  auto rd = [&](uint32_t off, uint32_t nbytes) {  // little-endian read of nbytes <= 8 bytes of the virtual message
+    uint64_t v = 0;
+#pragma unroll 1
+    for (uint32_t k = 0; k < nbytes; k++) {
+      const uint32_t i = off + k;
+      const uint64_t b = i < n ? (uint64_t)d[i] : ((prev >> (8 * (i - n))) & 0xFFull);
+      v |= b << (8 * k);
+    }
+    return v;
+  };
+  uint32_t p = 0;
+  uint64_t h;
+  if (len >= 32) {
+    uint64_t v1 = XP1 + XP2, v2 = XP2, v3 = 0, v4 = 0 - XP1;
+#pragma unroll 1
+    do {
+      v1 = xround(v1, rd(p, 8));
+      v2 = xround(v2, rd(p + 8, 8));
+      v3 = xround(v3, rd(p + 16, 8));
+      v4 = xround(v4, rd(p + 24, 8));
+      p += 32;
+    } while (p + 32 <= len);
+    h = xfinish_lanes(v1, v2, v3, v4);
+  } else {
+    h = XP5;
+  }
+  h += (uint64_t)len;
+#pragma unroll 1
+  while (p + 8 <= len) {
+    h ^= xround(0, rd(p, 8));
+    h = xrotl(h, 27) * XP1 + XP4;
+    p += 8;
+  }
+  if (p + 4 <= len) {
+    h ^= rd(p, 4) * XP1;
+    h = xrotl(h, 23) * XP2 + XP3;
+    p += 4;
+  }
+#pragma unroll 1
+  while (p < len) {
+    h ^= rd(p, 1) * XP5;
+    h = xrotl(h, 11) * XP1;
+    p++;
+  }
+  return xavalanche(h);
+}
+// the stripe state of one 64-byte block whose bytes are already in registers
+__device__ __forceinline__ uint64_t body_state_64(const uint4 (&d)[4]) {
+  uint64_t v1 = XP1 + XP2, v2 = XP2, v3 = 0, v4 = 0 - XP1;
+#pragma unroll
+  for (int st = 0; st < 2; st++) {
+    const uint4 x = d[2 * st], y = d[2 * st + 1];
+    v1 = xround(v1, ((uint64_t)x.y << 32) | x.x);
+    v2 = xround(v2, ((uint64_t)x.w << 32) | x.z);
+    v3 = xround(v3, ((uint64_t)y.y << 32) | y.x);
+    v4 = xround(v4, ((uint64_t)y.w << 32) | y.z);
+  }
+  return xfinish_lanes(v1, v2, v3, v4) + (uint64_t)(64 + 8);
+}
+
 // ---------------------------------------------------------------------------------------------
 // hash_fused_kernel: both stages in ONE kernel, warp-specialised.  A CTA owns tiles of 32 requests; seven BODY warps
 // stream the prompts (lane = block, the stripe states go to a shared-memory buffer [request][block]), the CHAIN warp
@@ -190,7 +256,7 @@ __device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.syn
 __device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int BC>
-__global__ void __launch_bounds__(kFusedWarps * 32, 3) hash_fused_kernel(HashArgs a) {
+__global__ void __launch_bounds__(kFusedWarps * 32, 5) hash_fused_kernel(HashArgs a) {
   __shared__ uint64_t buf[2][kFusedTile][33];
   __shared__ int s_nfull[2][kFusedTile];
   __shared__ int s_base[2], s_c0[2];
@@ -230,18 +296,18 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) hash_fused_kernel(HashArg
           nbar_sync(7, kFusedBody * 32);  // every body warp has read the old descriptors before they are replaced
         }
         if (warp == 0) {
-          s_nfull[b][lane] = d.nfull;  // (rows of the generic path are filled by the chain lane and flushed like the others)
+          s_nfull[b][lane] = d.fast ? d.nfull : 0;  // (rows of the generic path are written by hash_slow_kernel)
           if (lane == 0) {
             s_base[b] = base;
             s_c0[b] = c0;
           }
         }
         // body states of blocks [c0, c0+32) of this warp's requests
+        const int blk = c0 + lane;
         for (int rq = warp; rq < kFusedTile; rq += kFusedBody) {
           const int nf = __shfl_sync(0xffffffffu, d.nfull, rq);
           const int fs = __shfl_sync(0xffffffffu, d.fast ? 1 : 0, rq);
           const unsigned long long pp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(d.p), rq);
-          const int blk = c0 + lane;
           if (fs && blk < nf)
             buf[b][rq][lane] = block_body_state<BC>(reinterpret_cast<const uint8_t*>((uintptr_t)pp) + (size_t)blk * bc, bc);
         }
@@ -281,22 +347,14 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) hash_fused_kernel(HashArg
         const int b = q & 1, c0 = ch * 32;
         nbar_sync(FULL0 + b, NT);
         const int nb = min(32, d.nfull - c0);
-        for (int i = 0; i < nb; i++) {
-          if (d.fast)
+        if (d.fast) {
+          for (int i = 0; i < nb; i++) {
             prev = xchain_aligned(buf[b][lane][i], prev);
-          else
-            prev = xxh64_link<false>(d.p + (size_t)(c0 + i) * bc, (uint32_t)bc, prev);  // hashing.go:80-87
-          buf[b][lane][i] = prev;
-        }
-        if (ch == nchunks - 1 && r < a.R) {
-          if (d.rem > 0) {                                   // trailing partial block, hashing.go:89-95
-            const uint8_t* t = d.p + (size_t)d.nfull * bc;
-            const uint64_t h = ((reinterpret_cast<uintptr_t>(t) & 7) == 0) ? xxh64_link<true>(t, (uint32_t)d.rem, prev)
-                                                                            : xxh64_link<false>(t, (uint32_t)d.rem, prev);
-            a.hashes[(size_t)r * a.stride + d.nfull] = h;
+            buf[b][lane][i] = prev;
           }
-          a.n_hashes[r] = (uint16_t)(d.nfull + (d.rem > 0 ? 1 : 0));
         }
+        // (requests of the generic path and trailing partial blocks are finished by hash_slow_kernel)
+        if (ch == nchunks - 1 && r < a.R) a.n_hashes[r] = (uint16_t)(d.nfull + (d.rem > 0 ? 1 : 0));
         __threadfence_block();
         nbar_arrive(EMPTY0 + b, NT);
       }
@@ -304,18 +362,208 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 3) hash_fused_kernel(HashArg
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// hash_warp_kernel: both stages in one kernel WITHOUT any CTA-level synchronisation.  A WARP owns a tile of 32 requests:
+//   A  lane = block: the stripe states of 32 blocks of one request after the other go to the warp's shared-memory tile
+//      [request][block]; the next request's 64 bytes per lane are requested before the current block is digested;
+//   B  lane = request: the serial chain over the tile's rows, in place (32 chains in flight per warp);
+//   C  lane = block: the finished hashes leave the tile, 256 contiguous bytes per request.
+// Only __syncwarp between the phases: no warp ever waits for another one, the chain phases of some warps overlap the HBM
+// stream of the others, the 8-byte body states never travel through HBM and the second launch is gone.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWarpTileWarps = 8;
+
+template <int BC>
+__global__ void __launch_bounds__(kWarpTileWarps * 32, 3) hash_warp_kernel(HashArgs a) {
+  extern __shared__ __align__(16) unsigned char hw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t(*tile)[33] = reinterpret_cast<uint64_t(*)[33]>(hw_smem) + (size_t)warp * 32;
+  const int bc = BC ? BC : a.block_chars;
+  const int ntiles = (a.R + 31) / 32;
+  for (int t = blockIdx.x * kWarpTileWarps + warp; t < ntiles; t += gridDim.x * kWarpTileWarps) {
+    const int base = t * 32, r = base + lane;
+    ReqDesc d;
+    d.p = nullptr;
+    d.seed = 0;
+    d.nfull = 0;
+    d.rem = 0;
+    d.fast = false;
+    if (r < a.R) d = load_desc(a, r, bc);
+    const int nf_mine = d.fast ? d.nfull : 0;      // rows of the generic path belong to hash_slow_kernel
+    int maxfull = nf_mine;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) maxfull = max(maxfull, __shfl_xor_sync(0xffffffffu, maxfull, o));
+    uint64_t prev = d.seed;
+    for (int c0 = 0; c0 < maxfull; c0 += 32) {
+      const int blk = c0 + lane;
+      // ---- A: body states ----
+      if (BC == 64) {
+        uint4 cur[4], nxt[4];
+        bool con, non = false;
+        {
+          const int nf = __shfl_sync(0xffffffffu, nf_mine, 0);
+          const unsigned long long pp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(d.p), 0);
+          con = blk < nf;
+          if (con) {
+            const uint8_t* q = reinterpret_cast<const uint8_t*>((uintptr_t)pp) + (size_t)blk * 64;
+#pragma unroll
+            for (int k = 0; k < 4; k++) cur[k] = ldg16(q + 16 * k);
+          }
+        }
+#pragma unroll 1
+        for (int rq = 0; rq < 32; rq++) {
+          if (rq + 1 < 32) {
+            const int nf = __shfl_sync(0xffffffffu, nf_mine, rq + 1);
+            const unsigned long long pp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(d.p), rq + 1);
+            non = blk < nf;
+            if (non) {
+              const uint8_t* q = reinterpret_cast<const uint8_t*>((uintptr_t)pp) + (size_t)blk * 64;
+#pragma unroll
+              for (int k = 0; k < 4; k++) nxt[k] = ldg16(q + 16 * k);
+            }
+          } else {
+            non = false;
+          }
+          if (con) tile[rq][lane] = body_state_64(cur);
+#pragma unroll
+          for (int k = 0; k < 4; k++) cur[k] = nxt[k];
+          con = non;
+        }
+      } else {
+#pragma unroll 1
+        for (int rq = 0; rq < 32; rq++) {
+          const int nf = __shfl_sync(0xffffffffu, nf_mine, rq);
+          const unsigned long long pp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(d.p), rq);
+          if (blk < nf) tile[rq][lane] = block_body_state<BC>(reinterpret_cast<const uint8_t*>((uintptr_t)pp) + (size_t)blk * bc, bc);
+        }
+      }
+      __syncwarp();
+      // ---- B: the chain, lane = request ----
+      {
+        const int nb = min(32, nf_mine - c0);
+        for (int i = 0; i < nb; i++) {
+          prev = xchain_aligned(tile[lane][i], prev);
+          tile[lane][i] = prev;
+        }
+      }
+      __syncwarp();
+      // ---- C: hashes out ----
+#pragma unroll 4
+      for (int rq = 0; rq < 32; rq++) {
+        const int nf = __shfl_sync(0xffffffffu, nf_mine, rq);
+        if (blk < nf) a.hashes[(size_t)(base + rq) * a.stride + blk] = tile[rq][lane];
+      }
+      __syncwarp();
+    }
+    if (r < a.R) a.n_hashes[r] = (uint16_t)(d.nfull + (d.rem > 0 ? 1 : 0));
+  }
+}
+
+// hash_chain_warp_kernel: the serial stage with one WARP per tile of 32 requests and no CTA-level synchronisation: the
+// whole batch's chains are in flight at once (2048 warps for 64K requests, a fraction of the machine's 9472 warp slots), so
+// the kernel takes about one chain's latency plus one tile load and store.  Also finishes the generic path (block sizes that
+// are not a multiple of 32, unaligned prompts), trailing partial blocks (hashing.go:89-95) and n_hashes.
+constexpr int kChainWarpsPerCta = 4;
+__global__ void __launch_bounds__(kChainWarpsPerCta * 32) hash_chain_warp_kernel(HashArgs a) {
+  __shared__ uint64_t tiles[kChainWarpsPerCta][32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t(*tile)[33] = tiles[warp];
+  const int bc = a.block_chars;
+  const int ntiles = (a.R + 31) / 32;
+  for (int t = blockIdx.x * kChainWarpsPerCta + warp; t < ntiles; t += gridDim.x * kChainWarpsPerCta) {
+    const int base = t * 32, r = base + lane;
+    ReqDesc d;
+    d.p = nullptr;
+    d.seed = 0;
+    d.nfull = 0;
+    d.rem = 0;
+    d.fast = false;
+    if (r < a.R) d = load_desc(a, r, bc);
+    const int nf_fast = d.fast ? d.nfull : 0;
+    int maxfast = nf_fast;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) maxfast = max(maxfast, __shfl_xor_sync(0xffffffffu, maxfast, o));
+    uint64_t prev = d.seed;
+    for (int c0 = 0; c0 < maxfast; c0 += 32) {
+      const int blk = c0 + lane;
+#pragma unroll 8
+      for (int rq = 0; rq < 32; rq++) {  // body states in: 256 contiguous bytes per request
+        const int nf = __shfl_sync(0xffffffffu, nf_fast, rq);
+        if (blk < nf) tile[rq][lane] = a.hashes[(size_t)(base + rq) * a.stride + blk];
+      }
+      __syncwarp();
+      const int nb = min(32, nf_fast - c0);
+      for (int i = 0; i < nb; i++) {      // the chain: lane = request
+        prev = xchain_aligned(tile[lane][i], prev);
+        tile[lane][i] = prev;
+      }
+      __syncwarp();
+#pragma unroll 8
+      for (int rq = 0; rq < 32; rq++) {  // hashes out
+        const int nf = __shfl_sync(0xffffffffu, nf_fast, rq);
+        if (blk < nf) a.hashes[(size_t)(base + rq) * a.stride + blk] = tile[rq][lane];
+      }
+      __syncwarp();
+    }
+    if (r < a.R) {
+      uint64_t* out = a.hashes + (size_t)r * a.stride;
+      if (!d.fast)
+        for (int i = 0; i < d.nfull; i++) out[i] = prev = link_slow(d.p + (size_t)i * bc, (uint32_t)bc, prev);  // hashing.go:79-87
+      if (d.rem > 0) out[d.nfull] = link_slow(d.p + (size_t)d.nfull * bc, (uint32_t)d.rem, prev);               // :89-95
+      a.n_hashes[r] = (uint16_t)(d.nfull + (d.rem > 0 ? 1 : 0));
+    }
+  }
+}
+
+// What the fused kernels leave: requests whose block size is not a multiple of 32 or whose start is not 16-byte aligned
+// (hashed here entirely, hashing.go:79-87) and trailing partial blocks (hashing.go:89-95).  One thread per request; a
+// request that needs neither returns after reading its descriptor.  Kept out of the fused kernel because a slow path's
+// registers are the whole kernel's registers (68 -> 48 per thread, 3 -> 5 CTAs per SM).
+__global__ void __launch_bounds__(256) hash_slow_kernel(HashArgs a) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.R) return;
+  const int bc = a.block_chars;
+  const ReqDesc d = load_desc(a, r, bc);
+  if (d.fast && d.rem == 0) return;
+  uint64_t* out = a.hashes + (size_t)r * a.stride;
+  uint64_t prev = d.seed;
+  if (d.fast) {
+    if (d.nfull > 0) prev = out[d.nfull - 1];
+  } else {
+    for (int i = 0; i < d.nfull; i++) out[i] = prev = link_slow(d.p + (size_t)i * bc, (uint32_t)bc, prev);
+  }
+  if (d.rem > 0) out[d.nfull] = link_slow(d.p + (size_t)d.nfull * bc, (uint32_t)d.rem, prev);
+}
+
 int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
-  const int stages0 = a.stage_mask ? a.stage_mask : 7;
-  if ((stages0 & 4) && a.block_chars > 0 && (a.block_chars & 31) == 0) {  // default: the fused kernel
-    const int ntiles = (a.R + kFusedTile - 1) / kFusedTile;
+  const int stages0 = a.stage_mask ? a.stage_mask : 3;
+  if ((stages0 & 8) && a.block_chars > 0 && (a.block_chars & 31) == 0) {  // default: the warp-tile fused kernel
+    const int ntiles = (a.R + 31) / 32;
     int blocks = sm_count * 3;
+    const int need = (ntiles + kWarpTileWarps - 1) / kWarpTileWarps;
+    if (blocks > need) blocks = need;
+    const size_t smem = (size_t)kWarpTileWarps * 32 * 33 * 8;
+    if (a.block_chars == 64) {
+      cudaFuncSetAttribute(hash_warp_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      hash_warp_kernel<64><<<blocks, kWarpTileWarps * 32, smem, s>>>(a);
+    } else {
+      cudaFuncSetAttribute(hash_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      hash_warp_kernel<0><<<blocks, kWarpTileWarps * 32, smem, s>>>(a);
+    }
+    hash_slow_kernel<<<(a.R + 255) / 256, 256, 0, s>>>(a);
+    return 2;
+  }
+  if ((stages0 & 4) && a.block_chars > 0 && (a.block_chars & 31) == 0) {  // the warp-specialised fused kernel (CTA tiles)
+    const int ntiles = (a.R + kFusedTile - 1) / kFusedTile;
+    int blocks = sm_count * 5;
     if (blocks > ntiles) blocks = ntiles;
     if (a.block_chars == 64)
       hash_fused_kernel<64><<<blocks, kFusedWarps * 32, 0, s>>>(a);
     else
       hash_fused_kernel<0><<<blocks, kFusedWarps * 32, 0, s>>>(a);
-    return 1;
+    hash_slow_kernel<<<(a.R + 255) / 256, 256, 0, s>>>(a);
+    return 2;
   }
   int launched = 0;
   const int stages = (stages0 & 3) ? (stages0 & 3) : 3;
@@ -330,8 +578,13 @@ int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
     launched++;
   }
   if (!(stages & 2)) return launched;
-  const int ntiles = (a.R + kTileReq - 1) / kTileReq;
-  hash_chain_kernel<<<ntiles, kHashWarps * 32, 0, s>>>(a);
+  if (stages0 & 16) {  // the CTA-tile chain kernel of round 1 (diagnostics)
+    const int ntiles = (a.R + kTileReq - 1) / kTileReq;
+    hash_chain_kernel<<<ntiles, kHashWarps * 32, 0, s>>>(a);
+  } else {
+    const int ntiles = (a.R + 31) / 32;
+    hash_chain_warp_kernel<<<(ntiles + kChainWarpsPerCta - 1) / kChainWarpsPerCta, kChainWarpsPerCta * 32, 0, s>>>(a);
+  }
   return launched + 1;
 }
 

@@ -165,7 +165,9 @@ struct ScoreArgs {
   int32_t filter_kind[4];
   double filter_param[4][3];
   uint32_t* filter_mask_out;    // [R][mask_words] or null: the candidate set after the filter chain
+  int32_t only_deferred;        // full-matrix kernel: score only the requests the sparse kernel marked pick == kPickDeferred
 };
+constexpr int32_t kPickDeferred = -2;
 
 struct HashArgs {
   int32_t R;

@@ -15,9 +15,13 @@
 // So a request costs O(matched blocks + exceptions) instead of O(M) — bit-identical picks, scores and
 // tie counts (tests compare against the oracle and against the generic kernel).
 //
-// Work split: a group of G = row_words/4 lanes serves one request, so a warp serves 32/G requests at once; per-request
-// match counters (natural endpoint order) and the bitmap of endpoints that have one live in shared memory.  The table is
-// the device-resident index of prefix_table.cuh: a hit brings its endpoint set along in the 32-byte slot.
+// Work split: a group of G = row_words/4 lanes serves one request, so a warp serves 32/G requests at once.  The table is
+// the device-resident index of prefix_table.cuh: a hit brings its endpoint set along in the 32-byte slot (up to 10 members
+// inline), so matchLongestPrefix is: probe -> each hit's lane adds 1 to its members' entries of a small per-request hash
+// table in shared memory (endpoint -> matched blocks, 64 entries) -> the entries are the exceptions.  A request whose
+// prefix is cached on more endpoints than the table holds (a system prompt cached everywhere) is DEFERRED: the kernel
+// writes pick = kPickDeferred and the full-matrix kernel (score_matrix.cu), launched right after with a filter, scores
+// it exactly — dense cases are what that kernel is for.
 #include "device_common.cuh"
 #include "prefix_table.cuh"
 
@@ -51,32 +55,112 @@ __device__ __forceinline__ double eval_exception(const ScoreArgs& a, int m, int 
   return acc;
 }
 
-template <int J, typename CNT, uint32_t SEQ>
+constexpr int kExcSlots = 64;   // per-request exception table (power of two)
+constexpr int kExcMax = 44;     // more distinct endpoints than this: defer the request to the full-matrix kernel
+
+struct ExcTable {
+  uint32_t tab[kExcSlots];      // (endpoint + 1) << 16 | matched blocks; 0 = empty
+  uint8_t list[kExcSlots];      // slots in insertion order
+  uint32_t n;                   // entries of list
+  uint32_t overflow;
+  uint32_t pad[2];
+};
+
+__device__ __forceinline__ uint32_t exc_home(uint32_t m) { return (m * 0x9E3779B1u) >> 26; }  // 6 bits
+
+// res[server]++ (approximateprefix/plugin.go:229-231)
+__device__ __forceinline__ void exc_add(ExcTable* t, uint32_t m, uint32_t len = 1u) {
+  const uint32_t key = (m + 1u) << 16;
+  uint32_t j = exc_home(m);
+  for (int probes = 0; probes < kExcSlots; probes++, j = (j + 1) & (kExcSlots - 1)) {
+    uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&t->tab[j]);
+    if (cur == 0) {
+      cur = atomicCAS(&t->tab[j], 0u, key | len);
+      if (cur == 0) {
+        const uint32_t pos = atomicAdd(&t->n, 1u);
+        if (pos < (uint32_t)kExcSlots) t->list[pos] = (uint8_t)j;
+        if (pos >= (uint32_t)kExcMax) t->overflow = 1u;
+        return;
+      }
+    }
+    if ((cur >> 16) == m + 1u) {
+      atomicAdd(&t->tab[j], len);
+      return;
+    }
+  }
+  t->overflow = 1u;
+}
+__device__ __forceinline__ bool exc_has(const ExcTable* t, uint32_t m) {
+  uint32_t j = exc_home(m);
+  for (int probes = 0; probes < kExcSlots; probes++, j = (j + 1) & (kExcSlots - 1)) {
+    const uint32_t cur = t->tab[j];
+    if (cur == 0) return false;
+    if ((cur >> 16) == m + 1u) return true;
+  }
+  return false;
+}
+static __device__ __noinline__ void exc_add_row(ExcTable* t, const uint32_t* row, int nw) {
+  for (int w0 = 0; w0 < nw && !*reinterpret_cast<volatile uint32_t*>(&t->overflow); w0++) {
+    uint32_t x = __ldg(row + w0);
+    while (x) {
+      const int k = __ffs(x) - 1;
+      x &= x - 1;
+      exc_add(t, (uint32_t)(w0 * 32 + k));
+    }
+  }
+}
+// member k of an inline set held as {w = ep0 | ep1 << 16, hi = ep2..ep9}
+__device__ __forceinline__ uint32_t slot_member(uint32_t w, const uint4& hi, uint32_t k) {
+  const uint32_t x = k < 2 ? w : (k < 4 ? hi.x : (k < 6 ? hi.y : (k < 8 ? hi.z : hi.w)));
+  return (k & 1) ? (x >> 16) : (x & 0xFFFFu);
+}
+// do two inline sets (same raw cnt word, not rows) have the same members?
+__device__ __forceinline__ bool same_inline_set(uint32_t c, uint32_t w0, const uint4& h0, uint32_t w1, const uint4& h1) {
+  bool same = ((w0 ^ w1) & (c >= 2 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+  if (c > 2) same = same && ((h0.x ^ h1.x) & (c >= 4 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+  if (c > 4) same = same && ((h0.y ^ h1.y) & (c >= 6 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+  if (c > 6) same = same && ((h0.z ^ h1.z) & (c >= 8 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+  if (c > 8) same = same && ((h0.w ^ h1.w) & (c >= 10 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+  return same;
+}
+// order-independent form of best_update (the exceptions of a lane arrive in table order, not ascending)
+__device__ __forceinline__ void best_update_any(Best& b, double s, int m, int tie_mode, uint32_t areq, uint32_t seed_hi) {
+  const bool first = b.m < 0;
+  const bool gt = first || s > b.score;
+  const bool eq = !first && s == b.score;
+  if (tie_mode) {
+    if (gt || eq) {
+      const uint32_t pr = tie_prio(areq, m, seed_hi);
+      if (gt || pr > b.prio || (pr == b.prio && m < b.m)) {
+        b.prio = pr;
+        b.m = m;
+      }
+    }
+  } else {
+    b.m = gt ? m : ((eq && m < b.m) ? m : b.m);
+  }
+  b.score = gt ? s : b.score;
+  b.cnt = gt ? 1 : b.cnt + (eq ? 1 : 0);
+}
+
+template <int J, uint32_t SEQ>
 __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const __grid_constant__ ScoreArgs a) {
   const int LOG_EPL = a.geo.log_epl;
   constexpr int RW = J * 32;                       // words per PERMUTED bit row (LoRA class planes, tie masks)
   constexpr int G = (RW / 4 < 32) ? RW / 4 : 32;   // lanes per request
   constexpr int PW = RW / G;                       // permuted words per lane
   constexpr int RPW = 32 / G;                      // requests per warp
-  const int MPAD = a.geo.Mpad;
-  const int NW = MPAD >> 5;                        // words of a NATURAL-order bitmap (overflow rows, touched bitmap)
-  const int WPL = NW / G;                          // ... per lane (>= 1 for every geometry of make_geo)
-  // per request in shared memory: match counters (natural endpoint order) + the bitmap of endpoints with a match
-  const int REQ_BYTES = MPAD * (int)sizeof(CNT) + NW * 4;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ ExcTable s_exc[kSparseWarps * RPW];
   const Plan& plan = a.plan;
   const int M = a.geo.M;
+  const int NW = a.geo.Mpad >> 5;                  // words of a natural-order overflow row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gi = lane / G, gl = lane % G;
-  unsigned char* mine = smem_raw + (size_t)(warp * RPW + gi) * REQ_BYTES;
-  CNT* cnt = reinterpret_cast<CNT*>(mine);
-  uint32_t* touched = reinterpret_cast<uint32_t*>(mine + MPAD * sizeof(CNT));
+  ExcTable* exc = &s_exc[warp * RPW + gi];
 
-  // zero everything once; afterwards each request re-zeroes exactly what it touched
-  {
-    uint32_t* z = reinterpret_cast<uint32_t*>(smem_raw);
-    const int nwords = kSparseWarps * RPW * REQ_BYTES / 4;
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) z[i] = 0;
+  {  // zero the tables once; afterwards each request re-zeroes exactly the entries it used
+    uint32_t* z = reinterpret_cast<uint32_t*>(s_exc);
+    for (int i = threadIdx.x; i < (int)(sizeof(s_exc) / 4); i += blockDim.x) z[i] = 0;
   }
   __syncthreads();
 
@@ -104,16 +188,17 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
     const AdapterSummary sm = a.summ[ad];  // issued early: only consumed after the probe phase
 
     // ---------------- matchLongestPrefix: probe U*G hashes per round, stop at the first global miss ----------------
-    // A hit returns the endpoint set with the slot itself (up to 8 members inline).  Consecutive blocks of a prompt are
-    // normally cached on the same endpoints: hits whose slots carry identical inline sets are run-length merged, lane k of
-    // the request's group bumps member k's counter by the run length.
+    uint32_t ref_raw = 0, ref_w = 0;           // the request's first hit: raw cnt word and members (see below)
+    uint4 ref_hi = make_uint4(0, 0, 0, 0);
+    bool use_table = false;                    // uniform within the request's lane group
+    int n_same = 0;                            // matched blocks so far, all carrying the reference set
     if (have_table) {
       constexpr int U = 4;            // hashes probed per lane per round (independent loads in flight)
       bool stop = n == 0;
       int c0 = 0;
       while (__any_sync(0xffffffffu, !stop)) {
         uint64_t h[U], idx[U];
-        uint4 lo[U];   // {key.lo, key.hi, cnt, ovf}; the members (second half of the slot, same sector) are loaded per run
+        uint4 lo[U];   // {key.lo, key.hi, cnt, ep0 | ep1 << 16}
         bool act[U], hit[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -123,8 +208,10 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
           idx[u] = h[u] & slot_mask;
         }
 #pragma unroll
-        for (int u = 0; u < U; u++)
+        for (int u = 0; u < U; u++) {
+          lo[u] = make_uint4(0u, 0u, kCntFree, 0u);
           if (act[u]) lo[u] = ldg16(&slots[idx[u]]);
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {                           // indexer.Get, indexer.go:86-102
           hit[u] = false;
@@ -132,7 +219,7 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
             for (;;) {
               if (lo[u].z == kCntFree) break;                   // never-used slot: hash unknown
               if ((((uint64_t)lo[u].y << 32) | lo[u].x) == h[u]) {
-                hit[u] = lo[u].z != 0;                          // emptied set == deleted key
+                hit[u] = (lo[u].z & kCntMask) != 0;             // emptied set == deleted key
                 break;
               }
               idx[u] = (idx[u] + 1) & slot_mask;
@@ -152,99 +239,95 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
             if (nh_u < G) open = false;
           }
         }
+        // every counted hit adds 1 to its members' entries: the members beyond the first two sit in the second half of
+        // the slot (same 32-byte sector, already in L1); all those loads are issued before the first use
+        uint4 hi[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          int nh_u = nh_total - u * G;
-          nh_u = nh_u < 0 ? 0 : (nh_u > G ? G : nh_u);
-          if (__all_sync(0xffffffffu, nh_u == 0)) continue;
-          // the members: second 16 bytes of the slot (the sector is already in L1)
-          uint4 hi = make_uint4(0, 0, 0, 0);
-          if (gl < nh_u && lo[u].w == kNoRow) hi = ldg16(reinterpret_cast<const uint4*>(&slots[idx[u]]) + 1);
-          // run boundaries: a hit starts a new run unless its inline set equals the previous hit's, member for member
-          const uint32_t pc = __shfl_up_sync(0xffffffffu, lo[u].z, 1, G), po = __shfl_up_sync(0xffffffffu, lo[u].w, 1, G);
-          const uint32_t p0 = __shfl_up_sync(0xffffffffu, hi.x, 1, G), p1 = __shfl_up_sync(0xffffffffu, hi.y, 1, G);
-          const uint32_t p2 = __shfl_up_sync(0xffffffffu, hi.z, 1, G), p3 = __shfl_up_sync(0xffffffffu, hi.w, 1, G);
-          const uint32_t c = lo[u].z;
-          bool same = gl > 0 && lo[u].w == kNoRow && po == kNoRow && pc == c;
-          if (same) {  // compare the first c members (the tail of ep[] is unspecified)
-            const uint32_t m1 = c >= 2 ? 0xFFFFFFFFu : 0x0000FFFFu;
-            same = ((p0 ^ hi.x) & m1) == 0;
-            if (c > 2) same = same && ((p1 ^ hi.y) & (c >= 4 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
-            if (c > 4) same = same && ((p2 ^ hi.z) & (c >= 6 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
-            if (c > 6) same = same && ((p3 ^ hi.w) & (c >= 8 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+          hit[u] = hit[u] && (u * G + gl) < nh_total;
+          hi[u] = make_uint4(0, 0, 0, 0);
+          if (hit[u] && !(lo[u].z & kCntRow) && (lo[u].z & kCntMask) > 2u)
+            hi[u] = ldg16(reinterpret_cast<const uint4*>(&slots[idx[u]]) + 1);
+        }
+        // The common case: every matched block of the request is cached on the SAME endpoints (a prefix is cached as a whole),
+        // i.e. all hits carry the same inline set as the request's first hit.  Then the exceptions are that set's members,
+        // each with the number of matched blocks — no table needed.  The first hit that differs switches the request to the
+        // table: the reference set is entered with the count so far, every later hit adds 1 to its own members.
+        if (c0 == 0) {  // the first hit of the request: lane 0 of the group, sub-round 0
+          ref_raw = __shfl_sync(0xffffffffu, hit[0] ? lo[0].z : 0u, gi * G);
+          ref_w = __shfl_sync(0xffffffffu, lo[0].w, gi * G);
+          ref_hi.x = __shfl_sync(0xffffffffu, hi[0].x, gi * G);
+          ref_hi.y = __shfl_sync(0xffffffffu, hi[0].y, gi * G);
+          ref_hi.z = __shfl_sync(0xffffffffu, hi[0].z, gi * G);
+          ref_hi.w = __shfl_sync(0xffffffffu, hi[0].w, gi * G);
+          if (ref_raw & kCntRow) use_table = true;               // a bitset row: always through the table
+        }
+        bool differs = false;
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (hit[u]) differs |= lo[u].z != ref_raw || !same_inline_set(ref_raw & kCntMask, ref_w, ref_hi, lo[u].w, hi[u]);
+        {
+          const uint32_t db = __ballot_sync(0xffffffffu, differs);
+          const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi * G));
+          if (!use_table && (db & gmask)) {                      // (uniform within the request's lane group)
+            use_table = true;
+            if (n_same > 0 && !(ref_raw & kCntRow))
+              for (uint32_t k = gl; k < (ref_raw & kCntMask); k += G) exc_add(exc, slot_member(ref_w, ref_hi, k), (uint32_t)n_same);
           }
-          const bool boundary = gl < nh_u && !same;
-          const uint32_t ball = __ballot_sync(0xffffffffu, boundary);
-          uint32_t bm = (G == 32) ? ball : ((ball >> (gi * G)) & ((1u << G) - 1u));
-          while (__any_sync(0xffffffffu, bm != 0)) {
-            int s0 = 0, len = 0;
-            if (bm) {
-              s0 = __ffs(bm) - 1;
-              bm &= bm - 1;
-              len = (bm ? (__ffs(bm) - 1) : nh_u) - s0;
-            }
-            const int src = gi * G + s0;
-            const uint32_t rc = __shfl_sync(0xffffffffu, lo[u].z, src), ro = __shfl_sync(0xffffffffu, lo[u].w, src);
-            const uint32_t e0 = __shfl_sync(0xffffffffu, hi.x, src), e1 = __shfl_sync(0xffffffffu, hi.y, src);
-            const uint32_t e2 = __shfl_sync(0xffffffffu, hi.z, src), e3 = __shfl_sync(0xffffffffu, hi.w, src);
-            if (len > 0) {
-              if (ro == kNoRow) {                                 // inline set: lane k owns member k
-                if (gl < (int)rc && gl < kInlineEps) {
-                  const uint32_t wsel = (gl >> 1) == 0 ? e0 : ((gl >> 1) == 1 ? e1 : ((gl >> 1) == 2 ? e2 : e3));
-                  const int m = (int)((gl & 1) ? (wsel >> 16) : (wsel & 0xFFFFu));
-                  const CNT old = cnt[m];                         // res[server] += len
-                  cnt[m] = (CNT)(old + (CNT)len);
-                  if (old == 0) atomicOr(&touched[m >> 5], 1u << (m & 31));
-                }
-              } else {                                            // a set of more than 8: one bitset row, natural order
-                for (int q = 0; q < WPL; q++) {
-                  const int w = gl * WPL + q;
-                  uint32_t x = __ldg(ovf_rows + (size_t)ro * NW + w);
-                  touched[w] |= x;                                // this lane owns word w of the bitmap in this step
-                  while (x) {
-                    const int k = __ffs(x) - 1;
-                    x &= x - 1;
-                    cnt[w * 32 + k] += (CNT)len;
-                  }
-                }
+        }
+        if (!use_table) n_same += nh_total;
+        if (__any_sync(0xffffffffu, use_table)) {                // (warp-uniform) some request of this warp needs its table
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            if (!__any_sync(0xffffffffu, hit[u] && use_table)) continue;
+            if (hit[u] && use_table) {
+              const uint32_t c = lo[u].z & kCntMask;
+              if (!(lo[u].z & kCntRow)) {
+                const uint32_t cc = c < (uint32_t)kInlineEps ? c : (uint32_t)kInlineEps;
+#pragma unroll 1
+                for (uint32_t k = 0; k < cc; k++) exc_add(exc, slot_member(lo[u].w, hi[u], k));
+              } else {                                           // a set of more than 10: one bitset row, natural order
+                exc_add_row(exc, ovf_rows + (size_t)lo[u].w * NW, NW);
               }
             }
-            __syncwarp();  // members of the next run may alias this run's counters
           }
         }
         c0 += U * G;
         if (nh_total < U * G || c0 >= n) stop = true;
       }
+      __syncwarp();
     }
 
     // ---------------- exceptions: endpoints with a non-zero match count ----------------
     const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
+    const uint32_t nl = exc->n;
+    const bool deferred = exc->overflow != 0;
     Best best = best_none();
     int xg = 0;
-    for (int q = 0; q < WPL; q++) {
-      const int w = gl * WPL + q;
-      uint32_t x = touched[w];
-      while (x) {                                                 // ascending k == ascending m for this lane
-        const int k = __ffs(x) - 1;
-        x &= x - 1;
-        const int m = w * 32 + k;
-        int c = (int)cnt[m];   // stored modulo 2^bits(CNT); a touched slot holds c >= 1, so 0 means 2^bits
-        if (c == 0) c = 1 << (8 * (int)sizeof(CNT));
-        cnt[m] = 0;
-        if (m < M) {
-          const uint32_t pos = perm_bitpos((uint32_t)m, LOG_EPL);
-          const int wi = (int)(pos >> 5), kb = (int)(pos & 31);
-          const uint32_t clo = __ldg(a.cls_lo + (size_t)ad * RW + wi), chi = __ldg(a.cls_hi + (size_t)ad * RW + wi);
-          const uint32_t tmw = __ldg(a.tiemask + (size_t)ad * RW + wi);  // bit kb: G[ad][m] == gmax
-          const int cls = (int)((clo >> kb) & 1u) | ((int)((chi >> kb) & 1u) << 1);
-          const double s_true = eval_exception<SEQ>(a, m, c, n, cls);
-          best_update(best, s_true, m, tie_mode, areq, plan.seed_hi);
-          xg += (int)((tmw >> kb) & 1u);
+    auto consider = [&](int m, int c) {  // one exception: endpoint m matched c blocks
+      if (m < M) {
+        const uint32_t pos = perm_bitpos((uint32_t)m, LOG_EPL);
+        const int wi = (int)(pos >> 5), kb = (int)(pos & 31);
+        const uint32_t clo = __ldg(a.cls_lo + (size_t)ad * RW + wi), chi = __ldg(a.cls_hi + (size_t)ad * RW + wi);
+        const uint32_t tmw = __ldg(a.tiemask + (size_t)ad * RW + wi);  // bit kb: G[ad][m] == gmax
+        const int cls = (int)((clo >> kb) & 1u) | ((int)((chi >> kb) & 1u) << 1);
+        const double s_true = eval_exception<SEQ>(a, m, c, n, cls);
+        best_update_any(best, s_true, m, tie_mode, areq, plan.seed_hi);
+        xg += (int)((tmw >> kb) & 1u);
+      }
+    };
+    if (!deferred) {
+      if (!use_table) {  // every matched block carries the reference set: its members are the exceptions
+        if (n_same > 0)
+          for (uint32_t k = gl; k < (ref_raw & kCntMask); k += G) consider((int)slot_member(ref_w, ref_hi, k), n_same);
+      } else {
+        for (uint32_t j0 = gl; j0 < nl; j0 += G) {
+          const uint32_t e = exc->tab[exc->list[j0]];
+          consider((int)(e >> 16) - 1, (int)(e & 0xFFFFu));
         }
       }
     }
-    // reduce over the request's lane group. Exception m are not globally ascending across lanes: merge rules
-    // (lowest index / highest priority) are order independent.
+    // reduce over the request's lane group (the merge rules — lowest index / highest priority — are order independent)
     best_group_reduce<G>(best, tie_mode);
 #pragma unroll
     for (int o = G / 2; o; o >>= 1) xg += __shfl_xor_sync(0xffffffffu, xg, o);
@@ -267,7 +350,7 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
     if (tie_mode) {  // warp-uniform: the shuffles below need every lane, whichever groups actually have a tie
       // seeded-random tie-break: the arg-max member with the highest priority, over
       // (precomputed tie set minus exceptions) ∪ (exceptions that tie)
-      const bool need = !exc_wins && ties > 1;  // uniform within a request's lane group only
+      const bool need = !deferred && !exc_wins && ties > 1;  // uniform within a request's lane group only
       Best b2 = best_none();
       if (need && exc_ties && gl == 0) b2 = best;  // already reduced over the group
       if (need) {
@@ -280,7 +363,15 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
             const int k = __ffs(x) - 1;
             x &= x - 1;
             const int m = (((j << LOG_EPL) + k) << 5) + ln;
-            if (m < M && !((touched[m >> 5] >> (m & 31)) & 1u)) best_update(b2, sm.gmax, m, tie_mode, areq, plan.seed_hi);
+            bool is_exc;
+            if (use_table) {
+              is_exc = exc_has(exc, (uint32_t)m);
+            } else {
+              is_exc = false;
+              if (n_same > 0)
+                for (uint32_t kk = 0; kk < (ref_raw & kCntMask); kk++) is_exc |= slot_member(ref_w, ref_hi, kk) == (uint32_t)m;
+            }
+            if (m < M && !is_exc) best_update_any(b2, sm.gmax, m, tie_mode, areq, plan.seed_hi);
           }
         }
       }
@@ -289,35 +380,46 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
       if (need) pick = b2.m;
     }
     __syncwarp();
-    for (int q = 0; q < WPL; q++) touched[gl * WPL + q] = 0;
+    // reset the table: the listed entries, or all of it after an overflow (the list may be incomplete then)
+    if (deferred) {
+      for (int j0 = gl; j0 < kExcSlots; j0 += G) exc->tab[j0] = 0;
+    } else {
+      for (uint32_t j0 = gl; j0 < nl; j0 += G) exc->tab[exc->list[j0]] = 0;
+    }
+    if (gl == 0) {
+      exc->n = 0;
+      exc->overflow = 0;
+    }
     // the warp-level shuffles above need every lane; only now drop the padding groups
     if (valid && gl == 0) {
-      a.pick[r] = pick;
-      a.pick_score[r] = pick >= 0 ? score : 0.0;
-      a.tie_count[r] = pick >= 0 ? ties : 0;
+      if (deferred) {
+        a.pick[r] = kPickDeferred;   // scored by the full-matrix kernel launched right after this one
+      } else {
+        a.pick[r] = pick;
+        a.pick_score[r] = pick >= 0 ? score : 0.0;
+        a.tie_count[r] = pick >= 0 ? ties : 0;
+      }
       if (a.total_out) a.total_out[r] = (uint16_t)n;
     }
     __syncwarp();
   }
 }
 
-template <int J, typename CNT, uint32_t SEQ>
+template <int J, uint32_t SEQ>
 static int launch_sparse_inst(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   constexpr int RW = J * 32;
   constexpr int G = (RW / 4 < 32) ? RW / 4 : 32;
   constexpr int RPW = 32 / G;
-  auto kernel = pick_sparse_kernel<J, CNT, SEQ>;
-  const size_t smem = (size_t)kSparseWarps * RPW * ((size_t)a.geo.Mpad * sizeof(CNT) + (size_t)(a.geo.Mpad >> 5) * 4);
-  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kernel = pick_sparse_kernel<J, SEQ>;
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSparseWarps * 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSparseWarps * 32, 0);
   if (occ < 1) occ = 1;
   const int per_block = kSparseWarps * RPW;
   int blocks = sm_count * occ;
   const int need = (a.R + per_block - 1) / per_block;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
-  kernel<<<blocks, kSparseWarps * 32, smem, s>>>(a);
+  kernel<<<blocks, kSparseWarps * 32, 0, s>>>(a);
   return 1;
 }
 
@@ -327,33 +429,34 @@ constexpr uint32_t sparse_seq(int k, Rest... rest) {
   return (uint32_t)(k + 1) | (sparse_seq(rest...) << 4);
 }
 
-template <int J, typename CNT>
+template <int J>
 static int launch_sparse_seq(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   constexpr uint32_t EPL_ = sparse_seq(STEP_EP_TERM, STEP_PREFIX, STEP_LORA);  // queue,kv folded | prefix | lora
   constexpr uint32_t EP_ = sparse_seq(STEP_EP_TERM, STEP_PREFIX);              // the reference's default config
-  if (a.plan.seq == EPL_) return launch_sparse_inst<J, CNT, EPL_>(a, s, sm_count);
-  if (a.plan.seq == EP_) return launch_sparse_inst<J, CNT, EP_>(a, s, sm_count);
-  return launch_sparse_inst<J, CNT, 0>(a, s, sm_count);
-}
-
-template <int J>
-static int launch_sparse_geo(const ScoreArgs& a, cudaStream_t s, int sm_count) {
-  const int maxn = a.hashes ? a.hash_stride : 0;
-  if (maxn <= 256) return launch_sparse_seq<J, uint8_t>(a, s, sm_count);  // incl. defaultMaxPrefixBlocks
-  return launch_sparse_seq<J, uint16_t>(a, s, sm_count);
+  if (a.plan.seq == EPL_) return launch_sparse_inst<J, EPL_>(a, s, sm_count);
+  if (a.plan.seq == EP_) return launch_sparse_inst<J, EP_>(a, s, sm_count);
+  return launch_sparse_inst<J, 0>(a, s, sm_count);
 }
 
 // Applicable when: unmasked, not dense, no per-pair diagnostics, plan flagged sparse_ok, summaries present.
+// Returns the number of launches: the sparse kernel plus the full-matrix kernel restricted to the requests it deferred.
 int launch_pick_sparse(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
   if (!a.plan.sparse_ok || !a.summ || !a.tiemask || a.cand_mask || a.dense || a.match_out || a.scores_out) return 0;
-  if (a.geo.Mpad > 65535 + 1) return 0;  // inline members are uint16
+  if (a.geo.Mpad > 65536) return 0;  // inline members are uint16
+  int launched;
   switch (a.geo.J) {
-    case 1: return launch_sparse_geo<1>(a, s, sm_count);
-    case 2: return launch_sparse_geo<2>(a, s, sm_count);
-    case 4: return launch_sparse_geo<4>(a, s, sm_count);
-    default: return launch_sparse_geo<8>(a, s, sm_count);
+    case 1: launched = launch_sparse_seq<1>(a, s, sm_count); break;
+    case 2: launched = launch_sparse_seq<2>(a, s, sm_count); break;
+    case 4: launched = launch_sparse_seq<4>(a, s, sm_count); break;
+    default: launched = launch_sparse_seq<8>(a, s, sm_count); break;
   }
+  if (a.table && a.hashes) {  // only a request with prefix matches can overflow its exception table
+    ScoreArgs d = a;
+    d.only_deferred = 1;
+    launched += launch_score_matrix(d, s, sm_count);
+  }
+  return launched;
 }
 
 }  // namespace eppscore

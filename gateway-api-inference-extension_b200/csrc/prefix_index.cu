@@ -80,20 +80,21 @@ struct DevX {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
   }
   __device__ __forceinline__ uint32_t cas32(uint32_t* p, uint32_t cmp, uint32_t val) { return atomicCAS(p, cmp, val); }
+  __device__ __forceinline__ uint32_t cas_acquire32(uint32_t* p, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.acquire.gpu.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+    return old;
+  }
   __device__ __forceinline__ uint64_t cas64(uint64_t* p, uint64_t cmp, uint64_t val) {
     return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)val);
   }
   __device__ __forceinline__ void add64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
-  __device__ __forceinline__ void fence() { __threadfence(); }
+  __device__ __forceinline__ void fence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
   __device__ __forceinline__ void lock(uint32_t* p) {
-    while (atomicCAS(p, 0u, 1u) != 0u) {
+    while (cas_acquire32(p, 0u, 1u) != 0u) {
     }
-    __threadfence();
   }
-  __device__ __forceinline__ void unlock(uint32_t* p) {
-    __threadfence();
-    atomicExch(p, 0u);
-  }
+  __device__ __forceinline__ void unlock(uint32_t* p) { st_release32(p, 0u); }
   __device__ __forceinline__ uint64_t smem_cas64(uint64_t* p, uint64_t cmp, uint64_t val) {
     return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)val);
   }
@@ -161,13 +162,13 @@ __global__ void table_rehash_kernel(const TSlot* old_slots, uint64_t old_cap, Ta
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 lo = __ldcg(reinterpret_cast<const uint4*>(old_slots + i));
     const uint32_t cnt = lo.z;
-    if (cnt == kCntFree || cnt == 0) continue;
+    if (cnt == kCntFree || (cnt & kCntMask) == 0) continue;
     const uint4 hi = __ldcg(reinterpret_cast<const uint4*>(old_slots + i) + 1);
     const uint64_t key = ((uint64_t)lo.y << 32) | lo.x;
     for (uint64_t j = key & mask;; j = (j + 1) & mask) {
       if (atomicCAS(&ns[j].cnt, kCntFree, kCntLock) == kCntFree) {  // keys are unique: claim, fill, publish
         ns[j].key = key;
-        ns[j].ovf = lo.w;
+        *slot_row_id(&ns[j]) = lo.w;  // ep[0..1] (or the row id)
         *(reinterpret_cast<uint4*>(&ns[j]) + 1) = hi;
         __threadfence();
         atomicExch(&ns[j].cnt, cnt);

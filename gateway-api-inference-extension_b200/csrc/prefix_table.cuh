@@ -2,9 +2,10 @@
 // DEVICE-RESIDENT data structure: both halves of the reference's `indexer` live in HBM and are maintained by kernels.
 //
 //   hashToPods  map[blockHash]podSet  (indexer.go:34)  ->  open-addressing table of 32-byte slots (one DRAM/L2 sector):
-//        { key u64 | cnt u32 | ovf u32 | ep u16[8] }   linear probing from (hash & mask), load <= 0.5.
-//        Sets of up to 8 endpoints are stored INLINE in the slot — a probe that hits needs no second access; a block cached on
-//        more endpoints points at a bitset row (natural bit order, Mpad bits) in an overflow pool.  `cnt == 0` is an emptied
+//        { key u64 | cnt u32 | ep u16[10] }   linear probing from (hash & mask), load <= 0.5.
+//        Sets of up to 10 endpoints are stored INLINE in the slot, sorted — a probe that hits needs no second access (the first
+//        16 bytes already carry two members: enough for the unique tail blocks of a prompt); a block cached on more
+//        endpoints points at a bitset row (natural bit order, Mpad bits) in an overflow pool (row id in ep[0..1]).  `cnt == 0` is an emptied
 //        set (the reference deletes the key, indexer.go:109-112: a probe treats it as a miss); dead slots are reclaimed when
 //        the table is rebuilt (prefix_index.cu).
 //   podToLRU    map[ServerID]*lru.Cache (indexer.go:35) ->  per endpoint a LOG-STRUCTURED exact LRU:
@@ -17,7 +18,7 @@
 //
 // PreRequest for a batch (plugin.go:169-197: for r in order: indexer.Add(hashes[r], pick[r])) runs as ONE kernel with one
 // CTA per endpoint: Adds for different endpoints only ever touch different members of the sets, so they commute; within an
-// endpoint the calls are replayed in request order, CHUNKS of up to min(1024, capacity) touches at a time:
+// endpoint the calls are replayed in request order, CHUNKS of up to min(2048, capacity) touches at a time:
 //     dedupe the chunk (last touch wins) -> look every distinct key up -> append / insert in last-touch order (new keys also
 //     join hashToPods) -> evict the oldest live entries while len > capacity (they leave hashToPods).
 // A chunk never evicts a key it touched itself (it holds at most `capacity` distinct keys), which is the only case where the
@@ -39,17 +40,21 @@
 
 namespace eppscore {
 
-constexpr int kInlineEps = 8;
+constexpr int kInlineEps = 10;
 constexpr uint32_t kCntFree = 0xFFFFFFFFu;  // slot never used
 constexpr uint32_t kCntLock = 0x80000000u;  // slot held by an updater (never visible to the scoring kernels)
+constexpr uint32_t kCntRow = 0x40000000u;   // the set is a bitset row of the overflow pool; its id is the u32 at ep[0..1]
+constexpr uint32_t kCntMask = 0x3FFFFFFFu;  // |set|
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 
 struct alignas(32) TSlot {
   uint64_t key;
-  uint32_t cnt;  // kCntFree | (kCntLock |) |set|
-  uint32_t ovf;  // kNoRow: members inline in ep[0..cnt); else the set is bitset row `ovf` of the overflow pool
-  uint16_t ep[kInlineEps];
+  uint32_t cnt;               // kCntFree | (kCntLock |) (kCntRow |) |set|
+  uint16_t ep[kInlineEps];    // inline: the members, ascending, in ep[0..|set|); row mode: ep[0..1] = row id
 };
+static_assert(sizeof(TSlot) == 32, "one 32-byte sector per slot");
+// As the scoring kernels load it: lo = {key.lo, key.hi, cnt, ep0 | ep1 << 16}, hi = {ep2|ep3<<16, ..., ep8|ep9<<16}.
+PT_HD uint32_t* slot_row_id(TSlot* s) { return reinterpret_cast<uint32_t*>(&s->ep[0]); }
 
 // What the scoring kernels need (first four fields) + the updaters' bookkeeping.  Lives in DEVICE memory: kernels take a
 // pointer to it, so a table rebuild (new arrays) does not invalidate captured CUDA graphs.
@@ -92,9 +97,11 @@ struct LruView {
   uint32_t error;       // sticky: 1 = capacity request above max_cap
 };
 
-constexpr int kCommitThreads = 256;
-constexpr int kChunkMax = 1024;              // touches per parallel chunk
+constexpr int kCommitThreads = 512;
+constexpr int kChunkMax = 2048;              // touches per parallel chunk
 constexpr int kDedupSlots = 2 * kChunkMax;   // CTA-local dedupe set
+constexpr int kPicksPerThread = 8;           // the pick array is scanned in windows of 8 * 512 requests
+constexpr int kPickWindow = kPicksPerThread * kCommitThreads;
 static_assert(kChunkMax == 4 * kCommitThreads, "process_chunk: thread t owns touches [4t, 4t+4)");
 
 PT_HD uint64_t lru_home(uint64_t k) {
@@ -135,10 +142,8 @@ struct TableOps {
       const uint32_t c = x.ld_acquire32(&slots[i].cnt);
       if (c == kCntFree) {
         if (!create) return -1;
-        if (x.cas32(&slots[i].cnt, kCntFree, kCntLock) == kCntFree) {  // claimed and locked, empty set
-          x.fence();
+        if (x.cas_acquire32(&slots[i].cnt, kCntFree, kCntLock) == kCntFree) {  // claimed and locked, empty set
           x.st64(&slots[i].key, h);
-          x.st32(&slots[i].ovf, kNoRow);
           x.add64(&tv->used, 1ULL);
           *cnt = 0;
           return (long long)i;
@@ -147,8 +152,7 @@ struct TableOps {
       }
       if (c & kCntLock) continue;  // held (maybe being created): its key is not stable yet
       if (x.ld64(&slots[i].key) == h) {
-        if (x.cas32(&slots[i].cnt, c, c | kCntLock) == c) {
-          x.fence();
+        if (x.cas_acquire32(&slots[i].cnt, c, c | kCntLock) == c) {
           *cnt = c;
           return (long long)i;
         }
@@ -162,8 +166,7 @@ struct TableOps {
     }
   }
   static PT_HD void unlock_slot(X& x, TableView* tv, long long i, uint32_t cnt) {
-    x.fence();
-    x.st_release32(&tv->slots[i].cnt, cnt);
+    x.st_release32(&tv->slots[i].cnt, cnt);  // release: every store of the critical section is visible before the unlock
   }
   static PT_HD uint32_t alloc_row(X& x, TableView* tv) {
     uint32_t r = kNoRow;
@@ -197,27 +200,37 @@ struct TableOps {
   }
   // hashToPods[h].insert(p)   (indexer.go:75-82)
   static PT_HD void set_member(X& x, TableView* tv, uint64_t h, uint32_t p) {
-    uint32_t c;
-    const long long i = lock_slot(x, tv, h, true, &c);
+    uint32_t raw;
+    const long long i = lock_slot(x, tv, h, true, &raw);
     if (i < 0) return;
     TSlot* s = &tv->slots[i];
-    const uint32_t ovf = x.ld32(&s->ovf);
-    uint32_t nc = c;
-    if (ovf != kNoRow) {
-      uint32_t* w = tv->ovf_rows + (size_t)ovf * tv->row_words + (p >> 5);
+    const uint32_t c = raw & kCntMask;
+    uint32_t nraw = raw;
+    if (raw & kCntRow) {
+      const uint32_t r = x.ld32(slot_row_id(s));
+      uint32_t* w = tv->ovf_rows + (size_t)r * tv->row_words + (p >> 5);
       const uint32_t old = x.ld32(w), bit = 1u << (p & 31);
       if (!(old & bit)) {
         x.st32(w, old | bit);
-        nc = c + 1;
+        nraw = raw + 1;
       }
     } else {
+      // the inline members are kept SORTED: equal sets have equal representations whatever the order in which the
+      // endpoints' CTAs got to the slot — the scoring kernels merge consecutive hits by comparing the slots' member words,
+      // and replicas that replay the same commits hold bit-identical sets
       bool present = false;
-      for (uint32_t k = 0; k < c; k++) present |= (x.ld16(&s->ep[k]) == (uint16_t)p);
+      uint32_t pos = c;
+      for (uint32_t k = 0; k < c; k++) {
+        const uint32_t m = x.ld16(&s->ep[k]);
+        present |= (m == p);
+        if (m > p && pos == c) pos = k;
+      }
       if (!present) {
         if (c < (uint32_t)kInlineEps) {
-          x.st16(&s->ep[c], (uint16_t)p);
-          nc = c + 1;
-        } else {  // the ninth member: move the set to a bitset row
+          for (uint32_t k = c; k > pos; k--) x.st16(&s->ep[k], (uint16_t)x.ld16(&s->ep[k - 1]));
+          x.st16(&s->ep[pos], (uint16_t)p);
+          nraw = raw + 1;
+        } else {  // one member too many for the slot: move the set to a bitset row
           const uint32_t r = alloc_row(x, tv);
           if (r != kNoRow) {
             uint32_t* row = tv->ovf_rows + (size_t)r * tv->row_words;
@@ -226,45 +239,46 @@ struct TableOps {
               x.st32(&row[m >> 5], x.ld32(&row[m >> 5]) | (1u << (m & 31)));
             }
             x.st32(&row[p >> 5], x.ld32(&row[p >> 5]) | (1u << (p & 31)));
-            x.st32(&s->ovf, r);
-            nc = c + 1;
+            x.st32(slot_row_id(s), r);
+            nraw = (raw + 1) | kCntRow;
           }
         }
       }
     }
-    if (c == 0 && nc == 1) x.add64(&tv->live, 1ULL);
-    unlock_slot(x, tv, i, nc);
+    if (c == 0 && (nraw & kCntMask) == 1) x.add64(&tv->live, 1ULL);
+    unlock_slot(x, tv, i, nraw);
   }
   // the eviction callback / RemovePod: delete(hashToPods[h], p); an emptied set behaves as a deleted key (indexer.go:105-115)
   static PT_HD void clear_member(X& x, TableView* tv, uint64_t h, uint32_t p) {
-    uint32_t c;
-    const long long i = lock_slot(x, tv, h, false, &c);
+    uint32_t raw;
+    const long long i = lock_slot(x, tv, h, false, &raw);
     if (i < 0) return;
     TSlot* s = &tv->slots[i];
-    const uint32_t ovf = x.ld32(&s->ovf);
-    uint32_t nc = c;
-    if (ovf != kNoRow) {
-      uint32_t* w = tv->ovf_rows + (size_t)ovf * tv->row_words + (p >> 5);
+    const uint32_t c = raw & kCntMask;
+    uint32_t nraw = raw;
+    if (raw & kCntRow) {
+      const uint32_t r = x.ld32(slot_row_id(s));
+      uint32_t* w = tv->ovf_rows + (size_t)r * tv->row_words + (p >> 5);
       const uint32_t old = x.ld32(w), bit = 1u << (p & 31);
       if (old & bit) {
         x.st32(w, old & ~bit);
-        nc = c - 1;
-        if (nc == 0) {
-          free_row(x, tv, ovf);
-          x.st32(&s->ovf, kNoRow);
+        nraw = raw - 1;
+        if ((nraw & kCntMask) == 0) {  // the set stays a row until it is empty
+          free_row(x, tv, r);
+          nraw = 0;
         }
       }
     } else {
       for (uint32_t k = 0; k < c; k++) {
         if (x.ld16(&s->ep[k]) == (uint16_t)p) {
-          x.st16(&s->ep[k], x.ld16(&s->ep[c - 1]));  // swap-remove keeps the list dense
-          nc = c - 1;
+          for (uint32_t j = k; j + 1 < c; j++) x.st16(&s->ep[j], (uint16_t)x.ld16(&s->ep[j + 1]));  // stays sorted and dense
+          nraw = raw - 1;
           break;
         }
       }
     }
-    if (c > 0 && nc == 0) x.add64(&tv->live, ~0ULL);
-    unlock_slot(x, tv, i, nc);
+    if (c > 0 && (nraw & kCntMask) == 0) x.add64(&tv->live, ~0ULL);
+    unlock_slot(x, tv, i, nraw);
   }
 };
 
@@ -305,7 +319,7 @@ struct CommitSmem {
   uint32_t mslot[kChunkMax];       // map entry of each final touch (0xFFFFFFFF: new key)
   uint16_t tslot[kChunkMax];       // dedupe slot of each touch
   uint16_t trank[kChunkMax];       // rank of each final touch among the finals (last-touch order)
-  uint32_t req[kCommitThreads];    // requests of this endpoint found in the current window of picks
+  uint32_t req[kPickWindow];       // requests of this endpoint found in the current window of picks
   uint32_t scan[kCommitThreads];   // block-scan workspace
   uint64_t wkey[kCommitThreads];   // window of log keys (eviction / compaction)
   uint32_t wslot[kCommitThreads];
@@ -604,17 +618,21 @@ struct IndexProgram {
     bool created = x.ld32(&d->created) != 0;
     const int32_t cap_req = a.cap_req ? a.cap_req[p] : a.single_cap;
     uint32_t fill = 0, cap = 0, chunk_cap = 0;
-    for (int32_t r0 = 0; r0 < a.R; r0 += kCommitThreads) {
-      // this endpoint's requests in the window, in request order
+    for (int32_t r0 = 0; r0 < a.R; r0 += kPickWindow) {
+      // this endpoint's requests in the window, in request order: thread t looks at picks [r0 + 8t, r0 + 8t + 8)
       x.par([&](int tid) {
-        const int32_t r = r0 + tid;
-        sm->scan[tid] = (r < a.R && a.pick[r] == (int32_t)p) ? 1u : 0u;
+        uint32_t c = 0;
+        const int32_t rb = r0 + tid * kPicksPerThread;
+        for (int32_t k = 0; k < kPicksPerThread; k++) c += (rb + k < a.R && a.pick[rb + k] == (int32_t)p) ? 1u : 0u;
+        sm->scan[tid] = c;
       });
       const uint32_t nreq = x.scan(sm->scan, &sm->total);
       if (nreq == 0) continue;
       x.par([&](int tid) {
-        const bool mine = (tid + 1 < kCommitThreads ? sm->scan[tid + 1] : nreq) != sm->scan[tid];
-        if (mine) sm->req[sm->scan[tid]] = (uint32_t)(r0 + tid);
+        uint32_t at = sm->scan[tid];
+        const int32_t rb = r0 + tid * kPicksPerThread;
+        for (int32_t k = 0; k < kPicksPerThread; k++)
+          if (rb + k < a.R && a.pick[rb + k] == (int32_t)p) sm->req[at++] = (uint32_t)(rb + k);
       });
       if (!created) {
         ensure_created(cap_req);
@@ -718,14 +736,15 @@ template <class X>
 PT_HD uint32_t table_get(X& x, const TableView* tv, uint64_t h, uint32_t* bits, uint32_t words) {
   for (uint32_t w = 0; w < words; w++) bits[w] = 0;
   for (uint64_t i = h & tv->mask, n = 0; n <= tv->mask; i = (i + 1) & tv->mask, n++) {
-    const TSlot* s = &tv->slots[i];
-    const uint32_t c = x.ld32(&s->cnt);
-    if (c == kCntFree) return 0;
+    TSlot* s = &tv->slots[i];
+    const uint32_t raw = x.ld32(&s->cnt);
+    if (raw == kCntFree) return 0;
     if (x.ld64(&s->key) != h) continue;
+    const uint32_t c = raw & kCntMask;
     if (c == 0) return 0;
-    const uint32_t ovf = x.ld32(&s->ovf);
-    if (ovf != kNoRow) {
-      for (uint32_t w = 0; w < words && w < tv->row_words; w++) bits[w] = x.ld32(&tv->ovf_rows[(size_t)ovf * tv->row_words + w]);
+    if (raw & kCntRow) {
+      const uint32_t r = x.ld32(slot_row_id(s));
+      for (uint32_t w = 0; w < words && w < tv->row_words; w++) bits[w] = x.ld32(&tv->ovf_rows[(size_t)r * tv->row_words + w]);
     } else {
       for (uint32_t k = 0; k < c; k++) {
         const uint32_t m = x.ld16(&s->ep[k]);

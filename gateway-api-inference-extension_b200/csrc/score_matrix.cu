@@ -53,6 +53,12 @@ __device__ __forceinline__ LatPair lat_pair(const double* tp, double tpot_genera
 template <uint32_t SEQ, bool MASKED, bool DIAG, bool LAT>
 __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const __grid_constant__ ScoreArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (a.only_deferred) {  // the pass behind pick_sparse: normally nothing was deferred — leave before staging anything
+    bool any = false;
+    const int gw0 = blockIdx.x * kMatrixWarps + (threadIdx.x >> 5), nw0 = gridDim.x * kMatrixWarps;
+    for (long long r = gw0 + (long long)(threadIdx.x & 31) * nw0; r < a.R; r += 32LL * nw0) any |= a.pick[r] == kPickDeferred;
+    if (!__syncthreads_or(any ? 1 : 0)) return;
+  }
   const Plan& plan = a.plan;
   const int M = a.geo.M, MPAD = a.geo.Mpad, J = a.geo.J, LOG_EPL = a.geo.log_epl, EPL = 1 << LOG_EPL;
   const int RW = a.geo.row_words;
@@ -110,6 +116,7 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
 
   const int gw = blockIdx.x * kMatrixWarps + warp, nw = gridDim.x * kMatrixWarps;
   for (int r = gw; r < a.R; r += nw) {
+    if (a.only_deferred && a.pick[r] != kPickDeferred) continue;  // (warp-uniform) the sparse kernel already scored it
     // ---------------- matchLongestPrefix into the shared-memory counters ----------------
     uint32_t any[kMaxJ];
 #pragma unroll
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
       bool touched_any = false;
       for (int c0 = 0; !stop; c0 += 32) {
         const int i = c0 + lane;
-        uint4 lo = make_uint4(0, 0, 0, kNoRow), hi = make_uint4(0, 0, 0, 0);
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);  // lo = {key.lo, key.hi, cnt, ep0|ep1<<16}, hi = ep2..ep9
         bool hit = false;
         if (i < n) {
           const uint64_t h = a.hashes[(size_t)r * a.hash_stride + i];
@@ -135,8 +142,8 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
             lo = ldg16(&slots[idx]);
             if (lo.z == kCntFree) break;                    // never-used slot: hash unknown
             if ((((uint64_t)lo.y << 32) | lo.x) == h) {
-              hit = lo.z != 0;                              // emptied set == deleted key
-              if (hit) hi = ldg16(reinterpret_cast<const uint4*>(&slots[idx]) + 1);
+              hit = (lo.z & kCntMask) != 0;                 // emptied set == deleted key
+              if (hit && !(lo.z & kCntRow) && (lo.z & kCntMask) > 2u) hi = ldg16(reinterpret_cast<const uint4*>(&slots[idx]) + 1);
               break;
             }
             idx = (idx + 1) & slot_mask;
@@ -144,30 +151,32 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
         }
         const uint32_t miss = __ballot_sync(0xffffffffu, !hit);
         const int nh = miss ? (__ffs(miss) - 1) : 32;       // blocks matched before the first global miss
-        // consecutive blocks are normally cached on the same endpoints: hits with identical inline sets form one run
-        const uint32_t pc = __shfl_up_sync(0xffffffffu, lo.z, 1), po = __shfl_up_sync(0xffffffffu, lo.w, 1);
+        // consecutive blocks are normally cached on the same endpoints: hits with identical (sorted) inline sets form one run
+        const uint32_t pc = __shfl_up_sync(0xffffffffu, lo.z, 1), pw = __shfl_up_sync(0xffffffffu, lo.w, 1);
         const uint32_t p0 = __shfl_up_sync(0xffffffffu, hi.x, 1), p1 = __shfl_up_sync(0xffffffffu, hi.y, 1);
         const uint32_t p2 = __shfl_up_sync(0xffffffffu, hi.z, 1), p3 = __shfl_up_sync(0xffffffffu, hi.w, 1);
-        const uint32_t c = lo.z;
-        bool same = lane > 0 && lo.w == kNoRow && po == kNoRow && pc == c;
+        const uint32_t c = lo.z & kCntMask;
+        bool same = lane > 0 && !(lo.z & kCntRow) && pc == lo.z;
         if (same) {
-          same = ((p0 ^ hi.x) & (c >= 2 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
-          if (c > 2) same = same && ((p1 ^ hi.y) & (c >= 4 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
-          if (c > 4) same = same && ((p2 ^ hi.z) & (c >= 6 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
-          if (c > 6) same = same && ((p3 ^ hi.w) & (c >= 8 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+          same = ((pw ^ lo.w) & (c >= 2 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+          if (c > 2) same = same && ((p0 ^ hi.x) & (c >= 4 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+          if (c > 4) same = same && ((p1 ^ hi.y) & (c >= 6 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+          if (c > 6) same = same && ((p2 ^ hi.z) & (c >= 8 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
+          if (c > 8) same = same && ((p3 ^ hi.w) & (c >= 10 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
         }
         uint32_t bm = __ballot_sync(0xffffffffu, lane < nh && !same);
         while (bm) {
           const int s0 = __ffs(bm) - 1;
           bm &= bm - 1;
           const int len = (bm ? (__ffs(bm) - 1) : nh) - s0;
-          const uint32_t rc = __shfl_sync(0xffffffffu, lo.z, s0), ro = __shfl_sync(0xffffffffu, lo.w, s0);
+          const uint32_t rraw = __shfl_sync(0xffffffffu, lo.z, s0), ew = __shfl_sync(0xffffffffu, lo.w, s0);
           const uint32_t e0 = __shfl_sync(0xffffffffu, hi.x, s0), e1 = __shfl_sync(0xffffffffu, hi.y, s0);
           const uint32_t e2 = __shfl_sync(0xffffffffu, hi.z, s0), e3 = __shfl_sync(0xffffffffu, hi.w, s0);
           touched_any = true;
-          if (ro == kNoRow) {                               // inline set: lane k bumps member k (res[server] += len)
-            if (lane < (int)rc && lane < kInlineEps) {
-              const uint32_t wsel = (lane >> 1) == 0 ? e0 : ((lane >> 1) == 1 ? e1 : ((lane >> 1) == 2 ? e2 : e3));
+          if (!(rraw & kCntRow)) {                          // inline set: lane k bumps member k (res[server] += len)
+            if (lane < (int)(rraw & kCntMask) && lane < kInlineEps) {
+              const int wq = (lane - 2) >> 1;
+              const uint32_t wsel = lane < 2 ? ew : (wq == 0 ? e0 : (wq == 1 ? e1 : (wq == 2 ? e2 : e3)));
               const uint32_t m = (lane & 1) ? (wsel >> 16) : (wsel & 0xFFFFu);
               const uint32_t pos = perm_bitpos(m, LOG_EPL);
               const int ci = (int)((pos >> 5) << LOG_EPL) + (int)(pos & 31);  // compact counter index of endpoint m
@@ -175,9 +184,9 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
               else cnt8[ci] += (uint8_t)len;
               atomicOr(&tperm[pos >> 5], 1u << (pos & 31));
             }
-          } else {                                          // more than 8 members: a natural-order bitset row
+          } else {                                          // more than 10 members: a natural-order bitset row (id in ew)
             for (int w = lane; w < NW; w += 32) {
-              uint32_t x = __ldg(ovf_rows + (size_t)ro * NW + w);
+              uint32_t x = __ldg(ovf_rows + (size_t)ew * NW + w);
               while (x) {
                 const int k = __ffs(x) - 1;
                 x &= x - 1;

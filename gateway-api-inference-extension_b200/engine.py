@@ -234,6 +234,22 @@ class Engine:
             a.ptr(model_seed, np.uint64), block_chars, max_blocks, hashes.ctypes.data, n.ctypes.data, None))
         return hashes[:R], n[:R]
 
+    @staticmethod
+    def hash_prompts_host(prompt_bytes, prompt_off, model_seed=None, prompt_len=None, block_chars=64, max_blocks=256, stride=0,
+                          n_threads=0, out=None):
+        """hashPrompt on the host cores (library worker pool).  Returns (hashes [R, stride], n_hashes [R])."""
+        R = len(prompt_off) - 1
+        stride = stride or max_blocks
+        a = _Args(False)
+        if out is None:
+            out = (np.empty((max(R, 1), stride), np.uint64), np.empty(max(R, 1), np.uint16))
+        rc = capi.lib().eppscore_hash_prompts_host(R, a.ptr(prompt_bytes, np.uint8), a.ptr(prompt_off, np.int64),
+                                                   a.ptr(prompt_len, np.int32), a.ptr(model_seed, np.uint64), block_chars, max_blocks,
+                                                   out[0].ctypes.data, stride, out[1].ctypes.data, n_threads)
+        if rc != 0:
+            raise EppscoreError(rc, "eppscore_hash_prompts_host")
+        return out[0][:R], out[1][:R]
+
     def count_fields(self, prompt_bytes, prompt_off, prompt_len=None):
         """len(strings.Fields(prompt)) per request, computed on the device (host arrays in and out)."""
         R = len(prompt_off) - 1

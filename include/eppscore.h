@@ -245,8 +245,11 @@ const char *eppscore_last_error(const struct eppscore_engine *e); /* e may be NU
 int32_t eppscore_get_stats(const struct eppscore_engine *e, eppscore_stats *out);
 /* Diagnostics knobs (profiling / A-B runs only; never needed for correct operation):
  *   key 1: 1 = always use the fully general kernels (same as env EPPSCORE_FORCE_GENERIC=1), 0 = normal dispatch;
- *   key 2: hash stage mask — bit 2 (default 7): the fused body+chain kernel; with bit 2 clear the two-kernel form:
- *          bit 0 run the body kernel, bit 1 run the chain kernel. */
+ *   key 2: hash stage mask (default 3 = the two-kernel form: bit 0 run the body kernel, bit 1 run the chain kernel, with
+ *          bit 4 the CTA-tile chain kernel of round 1 instead of the warp-tile one).  Experimental single-kernel forms, both
+ *          measured SLOWER than the two kernels on B200 (a warp in its chain phase has no loads in flight): bit 3 the
+ *          warp-tile fused kernel, bit 2 the CTA-tile warp-specialised fused kernel;
+ *   key 3: requests per chunk of a host-location batch (0: never chunk). */
 int32_t eppscore_set_debug(struct eppscore_engine *e, int32_t key, int64_t value);
 
 /* ---- snapshot (replaces the per-request deep clone, director.go:342-349) ---- */
@@ -270,6 +273,13 @@ int32_t eppscore_hash_prompts(struct eppscore_engine *e, int32_t R, int32_t loca
 int32_t eppscore_count_fields(struct eppscore_engine *e, int32_t R, int32_t location, const uint8_t *prompt_bytes,
                               const int64_t *prompt_off, const int32_t *prompt_len /*optional*/, int32_t *out,
                               void *stream);
+/* hashPrompt on the HOST cores (a persistent worker pool inside the library; n_threads <= 0: all of them) for callers that
+ * ship hashes_in instead of prompt bytes: 8 bytes per 64-byte block cross PCIe instead of 64.  hashes_out [R*hash_stride]
+ * (hash_stride >= max_blocks; entries past n_hashes_out[r] are zero).  Needs no engine and no GPU. */
+int32_t eppscore_hash_prompts_host(int32_t R, const uint8_t *prompt_bytes, const int64_t *prompt_off,
+                                   const int32_t *prompt_len /*optional*/, const uint64_t *model_seed, int32_t block_chars,
+                                   int32_t max_blocks, uint64_t *hashes_out, int32_t hash_stride, uint16_t *n_hashes_out,
+                                   int32_t n_threads);
 /* host helper: XXH64(model || salt), hashing.go:70-77 */
 uint64_t eppscore_model_seed(const void *model, size_t model_len, const void *salt, size_t salt_len);
 uint64_t eppscore_xxh64(const void *data, size_t len, uint64_t seed);

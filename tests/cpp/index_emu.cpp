@@ -37,6 +37,7 @@ struct EmuX {
     if (o == c) *p = v;
     return o;
   }
+  uint32_t cas_acquire32(uint32_t* p, uint32_t c, uint32_t v) { return cas32(p, c, v); }
   uint64_t cas64(uint64_t* p, uint64_t c, uint64_t v) {
     const uint64_t o = *p;
     if (o == c) *p = v;
@@ -83,7 +84,7 @@ struct Emu {
       set_slots(ncap);
       tv.used = tv.live = 0;
       for (const TSlot& s : old) {
-        if (s.cnt == kCntFree || s.cnt == 0) continue;
+        if (s.cnt == kCntFree || (s.cnt & kCntMask) == 0) continue;
         uint64_t j = s.key & tv.mask;
         while (slots[j].cnt != kCntFree) j = (j + 1) & tv.mask;
         slots[j] = s;

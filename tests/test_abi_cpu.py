@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 import _pkg
@@ -98,3 +99,25 @@ def test_invalid_config_rejected(pkg):
     cfg = pkg.default_config([("latency", 1.0)])
     cfg.n_filters = 9
     rejected(cfg, b"n_filters")
+
+
+def test_host_hash_pool_matches_oracle(pkg, xxh_kat):
+    """eppscore_hash_prompts_host (the library's host-side hashPrompt, worker pool) against the chained XXH64 KATs and the
+    oracle on ragged prompts, odd block sizes, truncation — no GPU involved."""
+    from oracle import oracle_py as o
+    from tests.helpers import synth_ragged_prompts
+    for c in xxh_kat["chains"][:40]:
+        p = np.frombuffer(bytes.fromhex(c["prompt_hex"]), np.uint8)
+        h, n = pkg.Engine.hash_prompts_host(p if len(p) else np.zeros(1, np.uint8), np.array([0, len(p)], np.int64),
+                                            np.array([int(c["seed"], 16)], np.uint64), block_chars=c["block_chars"],
+                                            max_blocks=c["max_blocks"], n_threads=1)
+        want = [int(x, 16) for x in c["hashes"]]
+        assert int(n[0]) == len(want) and [int(x) for x in h[0, : n[0]]] == want
+    data, off = synth_ragged_prompts(3000, max_len=900, seed=3)
+    seeds = np.arange(3000, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    for bc, mb in ((64, 256), (32, 7), (20, 9), (4, 300)):
+        h, n = pkg.Engine.hash_prompts_host(data, off, seeds, block_chars=bc, max_blocks=mb, n_threads=8)
+        for r in range(0, 3000, 7):
+            want = o.hash_prompt(data[off[r]: off[r + 1]], int(seeds[r]), bc, mb)
+            assert int(n[r]) == len(want) and np.array_equal(h[r, : n[r]], want), (bc, mb, r)
+            assert not h[r, n[r]:].any()

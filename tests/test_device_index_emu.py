@@ -146,14 +146,14 @@ def test_inline_sets_overflow_rows_and_raw_deltas(emu):
     h = L.emu_new(M, 1 << 12, 1000, 0)
     idx = o.Index(1000)
     chain = np.arange(100, 132, dtype=np.uint64)          # one 32-block prompt cached on more and more endpoints
-    eps = [3, 700, 41, 9, 1023, 512, 77, 300]
+    eps = [3, 700, 41, 9, 1023, 512, 77, 300, 2, 1000]
     for ep in eps:
         _add(L, h, chain, ep)
         idx.add(chain, ep, 0)
-    assert L.emu_stat(h, 3) == 0                          # eight members still fit the slot
+    assert L.emu_stat(h, 3) == 0                          # ten members still fit the slot
     for k in chain:
         assert _get(L, h, k) == set(eps)
-    for ep in (5, 6, 7, 900):                             # the ninth member moves each set to a bitset row
+    for ep in (5, 6, 7, 900):                             # the eleventh member moves each set to a bitset row
         _add(L, h, chain[:16], ep)
         idx.add(chain[:16], ep, 0)
     assert L.emu_stat(h, 3) == 16
