@@ -3,7 +3,7 @@
 scorers (queue 2, kv 2, prefix 3, lora 1), 2 KB shared-prefix prompts, on N B200s of one node.
 
 A "step" = one pass of the hot path over one batch of R requests per GPU:
-    prepare_endpoints + prepare_adapters (side stream) ‖ hash_bodies + hash_chain_warp (chained XXH64 of every prompt)  →  pick_sparse (table probe, 4 scorers, weighted float64 sum, arg-max pick) + the full-matrix kernel
+    prepare_endpoints + prepare_adapters (side stream) ‖ hash_bodies + hash_chain (chained XXH64 of every prompt)  →  pick_sparse (table probe, 4 scorers, weighted float64 sum, arg-max pick) + the full-matrix kernel
     on the requests pick_sparse deferred — 6 kernel launches replayed as one CUDA graph, nothing else.
 `value`  : whole-job picks/s with the inputs already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same metric through the C ABI with HOST (pinned) buffers: H2D of prompts/seeds/adapters
@@ -303,7 +303,7 @@ def run_gpu(args):
         w_nh = torch.empty(W, dtype=torch.int16, device=dev)
     if world > 1:
         for t in (w_pick, w_hash, w_nh):
-            dist.broadcast(t, src=0)
+            dist.broadcast(t.view(torch.uint8), src=0)  # (NCCL has no int16: ship the bytes)
     if not np.array_equal(w_pick.cpu().numpy(), warm["pick"]):
         raise SystemExit(f"bench: rank {rank}: the broadcast commit stream differs from this rank's oracle")
     torch.cuda.synchronize()
@@ -519,7 +519,7 @@ def run_gpu(args):
                 ev[4 * k + 1].record(stream)
             if world > 1:  # the shards' commits, concatenated in rank order == global request order
                 dist.all_gather_into_tensor(g_pick, outc["pick"])
-                dist.all_gather_into_tensor(g_nh, outc["total_blocks"])
+                dist.all_gather_into_tensor(g_nh.view(torch.uint8), outc["total_blocks"].view(torch.uint8))
                 dist.all_gather_into_tensor(g_hash, outc["hashes_out"])
                 cp, ch, cn = g_pick, g_hash, g_nh
             else:
@@ -694,16 +694,18 @@ def run_gpu(args):
             (e or eng).schedule(R, hashes_in=hh, n_hashes_in=nn, hash_stride=MAX_BLOCKS, adapter_id=dsets[i % NSETS]["adapters"],
                                 request_base=rank * R, device=True, stream=sptr, out=out)
 
-        t_hash = time_kernel(hash_only)         # hash_bodies + hash_chain_warp
+        t_hash = time_kernel(hash_only)         # hash_bodies + hash_chain
         eng.set_debug(2, 1)                     # diagnostics knob: body kernel only
         t_bodies = time_kernel(hash_only)
-        eng.set_debug(2, 2)                     # chain kernel only (re-chains the buffer in place: same work)
+        eng.set_debug(2, 18)                    # chain kernel only (re-chains the buffer in place: same work)
         t_chain = time_kernel(hash_only)
+        eng.set_debug(2, 2)                     # the warp-tile form of the chain kernel
+        t_chain_w = time_kernel(hash_only)
         eng.set_debug(2, 8)                     # experimental: the warp-tile fused kernel
         t_wfused = time_kernel(hash_only)
         eng.set_debug(2, 4)                     # experimental: the CTA-tile (warp-specialised) fused kernel
         t_cta = time_kernel(hash_only)
-        eng.set_debug(2, 3)
+        eng.set_debug(2, 19)
         for i in range(NSETS):                  # real hashes for the pick-only timing below
             hash_only(i)
         torch.cuda.synchronize()
@@ -722,12 +724,12 @@ def run_gpu(args):
         bytes_chain = R * (2 * B * 8 + 8 + 16 + 2)                            # body states in, hashes out, seed, offsets, count
         bytes_pick = R * ((hits + 1) * 8 + (hits + 1) * 32 + 2 + 4 + 16 + 16)   # hashes read, slots probed, count, adapter, summary, outputs
         bytes_prep = M * (8 + 8 + 8 + 8 + 8 + 4 + 4) + M * 8 * 3 + (A + 1) * (3 * M // 8 + 16)
-        kern = {"hash_bodies_kernel": (t_bodies, bytes_bodies), "hash_chain_warp_kernel": (t_chain, bytes_chain), "pick_sparse_kernel (+ deferred full-matrix pass)": (t_pick, bytes_pick),
+        kern = {"hash_bodies_kernel": (t_bodies, bytes_bodies), "hash_chain_kernel": (t_chain, bytes_chain), "pick_sparse_kernel (+ deferred full-matrix pass)": (t_pick, bytes_pick),
                 "prepare_snapshot (2 kernels, side stream)": (t_prep, bytes_prep)}
         extra["kernels"] = {k: {"us": t * 1e6, "algorithmic_bytes": b, "gbs": b / t / 1e9, "frac_of_peak": b / t / 1e9 / peak,
                                 "traffic": traffic.get(k.split(" ")[0])}
                             for k, (t, b) in kern.items()}
-        extra["kernels"]["hash stage"] = {"bodies_plus_chain_us": t_hash * 1e6,
+        extra["kernels"]["hash stage"] = {"bodies_plus_chain_us": t_hash * 1e6, "chain_warp_tile_form_us": t_chain_w * 1e6,
                                           "experimental_single_kernel_forms_us": {"warp_tile_fused": t_wfused * 1e6, "cta_tile_fused": t_cta * 1e6},
                                           "note": "fusing the serial chain into the streaming kernel is slower on B200: a warp in its chain phase has no loads in flight"}
         extra["kernels"]["avg_blocks_per_request"] = B
@@ -956,7 +958,7 @@ def run_gpu(args):
 
     if rank == 0:
         cfg = config_dict(world)
-        cfg["step"] = ("prepare_endpoints + prepare_adapters (side stream) || hash_bodies + hash_chain_warp, then pick_sparse + the full-matrix pass over "
+        cfg["step"] = ("prepare_endpoints + prepare_adapters (side stream) || hash_bodies + hash_chain, then pick_sparse + the full-matrix pass over "
                        "deferred requests; snapshot re-prepared every step")
         cfg["cuda_graph"] = use_graph
         line = {"metric": METRIC, "value": value, "unit": "picks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -51,7 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        extra = os.environ.get("EPPSCORE_NVCC_EXTRA", "").split()  # experiments only (e.g. -DEPP_SPARSE_MINBLOCKS=5)
+        cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r
 
@@ -84,9 +85,9 @@ def build_host_test(force: bool = False) -> str:
     """C++ host mirror tests (host/host_test.cpp): plain g++, linked against libeppscore.so."""
     build()
     src = os.path.join(HERE, "host", "host_test.cpp")
-    deps = [src, os.path.join(HERE, "host", "epp_scheduler.hpp"), LIB]
+    deps = [src, LIB] + [os.path.join(HERE, "host", h) for h in ("epp_scheduler.hpp", "epp_types.hpp", "host_eval.hpp", "coalescer.hpp")]
     if force or _stale(HOST_TEST, deps):
-        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", src, "-o", HOST_TEST, "-L" + HERE, "-leppscore",
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", src, "-o", HOST_TEST, "-pthread", "-L" + HERE, "-leppscore",
                "-Wl,-rpath,$ORIGIN/.."]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

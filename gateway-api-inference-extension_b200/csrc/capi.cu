@@ -64,7 +64,8 @@ struct eppscore_engine {
   std::string err;
   uint64_t launches = 0;
   bool force_generic = false;  // EPPSCORE_FORCE_GENERIC=1 / eppscore_set_debug(1): skip the specialised kernels
-  int32_t hash_stage_mask = 3;  // eppscore_set_debug(2): profiling only (see include/eppscore.h)
+  bool use_pdl = true;          // eppscore_set_debug(4): programmatic dependent launch between the kernels of a batch
+  int32_t hash_stage_mask = 19;  // eppscore_set_debug(2): profiling only (see include/eppscore.h)
 
   // snapshot
   bool have_snapshot = false;
@@ -267,6 +268,7 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s, S
   const bool wait_snapshot = capturing ? (e->snapshot_capture_id != 0 && e->snapshot_capture_id == cap_id)
                                        : (e->snapshot_capture_id == 0 && s != e->snapshot_stream);
 
+  bool hashed_here = false;
   ScoreArgs a{};
   a.geo = e->geo;
   a.geo.M = e->M;
@@ -352,7 +354,9 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s, S
         h.stride = mb;
         h.n_hashes = sc.s_nh.as<uint16_t>();
         h.stage_mask = e->hash_stage_mask;
+        h.pdl = e->use_pdl ? 1 : 0;
         e->launches += launch_hash_prompts(h, s, e->sm_count);
+        hashed_here = true;
         a.hashes = hashes;
         a.n_hashes = h.n_hashes;
         a.hash_stride = mb;
@@ -361,6 +365,9 @@ int32_t schedule_device(eppscore_engine* e, const DevBatch& b, cudaStream_t s, S
     }
   }
   if (wait_snapshot) CK(e, cudaStreamWaitEvent(s, e->ev_snapshot, 0));
+  // programmatic dependent launch when the previous kernel of the stream is this batch's hash kernel (the snapshot event,
+  // when there is one, stays a full dependency of the pick kernel)
+  a.pdl = (e->use_pdl && hashed_here) ? 1 : 0;
   // dispatch: specialised fast paths first, the fully general kernels otherwise
   int launched = 0;
   if (!e->force_generic) launched = dense ? launch_score_dense_fast(a, s, e->sm_count) : launch_pick_sparse(a, s, e->sm_count);
@@ -633,6 +640,10 @@ int32_t eppscore_set_debug(eppscore_engine* e, int32_t key, int64_t value) {
   }
   if (key == 3) {
     e->host_chunk = (int32_t)value;
+    return EPPSCORE_OK;
+  }
+  if (key == 4) {
+    e->use_pdl = value != 0;
     return EPPSCORE_OK;
   }
   return fail(e, EPPSCORE_ERR_INVALID, "unknown debug key");

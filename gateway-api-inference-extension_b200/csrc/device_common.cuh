@@ -2,9 +2,33 @@
 // All float64 arithmetic goes through the _rn intrinsics: never contracted into FMA, so every
 // product and sum rounds exactly like the reference's Go code on GOARCH=amd64 (SURVEY.md "Key facts").
 #pragma once
+#include <utility>
+
 #include "kernels.cuh"
 
 namespace eppscore {
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start while
+// the previous kernel of its stream is still running; it blocks in pdl_wait() until that kernel has completed and its
+// writes are visible.  Both are no-ops for an ordinary launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// launch with the programmatic-serialization attribute (pdl = false: an ordinary launch)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_maybe_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ double clamp01(double s) {  // enforceScoreRange, scheduler_profile.go:194-202
   if (s < 0.0) return 0.0;
@@ -23,6 +47,12 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int o) {
   int lo = __double2loint(v), hi = __double2hiint(v);
   lo = __shfl_xor_sync(0xffffffffu, lo, o);
   hi = __shfl_xor_sync(0xffffffffu, hi, o);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src);
+  hi = __shfl_sync(0xffffffffu, hi, src);
   return __hiloint2double(hi, lo);
 }
 __device__ __forceinline__ long long shfl_xor_i64(long long v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }

@@ -77,6 +77,7 @@ constexpr int kBodyWarps = 8;
 
 template <int BC>
 __global__ void __launch_bounds__(kBodyWarps * 32) hash_bodies_kernel(HashArgs a) {
+  pdl_launch_dependents();  // the chain kernel may be brought up while this grid drains
   const int lane = threadIdx.x & 31;
   const int bc = BC ? BC : a.block_chars;
   const int gw = blockIdx.x * kBodyWarps + (threadIdx.x >> 5), nw = gridDim.x * kBodyWarps;
@@ -97,6 +98,8 @@ constexpr int kTileReq = 32 * kChainWarps;      // requests per tile
 constexpr int kMoveReq = kTileReq / kHashWarps; // requests each warp moves
 
 __global__ void __launch_bounds__(kHashWarps * 32) hash_chain_kernel(HashArgs a) {
+  pdl_wait();               // the body states come from the previous kernel of the stream
+  pdl_launch_dependents();
   __shared__ uint64_t body[kTileReq][33];
   __shared__ int s_nfull[kTileReq], s_fast[kTileReq], s_maxfull[kChainWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(256) hash_slow_kernel(HashArgs a) {
 
 int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
-  const int stages0 = a.stage_mask ? a.stage_mask : 3;
+  const int stages0 = a.stage_mask ? a.stage_mask : 19;  // bodies + the CTA-tile chain kernel (12.4 us; the warp-tile form measured 14.5 us)
   if ((stages0 & 8) && a.block_chars > 0 && (a.block_chars & 31) == 0) {  // default: the warp-tile fused kernel
     const int ntiles = (a.R + 31) / 32;
     int blocks = sm_count * 3;
@@ -580,7 +583,7 @@ int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
   if (!(stages & 2)) return launched;
   if (stages0 & 16) {  // the CTA-tile chain kernel of round 1 (diagnostics)
     const int ntiles = (a.R + kTileReq - 1) / kTileReq;
-    hash_chain_kernel<<<ntiles, kHashWarps * 32, 0, s>>>(a);
+    launch_maybe_pdl(a.pdl != 0 && launched > 0, hash_chain_kernel, dim3(ntiles), dim3(kHashWarps * 32), 0, s, a);
   } else {
     const int ntiles = (a.R + 31) / 32;
     hash_chain_warp_kernel<<<(ntiles + kChainWarpsPerCta - 1) / kChainWarpsPerCta, kChainWarpsPerCta * 32, 0, s>>>(a);

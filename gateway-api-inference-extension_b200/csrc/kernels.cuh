@@ -166,6 +166,7 @@ struct ScoreArgs {
   double filter_param[4][3];
   uint32_t* filter_mask_out;    // [R][mask_words] or null: the candidate set after the filter chain
   int32_t only_deferred;        // full-matrix kernel: score only the requests the sparse kernel marked pick == kPickDeferred
+  int32_t pdl;                  // launch the pick kernels with programmatic dependent launch (they follow the hash kernels)
 };
 constexpr int32_t kPickDeferred = -2;
 
@@ -180,6 +181,7 @@ struct HashArgs {
   uint64_t* hashes;         // [R][stride]
   int32_t stride;
   uint16_t* n_hashes;       // [R]
+  int32_t pdl;              // launch the chain kernel with programmatic dependent launch
   int32_t stage_mask;       // diagnostics: bit 2 fused kernel (default); else bit 0 body kernel, bit 1 chain kernel
 };
 

@@ -28,6 +28,9 @@
 namespace eppscore {
 
 constexpr int kSparseWarps = 8;
+#ifndef EPP_SPARSE_MINBLOCKS
+#define EPP_SPARSE_MINBLOCKS 4  // CTAs per SM the register allocation aims at (64 registers per thread)
+#endif
 
 // Score of an exception endpoint with the scorer sequence known at compile time (SEQ packs kind+1 per step,
 // 4 bits each; SEQ == 0 selects the runtime-generic eval_steps).  The prefix term comes from the engine-wide
@@ -144,7 +147,7 @@ __device__ __forceinline__ void best_update_any(Best& b, double s, int m, int ti
 }
 
 template <int J, uint32_t SEQ>
-__global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const __grid_constant__ ScoreArgs a) {
+__global__ void __launch_bounds__(kSparseWarps * 32, EPP_SPARSE_MINBLOCKS) pick_sparse_kernel(const __grid_constant__ ScoreArgs a) {
   const int LOG_EPL = a.geo.log_epl;
   constexpr int RW = J * 32;                       // words per PERMUTED bit row (LoRA class planes, tie masks)
   constexpr int G = (RW / 4 < 32) ? RW / 4 : 32;   // lanes per request
@@ -178,6 +181,8 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
     ovf_rows = a.table->ovf_rows;
   }
 
+  pdl_wait();               // the hashes come from the previous kernel of the stream (everything above overlaps its tail)
+  pdl_launch_dependents();
   const int wstride = gridDim.x * kSparseWarps * RPW;
   for (int rbase = (blockIdx.x * kSparseWarps + warp) * RPW; rbase < a.R; rbase += wstride) {
     const int r = rbase + gi;
@@ -264,8 +269,10 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
         }
         bool differs = false;
 #pragma unroll
-        for (int u = 0; u < U; u++)
+        for (int u = 0; u < U; u++) {
+          if (!__any_sync(0xffffffffu, hit[u])) continue;        // (warp-uniform) no hit in this sub-round
           if (hit[u]) differs |= lo[u].z != ref_raw || !same_inline_set(ref_raw & kCntMask, ref_w, ref_hi, lo[u].w, hi[u]);
+        }
         {
           const uint32_t db = __ballot_sync(0xffffffffu, differs);
           const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi * G));
@@ -328,9 +335,34 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 4) pick_sparse_kernel(const
       }
     }
     // reduce over the request's lane group (the merge rules — lowest index / highest priority — are order independent)
-    best_group_reduce<G>(best, tie_mode);
-#pragma unroll
-    for (int o = G / 2; o; o >>= 1) xg += __shfl_xor_sync(0xffffffffu, xg, o);
+    const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi * G));
+    if (tie_mode == 0) {
+      // max-score with lowest-index ties through integer reductions (redux.sync): float64 scores order like their bit
+      // patterns after the usual sign fold (scores are finite and never -0.0: the sum starts from +0.0)
+      unsigned long long key = 0ULL;
+      if (best.m >= 0) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(best.score);
+        key = (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+      }
+      const uint32_t khi = (uint32_t)(key >> 32), klo = (uint32_t)key;
+      const uint32_t mh = __reduce_max_sync(gmask, khi);
+      const uint32_t ml = __reduce_max_sync(gmask, khi == mh ? klo : 0u);
+      const bool win = best.m >= 0 && khi == mh && klo == ml;
+      const int cnt_all = (int)__reduce_add_sync(gmask, win ? (uint32_t)best.cnt : 0u);
+      const int m_min = (int)__reduce_min_sync(gmask, win ? (uint32_t)best.m : 0x7fffffffu);
+      const int src = __ffs(__ballot_sync(0xffffffffu, win) & gmask) - 1;  // a lane that holds the winning score
+      const double s_win = shfl_f64(best.score, src < 0 ? lane : src);     // (every lane takes part in the shuffle)
+      if (cnt_all > 0) {
+        best.score = s_win;
+        best.m = m_min;
+        best.cnt = cnt_all;
+      } else {
+        best = best_none();
+      }
+    } else {
+      best_group_reduce<G>(best, tie_mode);
+    }
+    xg = (int)__reduce_add_sync(gmask, (uint32_t)xg);
 
     // ---------------- combine with the per-adapter summary ----------------
     int pick, ties;
@@ -419,7 +451,7 @@ static int launch_sparse_inst(const ScoreArgs& a, cudaStream_t s, int sm_count) 
   const int need = (a.R + per_block - 1) / per_block;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
-  kernel<<<blocks, kSparseWarps * 32, 0, s>>>(a);
+  launch_maybe_pdl(a.pdl != 0, kernel, dim3(blocks), dim3(kSparseWarps * 32), 0, s, a);
   return 1;
 }
 

@@ -53,6 +53,7 @@ __device__ __forceinline__ LatPair lat_pair(const double* tp, double tpot_genera
 template <uint32_t SEQ, bool MASKED, bool DIAG, bool LAT>
 __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const __grid_constant__ ScoreArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_wait();  // (no-op unless launched behind pick_sparse / the hash kernels with programmatic dependent launch)
   if (a.only_deferred) {  // the pass behind pick_sparse: normally nothing was deferred — leave before staging anything
     bool any = false;
     const int gw0 = blockIdx.x * kMatrixWarps + (threadIdx.x >> 5), nw0 = gridDim.x * kMatrixWarps;
@@ -711,7 +712,7 @@ static int launch_matrix(K kernel, const ScoreArgs& a, bool masked, bool lat, cu
   int blocks = sm_count * occ;  // persistent: one wave, warps stride over requests
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
-  kernel<<<blocks, kMatrixWarps * 32, smem, s>>>(a);
+  launch_maybe_pdl(a.pdl != 0, kernel, dim3(blocks), dim3(kMatrixWarps * 32), smem, s, a);
   return 1;
 }
 

@@ -25,104 +25,10 @@
 #include <vector>
 
 #include "../../include/eppscore.h"
+#include "epp_types.hpp"
+#include "host_eval.hpp"
 
 namespace epp {
-
-struct NamespacedName {
-  std::string Namespace, Name;
-  std::string String() const { return Namespace + "/" + Name; }
-  bool operator==(const NamespacedName& o) const { return Namespace == o.Namespace && Name == o.Name; }
-};
-
-// fwkdl.Metrics — the fields this path reads
-struct Metrics {
-  std::map<std::string, int> ActiveModels, WaitingModels;
-  int MaxActiveModels = 0;
-  int RunningRequestsSize = 0;
-  int WaitingQueueSize = 0;
-  double KVCacheUsagePercent = 0.0;
-  int CacheBlockSize = 0;   // tokens; autotune source for the prefix block size (approximateprefix/plugin.go:238-250)
-  int CacheNumBlocks = 0;   // autotune source for the per-endpoint LRU capacity (plugin.go:207-216)
-};
-
-struct EndpointMetadata {
-  NamespacedName NamespacedName_;
-  std::map<std::string, std::string> Labels;
-};
-
-struct Endpoint {
-  EndpointMetadata Metadata;
-  Metrics Metrics_;
-  // attrconcurrency.InFlightLoad.Tokens (token_load.go:91-95); < 0 here = attribute absent
-  int64_t InFlightTokens = -1;
-  const EndpointMetadata* GetMetadata() const { return &Metadata; }
-  const Metrics* GetMetrics() const { return &Metrics_; }
-};
-inline Endpoint NewEndpoint(const std::string& name, const Metrics& m, const std::string& ns = "") {
-  Endpoint e;
-  e.Metadata.NamespacedName_ = NamespacedName{ns, name};
-  e.Metrics_ = m;
-  return e;
-}
-
-struct InferenceRequest {
-  std::string RequestId;
-  std::string TargetModel;
-  std::string Prompt;     // getUserInputBytes() output (hashing.go:106-135): Completions prompt or marshalled messages
-  std::string CacheSalt;
-  std::map<std::string, std::string> Headers;  // "x-slo-ttft-ms" / "x-slo-tpot-ms" feed the latency path
-};
-
-// len(strings.Fields(s)) (predictedlatency/plugin.go:286): runs of unicode.IsSpace separate fields.  Go decodes
-// runes with utf8.DecodeRuneInString (any invalid or short sequence = U+FFFD, width 1); because a lead byte is never
-// a continuation byte, a byte belongs to a space rune exactly when it is an ASCII space or lies inside one of the
-// UTF-8 encodings of U+0085, U+00A0, U+1680, U+2000..U+200A, U+2028, U+2029, U+202F, U+205F, U+3000 — the same
-// byte-pattern rule the device kernel uses (csrc/fields_kernel.cu; fuzzed against the oracle's rune decoder).
-inline int CountFields(const std::string& str) {
-  const size_t n = str.size();
-  const unsigned char* s = reinterpret_cast<const unsigned char*>(str.data());
-  int count = 0;
-  bool prev_space = true;
-  size_t cover = 0;  // bytes [i, cover) still belong to a multi-byte space rune
-  for (size_t i = 0; i < n; i++) {
-    const unsigned b = s[i];
-    bool sp = (b >= 9 && b <= 13) || b == 32 || i < cover;
-    if (b == 0xC2 && i + 1 < n && (s[i + 1] == 0x85 || s[i + 1] == 0xA0)) {
-      sp = true;
-      cover = i + 2;
-    } else if (i + 2 < n) {
-      const unsigned b1 = s[i + 1], b2 = s[i + 2];
-      if ((b == 0xE1 && b1 == 0x9A && b2 == 0x80) ||
-          (b == 0xE2 && b1 == 0x80 && ((b2 >= 0x80 && b2 <= 0x8A) || b2 == 0xA8 || b2 == 0xA9 || b2 == 0xAF)) ||
-          (b == 0xE2 && b1 == 0x81 && b2 == 0x9F) || (b == 0xE3 && b1 == 0x80 && b2 == 0x80)) {
-        sp = true;
-        cover = i + 3;
-      }
-    }
-    if (!sp && prev_space) count++;
-    prev_space = sp;
-  }
-  return count;
-}
-
-struct ScoredEndpoint {
-  const Endpoint* Endpoint_ = nullptr;
-  int Index = -1;  // position in the candidate slice given to Schedule
-  double Score = 0.0;
-  int TieCount = 0;  // size of the arg-max set the reference would shuffle over (picker/maxscore/picker.go:91-102)
-};
-struct ProfileRunResult {
-  std::vector<ScoredEndpoint> TargetEndpoints;
-};
-struct SchedulingResult {
-  std::map<std::string, ProfileRunResult> ProfileResults;
-  std::string PrimaryProfileName;
-};
-
-// errcommon.Error{Code: Internal, ...} / fmt.Errorf of the reference, as an exception with the same text
-struct SchedulingError : std::runtime_error {
-  using std::runtime_error::runtime_error;
-};
 
 // ---- plugins (descriptors) ----
 struct Scorer {
@@ -199,7 +105,7 @@ inline DeviceFilter SLOHeadroomTierFilter(double epsilonExploreNeg = 0.01) {
 }
 
 struct MaxScorePicker {
-  int MaxNumOfEndpoints = 1;  // picker.DefaultMaxNumOfEndpoints (picker/common.go:36); only 1 is supported on the GPU path
+  int MaxNumOfEndpoints = 1;  // picker.DefaultMaxNumOfEndpoints (picker/common.go:36); > 1: top-k from the engine's score rows
   int Mode = EPPSCORE_PICK_MAX_SCORE;
 };
 // weighted-random-picker (A-Res, picker/weightedrandom/picker.go:111-155) and random-picker (picker/random/picker.go:85-101):
@@ -247,6 +153,10 @@ struct SchedulerConfig {
   int64_t PrefixCapacity = 1 << 18;
   int TieMode = EPPSCORE_TIE_LOWEST_INDEX;
   uint64_t TieSeed = 0;
+  // Batches of at most this many requests whose profile is request-independent (queue / kv / running / lora / token-load
+  // scorers, no device filters, max-score picker, lowest-index ties) are evaluated on the host (SmallBatchCpu): a launch
+  // costs tens of microseconds, a 1 x 4 queue-scorer Schedule a fraction of one.  0 disables the route.
+  int CpuBatchThreshold = 8;
 };
 
 class Scheduler {
@@ -256,8 +166,23 @@ class Scheduler {
     eppscore_config_default(&c);
     const auto& sc = cfg.Profile.scorers();
     if (sc.size() > EPPSCORE_MAX_SCORERS) throw SchedulingError("too many scorers in profile");
-    if (cfg.Profile.picker().MaxNumOfEndpoints != 1) throw SchedulingError("GPU path supports maxNumOfEndpoints == 1 only");
+    if (cfg.Profile.picker().MaxNumOfEndpoints < 1) throw SchedulingError("maxNumOfEndpoints must be >= 1");
+    if (cfg.Profile.picker().MaxNumOfEndpoints > 1 && cfg.Profile.picker().Mode != EPPSCORE_PICK_MAX_SCORE)
+      throw SchedulingError("maxNumOfEndpoints > 1 is supported for the max-score picker only");
     c.n_scorers = (int32_t)sc.size();
+    {  // the small-batch CPU route applies to request-independent profiles only
+      std::vector<int32_t> kinds;
+      std::vector<double> weights;
+      for (auto& w : sc) {
+        kinds.push_back(w.Scorer_->Kind);
+        weights.push_back(w.Weight());
+      }
+      double thr = 4194304.0;
+      for (auto& w : sc)
+        if (auto* tl = dynamic_cast<TokenLoadScorer*>(w.Scorer_.get())) thr = (double)tl->QueueThresholdTokens;
+      cpu_route_ok_ = cfg.CpuBatchThreshold > 0 && cfg.Profile.device_filters().empty() && cfg.Profile.picker().Mode == EPPSCORE_PICK_MAX_SCORE &&
+                      cfg.Profile.picker().MaxNumOfEndpoints == 1 && cfg.TieMode == EPPSCORE_TIE_LOWEST_INDEX && cpu_.Configure(kinds, weights, thr);
+    }
     for (size_t i = 0; i < sc.size(); i++) {
       c.scorer_kind[i] = sc[i].Scorer_->Kind;
       c.scorer_weight[i] = sc[i].Weight();
@@ -307,6 +232,31 @@ class Scheduler {
     if (R == 0) return out;
     if (M == 0) {  // scheduler_profile.go:119-121 → single_profile_handler.go:89-91
       for (auto& o : out) o.error = "failed to run scheduler profile '" + cfg_.ProfileName + "'";
+      return out;
+    }
+    if (cpu_route_ok_ && R <= cfg_.CpuBatchThreshold) {  // tiny batch, request-independent profile: stay on the host
+      std::vector<int> all((size_t)M);
+      for (int m = 0; m < M; m++) all[m] = m;
+      for (int r = 0; r < R; r++) {
+        std::vector<int> cand = all;
+        for (auto& f : cfg_.Profile.filters()) {
+          cand = f->Filter_(requests[r], endpoints, cand);
+          if (cand.empty()) break;
+        }
+        const CpuPick p = cpu_.Schedule(endpoints, requests[r].TargetModel, cfg_.Profile.filters().empty() ? nullptr : &cand);
+        if (p.pick < 0) {
+          out[r].error = "failed to run scheduler profile '" + cfg_.ProfileName + "'";
+          continue;
+        }
+        ScoredEndpoint se;
+        se.Endpoint_ = &endpoints[(size_t)p.pick];
+        se.Index = p.pick;
+        se.Score = p.score;
+        se.TieCount = p.tie_count;
+        out[r].result.ProfileResults[cfg_.ProfileName].TargetEndpoints.push_back(se);
+        out[r].result.PrimaryProfileName = cfg_.ProfileName;
+      }
+      cpu_routed_ += (uint64_t)R;
       return out;
     }
     PackSnapshot(endpoints);
@@ -393,6 +343,12 @@ class Scheduler {
     b.tie_count = ties.data();
     b.total_blocks = last_nh_.data();
     b.hashes_out = want_prefix ? last_hashes_.data() : nullptr;
+    const int topk = cfg_.Profile.picker().MaxNumOfEndpoints;
+    std::vector<double> all_scores;
+    if (topk > 1) {  // the whole weightedScorePerEndpoint map, NaN for non-candidates (scheduler_profile.go:155-174)
+      all_scores.resize((size_t)R * M);
+      b.scores_out = all_scores.data();
+    }
     if (eppscore_schedule_batch(eng_, &b) != EPPSCORE_OK) throw SchedulingError(std::string("eppscore_schedule_batch: ") + eppscore_last_error(eng_));
     last_endpoints_ = &endpoints;
     for (int r = 0; r < R; r++) {
@@ -407,9 +363,22 @@ class Scheduler {
       se.TieCount = ties[r];
       out[r].result.ProfileResults[cfg_.ProfileName].TargetEndpoints.push_back(se);
       out[r].result.PrimaryProfileName = cfg_.ProfileName;
+      if (topk > 1) {  // picker/maxscore/picker.go:104-106: the next best candidates, descending score
+        auto& te = out[r].result.ProfileResults[cfg_.ProfileName].TargetEndpoints;
+        for (const auto& pr : TopK(all_scores.data() + (size_t)r * M, M, topk)) {
+          if (pr.first == se.Index) continue;
+          if ((int)te.size() >= topk) break;
+          ScoredEndpoint o2;
+          o2.Endpoint_ = &endpoints[(size_t)pr.first];
+          o2.Index = pr.first;
+          o2.Score = pr.second;
+          te.push_back(o2);
+        }
+      }
     }
     return out;
   }
+  uint64_t CpuRoutedRequests() const { return cpu_routed_; }
 
   // PreRequest for the last ScheduleBatch (approximateprefix/plugin.go:169-197): records the picks in the index.
   void PreRequest(const std::vector<BatchItem>& results) {
@@ -527,6 +496,9 @@ class Scheduler {
   }
 
   SchedulerConfig cfg_;
+  SmallBatchCpu cpu_;
+  bool cpu_route_ok_ = false;
+  uint64_t cpu_routed_ = 0;
   eppscore_engine* eng_ = nullptr;
   const LatencyScorer* latency_scorer_ = nullptr;
   std::unordered_map<std::string, int> adapter_ids_;

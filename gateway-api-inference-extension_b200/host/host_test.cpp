@@ -13,6 +13,14 @@
 #include <cstring>
 
 #include "epp_scheduler.hpp"
+#include "coalescer.hpp"
+
+#include <atomic>
+#include <thread>
+
+// 0: every batch goes to the GPU; 8: tiny request-independent batches take the host route (SmallBatchCpu).  The suite runs
+// under both settings with the SAME expectations.
+static int g_cpu_threshold = 0;
 
 using namespace epp;
 
@@ -38,6 +46,7 @@ static Metrics M_(int queue, double kv, int maxActive, std::vector<std::string> 
 static SchedulerConfig DefaultFourScorerConfig() {
   // scheduler_test.go:49-57: kv, queue, prefix, lora — all weight 1, max-score picker
   SchedulerConfig c;
+  c.CpuBatchThreshold = g_cpu_threshold;
   c.Profile.WithScorers({NewWeightedScorer(std::make_shared<KVCacheUtilizationScorer>(), 1),
                          NewWeightedScorer(std::make_shared<QueueScorer>(), 1),
                          NewWeightedScorer(std::make_shared<PrefixCacheScorer>(), 1),
@@ -96,6 +105,8 @@ static void TestFilterChain() {
     auto f1 = std::make_shared<NameFilter>(std::vector<std::string>{"pod1", "pod2", "pod3"});
     auto f2 = std::make_shared<NameFilter>(std::vector<std::string>{"pod1", "pod2"});
     SchedulerConfig c;
+    c.CpuBatchThreshold = g_cpu_threshold;
+  c.CpuBatchThreshold = g_cpu_threshold;
     c.Profile.WithFilters({f1, f2})
         .WithScorers({NewWeightedScorer(std::make_shared<QueueScorer>(), 1), NewWeightedScorer(std::make_shared<KVCacheUtilizationScorer>(), 1)})
         .WithPicker(MaxScorePicker{});
@@ -114,6 +125,8 @@ static void TestFilterChain() {
     auto fall = std::make_shared<NameFilter>(std::vector<std::string>{});
     auto never = std::make_shared<NameFilter>(std::vector<std::string>{"pod1"});
     SchedulerConfig c;
+    c.CpuBatchThreshold = g_cpu_threshold;
+  c.CpuBatchThreshold = g_cpu_threshold;
     c.Profile.WithFilters({f1, fall, never}).WithScorers({NewWeightedScorer(std::make_shared<QueueScorer>(), 1)}).WithPicker(MaxScorePicker{});
     c.MaxEndpoints = 8;
     c.PrefixCapacity = 64;
@@ -139,6 +152,7 @@ static std::vector<Endpoint> Pods(std::vector<std::tuple<int, int, double, std::
 static void TestIntegrationRouting() {
   // testdata/default-config.yaml: queue, kv, prefix, lora (weight 1)
   SchedulerConfig c;
+  c.CpuBatchThreshold = g_cpu_threshold;
   c.Profile.WithScorers({NewWeightedScorer(std::make_shared<QueueScorer>(), 1), NewWeightedScorer(std::make_shared<KVCacheUtilizationScorer>(), 1),
                          NewWeightedScorer(std::make_shared<PrefixCacheScorer>(), 1), NewWeightedScorer(std::make_shared<LoraAffinityScorer>(), 1)})
       .WithPicker(MaxScorePicker{});
@@ -157,6 +171,7 @@ static void TestIntegrationRouting() {
 static void TestPrefixCompletionViaPreRequest() {
   // BlockSizeTokens 1 (4 chars), no autotune: "aaaaaa" → 2 hashes; after PreRequest(pick) "aaaabbbb" matches 1 of 2 there
   SchedulerConfig c;
+  c.CpuBatchThreshold = g_cpu_threshold;
   c.Profile.WithScorers({NewWeightedScorer(std::make_shared<PrefixCacheScorer>(), 1)}).WithPicker(MaxScorePicker{});
   c.Prefix.AutoTune = false;
   c.Prefix.BlockSizeTokens = 1;
@@ -182,6 +197,7 @@ static void TestPrefixCompletionViaPreRequest() {
 
 static void TestTokenLoadScorer() {
   SchedulerConfig c;
+  c.CpuBatchThreshold = g_cpu_threshold;
   c.Profile.WithScorers({NewWeightedScorer(std::make_shared<TokenLoadScorer>(1000), 1)}).WithPicker(MaxScorePicker{});
   c.MaxEndpoints = 8;
   Scheduler s(c);
@@ -204,6 +220,7 @@ static void TestTokenLoadScorer() {
 struct LatEp { double th, ph; int dispatched; };
 static int LatencyPick(const std::vector<LatEp>& info, double* score, int* ties) {
   SchedulerConfig c;
+  c.CpuBatchThreshold = g_cpu_threshold;
   auto prod = std::make_shared<PredictedLatencyProducer>();
   prod->StreamingMode = true;
   prod->TTFTCoeffs["num_request_waiting"] = 1.0;
@@ -233,6 +250,7 @@ static int LatencyPick(const std::vector<LatEp>& info, double* score, int* ties)
 // positive tier is selected (epsilon 0) resp. the negative one (epsilon 1)
 static int TierFilterPick(double epsilon) {
   SchedulerConfig c;
+  c.CpuBatchThreshold = g_cpu_threshold;
   auto prod = std::make_shared<PredictedLatencyProducer>();
   prod->StreamingMode = true;
   prod->TTFTCoeffs["num_request_waiting"] = 1.0;
@@ -274,6 +292,8 @@ static void TestLatencyScorer() {
   // TestScoreCompositeFallback (:190-208): no predictions => kv/queue/prefix composite
   {
     SchedulerConfig c;
+    c.CpuBatchThreshold = g_cpu_threshold;
+  c.CpuBatchThreshold = g_cpu_threshold;
     auto prod = std::make_shared<PredictedLatencyProducer>();
     prod->HavePredictions = false;
     c.Profile.WithScorers({NewWeightedScorer(std::make_shared<LatencyScorer>(), 1)}).WithPicker(MaxScorePicker{}).WithPredictedLatencyProducer(prod);
@@ -298,6 +318,7 @@ static void TestWeightedRandomPicker() {
   // "Multi-tier weighted test": scores 100, 90, 50, 30, 20 -> P = score / 290, +-5 % over 10000 picks
   const double scores[5] = {100, 90, 50, 30, 20};
   SchedulerConfig c;
+  c.CpuBatchThreshold = g_cpu_threshold;
   c.Profile.WithScorers({NewWeightedScorer(std::make_shared<KVCacheUtilizationScorer>(), 100)}).WithPicker(WeightedRandomPicker{});
   c.MaxEndpoints = 8;
   c.TieSeed = 2024;
@@ -315,15 +336,74 @@ static void TestWeightedRandomPicker() {
   for (int i = 0; i < 5; i++) CHECK(std::fabs(count[i] / 10000.0 - scores[i] / 290.0) <= 0.05);
 }
 
+// max-score-picker with maxNumOfEndpoints = 3 (picker/maxscore/picker_test.go:43-110): descending score, the engine's pick first
+static void TestTopK() {
+  SchedulerConfig c;
+  c.CpuBatchThreshold = g_cpu_threshold;
+  MaxScorePicker pk;
+  pk.MaxNumOfEndpoints = 3;
+  c.Profile.WithScorers({NewWeightedScorer(std::make_shared<KVCacheUtilizationScorer>(), 1)}).WithPicker(pk);
+  c.MaxEndpoints = 8;
+  Scheduler s(c);
+  std::vector<Endpoint> eps;
+  const double usage[5] = {0.80, 0.75, 0.70, 0.85, 0.75};  // scores 0.20, 0.25, 0.30, 0.15, 0.25
+  for (int i = 0; i < 5; i++) {
+    Metrics m;
+    m.KVCacheUsagePercent = usage[i];
+    eps.push_back(NewEndpoint("pod" + std::to_string(i + 1), m));
+  }
+  auto got = s.Schedule(InferenceRequest{"id", "m", "", ""}, eps);
+  const auto& te = got.ProfileResults.at("default").TargetEndpoints;
+  CHECK(te.size() == 3);
+  CHECK(te[0].Index == 2 && te[1].Index == 1 && te[2].Index == 4);  // 0.30, then the tie class {pod2, pod5}
+  CHECK(te[0].Score == 1 - 0.70 && te[1].Score == 1 - 0.75 && te[2].Score == 1 - 0.75);
+}
+
+// the coalescing front over the REAL scheduler: 32 caller threads, batches of up to 64, results handed back to their callers
+static void TestCoalescedSchedule() {
+  SchedulerConfig c = DefaultFourScorerConfig();
+  c.CpuBatchThreshold = 0;
+  Scheduler s(c);
+  auto eps = std::make_shared<const std::vector<Endpoint>>(std::vector<Endpoint>{
+      NewEndpoint("pod1", M_(0, 0.2, 2, {"foo", "bar"})), NewEndpoint("pod2", M_(0, 0.2, 2, {"foo", "critical"})),
+      NewEndpoint("pod3", M_(10, 0.8, 2, {"foo"}))});
+  BatchingScheduler<Scheduler> front(&s, std::chrono::microseconds(500), 64);
+  std::vector<std::thread> th;
+  std::atomic<int> bad{0};
+  for (int t = 0; t < 32; t++)
+    th.emplace_back([&, t] {
+      for (int i = 0; i < 20; i++) {
+        const bool crit = (t + i) % 2 == 0;
+        auto item = front.Schedule(InferenceRequest{std::to_string(t * 100 + i), crit ? "critical" : "bar", "", ""}, eps);
+        if (!item.error.empty()) { bad++; continue; }
+        const auto& se = item.result.ProfileResults.at("default").TargetEndpoints[0];
+        // scheduler_test.go:86-143: target "critical" -> pod2 with score 2.8; target "bar" -> pod1 by symmetry
+        if (se.Endpoint_->GetMetadata()->NamespacedName_.Name != (crit ? "pod2" : "pod1") || se.Score != 2.8) bad++;
+      }
+    });
+  for (auto& x : th) x.join();
+  CHECK(bad == 0);
+  const CoalescerStats st = front.stats();
+  CHECK(st.requests == 640 && st.batches < 640 && st.max_batch > 1);
+  std::printf("coalesced schedule: %llu requests in %llu engine batches (largest %llu)\n", (unsigned long long)st.requests,
+              (unsigned long long)st.batches, (unsigned long long)st.max_batch);
+}
+
 int main() {
   try {
-    TestSchedule();
-    TestFilterChain();
-    TestIntegrationRouting();
-    TestPrefixCompletionViaPreRequest();
-    TestTokenLoadScorer();
-    TestLatencyScorer();
-    TestWeightedRandomPicker();
+    for (int pass = 0; pass < 2; pass++) {
+      g_cpu_threshold = pass == 0 ? 0 : 8;
+      TestSchedule();
+      TestFilterChain();
+      TestIntegrationRouting();
+      TestPrefixCompletionViaPreRequest();
+      TestTokenLoadScorer();
+      TestLatencyScorer();
+      TestWeightedRandomPicker();
+      TestTopK();
+      std::printf("pass %d (CpuBatchThreshold = %d) done\n", pass, g_cpu_threshold);
+    }
+    TestCoalescedSchedule();
   } catch (const std::exception& e) {
     std::printf("FAIL exception: %s\n", e.what());
     return 2;

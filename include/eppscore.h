@@ -245,11 +245,12 @@ const char *eppscore_last_error(const struct eppscore_engine *e); /* e may be NU
 int32_t eppscore_get_stats(const struct eppscore_engine *e, eppscore_stats *out);
 /* Diagnostics knobs (profiling / A-B runs only; never needed for correct operation):
  *   key 1: 1 = always use the fully general kernels (same as env EPPSCORE_FORCE_GENERIC=1), 0 = normal dispatch;
- *   key 2: hash stage mask (default 3 = the two-kernel form: bit 0 run the body kernel, bit 1 run the chain kernel, with
- *          bit 4 the CTA-tile chain kernel of round 1 instead of the warp-tile one).  Experimental single-kernel forms, both
+ *   key 2: hash stage mask (default 19 = the two-kernel form: bit 0 run the body kernel, bit 1 run the chain kernel, bit 4
+ *          the CTA-tile chain kernel; without bit 4 the warp-tile chain kernel, 2 us slower at 64K requests).  Experimental single-kernel forms, both
  *          measured SLOWER than the two kernels on B200 (a warp in its chain phase has no loads in flight): bit 3 the
  *          warp-tile fused kernel, bit 2 the CTA-tile warp-specialised fused kernel;
- *   key 3: requests per chunk of a host-location batch (0: never chunk). */
+ *   key 3: requests per chunk of a host-location batch (0: never chunk);
+ *   key 4: 0 = ordinary launches, 1 (default) = programmatic dependent launch between the kernels of a batch. */
 int32_t eppscore_set_debug(struct eppscore_engine *e, int32_t key, int64_t value);
 
 /* ---- snapshot (replaces the per-request deep clone, director.go:342-349) ---- */

@@ -95,7 +95,7 @@ if "hash2" in what:
     for mask, name in ((1, "bodies only"), (2, "chain (warp tiles) only"), (18, "chain (r1 CTA tiles) only"), (8, "warp-tile fused"), (4, "CTA-tile fused")):
         eng.set_debug(2, mask)
         print(f"  {name:26s}: {timeit(hash_only):8.2f} us")
-    eng.set_debug(2, 3)
+    eng.set_debug(2, 19)
     for i in range(NS):
         hash_only(i)
 if "pick" in what:
