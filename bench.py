@@ -246,6 +246,10 @@ def run_gpu(args):
                                              max_blocks=MAX_BLOCKS, **kw), device=local)
 
     eng = make_engine()
+    if args.dev_split is not None:
+        eng.set_debug(5, args.dev_split)
+    if args.dev_streams is not None:
+        eng.set_debug(6, args.dev_streams)
     stream = torch.cuda.Stream(device=dev)  # an explicit stream: events and every launch below share it
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
@@ -955,6 +959,18 @@ def run_gpu(args):
                                                  "config_A": "1 request x 4 pods, queue-depth scorer only, single thread, 200000 calls"}
             except Exception as ex:  # noqa: BLE001
                 extra["cpu_baseline_goshape"] = {"error": repr(ex)}
+            # ---- the host layer above the C ABI (C++): BASELINE config A through the product's Scheduler (small-batch host
+            # route and forced-GPU route) and per-request latency through the coalescing front vs its window ----
+            try:
+                import subprocess
+                hb = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gateway-api-inference-extension_b200", "host", "host_bench")
+                if not getattr(args, "quick", False) and os.path.exists(hb):
+                    r = subprocess.run([hb, "64", "200"], capture_output=True, text=True, timeout=180)
+                    extra["host_layer"] = json.loads(r.stdout.strip().splitlines()[-1])
+                    extra["host_layer"]["note"] = ("C++ host mirror (host/epp_scheduler.hpp, coalescer.hpp) over libeppscore.so; coalescer: 64 "
+                                                   "closed-loop caller threads, 256 endpoints, 512-byte prompts, four default scorers")
+            except Exception as ex:  # noqa: BLE001
+                extra["host_layer"] = {"error": repr(ex)}
 
     if rank == 0:
         cfg = config_dict(world)
@@ -983,6 +999,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=["headline", "E"])
+    ap.add_argument("--dev-split", type=int, default=None, help="experiment: slices per device-resident batch (engine debug key 5)")
+    ap.add_argument("--dev-streams", type=int, default=None, help="experiment: streams the slices alternate over (engine debug key 6)")
     ap.add_argument("--quick", action="store_true", help="skip the side legs (per-kernel timing, §8f profiles, CPU baselines)")
     args = ap.parse_args()
     if args.warmup < 3:

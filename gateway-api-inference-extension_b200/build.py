@@ -94,3 +94,21 @@ def build_host_test(force: bool = False) -> str:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("g++ failed building host_test")
     return HOST_TEST
+
+
+HOST_BENCH = os.path.join(HERE, "host", "host_bench")
+
+
+def build_host_bench(force: bool = False) -> str:
+    """Host-layer timings (host/host_bench.cpp: config A through the product, coalescing-front latency); run by bench.py."""
+    build()
+    src = os.path.join(HERE, "host", "host_bench.cpp")
+    deps = [src, LIB] + [os.path.join(HERE, "host", h) for h in ("epp_scheduler.hpp", "epp_types.hpp", "host_eval.hpp", "coalescer.hpp")]
+    if force or _stale(HOST_BENCH, deps):
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", src, "-o", HOST_BENCH, "-pthread", "-L" + HERE, "-leppscore",
+               "-Wl,-rpath,$ORIGIN/.."]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed building host_bench")
+    return HOST_BENCH

@@ -99,13 +99,19 @@ struct eppscore_engine {
                        &s_score, &s_tie, &s_match, &s_total, &s_scores, &s_intok, &s_tslo, &s_pslo, &s_pred, &s_fields, &s_fmask};
       for (DevBuf* b : all) b->release();
     }
-  } sc[2];
+  } sc[4];
   // pinned staging for the small per-request results of a host batch: a D2H copy into the caller's (usually pageable)
   // arrays would block the host after every chunk and serialise the pipeline
   void* h_res = nullptr;
   size_t h_res_bytes = 0;
   cudaStream_t stream2 = nullptr;   // second copy/compute stream of the chunked host path
   int32_t host_chunk = 8192;        // requests per chunk of a host-location batch (eppscore_set_debug key 3)
+  // device-location batches cut into `dev_split` slices over `dev_streams` streams (the caller's + internal ones): the
+  // HBM-bound body hashing of slice i+1 runs under the latency-bound chain and probe kernels of slice i
+  // (eppscore_set_debug keys 5 and 6)
+  int32_t dev_split = 1, dev_streams = 2;
+  cudaStream_t split_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 };
 using Scratch = eppscore_engine::Scratch;
 
@@ -584,8 +590,15 @@ void eppscore_destroy(eppscore_engine* e) {
                     &e->raw_kv, &e->raw_queue, &e->raw_running, &e->raw_act, &e->raw_wait, &e->raw_nmodels, &e->raw_max,
                     &e->fold_unmasked, &e->fold_masked, &e->cls_lo, &e->cls_hi, &e->summ, &e->tiemask, &e->prefix_lut2d, &e->c_pick, &e->c_hash, &e->c_nh,
                     &e->c_ep, &e->c_op};
-  e->sc[0].release();
-  e->sc[1].release();
+  for (auto& x : e->sc) x.release();
+  for (int i = 0; i < 3; i++) {
+    if (e->split_stream[i]) {
+      cudaStreamSynchronize(e->split_stream[i]);
+      cudaStreamDestroy(e->split_stream[i]);
+    }
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->h_res) cudaFreeHost(e->h_res);
   if (e->stream2) {
     cudaStreamSynchronize(e->stream2);
@@ -644,6 +657,14 @@ int32_t eppscore_set_debug(eppscore_engine* e, int32_t key, int64_t value) {
   }
   if (key == 4) {
     e->use_pdl = value != 0;
+    return EPPSCORE_OK;
+  }
+  if (key == 5) {
+    e->dev_split = value < 1 ? 1 : (value > 64 ? 64 : (int32_t)value);
+    return EPPSCORE_OK;
+  }
+  if (key == 6) {
+    e->dev_streams = value < 1 ? 1 : (value > 4 ? 4 : (int32_t)value);
     return EPPSCORE_OK;
   }
   return fail(e, EPPSCORE_ERR_INVALID, "unknown debug key");
@@ -837,7 +858,54 @@ int32_t eppscore_schedule_batch(eppscore_engine* e, const eppscore_batch* b) {
     d.total_blocks = b->total_blocks;
     d.hashes_out = b->hashes_out;
     d.scores_out = b->scores_out;
-    return schedule_device(e, d, b->stream ? (cudaStream_t)b->stream : e->stream, e->sc[0]);
+    cudaStream_t cs = b->stream ? (cudaStream_t)b->stream : e->stream;
+    // R x M outputs, masks, supplied hashes and dense rows go as one slice (their layouts are not sliced here)
+    const bool sliceable = d.prompt_bytes && !d.hashes_in && !d.cand_mask && !d.dense_feat && !d.pred_out && !d.filter_mask_out &&
+                           !d.match_blocks && !d.scores_out && !d.input_tokens && !d.ttft_slo && !d.tpot_slo;
+    int K = e->dev_split;
+    if (!sliceable || e->dev_streams < 2) K = 1;
+    while (K > 1 && b->R / K < 2048) K--;
+    if (K <= 1) return schedule_device(e, d, cs, e->sc[0]);
+    // fork: the internal streams join the caller's stream (also inside a CUDA-graph capture), slice c goes to stream c mod S
+    const int S = e->dev_streams < K ? e->dev_streams : K;
+    if (!e->ev_fork) CK(e, cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < S - 1; i++) {
+      if (!e->split_stream[i]) CK(e, cudaStreamCreateWithFlags(&e->split_stream[i], cudaStreamNonBlocking));
+      if (!e->ev_join[i]) CK(e, cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
+    }
+    CK(e, cudaEventRecord(e->ev_fork, cs));
+    for (int i = 0; i < S - 1; i++) CK(e, cudaStreamWaitEvent(e->split_stream[i], e->ev_fork, 0));
+    const int32_t mbk = d.max_blocks > 0 ? d.max_blocks : e->cfg.max_blocks;
+    const int32_t per = ((b->R + K - 1) / K + 63) / 64 * 64;
+    for (int c = 0, base = 0; base < b->R; c++, base += per) {
+      DevBatch q = d;
+      q.R = std::min(per, b->R - base);
+      q.request_base = d.request_base + base;
+      q.prompt_off = d.prompt_off + base;
+      if (d.prompt_len) q.prompt_len = d.prompt_len + base;
+      if (d.model_seed) q.model_seed = d.model_seed + base;
+      if (d.adapter_id) q.adapter_id = d.adapter_id + base;
+      q.pick = d.pick + base;
+      q.pick_score = d.pick_score + base;
+      q.tie_count = d.tie_count + base;
+      if (d.total_blocks) q.total_blocks = d.total_blocks + base;
+      if (d.hashes_out) q.hashes_out = d.hashes_out + (size_t)base * mbk;
+      const int si = c % S;
+      rc = schedule_device(e, q, si == 0 ? cs : e->split_stream[si - 1], e->sc[si]);
+      if (rc != EPPSCORE_OK) break;
+    }
+    for (int i = 0; i < S - 1; i++) {  // join, also on the error path (a capture must not be left forked)
+      cudaEventRecord(e->ev_join[i], e->split_stream[i]);
+      cudaStreamWaitEvent(cs, e->ev_join[i], 0);
+    }
+    if (rc != EPPSCORE_OK) return rc;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(cs, &cap);
+    if (cap == cudaStreamCaptureStatusNone && cs != e->stream) {
+      CK(e, cudaEventRecord(e->ev_sched, cs));
+      e->sched_pending = true;
+    }
+    return EPPSCORE_OK;
   }
   // ---- host buffers: H2D, kernels, D2H, all inside this call ----
   // The batch is cut into chunks that alternate between two streams (each with its own scratch set): the H2D copy of

@@ -602,6 +602,29 @@ def test_device_resident_api_with_torch(pkg):
     assert np.array_equal(out["pick_score"].cpu().numpy(), want["pick_score"])
     assert np.array_equal(out["tie_count"].cpu().numpy(), want["tie_count"])
     assert eng.stats().kernel_launches >= 3
+    # the same batch cut into slices over several streams (engine debug keys 5 / 6), eagerly and inside a CUDA graph:
+    # requests are independent given (snapshot, table), so every cut gives the same results
+    d_in = dict(prompt_bytes=torch.from_numpy(prompts).to(dev), prompt_off=torch.from_numpy(off).to(dev),
+                model_seed=torch.from_numpy(seeds).to(dev), adapter_id=torch.from_numpy(ad).to(dev))
+    for split, streams in ((3, 2), (4, 3)):
+        eng.set_debug(5, split)
+        eng.set_debug(6, streams)
+        for v in out.values():
+            v.zero_()
+        with torch.cuda.stream(stream):
+            eng.schedule(R, device=True, stream=stream.cuda_stream, out=out, **d_in)
+        stream.synchronize()
+        for k in ("pick", "pick_score", "tie_count", "total_blocks"):
+            assert np.array_equal(out[k].cpu().numpy(), want[k]), (split, streams, k)
+    g = torch.cuda.CUDAGraph()
+    for v in out.values():
+        v.zero_()
+    with torch.cuda.graph(g, stream=stream):
+        eng.schedule(R, device=True, stream=stream.cuda_stream, out=out, **d_in)
+    g.replay()
+    torch.cuda.synchronize()
+    for k in ("pick", "pick_score", "tie_count", "total_blocks"):
+        assert np.array_equal(out[k].cpu().numpy(), want[k]), ("graph", k)
     eng.close()
 
 
