@@ -648,7 +648,7 @@ int32_t eppscore_set_debug(eppscore_engine* e, int32_t key, int64_t value) {
     return EPPSCORE_OK;
   }
   if (key == 2) {
-    e->hash_stage_mask = (int32_t)(value & 31);
+    e->hash_stage_mask = (int32_t)(value & 63);
     return EPPSCORE_OK;
   }
   if (key == 3) {

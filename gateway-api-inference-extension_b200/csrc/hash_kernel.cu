@@ -89,6 +89,95 @@ __global__ void __launch_bounds__(kBodyWarps * 32) hash_bodies_kernel(HashArgs a
   }
 }
 
+// hash_bodies_pipe_kernel: the same work as hash_bodies_kernel (lane = block of one request, a warp per request) as a
+// PERSISTENT grid with the loads software-pipelined: while a warp digests request k, the 64 bytes per lane of its request
+// k+1 are already in flight and the descriptor of request k+2 is being fetched.  The one-shot form pays two dependent
+// memory latencies (descriptor, then bytes) and a CTA launch per 8 requests with nothing to issue meanwhile: it runs at
+// 59 % issue utilisation with 11 warps per scheduler stalled on the scoreboard (profiles/r1_end_ncu_hash_fields.txt), and
+// the digest itself (28 64-bit multiplies per block) needs ~70 % of the issue slots at HBM speed.
+template <int BC>
+__global__ void __launch_bounds__(kBodyWarps * 32, 3) hash_bodies_pipe_kernel(HashArgs a) {
+  pdl_launch_dependents();  // the chain kernel may be brought up while this grid drains
+  const int lane = threadIdx.x & 31;
+  const int bc = BC ? BC : a.block_chars;
+  const int gw = blockIdx.x * kBodyWarps + (threadIdx.x >> 5), nw = gridDim.x * kBodyWarps;
+  if (BC != 64) {  // other block sizes: not pipelined
+    for (int r = gw; r < a.R; r += nw) {
+      const ReqDesc d = load_desc(a, r, bc);
+      if (!d.fast) continue;
+      for (int b = lane; b < d.nfull; b += 32) a.hashes[(size_t)r * a.stride + b] = block_body_state<BC>(d.p + (size_t)b * bc, bc);
+    }
+    return;
+  }
+  // descriptors travel as RAW loaded values (start, end) and are only interpreted one iteration later, so that nothing
+  // waits for them: {p, nfull, fast} of request k+1 are derived at the top of iteration k
+  struct Raw {
+    int64_t o, e;
+  };
+  auto load_raw = [&](int r) {
+    Raw w;
+    w.o = a.off[r];
+    w.e = a.len ? w.o + (int64_t)a.len[r] : a.off[r + 1];
+    return w;
+  };
+  auto derive = [&](const Raw& w, const uint8_t*& p, int& nfull) {  // load_desc without the seed; nfull = 0 unless fast
+    int64_t len = w.e - w.o;
+    p = a.bytes + w.o;
+    nfull = 0;
+    if (len >= 64) {
+      const int64_t cap = 64LL * (int64_t)a.max_blocks;
+      if (len > cap) len = cap;
+      nfull = (int)(len >> 6);
+    }
+    if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) nfull = 0;
+  };
+  int r = gw;
+  if (r >= a.R) return;
+  const uint8_t* p;
+  int nfull;
+  derive(load_raw(r), p, nfull);
+  Raw raw_n = {0, 0};
+  if (r + nw < a.R) raw_n = load_raw(r + nw);
+  uint4 cur[4];
+  bool on = lane < nfull;
+#pragma unroll
+  for (int k = 0; k < 4; k++) cur[k] = on ? ldg16(p + (size_t)lane * 64 + 16 * k) : make_uint4(0, 0, 0, 0);
+  for (;;) {
+    const int rn = r + nw, rnn = rn + nw;
+    const bool have_n = rn < a.R;
+    // the next request's bytes (its descriptor arrived during the previous digest), then the descriptor after that
+    const uint8_t* pn = p;
+    int nfull_n = 0;
+    if (have_n) derive(raw_n, pn, nfull_n);
+    uint4 nxt[4];
+    const bool on_n = lane < nfull_n;
+#pragma unroll
+    for (int k = 0; k < 4; k++) nxt[k] = on_n ? ldg16(pn + (size_t)lane * 64 + 16 * k) : make_uint4(0, 0, 0, 0);
+    if (rnn < a.R) raw_n = load_raw(rnn);
+    if (on) {
+      uint64_t v1 = XP1 + XP2, v2 = XP2, v3 = 0, v4 = 0 - XP1;
+#pragma unroll
+      for (int st = 0; st < 2; st++) {
+        const uint4 x = cur[2 * st], y = cur[2 * st + 1];
+        v1 = xround(v1, ((uint64_t)x.y << 32) | x.x);
+        v2 = xround(v2, ((uint64_t)x.w << 32) | x.z);
+        v3 = xround(v3, ((uint64_t)y.y << 32) | y.x);
+        v4 = xround(v4, ((uint64_t)y.w << 32) | y.z);
+      }
+      a.hashes[(size_t)r * a.stride + lane] = xfinish_lanes(v1, v2, v3, v4) + (uint64_t)(64 + 8);
+    }
+    // more than 32 full blocks (max_blocks > 32): the rest of this request, not pipelined
+    for (int b = lane + 32; b < nfull; b += 32) a.hashes[(size_t)r * a.stride + b] = block_body_state<64>(p + (size_t)b * 64, 64);
+    if (!have_n) break;
+    r = rn;
+    p = pn;
+    nfull = nfull_n;
+    on = on_n;
+#pragma unroll
+    for (int k = 0; k < 4; k++) cur[k] = nxt[k];
+  }
+}
+
 // One CTA (4 warps) per tile of 64 requests: all warps move the tile in and out (16 requests each, loads
 // batched), warps 0 and 1 run the 64 serial chains (lane = request).  The kernel is latency bound (each
 // link is ~35 dependent integer instructions), so the point is to keep many independent chains in flight
@@ -541,7 +630,7 @@ __global__ void __launch_bounds__(256) hash_slow_kernel(HashArgs a) {
 int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
   const int stages0 = a.stage_mask ? a.stage_mask : 19;  // bodies + the CTA-tile chain kernel (12.4 us; the warp-tile form measured 14.5 us)
-  if ((stages0 & 8) && a.block_chars > 0 && (a.block_chars & 31) == 0) {  // default: the warp-tile fused kernel
+  if ((stages0 & 8) && a.block_chars > 0 && (a.block_chars & 31) == 0) {  // experimental: the warp-tile fused kernel
     const int ntiles = (a.R + 31) / 32;
     int blocks = sm_count * 3;
     const int need = (ntiles + kWarpTileWarps - 1) / kWarpTileWarps;
@@ -572,12 +661,28 @@ int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
   const int stages = (stages0 & 3) ? (stages0 & 3) : 3;
   if ((stages & 1) && a.block_chars > 0 && (a.block_chars & 31) == 0) {
     long long blocks = ((long long)a.R + kBodyWarps - 1) / kBodyWarps;
-    const long long cap = (long long)sm_count * 64;      // grid-stride beyond a few waves
-    if (blocks > cap) blocks = cap;
-    if (a.block_chars == 64)
-      hash_bodies_kernel<64><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
-    else
-      hash_bodies_kernel<0><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
+    if (stages0 & 32) {  // the one-shot form of round 1 (diagnostics): a warp per request, a few waves of CTAs
+      const long long cap = (long long)sm_count * 64;
+      if (blocks > cap) blocks = cap;
+      if (a.block_chars == 64)
+        hash_bodies_kernel<64><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
+      else
+        hash_bodies_kernel<0><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
+    } else {             // persistent, software-pipelined
+      static int occ64 = 0, occ0 = 0;
+      if (!occ64) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, hash_bodies_pipe_kernel<64>, kBodyWarps * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, hash_bodies_pipe_kernel<0>, kBodyWarps * 32, 0);
+        if (occ64 < 1) occ64 = 1;
+        if (occ0 < 1) occ0 = 1;
+      }
+      const long long cap = (long long)sm_count * (a.block_chars == 64 ? occ64 : occ0);
+      if (blocks > cap) blocks = cap;
+      if (a.block_chars == 64)
+        hash_bodies_pipe_kernel<64><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
+      else
+        hash_bodies_pipe_kernel<0><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
+    }
     launched++;
   }
   if (!(stages & 2)) return launched;

@@ -117,14 +117,12 @@ __device__ __forceinline__ uint32_t slot_member(uint32_t w, const uint4& hi, uin
   const uint32_t x = k < 2 ? w : (k < 4 ? hi.x : (k < 6 ? hi.y : (k < 8 ? hi.z : hi.w)));
   return (k & 1) ? (x >> 16) : (x & 0xFFFFu);
 }
-// do two inline sets (same raw cnt word, not rows) have the same members?
-__device__ __forceinline__ bool same_inline_set(uint32_t c, uint32_t w0, const uint4& h0, uint32_t w1, const uint4& h1) {
-  bool same = ((w0 ^ w1) & (c >= 2 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
-  if (c > 2) same = same && ((h0.x ^ h1.x) & (c >= 4 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
-  if (c > 4) same = same && ((h0.y ^ h1.y) & (c >= 6 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
-  if (c > 6) same = same && ((h0.z ^ h1.z) & (c >= 8 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
-  if (c > 8) same = same && ((h0.w ^ h1.w) & (c >= 10 ? 0xFFFFFFFFu : 0x0000FFFFu)) == 0;
-  return same;
+// do two inline sets with the same raw cnt word (not rows) have the same members?  Slots are kept CANONICAL by the index
+// program (members sorted, unused entries 0xFFFF: prefix_table.cuh set_member / clear_member) and the second half of a slot
+// is loaded for neither or both (same count), so equal sets are equal words.  A stale entry could only make two equal sets
+// look different, which sends the request through its exception table — slower, never wrong.
+__device__ __forceinline__ bool same_inline_set(uint32_t w0, const uint4& h0, uint32_t w1, const uint4& h1) {
+  return ((w0 ^ w1) | (h0.x ^ h1.x) | (h0.y ^ h1.y) | (h0.z ^ h1.z) | (h0.w ^ h1.w)) == 0;
 }
 // order-independent form of best_update (the exceptions of a lane arrive in table order, not ascending)
 __device__ __forceinline__ void best_update_any(Best& b, double s, int m, int tie_mode, uint32_t areq, uint32_t seed_hi) {
@@ -271,7 +269,7 @@ __global__ void __launch_bounds__(kSparseWarps * 32, EPP_SPARSE_MINBLOCKS) pick_
 #pragma unroll
         for (int u = 0; u < U; u++) {
           if (!__any_sync(0xffffffffu, hit[u])) continue;        // (warp-uniform) no hit in this sub-round
-          if (hit[u]) differs |= lo[u].z != ref_raw || !same_inline_set(ref_raw & kCntMask, ref_w, ref_hi, lo[u].w, hi[u]);
+          if (hit[u]) differs |= lo[u].z != ref_raw || !same_inline_set(ref_w, ref_hi, lo[u].w, hi[u]);
         }
         {
           const uint32_t db = __ballot_sync(0xffffffffu, differs);

@@ -265,6 +265,7 @@ struct TableOps {
         nraw = raw - 1;
         if ((nraw & kCntMask) == 0) {  // the set stays a row until it is empty
           free_row(x, tv, r);
+          for (uint32_t k = 0; k < (uint32_t)kInlineEps; k++) x.st16(&s->ep[k], (uint16_t)0xFFFFu);  // canonical empty slot
           nraw = 0;
         }
       }
@@ -272,6 +273,7 @@ struct TableOps {
       for (uint32_t k = 0; k < c; k++) {
         if (x.ld16(&s->ep[k]) == (uint16_t)p) {
           for (uint32_t j = k; j + 1 < c; j++) x.st16(&s->ep[j], (uint16_t)x.ld16(&s->ep[j + 1]));  // stays sorted and dense
+          x.st16(&s->ep[c - 1], (uint16_t)0xFFFFu);  // canonical: unused entries read 0xFFFF, as in a never-used slot
           nraw = raw - 1;
           break;
         }
