@@ -50,7 +50,8 @@ __device__ __forceinline__ LatPair lat_pair(const double* tp, double tpot_genera
   return o;
 }
 
-template <uint32_t SEQ, bool MASKED, bool DIAG, bool LAT>
+// RND: the stochastic pickers (random / weighted-random) are compiled in; always for the runtime-generic SEQ == 0
+template <uint32_t SEQ, bool MASKED, bool DIAG, bool LAT, bool RND = (SEQ == 0)>
 __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const __grid_constant__ ScoreArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_wait();  // (no-op unless launched behind pick_sparse / the hash kernels with programmatic dependent launch)
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
     const uint32_t areq = tie_areq(a.request_base + r, plan.seed_lo);
     Best best = best_none();
     RBest rb_pos = rbest_none(), rb_all = rbest_none();  // stochastic pickers (runtime-generic variants only)
-    const int pick_mode = SEQ == 0 ? plan.pick_mode : 0;
+    const int pick_mode = RND ? plan.pick_mode : 0;
 
     // ---------------- Score (scheduler_profile.go:151-174) + Pick (maxscore/picker.go:87-115) ----------------
     // per-step constants hoisted out of the pair loop (compile-time step index when SEQ != 0)
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
           }
         }
         if (DIAG && a.scores_out && m < M) a.scores_out[(size_t)r * M + m] = cand ? acc : nan64();
-        if (SEQ == 0 && pick_mode != 0) {
+        if (RND && pick_mode != 0) {
           if (cand) {  // random: highest priority wins; weighted-random (A-Res): smallest -ln(U)/score among score > 0
             const uint32_t pr = tie_prio(areq, m, plan.seed_hi);
             rbest_update(rb_all, (double)pr, acc, m);
@@ -679,7 +680,7 @@ __global__ void __launch_bounds__(kMatrixWarps * 32) score_matrix_kernel(const _
       }
     }
     best_group_reduce<32>(best, tie_mode);
-    if (SEQ == 0 && pick_mode != 0) {  // warp-uniform
+    if (RND && pick_mode != 0) {  // warp-uniform
       rbest_warp_reduce(rb_pos);
       rbest_warp_reduce(rb_all);
       const RBest& w = rb_pos.m >= 0 ? rb_pos : rb_all;  // no positive score: the random picker (weightedrandom/picker.go:113-116)
@@ -729,11 +730,16 @@ constexpr uint32_t mseq(int k, Rest... rest) {
 #define T STEP_LATENCY
 #define MK(...) launch_matrix(score_matrix_kernel<mseq(__VA_ARGS__), MASKED, DIAG, false>, a, MASKED, false, s, sm_count)
 #define MKL(...) launch_matrix(score_matrix_kernel<mseq(__VA_ARGS__), MASKED, DIAG, true>, a, MASKED, true, s, sm_count)
+#define MKR(...) launch_matrix(score_matrix_kernel<mseq(__VA_ARGS__), MASKED, DIAG, false, true>, a, MASKED, false, s, sm_count)
 template <bool MASKED, bool DIAG>
 static int launch_matrix_seq(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   bool lat = false;
   for (int i = 0; i < a.plan.n_steps; i++) lat = lat || a.plan.kind[i] == STEP_LATENCY;
-  switch (a.plan.pick_mode == 0 ? a.plan.seq : 0xffffffffu) {  // stochastic pickers: the runtime-generic variants
+  if (a.plan.pick_mode != 0) {  // stochastic pickers: the default scorer sets have their own variants, the rest is runtime-generic
+    if (a.plan.seq == mseq(E, P, L)) return MKR(E, P, L);
+    if (a.plan.seq == mseq(E, P)) return MKR(E, P);
+  }
+  switch (a.plan.pick_mode == 0 ? a.plan.seq : 0xffffffffu) {
     case mseq(E): return MK(E);
     case mseq(E, P): return MK(E, P);
     case mseq(E, P, L): return MK(E, P, L);
@@ -751,6 +757,7 @@ static int launch_matrix_seq(const ScoreArgs& a, cudaStream_t s, int sm_count) {
 }
 #undef MK
 #undef MKL
+#undef MKR
 #undef T
 #undef E
 #undef P
