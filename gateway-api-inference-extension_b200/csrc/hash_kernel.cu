@@ -89,12 +89,14 @@ __global__ void __launch_bounds__(kBodyWarps * 32) hash_bodies_kernel(HashArgs a
   }
 }
 
-// hash_bodies_pipe_kernel: the same work as hash_bodies_kernel (lane = block of one request, a warp per request) as a
-// PERSISTENT grid with the loads software-pipelined: while a warp digests request k, the 64 bytes per lane of its request
-// k+1 are already in flight and the descriptor of request k+2 is being fetched.  The one-shot form pays two dependent
-// memory latencies (descriptor, then bytes) and a CTA launch per 8 requests with nothing to issue meanwhile: it runs at
-// 59 % issue utilisation with 11 warps per scheduler stalled on the scoreboard (profiles/r1_end_ncu_hash_fields.txt), and
-// the digest itself (28 64-bit multiplies per block) needs ~70 % of the issue slots at HBM speed.
+// hash_bodies_pipe_kernel (EXPERIMENT, stage-mask bit 32; not the default): the same work as hash_bodies_kernel (lane = block
+// of one request, a warp per request) as a PERSISTENT grid with the loads software-pipelined: while a warp digests request k,
+// the 64 bytes per lane of its request k+1 are in flight and the descriptor of request k+2 is being fetched.  The idea was
+// to hide the two dependent memory latencies (descriptor, then bytes) the one-shot form pays per warp.  Measured on B200
+// (tools/prof_step.py split, 64K x 2 KB): 32.9 us against 28.3 us for the one-shot form — 64 registers per thread instead
+// of 30 halve the resident warps (32 vs 64 per SM), and the hardware's own overlap of many short-lived warps hides more
+// latency than one prefetch per warp does.  Kept for the record; the digest itself (28 64-bit multiplies per block) needs
+// about 70 % of the issue slots at HBM speed, which is what bounds the one-shot form at 0.80 of the copy bandwidth.
 template <int BC>
 __global__ void __launch_bounds__(kBodyWarps * 32, 3) hash_bodies_pipe_kernel(HashArgs a) {
   pdl_launch_dependents();  // the chain kernel may be brought up while this grid drains
@@ -661,14 +663,14 @@ int launch_hash_prompts(const HashArgs& a, cudaStream_t s, int sm_count) {
   const int stages = (stages0 & 3) ? (stages0 & 3) : 3;
   if ((stages & 1) && a.block_chars > 0 && (a.block_chars & 31) == 0) {
     long long blocks = ((long long)a.R + kBodyWarps - 1) / kBodyWarps;
-    if (stages0 & 32) {  // the one-shot form of round 1 (diagnostics): a warp per request, a few waves of CTAs
+    if (!(stages0 & 32)) {  // default: a warp per request, a few waves of CTAs (28.3 us at 64K x 2 KB)
       const long long cap = (long long)sm_count * 64;
       if (blocks > cap) blocks = cap;
       if (a.block_chars == 64)
         hash_bodies_kernel<64><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
       else
         hash_bodies_kernel<0><<<(unsigned)blocks, kBodyWarps * 32, 0, s>>>(a);
-    } else {             // persistent, software-pipelined
+    } else {             // experimental: persistent, software-pipelined (measured slower: 32.9 us)
       static int occ64 = 0, occ0 = 0;
       if (!occ64) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, hash_bodies_pipe_kernel<64>, kBodyWarps * 32, 0);

@@ -248,9 +248,14 @@ int32_t eppscore_get_stats(const struct eppscore_engine *e, eppscore_stats *out)
  *   key 2: hash stage mask (default 19 = the two-kernel form: bit 0 run the body kernel, bit 1 run the chain kernel, bit 4
  *          the CTA-tile chain kernel; without bit 4 the warp-tile chain kernel, 2 us slower at 64K requests).  Experimental single-kernel forms, both
  *          measured SLOWER than the two kernels on B200 (a warp in its chain phase has no loads in flight): bit 3 the
- *          warp-tile fused kernel, bit 2 the CTA-tile warp-specialised fused kernel;
+ *          warp-tile fused kernel, bit 2 the CTA-tile warp-specialised fused kernel; bit 5 the persistent software-pipelined
+ *          body kernel (32.9 us against 28.3 us);
  *   key 3: requests per chunk of a host-location batch (0: never chunk);
- *   key 4: 0 = ordinary launches, 1 (default) = programmatic dependent launch between the kernels of a batch. */
+ *   key 4: 0 = ordinary launches, 1 (default) = programmatic dependent launch between the kernels of a batch;
+ *   key 5: slices a device-location batch is cut into (default 1), key 6: streams the slices alternate over (default 2;
+ *          the caller's stream plus internal ones, joined before the call returns — also inside a CUDA-graph capture).
+ *          Measured on B200 at 64K x 1024: 2 slices / 2 streams 77.0 us against 77.9 us unsliced, 4 or more slices slower
+ *          (each slice's chain and probe kernels are latency bound and pay their full latency per slice). */
 int32_t eppscore_set_debug(struct eppscore_engine *e, int32_t key, int64_t value);
 
 /* ---- snapshot (replaces the per-request deep clone, director.go:342-349) ---- */

@@ -609,16 +609,18 @@ def test_device_resident_api_with_torch(pkg):
     for split, streams in ((3, 2), (4, 3)):
         eng.set_debug(5, split)
         eng.set_debug(6, streams)
-        for v in out.values():
-            v.zero_()
         with torch.cuda.stream(stream):
+            for v in out.values():
+                v.zero_()
             eng.schedule(R, device=True, stream=stream.cuda_stream, out=out, **d_in)
         stream.synchronize()
         for k in ("pick", "pick_score", "tie_count", "total_blocks"):
             assert np.array_equal(out[k].cpu().numpy(), want[k]), (split, streams, k)
     g = torch.cuda.CUDAGraph()
-    for v in out.values():
-        v.zero_()
+    with torch.cuda.stream(stream):
+        for v in out.values():
+            v.zero_()
+    torch.cuda.synchronize()
     with torch.cuda.graph(g, stream=stream):
         eng.schedule(R, device=True, stream=stream.cuda_stream, out=out, **d_in)
     g.replay()

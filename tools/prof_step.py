@@ -107,13 +107,13 @@ if "step" in what:
     print(f"hash + pick     : {timeit(step):8.2f} us (direct launches, snapshot not re-prepared)")
 if "split" in what:
     # the body kernel's two forms, then the device-resident batch cut into slices over several streams (debug keys 5 / 6)
-    for mask, name in ((1, "bodies, pipelined"), (33, "bodies, one-shot (r1)")):
+    for mask, name in ((1, "bodies, one-shot"), (33, "bodies, pipelined (exp.)")):
         eng.set_debug(2, mask)
         print(f"  {name:26s}: {timeit(hash_only):8.2f} us")
     eng.set_debug(2, 19)
     for i in range(NS):
         hash_only(i)
-    for mask in (19, 51):
+    for mask in (19,):
         eng.set_debug(2, mask)
         for split, streams in ((1, 1), (2, 2), (4, 2), (4, 3), (8, 2), (8, 3), (8, 4), (16, 4)):
             eng.set_debug(5, split)
@@ -123,7 +123,7 @@ if "split" in what:
             step(0)
             torch.cuda.synchronize()
             ok = np.array_equal(out["pick"][:4096].cpu().numpy(), want["pick"]) and np.array_equal(out["pick_score"][:4096].cpu().numpy(), want["pick_score"])
-            print(f"hash + pick, bodies {'pipelined' if mask == 19 else 'one-shot '}, {split:2d} slices / {streams} streams: {t:8.2f} us  parity {'ok' if ok else 'FAILED'}")
+            print(f"hash + pick, {split:2d} slices / {streams} streams: {t:8.2f} us  parity {'ok' if ok else 'FAILED'}")
     eng.set_debug(2, 19)
     eng.set_debug(5, 1)
 if "e2e" in what:
