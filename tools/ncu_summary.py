@@ -7,7 +7,7 @@ import sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr, vals = rows[0], rows[2 + (int(sys.argv[2]) if len(sys.argv) > 2 else 0)]
+hdr, units, vals = rows[0], rows[1], rows[2 + (int(sys.argv[2]) if len(sys.argv) > 2 else 0)]
 want = ["Kernel Name", "gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
@@ -18,7 +18,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "smsp__inst_executed.sum", "sms
         "launch__grid_size", "launch__block_size"]
 for i, h in enumerate(hdr):
     if h in want:
-        print(f"{h:70s} {vals[i]}")
+        print(f"{h:70s} {vals[i]} {units[i]}")
 print("-- stalls (warps per issue-active cycle)")
 for i, h in enumerate(hdr):
     if "smsp__average_warps_issue_stalled" in h and "per_issue_active" in h:
