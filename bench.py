@@ -226,6 +226,8 @@ def run_gpu(args):
     import _pkg
     _pkg.load_build().build()
     pkg = _pkg.load()
+    import importlib
+    sharding = importlib.import_module(_pkg.NAME + ".sharding")   # the multi-GPU host helpers (commit-stream exchange)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -522,10 +524,7 @@ def run_gpu(args):
             if timed:
                 ev[4 * k + 1].record(stream)
             if world > 1:  # the shards' commits, concatenated in rank order == global request order
-                dist.all_gather_into_tensor(g_pick, outc["pick"])
-                dist.all_gather_into_tensor(g_nh.view(torch.uint8), outc["total_blocks"].view(torch.uint8))
-                dist.all_gather_into_tensor(g_hash, outc["hashes_out"])
-                cp, ch, cn = g_pick, g_hash, g_nh
+                cp, cn, ch = sharding.gather_commit_stream(dist, outc["pick"], outc["total_blocks"], outc["hashes_out"], g_pick, g_nh, g_hash)
             else:
                 cp, ch, cn = outc["pick"], outc["hashes_out"], outc["total_blocks"]
             if timed:

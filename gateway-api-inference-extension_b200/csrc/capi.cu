@@ -681,6 +681,12 @@ int32_t eppscore_set_snapshot(eppscore_engine* e, const eppscore_snapshot* s) {
   cudaStream_t st = (on_device && s->stream) ? (cudaStream_t)s->stream : e->stream;
   const size_t M = (size_t)s->M;
   const bool have_lora = s->lora_active && s->lora_waiting && s->lora_words > 0;
+  {  // the term / class-plane / summary buffers are rewritten below: a device-location batch that another stream launched
+     // against the previous snapshot must have finished with them (inside a capture the graph's own edges order this)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone && e->sched_pending) CK(e, cudaStreamWaitEvent(st, e->ev_sched, 0));
+  }
   // Host snapshots are copied into the engine's tile buffers; device snapshots (e.g. the buffer an NCCL
   // broadcast just filled) are used IN PLACE — they must stay valid until the next set_snapshot.
   if (!on_device) {

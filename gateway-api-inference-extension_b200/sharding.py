@@ -45,3 +45,17 @@ def shard_range(R_total: int, rank: int, world: int):
     start = R_total * rank // world
     stop = R_total * (rank + 1) // world
     return start, stop
+
+
+def gather_commit_stream(dist, pick, n_hashes, hashes, g_pick, g_nh, g_hash):
+    """The exchange step of the closed loop: every rank contributes its shard's PreRequest records — pick
+    i32[R], block count u16[R], block hashes u64[R, B] — and receives all shards concatenated in RANK order, which is global
+    request order when shard r holds requests [r*R, (r+1)*R).  The prefix index is a deterministic function of the ordered
+    commit stream (approximateprefix/plugin.go:169-197, indexer.go:52-83), so every rank that replays the gathered stream with
+    eppscore_commit_picks_device holds the same index.  Torch tensors (CUDA with NCCL, CPU with gloo); g_* are the
+    preallocated [world*R ...] outputs.  NCCL has no 16-bit integer type: the counts travel as bytes."""
+    import torch
+    dist.all_gather_into_tensor(g_pick, pick)
+    dist.all_gather_into_tensor(g_nh.view(torch.uint8), n_hashes.view(torch.uint8))
+    dist.all_gather_into_tensor(g_hash, hashes)
+    return g_pick, g_nh, g_hash

@@ -208,7 +208,10 @@ typedef struct eppscore_batch {
   uint64_t *hashes_out;        /* optional [R*max_blocks]: block hashes (state for eppscore_commit_picks / PreRequest) */
   double *scores_out;          /* optional [R*M]: the whole weightedScorePerEndpoint map (scheduler_profile.go:155-174),
                                   NaN for non-candidates — diagnostics / parity tests; 8*R*M bytes of HBM writes */
-  void *stream;                /* cudaStream_t for location==1 (NULL = engine stream); the call is async on it */
+  void *stream;                /* cudaStream_t for location==1 (NULL = engine stream); the call is async on it.  Index
+                                * mutations and eppscore_set_snapshot wait for the last device-location batch; the engine's
+                                * hash scratch is shared, so keep device-location batches that do not pass hashes_out on ONE
+                                * stream at a time (or give each its own hashes_out) */
   /* latency fold-in, per request (optional, NULL ⇒ 0) */
   const int32_t *input_tokens; /* [R] len(strings.Fields(prompt)) (predictedlatency/training.go:51); NULL with prompt_bytes given ⇒
                                 * counted on the device from those bytes (hosts whose PromptText() differs from the hashed

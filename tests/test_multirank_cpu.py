@@ -113,6 +113,65 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_closed_loop(rank, world, port, q):
+    """The closed loop over two ranks: schedule the own shard -> gather_commit_stream (picks, counts, block hashes in rank
+    order) -> replay ALL shards into the own index replica -> next batch sees the commits.  Every replica must equal the index
+    of a single process that ran the unsharded batches (LRU keys of every endpoint, and therefore the next batch's picks)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sharding", os.path.join(_pkg.PKG_DIR, "sharding.py"))
+    sharding = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sharding)
+    Mc, Rs, B, K = 48, 96, 8, 3           # endpoints, requests per rank and batch, blocks per prompt, batches
+    prof = o.make_profile(kinds(SCORERS))
+    seedv = o.model_seed("m")
+    idx = o.Index(default_lru=40)        # small LRUs: the replay also evicts
+    ref = o.Index(default_lru=40) if rank == 0 else None
+    picks_seen = []
+    for k in range(K):
+        snap = synth_snapshot(Mc, seed=100 + k)          # a fresh snapshot per batch (every rank builds the same one)
+        osnap = o.SnapshotData(**snap)
+        prompts, off, _ = synth_prompts(world * Rs, prompt_len=B * 64, groups=5, shared=4 * 64, seed=200 + k, prefix_seed=3)
+        ad = zipf_adapters(world * Rs, seed=300 + k)
+        seeds = np.full(world * Rs, seedv, np.uint64)
+        lo, hi = rank * Rs, (rank + 1) * Rs
+        res = o.schedule_batch(osnap, prof, idx, Rs, prompt_bytes=prompts[off[lo]:off[hi]], prompt_off=off[lo:hi + 1] - off[lo],
+                               model_seed=seeds[lo:hi], adapter_id=ad[lo:hi], request_base=lo, want_hashes=True, max_blocks=B)
+        hashes = np.ascontiguousarray(res["hashes_out"][:, :B])
+        g_pick = torch.empty(world * Rs, dtype=torch.int32)
+        g_nh = torch.empty(world * Rs, dtype=torch.uint16)
+        g_hash = torch.empty((world * Rs, B), dtype=torch.int64)
+        sharding.gather_commit_stream(dist, torch.from_numpy(res["pick"]), torch.from_numpy(res["total_blocks"]),
+                                      torch.from_numpy(hashes.view(np.int64)), g_pick, g_nh, g_hash)
+        idx.commit(g_pick.numpy(), g_hash.numpy().view(np.uint64), g_nh.numpy())
+        picks_seen.append(g_pick.numpy().copy())
+        if rank == 0:                                     # the single-process run of the same unsharded batch
+            whole = o.schedule_batch(osnap, prof, ref, world * Rs, prompt_bytes=prompts, prompt_off=off, model_seed=seeds,
+                                     adapter_id=ad, want_hashes=True, max_blocks=B)
+            assert np.array_equal(whole["pick"], g_pick.numpy()), f"batch {k}: sharded picks differ from the unsharded batch"
+            ref.commit(whole["pick"], np.ascontiguousarray(whole["hashes_out"][:, :B]), whole["total_blocks"])
+    # replicas identical: every rank's LRU contents, endpoint by endpoint, gathered on rank 0 and compared with the reference
+    keys = [list(idx.lru_keys(m) or []) for m in range(Mc)]   # None: the endpoint never got an LRU
+    flat = np.concatenate([np.array([len(x)], np.uint64) for x in keys] + [np.asarray(x, np.uint64) for x in keys])
+    width = torch.tensor([len(flat)], dtype=torch.int64)
+    widths = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(widths, width)
+    same_len = all(int(w.item()) == len(flat) for w in widths)
+    mine = torch.from_numpy(flat.view(np.int64).copy())
+    allk = [torch.empty_like(mine) for _ in range(world)] if same_len else None
+    if same_len:
+        dist.all_gather(allk, mine)
+    if rank == 0:
+        identical = same_len and all(torch.equal(allk[0], allk[r]) for r in range(world))
+        ref_keys = [list(ref.lru_keys(m) or []) for m in range(Mc)]
+        matches_ref = all(list(keys[m]) == list(ref_keys[m]) for m in range(Mc))
+        touched = sum(1 for m in range(Mc) if len(keys[m]) > 0)
+        evicting = max(len(x) for x in keys) == 40
+        q.put((bool(identical), bool(matches_ref), touched, bool(evicting)))
+    dist.destroy_process_group()
+
+
 def test_two_rank_sharding_matches_single_batch():
     port = 29500 + os.getpid() % 2000
     ctx = mp.get_context("spawn")
@@ -153,3 +212,17 @@ def test_snapshot_pack_roundtrip_and_alignment():
         assert off % 16 == 0
         assert np.array_equal(back[name], np.asarray(snap[name]).reshape(shape))
     assert sharding.shard_range(10, 0, 3) == (0, 3) and sharding.shard_range(10, 2, 3) == (6, 10)
+
+
+def test_two_rank_closed_loop_replicas_replay_the_gathered_commit_stream():
+    port = 33500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_closed_loop, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    identical, matches_ref, touched, evicting = q.get(timeout=5)
+    assert identical and matches_ref and touched >= 2 and evicting   # (some LRU is full: the replay also evicted)
