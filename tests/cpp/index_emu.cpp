@@ -211,6 +211,22 @@ long long emu_stat(void* h, int which) {
       for (auto& d : e->desc) t += (long long)(d.head - d.tail);
       return t;
     }
+    case 7: {  // slots that are NOT canonical: an inline set must be ascending with every unused entry 0xFFFF (the scoring
+               // kernel compares equal sets as words: pick_sparse.cu same_inline_set); a row slot's spare entries are free
+      long long bad = 0;
+      for (uint64_t i = 0; i <= e->tv.mask; i++) {
+        const TSlot& s = e->tv.slots[i];
+        if (s.cnt == kCntFree || (s.cnt & kCntRow)) continue;
+        const uint32_t c = s.cnt & kCntMask;
+        bool ok = c <= (uint32_t)kInlineEps;
+        for (uint32_t k = 0; ok && k < (uint32_t)kInlineEps; k++) {
+          if (k < c) ok = s.ep[k] != 0xFFFFu && (k == 0 || s.ep[k] > s.ep[k - 1]);
+          else ok = s.ep[k] == 0xFFFFu;
+        }
+        bad += ok ? 0 : 1;
+      }
+      return bad;
+    }
     default: return -1;
   }
 }

@@ -94,6 +94,7 @@ def test_random_single_adds_match_oracle(emu, M, lru, seed):
                 assert _get(L, h, key) == idx.get(int(key)), (step, int(key))
             _check_lrus(L, h, idx, list(used)[:20])
             assert L.emu_stat(h, 0) == idx.num_hashes()
+            assert L.emu_stat(h, 7) == 0                  # every slot canonical (sorted members, 0xFFFF filler)
     for key in universe:
         assert _get(L, h, key) == idx.get(int(key))
     _check_lrus(L, h, idx, sorted(used))
@@ -130,6 +131,7 @@ def test_batch_commit_matches_oracle(emu, M, lru, R, nmax, seed):
         seen.update(int(p) for p in pick if p >= 0)
         _check_lrus(L, h, idx, sorted(seen))
         assert L.emu_stat(h, 0) == idx.num_hashes()
+        assert L.emu_stat(h, 7) == 0
         for g in groups:
             for key in g[::5]:
                 assert _get(L, h, key) == idx.get(int(key))
@@ -164,6 +166,7 @@ def test_inline_sets_overflow_rows_and_raw_deltas(emu):
     assert _get(L, h, 100) == set() and L.emu_stat(h, 3) == 15 and L.emu_stat(h, 0) == 31
     assert L.emu_apply(h, 100, 44, 0) == 0
     assert _get(L, h, 100) == {44} and L.emu_stat(h, 0) == 32
+    assert L.emu_stat(h, 7) == 0                          # the slot that was a row is a canonical inline set again
     L.emu_free(h)
 
 
