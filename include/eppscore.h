@@ -233,7 +233,7 @@ typedef struct eppscore_stats {
   int64_t prefix_table_bytes;   /* device bytes: 32-byte slots + overflow bitset rows */
   int64_t lru_entries;          /* Σ per-endpoint LRU lengths (prefix_indexer_size metric, metrics.go:349) */
   int64_t lru_bytes;            /* device bytes of the per-endpoint LRU regions (maps + logs) */
-  int64_t prefix_overflow_rows; /* sets of more than 8 endpoints (bitset rows in use) */
+  int64_t prefix_overflow_rows; /* sets of more than 10 endpoints (bitset rows in use) */
   int64_t prefix_rebuilds;      /* table rebuilds so far */
   uint32_t index_error;         /* sticky device-side error flags of the index (0 = healthy) */
   uint32_t reserved;
@@ -295,7 +295,7 @@ uint64_t eppscore_xxh64(const void *data, size_t len, uint64_t seed);
 
 /* ---- prefix index (approximateprefix/indexer.go) ----
  * Both halves of the reference's indexer are DEVICE-RESIDENT and maintained by kernels: hashToPods as an open-addressing
- * table of 32-byte slots (sets of up to 8 endpoints inline, bitset rows beyond), podToLRU as one log-structured exact LRU
+ * table of 32-byte slots (sets of up to 10 endpoints inline, bitset rows beyond), podToLRU as one log-structured exact LRU
  * per endpoint (hashicorp/golang-lru semantics).  The host keeps no copy. */
 /* PreRequest for the batch (plugin.go:169-197): for r in order: indexer.Add(hashes[r], pick[r]) — one kernel, one CTA per
  * endpoint (Adds for different endpoints commute), calls replayed in request order within an endpoint.
