@@ -2,8 +2,8 @@
 
 The product is the C-ABI shared library `libeppscore.so` (include/eppscore.h) built from the
 hand-written sm_100a kernels under csrc/.  This package is the thin ctypes binding used by the
-tests, bench.py and the Python host mirror (`host.py`); it holds no arithmetic of its own and has
-no CPU fallback — loading fails loudly if the library has not been built, and `Engine()` fails
+tests and bench.py (the host mirror of the reference's plugin interface is C++: host/); it holds no arithmetic of its
+own and has no CPU fallback — loading fails loudly if the library has not been built, and `Engine()` fails
 loudly without a CUDA device.
 
 (The directory name contains hyphens, so it is registered under the import name `gaie_b200`
