@@ -259,12 +259,42 @@ class Scheduler {
       cpu_routed_ += (uint64_t)R;
       return out;
     }
-    PackSnapshot(endpoints);
-    // --- filters → candidate mask ---
-    const int mw = (M + 31) / 32;
+    // --- stable endpoint ids: the prefix index refers to endpoints by id (ServerID = NamespacedName, indexer.go:34-35), and
+    // neither the order nor the membership of the candidate list is stable between calls (datastore PodList, subsetting:
+    // director candidates.go:98).  An endpoint keeps the id it got when it was first seen; the engine's rows are ids, the
+    // list's positions are mapped to and from them.  When the list is exactly ids 0..M-1 in order (the common case, and every
+    // single-list use) nothing is remapped and no mask is needed. ---
+    std::vector<int> ids((size_t)M);
+    int Mx = 0;
+    bool identity = true;
+    {
+      std::vector<int> seen;
+      for (int m = 0; m < M; m++) {
+        ids[m] = IdOf(endpoints[(size_t)m].GetMetadata()->NamespacedName_.String());
+        Mx = std::max(Mx, ids[m] + 1);
+        identity = identity && ids[m] == m;
+      }
+      seen.assign((size_t)Mx, 0);
+      bool dup = false;
+      for (int m = 0; m < M; m++) dup = dup || seen[(size_t)ids[m]]++ > 0;
+      if (dup) {  // the same server twice in one list: positions are the only usable ids for this batch
+        for (int m = 0; m < M; m++) ids[m] = m;
+        Mx = M;
+        identity = true;
+      }
+    }
+    identity = identity && Mx == M;
+    if (Mx > cfg_.MaxEndpoints) throw SchedulingError("more endpoints than SchedulerConfig.MaxEndpoints");
+    if (!identity) remapped_batches_++;
+    std::vector<int> pos_of_id((size_t)Mx, -1);
+    for (int m = 0; m < M; m++) pos_of_id[(size_t)ids[m]] = m;
+    PackSnapshot(endpoints, ids, Mx);
+    // --- filters → candidate mask (rows are ids; ids without an endpoint in this list are never candidates) ---
+    const int mw = (Mx + 31) / 32;
     std::vector<uint32_t> mask;
     const bool have_filters = !cfg_.Profile.filters().empty();
-    if (have_filters) {
+    const bool need_mask = have_filters || !identity;
+    if (need_mask) {
       mask.assign((size_t)R * mw, 0u);
       std::vector<int> all((size_t)M);
       for (int m = 0; m < M; m++) all[m] = m;
@@ -274,7 +304,7 @@ class Scheduler {
           cand = f->Filter_(requests[r], endpoints, cand);
           if (cand.empty()) break;
         }
-        for (int m : cand) mask[(size_t)r * mw + (m >> 5)] |= 1u << (m & 31);
+        for (int m : cand) mask[(size_t)r * mw + (ids[m] >> 5)] |= 1u << (ids[m] & 31);
       }
     }
     // --- PrepareRequestData inputs (approximateprefix/plugin.go:140-165) ---
@@ -332,7 +362,7 @@ class Scheduler {
     b.block_chars = block_tokens * 4;
     b.max_blocks = max_blocks;
     b.adapter_id = adapter.data();
-    b.cand_mask = have_filters ? mask.data() : nullptr;
+    b.cand_mask = need_mask ? mask.data() : nullptr;
     if (latency_scorer_) {
       b.input_tokens = in_tokens.data();
       b.ttft_slo = ttft_slo.data();
@@ -346,31 +376,35 @@ class Scheduler {
     const int topk = cfg_.Profile.picker().MaxNumOfEndpoints;
     std::vector<double> all_scores;
     if (topk > 1) {  // the whole weightedScorePerEndpoint map, NaN for non-candidates (scheduler_profile.go:155-174)
-      all_scores.resize((size_t)R * M);
+      all_scores.resize((size_t)R * Mx);
       b.scores_out = all_scores.data();
     }
     if (eppscore_schedule_batch(eng_, &b) != EPPSCORE_OK) throw SchedulingError(std::string("eppscore_schedule_batch: ") + eppscore_last_error(eng_));
     last_endpoints_ = &endpoints;
+    last_ids_ = ids;
+    last_rows_ = Mx;
     for (int r = 0; r < R; r++) {
       if (pick[r] < 0) {  // "no endpoints available for the given request" → profile result nil → ProcessResults error
         out[r].error = "failed to run scheduler profile '" + cfg_.ProfileName + "'";
         continue;
       }
+      if (pick[r] >= Mx || pos_of_id[(size_t)pick[r]] < 0) throw SchedulingError("engine picked an endpoint that is not in the candidate list");
       ScoredEndpoint se;
-      se.Endpoint_ = &endpoints[(size_t)pick[r]];
-      se.Index = pick[r];
+      se.Endpoint_ = &endpoints[(size_t)pos_of_id[(size_t)pick[r]]];
+      se.Index = pos_of_id[(size_t)pick[r]];
       se.Score = score[r];
       se.TieCount = ties[r];
       out[r].result.ProfileResults[cfg_.ProfileName].TargetEndpoints.push_back(se);
       out[r].result.PrimaryProfileName = cfg_.ProfileName;
       if (topk > 1) {  // picker/maxscore/picker.go:104-106: the next best candidates, descending score
         auto& te = out[r].result.ProfileResults[cfg_.ProfileName].TargetEndpoints;
-        for (const auto& pr : TopK(all_scores.data() + (size_t)r * M, M, topk)) {
-          if (pr.first == se.Index) continue;
+        for (const auto& pr : TopK(all_scores.data() + (size_t)r * Mx, Mx, topk)) {  // (id, score), NaN rows skipped
+          const int pos = pos_of_id[(size_t)pr.first];
+          if (pos < 0 || pos == se.Index) continue;
           if ((int)te.size() >= topk) break;
           ScoredEndpoint o2;
-          o2.Endpoint_ = &endpoints[(size_t)pr.first];
-          o2.Index = pr.first;
+          o2.Endpoint_ = &endpoints[(size_t)pos];
+          o2.Index = pos;
           o2.Score = pr.second;
           te.push_back(o2);
         }
@@ -386,21 +420,54 @@ class Scheduler {
     const int R = (int)results.size();
     std::vector<int32_t> pick((size_t)R, -1);
     for (int r = 0; r < R; r++)
-      if (results[r].error.empty()) pick[r] = results[r].result.ProfileResults.at(cfg_.ProfileName).TargetEndpoints[0].Index;
-    std::vector<int32_t> cap(last_endpoints_->size(), 0);
-    for (size_t m = 0; m < cap.size(); m++)  // makeserver, plugin.go:207-216
-      cap[m] = (cfg_.Prefix.AutoTune && (*last_endpoints_)[m].GetMetrics()->CacheNumBlocks > 0) ? (*last_endpoints_)[m].GetMetrics()->CacheNumBlocks : 0;
+      if (results[r].error.empty()) pick[r] = last_ids_[(size_t)results[r].result.ProfileResults.at(cfg_.ProfileName).TargetEndpoints[0].Index];
+    std::vector<int32_t> cap((size_t)last_rows_, 0);
+    for (size_t m = 0; m < last_endpoints_->size(); m++)  // makeserver, plugin.go:207-216
+      cap[(size_t)last_ids_[m]] = (cfg_.Prefix.AutoTune && (*last_endpoints_)[m].GetMetrics()->CacheNumBlocks > 0) ? (*last_endpoints_)[m].GetMetrics()->CacheNumBlocks : 0;
     if (eppscore_commit_picks(eng_, R, pick.data(), last_hashes_.data(), last_nh_.data(), last_stride_, cap.data()) != EPPSCORE_OK)
       throw SchedulingError(std::string("eppscore_commit_picks: ") + eppscore_last_error(eng_));
   }
+
+  // indexer.RemovePod (indexer.go:167-182), called when a model server leaves the pool: its LRU and its memberships go, its
+  // id is free for the next new server.
+  void RemovePod(const std::string& namespaced_name) {
+    auto it = server_ids_.find(namespaced_name);
+    if (it == server_ids_.end()) return;
+    if (eppscore_prefix_remove_endpoint(eng_, it->second) != EPPSCORE_OK)
+      throw SchedulingError(std::string("eppscore_prefix_remove_endpoint: ") + eppscore_last_error(eng_));
+    free_ids_.push_back(it->second);
+    server_ids_.erase(it);
+  }
+  int ServerId(const std::string& namespaced_name) const {  // -1: never seen (or removed)
+    auto it = server_ids_.find(namespaced_name);
+    return it == server_ids_.end() ? -1 : it->second;
+  }
+  uint64_t RemappedBatches() const { return remapped_batches_; }  // batches whose list was not ids 0..M-1 in order
 
   const std::vector<uint16_t>& LastTotalBlocks() const { return last_nh_; }
   eppscore_engine* engine() { return eng_; }
 
  private:
   // Metrics maps → the packed SoA snapshot; adapter names get dictionary ids in first-seen order.
-  void PackSnapshot(const std::vector<Endpoint>& eps) {
-    const int M = (int)eps.size();
+  int IdOf(const std::string& namespaced_name) {
+    auto it = server_ids_.find(namespaced_name);
+    if (it != server_ids_.end()) return it->second;
+    int id;
+    if (!free_ids_.empty()) {
+      id = free_ids_.back();
+      free_ids_.pop_back();
+    } else {
+      id = (int)server_ids_.size();  // no free id ⇒ the ids in use are exactly 0..size-1
+    }
+    server_ids_.emplace(namespaced_name, id);
+    return id;
+  }
+
+  // rows of the snapshot are endpoint ids: endpoint eps[i] fills row ids[i]; rows without an endpoint stay zero (they are
+  // never candidates: the batch's mask excludes them)
+  void PackSnapshot(const std::vector<Endpoint>& eps, const std::vector<int>& ids, int rows) {
+    const int N = (int)eps.size();
+    const int M = rows;
     adapter_ids_.clear();
     for (auto& e : eps) {
       for (auto& kv : e.GetMetrics()->ActiveModels) adapter_ids_.emplace(kv.first, (int)adapter_ids_.size());
@@ -416,8 +483,9 @@ class Scheduler {
     std::vector<uint8_t> prefill((size_t)M, 0);
     bool have_tokens = false;
     const PredictedLatencyProducer* prod = cfg_.Profile.producer().get();
-    for (int m = 0; m < M; m++) {
-      const Endpoint& ep = eps[(size_t)m];
+    for (int i = 0; i < N; i++) {
+      const int m = ids[(size_t)i];  // the endpoint's row
+      const Endpoint& ep = eps[(size_t)i];
       if (ep.InFlightTokens >= 0) {
         tokens[m] = ep.InFlightTokens;
         have_tokens = true;
@@ -464,8 +532,9 @@ class Scheduler {
       lp.composite_prefix = latency_scorer_->CompositePrefixWeight;
       if (eppscore_set_latency_params(eng_, &lp) != EPPSCORE_OK) throw SchedulingError(std::string("eppscore_set_latency_params: ") + eppscore_last_error(eng_));
     }
-    for (int m = 0; m < M; m++) {
-      const Metrics* x = eps[(size_t)m].GetMetrics();
+    for (int i = 0; i < N; i++) {
+      const int m = ids[(size_t)i];
+      const Metrics* x = eps[(size_t)i].GetMetrics();
       kv[m] = x->KVCacheUsagePercent;
       queue[m] = x->WaitingQueueSize;
       running[m] = x->RunningRequestsSize;
@@ -507,6 +576,11 @@ class Scheduler {
   std::vector<uint16_t> last_nh_;
   int32_t last_stride_ = 1;
   const std::vector<Endpoint>* last_endpoints_ = nullptr;
+  std::vector<int> last_ids_;                       // list position -> endpoint id of the last engine batch
+  int last_rows_ = 0;
+  std::unordered_map<std::string, int> server_ids_;  // ServerID (NamespacedName) -> stable endpoint id
+  std::vector<int> free_ids_;
+  uint64_t remapped_batches_ = 0;
 };
 
 inline Scheduler* NewSchedulerWithConfig(const SchedulerConfig& c) { return new Scheduler(c); }
