@@ -263,7 +263,7 @@ class Scheduler {
     // neither the order nor the membership of the candidate list is stable between calls (datastore PodList, subsetting:
     // director candidates.go:98).  An endpoint keeps the id it got when it was first seen; the engine's rows are ids, the
     // list's positions are mapped to and from them.  When the list is exactly ids 0..M-1 in order (the common case, and every
-    // single-list use) nothing is remapped and no mask is needed. ---
+    // single-list use) nothing is remapped; a mask is only needed when some row has no endpoint in this list. ---
     std::vector<int> ids((size_t)M);
     int Mx = 0;
     bool identity = true;
@@ -293,7 +293,7 @@ class Scheduler {
     const int mw = (Mx + 31) / 32;
     std::vector<uint32_t> mask;
     const bool have_filters = !cfg_.Profile.filters().empty();
-    const bool need_mask = have_filters || !identity;
+    const bool need_mask = have_filters || Mx != M;  // a pure permutation of the rows has no holes: no mask, the fast path stays
     if (need_mask) {
       mask.assign((size_t)R * mw, 0u);
       std::vector<int> all((size_t)M);
