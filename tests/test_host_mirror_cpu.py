@@ -46,3 +46,13 @@ def test_stable_endpoint_ids_across_reordered_extended_and_reduced_lists():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "host ids: all checks passed" in r.stdout
+
+
+def test_host_mirror_under_thread_sanitizer():
+    """The same program under ThreadSanitizer: the coalescing front drives the REAL Scheduler class from 32 caller threads
+    (one engine call at a time is the engine's contract — the front has to provide it)."""
+    exe = _build("host_test_cpu_tsan", ["-fsanitize=thread"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ThreadSanitizer" not in r.stderr, r.stderr
+    assert "all checks passed" in r.stdout
