@@ -1194,7 +1194,7 @@ def test_replicas_replay_the_commit_stream(pkg):
 
 
 def test_sets_beyond_eight_endpoints_and_universal_prefix(pkg):
-    """Blocks cached on more than 8 endpoints live in bitset rows; a system prompt cached on EVERY endpoint makes every endpoint
+    """Blocks cached on more than 10 endpoints live in bitset rows; a system prompt cached on EVERY endpoint makes every endpoint
     an exception of the sparse pick.  One batch builds those sets concurrently (every endpoint's CTA adds itself to the same
     16 slots); the sparse and the full-matrix kernels must both agree with the oracle afterwards."""
     M, R = 200, 3000
