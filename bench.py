@@ -967,7 +967,10 @@ def run_gpu(args):
         if world == 1:
             cores = os.cpu_count() or 1
             Rc = 65536
-            thr_c, tried_c = best_thread_count(lambda c, n: oracle_batch(o, osnap, prof, idx, seed, sets[0], n, c), Rc, cores)
+            try:
+                thr_c, tried_c = best_thread_count(lambda c, n: oracle_batch(o, osnap, prof, idx, seed, sets[0], n, c), Rc, cores)
+            except Exception as ex:  # noqa: BLE001  (never lose the bench line over the choice of a thread count)
+                thr_c, tried_c = cores, {"error": repr(ex)}
             t_mt, n_mt = time_oracle(o, osnap, prof, idx, seed, sets[0], Rc, thr_c)
             t_1, n_1 = time_oracle(o, osnap, prof, idx, seed, sets[0], 4096, 1, min_seconds=1.0, max_iters=5)
             extra["cpu_baseline"] = {"value": Rc / t_mt, "unit": "picks/s", "cores": thr_c, "kind": "port",
