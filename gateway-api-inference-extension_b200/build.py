@@ -14,6 +14,9 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeppscore.so")
 SOURCES = ["capi.cu", "hash_kernel.cu", "prepare_kernel.cu", "score_generic.cu", "score_matrix.cu", "score_dense.cu", "pick_sparse.cu",
            "prefix_index.cu", "fields_kernel.cu", "host_path.cu"]
+# host-only C++ compiled by g++ directly (AVX-512 intrinsics: kept away from nvcc's front end); the ISA flags apply to this
+# file alone and its one entry point is only called after a run-time CPU check (host_path.cu)
+CPP_SOURCES = [("host_hash_simd.cpp", ["-mavx512f", "-mavx512dq"])]
 HEADERS = ["kernels.cuh", "device_common.cuh", "xxh64.cuh", "prefix_index.hpp", "prefix_table.cuh",
            os.path.join("..", "..", "include", "eppscore.h")]
 
@@ -64,8 +67,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     raise RuntimeError(f"nvcc failed on {src}")
                 if verbose:
                     sys.stderr.write(r.stdout + r.stderr)
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
-    if force or jobs or _stale(LIB, objs):
+    cpp_built = False
+    for src, isa in CPP_SOURCES:
+        obj = os.path.join(OBJ, src.replace(".cpp", ".o"))
+        if force or _stale(obj, [os.path.join(CSRC, src), os.path.abspath(__file__)]):
+            r = subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-ffp-contract=off"] + isa + ["-c", os.path.join(CSRC, src), "-o", obj],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"g++ failed on {src}")
+            cpp_built = True
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES] + [os.path.join(OBJ, s.replace(".cpp", ".o")) for s, _ in CPP_SOURCES]
+    if force or jobs or cpp_built or _stale(LIB, objs):
         cmd = [nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

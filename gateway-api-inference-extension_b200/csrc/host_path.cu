@@ -27,6 +27,27 @@ inline uint64_t link_host(const uint8_t* d, uint32_t n, uint64_t prev) {
   return eppscore::xxh64_link<false>(d, n, prev);
 }
 
+// The same link when the block size is a multiple of 32 (the default 64): the four-lane stripe state depends on the block's
+// own bytes only, the chain value enters as the message's last 8 bytes — one tail round + avalanche (xxh64.cuh: the device
+// kernels' hash_bodies / hash_chain split).  No copy of the block, 64-bit loads; the out-of-order core overlaps the next
+// block's stripes with this block's serial tail.
+inline uint64_t ld64(const uint8_t* p) {
+  uint64_t v;
+  memcpy(&v, p, 8);  // little-endian host
+  return v;
+}
+inline uint64_t link_host_stripes(const uint8_t* d, uint32_t n, uint64_t prev) {
+  using namespace eppscore;
+  uint64_t v1 = XP1 + XP2, v2 = XP2, v3 = 0, v4 = 0 - XP1;
+  for (uint32_t s = 0; s < n; s += 32) {
+    v1 = xround(v1, ld64(d + s));
+    v2 = xround(v2, ld64(d + s + 8));
+    v3 = xround(v3, ld64(d + s + 16));
+    v4 = xround(v4, ld64(d + s + 24));
+  }
+  return xchain_aligned(xfinish_lanes(v1, v2, v3, v4) + (uint64_t)(n + 8), prev);
+}
+
 int32_t hash_one(const uint8_t* p, int64_t len, uint64_t seed, int32_t bc, int32_t max_blocks, uint64_t* out) {
   if (bc <= 0 || len < bc) return 0;                       // hashing.go:51-60
   const int64_t cap = (int64_t)bc * max_blocks;
@@ -34,9 +55,28 @@ int32_t hash_one(const uint8_t* p, int64_t len, uint64_t seed, int32_t bc, int32
   uint64_t prev = seed;
   int32_t n = 0;
   int64_t o = 0;
-  for (; o + bc <= len; o += bc) out[n++] = prev = link_host(p + o, (uint32_t)bc, prev);   // :79-87
+  if ((bc & 31) == 0) {
+    for (; o + bc <= len; o += bc) out[n++] = prev = link_host_stripes(p + o, (uint32_t)bc, prev);   // :79-87
+  } else {
+    for (; o + bc <= len; o += bc) out[n++] = prev = link_host(p + o, (uint32_t)bc, prev);
+  }
   if (o < len) out[n++] = link_host(p + o, (uint32_t)(len - o), prev);                     // trailing partial block :89-95
   return n;
+}
+
+// eight requests at a time, one per AVX-512 lane (host_hash_simd.cpp, compiled with -mavx512f -mavx512dq; used only when the
+// CPU has both)
+extern "C" void eppscore_host_hash8_avx512(const uint8_t* bytes, const int64_t* off, const uint64_t* seed, int32_t bc, int32_t nfull,
+                                           uint64_t* hashes, const int64_t* row, uint64_t* last, int32_t groups);
+extern "C" int32_t eppscore_host_hash8_compiled(void);
+
+bool have_simd8() {
+#if defined(__x86_64__)
+  static const bool ok = eppscore_host_hash8_compiled() != 0 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq");
+  return ok;
+#else
+  return false;
+#endif
 }
 
 struct Job {
@@ -50,6 +90,7 @@ struct Job {
   uint16_t* nh = nullptr;
   std::atomic<int32_t> next{0};
   int32_t chunk = 64;
+  bool simd8 = false;   // block size a multiple of 32 and the CPU has AVX-512 F + DQ
 };
 
 void run_job(Job* j) {
@@ -57,7 +98,40 @@ void run_job(Job* j) {
     const int32_t r0 = j->next.fetch_add(j->chunk, std::memory_order_relaxed);
     if (r0 >= j->R) return;
     const int32_t r1 = r0 + j->chunk < j->R ? r0 + j->chunk : j->R;
-    for (int32_t r = r0; r < r1; r++) {
+    int32_t r = r0;
+    if (j->simd8) {
+      const int32_t bc = j->bc;
+      const int64_t cap = (int64_t)bc * j->max_blocks;
+      // 32 requests (four independent groups of eight fill the multiplier pipeline) while they last, then 8
+      for (int W = 32; W >= 8; W -= 24) {
+        for (; r + W <= r1; r += W) {
+          int64_t o8[32], l8[32], row8[32];
+          uint64_t s8[32], last8[32];
+          bool same = true;
+          for (int k = 0; k < W; k++) {
+            o8[k] = j->off[r + k];
+            int64_t l = j->len ? (int64_t)j->len[r + k] : j->off[r + k + 1] - o8[k];
+            if (l > cap) l = cap;                              // hashing.go:62-65
+            l8[k] = l;
+            s8[k] = j->seed ? j->seed[r + k] : 0;
+            row8[k] = (int64_t)(r + k) * j->stride;
+            same = same && l / bc == l8[0] / bc;
+          }
+          const int32_t nfull = (int32_t)(l8[0] / bc);
+          if (!same || nfull == 0) break;                      // mixed lengths: narrower groups, then the scalar loop, take over
+          eppscore_host_hash8_avx512(j->bytes, o8, s8, bc, nfull, j->hashes, row8, last8, W / 8);
+          for (int k = 0; k < W; k++) {
+            uint64_t* out = j->hashes + (size_t)row8[k];
+            int32_t n = nfull;
+            const int64_t done = (int64_t)nfull * bc;
+            if (done < l8[k]) out[n++] = link_host(j->bytes + o8[k] + done, (uint32_t)(l8[k] - done), last8[k]);  // partial block :89-95
+            for (int32_t i = n; i < j->stride; i++) out[i] = 0;
+            j->nh[r + k] = (uint16_t)n;
+          }
+        }
+      }
+    }
+    for (; r < r1; r++) {
       const int64_t o = j->off[r];
       const int64_t l = j->len ? (int64_t)j->len[r] : j->off[r + 1] - o;
       uint64_t* out = j->hashes + (size_t)r * j->stride;
@@ -157,6 +231,7 @@ extern "C" int32_t eppscore_hash_prompts_host(int32_t R, const uint8_t* prompt_b
   j.stride = hash_stride;
   j.hashes = hashes_out;
   j.nh = n_hashes_out;
+  j.simd8 = (block_chars & 31) == 0 && have_simd8();
   j.chunk = R / (n_threads * 8) > 16 ? (R / (n_threads * 8) < 256 ? R / (n_threads * 8) : 256) : 16;
   if (n_threads == 1) run_job(&j);
   else pool().run(&j, n_threads);

@@ -121,3 +121,46 @@ def test_host_hash_pool_matches_oracle(pkg, xxh_kat):
             want = o.hash_prompt(data[off[r]: off[r + 1]], int(seeds[r]), bc, mb)
             assert int(n[r]) == len(want) and np.array_equal(h[r, : n[r]], want), (bc, mb, r)
             assert not h[r, n[r]:].any()
+
+
+def test_host_hash_eight_lane_path_matches_oracle(pkg):
+    """The eight-requests-per-register form of the host hashPrompt (csrc/host_hash_simd.cpp; taken when the CPU has AVX-512 F + DQ,
+    the block size is a multiple of 32 and eight consecutive requests have the same number of full blocks) against the oracle:
+    uniform prompts (every group takes it), uniform prompts with a trailing partial block, truncation at max_blocks, explicit
+    lengths with padded starts, and a mix of uniform runs and ragged prompts so that groups switch between the two paths.
+    On a CPU without AVX-512 the same calls run the scalar path: the test still holds."""
+    from oracle import oracle_py as o
+    rng = np.random.default_rng(5)
+
+    def check(data, off, seeds, bc, mb, lens=None, threads=4, every=1):
+        h, n = pkg.Engine.hash_prompts_host(data, off, seeds, prompt_len=lens, block_chars=bc, max_blocks=mb, n_threads=threads)
+        for r in range(0, len(off) - 1, every):
+            ln = int(lens[r]) if lens is not None else int(off[r + 1] - off[r])
+            want = o.hash_prompt(data[off[r]: off[r] + ln], int(seeds[r]), bc, mb)
+            assert int(n[r]) == len(want), (bc, mb, r, int(n[r]), len(want))
+            assert np.array_equal(h[r, : n[r]], want), (bc, mb, r)
+            assert not h[r, n[r]:].any()
+
+    R = 203                                                     # not a multiple of 8: a scalar tail in every chunk
+    for plen, bc, mb in ((2048, 64, 32), (2048 + 37, 64, 64), (4096, 64, 20), (640, 32, 256), (960, 96, 16), (50, 64, 8)):
+        data = rng.integers(0, 256, size=R * plen, dtype=np.uint8)
+        off = np.arange(R + 1, dtype=np.int64) * plen
+        seeds = rng.integers(0, 2 ** 63, size=R, dtype=np.uint64)
+        check(data, off, seeds, bc, mb, threads=1)
+        check(data, off, seeds, bc, mb, threads=4)
+    # padded starts + explicit lengths (the host layer's layout), lengths equal within runs of 8..40 requests, ragged between
+    lens, starts, total = [], [], 0
+    while len(lens) < 600:
+        run, ln = int(rng.integers(1, 40)), int(rng.integers(0, 1500))
+        for _ in range(run):
+            ln_r = ln if rng.random() < 0.9 else int(rng.integers(0, 1500))
+            total = (total + 15) // 16 * 16
+            starts.append(total)
+            lens.append(ln_r)
+            total += ln_r
+    Rm = len(lens)
+    data = rng.integers(0, 256, size=total + 64, dtype=np.uint8)
+    off = np.array(starts + [total], np.int64)
+    seeds = rng.integers(0, 2 ** 63, size=Rm, dtype=np.uint64)
+    check(data, off, seeds, 64, 256, lens=np.array(lens, np.int32), threads=3)
+    check(data, off, seeds, 32, 11, lens=np.array(lens, np.int32), threads=2)
