@@ -512,9 +512,13 @@ def run_gpu(args):
     want = oracle_batch(o, osnap, prof, idx, seed, sets[(3 + e2e_steps - 1) % NSETS], n_chk, base=rank * R)
     if not (np.array_equal(res["pick"][:n_chk], want["pick"]) and np.array_equal(res["pick_score"][:n_chk], want["pick_score"])):
         raise SystemExit("bench: e2e picks differ from the oracle")
-    hh_value, hh_dt, _, res = time_host(e2e_hosthash_step, e2e_steps)
-    if not (np.array_equal(res["pick"][:n_chk], want["pick"]) and np.array_equal(res["pick_score"][:n_chk], want["pick_score"])):
-        raise SystemExit("bench: e2e (host-hash mode) picks differ from the oracle")
+    hh_error = None
+    try:
+        hh_value, hh_dt, _, res = time_host(e2e_hosthash_step, e2e_steps)
+        if not (np.array_equal(res["pick"][:n_chk], want["pick"]) and np.array_equal(res["pick_score"][:n_chk], want["pick_score"])):
+            hh_error = "picks differ from the oracle"   # reported in the line (an extra leg must not take the headline down)
+    except Exception as ex:  # noqa: BLE001
+        hh_value, hh_dt, hh_error = 0.0, 0.0, repr(ex)
     apply_snapshot(eng)
 
     # ---- closed loop: schedule -> PreRequest commit -> schedule ..., the commit inside the timed region.  The snapshot
@@ -696,7 +700,10 @@ def run_gpu(args):
         extra["e2e_host_hash"] = {"value": hh_value, "unit": "picks/s", "h2d_bytes_per_step": h2d_hh, "d2h_bytes_per_step": d2h,
                                   "ms_per_step": 1e3 * hh_dt, "host_threads": os.cpu_count(),
                                   "note": "prompts hashed on the host cores (eppscore_hash_prompts_host) inside the timed region; "
-                                          "hashes_in crosses PCIe instead of the prompt bytes; picks bit-equal"}
+                                          "hashes_in crosses PCIe instead of the prompt bytes; "
+                                          + ("picks bit-equal" if hh_error is None else "FAILED: " + hh_error)}
+        if hh_error is not None:
+            extra["e2e_host_hash"]["error"] = hh_error
     if rank == 0 and full:
         peak, peak_src = peaks()
         traffic = {}
