@@ -12,8 +12,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeppscore.so")
-SOURCES = ["capi.cu", "hash_kernel.cu", "prepare_kernel.cu", "score_generic.cu", "score_matrix.cu", "score_dense.cu", "pick_sparse.cu",
+SOURCES = ["capi.cu", "hash_kernel.cu", "prepare_kernel.cu", "score_generic.cu", "score_dense.cu", "pick_sparse.cu",
            "prefix_index.cu", "fields_kernel.cu", "host_path.cu"]
+# score_matrix.cu holds 56 instantiations of one kernel template: compiled as four objects (one (MASKED, DIAG) combination each,
+# -DEPP_MATRIX_PART=k) so that they build in parallel
+PART_SOURCES = [("score_matrix.cu", f"score_matrix_p{k}.o", [f"-DEPP_MATRIX_PART={k}"]) for k in range(4)]
 # host-only C++ compiled by g++ directly (AVX-512 intrinsics: kept away from nvcc's front end); the ISA flags apply to this
 # file alone and its one entry point is only called after a run-time CPU check (host_path.cu)
 CPP_SOURCES = [("host_hash_simd.cpp", ["-mavx512f", "-mavx512dq"])]
@@ -47,15 +50,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     jobs = []
-    for src in SOURCES:
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    for src, objname, defs in PART_SOURCES + [(s_, s_.replace(".cu", ".o"), []) for s_ in SOURCES]:  # the slow parts first
+        obj = os.path.join(OBJ, objname)
         if force or _stale(obj, [os.path.join(CSRC, src)] + hdrs):
-            jobs.append((src, obj))
+            jobs.append((src, obj, defs))
 
     def compile_one(job):
-        src, obj = job
+        src, obj, defs = job
         extra = os.environ.get("EPPSCORE_NVCC_EXTRA", "").split()  # experiments only (e.g. -DEPP_SPARSE_MINBLOCKS=5)
-        cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc()] + NVCC_FLAGS + defs + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r
 
@@ -77,7 +80,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(r.stdout + r.stderr)
                 raise RuntimeError(f"g++ failed on {src}")
             cpp_built = True
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES] + [os.path.join(OBJ, s.replace(".cpp", ".o")) for s, _ in CPP_SOURCES]
+    objs = ([os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES] + [os.path.join(OBJ, o_) for _, o_, _ in PART_SOURCES] +
+            [os.path.join(OBJ, s.replace(".cpp", ".o")) for s, _ in CPP_SOURCES])
     if force or jobs or cpp_built or _stale(LIB, objs):
         cmd = [nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)

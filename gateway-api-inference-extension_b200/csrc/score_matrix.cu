@@ -764,12 +764,37 @@ static int launch_matrix_seq(const ScoreArgs& a, cudaStream_t s, int sm_count) {
 #undef L
 #undef Q
 
+// The file is compiled four times (build.py: -DEPP_MATRIX_PART=0..3), one (MASKED, DIAG) combination of the kernel per object,
+// so the 56 instantiations build in parallel (one translation unit took over three minutes); without the macro everything
+// lands in one object.  The kernels are the same instantiations either way.
+#ifndef EPP_MATRIX_PART
+#define EPP_MATRIX_PART -1
+#endif
+int launch_matrix_part0(const ScoreArgs& a, cudaStream_t s, int sm_count);  // unmasked
+int launch_matrix_part1(const ScoreArgs& a, cudaStream_t s, int sm_count);  // unmasked, diagnostics outputs
+int launch_matrix_part2(const ScoreArgs& a, cudaStream_t s, int sm_count);  // masked
+int launch_matrix_part3(const ScoreArgs& a, cudaStream_t s, int sm_count);  // masked, diagnostics outputs
+#if EPP_MATRIX_PART == -1 || EPP_MATRIX_PART == 0
+int launch_matrix_part0(const ScoreArgs& a, cudaStream_t s, int sm_count) { return launch_matrix_seq<false, false>(a, s, sm_count); }
+#endif
+#if EPP_MATRIX_PART == -1 || EPP_MATRIX_PART == 1
+int launch_matrix_part1(const ScoreArgs& a, cudaStream_t s, int sm_count) { return launch_matrix_seq<false, true>(a, s, sm_count); }
+#endif
+#if EPP_MATRIX_PART == -1 || EPP_MATRIX_PART == 2
+int launch_matrix_part2(const ScoreArgs& a, cudaStream_t s, int sm_count) { return launch_matrix_seq<true, false>(a, s, sm_count); }
+#endif
+#if EPP_MATRIX_PART == -1 || EPP_MATRIX_PART == 3
+int launch_matrix_part3(const ScoreArgs& a, cudaStream_t s, int sm_count) { return launch_matrix_seq<true, true>(a, s, sm_count); }
+#endif
+
+#if EPP_MATRIX_PART == -1 || EPP_MATRIX_PART == 0
 // every (request, endpoint) pair scored; any plan without pair columns
 int launch_score_matrix(const ScoreArgs& a, cudaStream_t s, int sm_count) {
   if (a.R <= 0) return 0;
   const bool diag = a.match_out != nullptr || a.scores_out != nullptr || a.lat.pred_out != nullptr;  // diagnostics variants keep the R x M stores out of the hot loop
-  if (a.cand_mask) return diag ? launch_matrix_seq<true, true>(a, s, sm_count) : launch_matrix_seq<true, false>(a, s, sm_count);
-  return diag ? launch_matrix_seq<false, true>(a, s, sm_count) : launch_matrix_seq<false, false>(a, s, sm_count);
+  if (a.cand_mask) return diag ? launch_matrix_part3(a, s, sm_count) : launch_matrix_part2(a, s, sm_count);
+  return diag ? launch_matrix_part1(a, s, sm_count) : launch_matrix_part0(a, s, sm_count);
 }
+#endif
 
 }  // namespace eppscore
